@@ -1,0 +1,234 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/src) here.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+    python oracle/make_golden.py [name ...]
+The fixtures are committed; the GPU box only reads them.
+"""
+import os
+import re
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from genofix_b200 import synth  # noqa: E402  (input generator only)
+from oracle import ref_harness as rh  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name -> (pedigree spec, n_snps, error rate, missing rate, drop-genotype fraction, correctMatrix params)
+GENOFIX_DEFAULTS = dict(threshold_pair=0.5, threshold_single=0.64, back=2, init_filter_p=0.95,
+                        filter_e=0.99, tiethreshold=0.4, err_thresh=1)       # genofix.py:95-112
+SIMULATE_DEFAULTS = dict(threshold_pair=0.5, threshold_single=0.7, back=2, init_filter_p=0.9,
+                         filter_e=0.8, tiethreshold=0.05, err_thresh=1)      # simulate.py:89-113
+CASES = {
+    "toy_a": dict(ped=dict(n_animals=60, n_generations=5, sire_frac=0.3, dam_frac=0.6, seed=7),
+                  n_snps=30, err=0.03, miss=0.03, drop=0.0, params=GENOFIX_DEFAULTS),
+    "toy_b": dict(ped=dict(n_animals=96, n_generations=6, sire_frac=0.25, dam_frac=0.5, seed=11,
+                           related_mating_p=0.6, unknown_parents_frac=0.1),
+                  n_snps=32, err=0.02, miss=0.05, drop=0.12, params=SIMULATE_DEFAULTS),
+    "deep": dict(ped=dict(n_animals=180, n_generations=15, sire_frac=0.34, dam_frac=0.5, seed=23,
+                          related_mating_p=0.5, unknown_parents_frac=0.1),
+                 n_snps=24, err=0.02, miss=0.03, drop=0.0,
+                 params=dict(GENOFIX_DEFAULTS, init_filter_p=0.9)),
+    # D16: a loopy blanket whose shared ancestor is unobserved + contradictory evidence -> NaN rank
+    "nan_loop": dict(ped="crafted_nan", n_snps=6, err=0.0, miss=0.0, drop=0.0, params=GENOFIX_DEFAULTS),
+    "example_fam": dict(ped="example.fam", n_snps=12, err=0.01, miss=0.0, drop=0.0,
+                        params=GENOFIX_DEFAULTS),
+}
+
+
+def build_inputs(case):
+    if case["ped"] == "example.fam":
+        rows = np.loadtxt("/root/reference/examples/simulate/example.fam", dtype=np.int64, usecols=(0, 1, 2, 3))
+        # founders that only appear as parents need rows for the gene drop; order parents first
+        known = set(rows[:, 0])
+        extra = []
+        for col, sex in ((1, 1), (2, 2)):
+            for p in np.unique(rows[:, col]):
+                if p > 0 and p not in known:
+                    extra.append((p, 0, 0, sex))
+                    known.add(p)
+        drop_rows = np.array(extra + [tuple(r) for r in rows], dtype=np.int64)
+        drop_rows = topo_sort(drop_rows)
+        ped_rows = rows
+    elif case["ped"] == "crafted_nan":
+        # A(1) x X(2) -> S(4);  A(1) x Y(3) -> D(5);  S x D -> 6,7,8 ; extra founders 9,10 -> 11
+        drop_rows = np.array([[1, 0, 0, 1], [2, 0, 0, 2], [3, 0, 0, 2], [9, 0, 0, 1], [10, 0, 0, 2],
+                              [4, 1, 2, 1], [5, 1, 3, 2], [6, 4, 5, 1], [7, 4, 5, 2], [8, 4, 5, 1],
+                              [11, 9, 10, 2]], dtype=np.int64)
+        ped_rows = drop_rows
+    else:
+        drop_rows = synth.make_pedigree(**case["ped"])
+        ped_rows = drop_rows
+    truth = synth.gene_drop(drop_rows, case["n_snps"], seed=1234)
+    obs = synth.inject_errors(truth, case["err"], seed=1234)
+    if case["miss"] > 0:
+        obs = synth.inject_missing(obs, case["miss"], seed=4321)
+    ids = drop_rows[:, 0].copy()
+    if case["ped"] == "crafted_nan":
+        r = {int(k): i for i, k in enumerate(ids)}
+        obs[r[4], 0] = 9   # S missing
+        obs[r[1], 0] = 9   # shared grandsire A missing
+        obs[r[5], 0] = 2   # D = 2 ...
+        obs[r[3], 0] = 0   # ... but her dam Y = 0  -> P(evidence) = 0 inside K's component
+        obs[r[7], 3] = 9
+    if case["drop"] > 0:
+        rs = np.random.Generator(np.random.PCG64(99))
+        keep = rs.random(len(ids)) >= case["drop"]
+        ids, truth, obs = ids[keep], truth[keep], obs[keep]
+    return ped_rows, ids, truth, obs
+
+
+def topo_sort(rows):
+    by = {int(r[0]): r for r in rows}
+    out, done = [], set()
+
+    def visit(k):
+        stack = [k]
+        while stack:
+            x = stack[-1]
+            if x in done:
+                stack.pop()
+                continue
+            pend = [int(p) for p in by[x][1:3] if p > 0 and int(p) in by and int(p) not in done]
+            if pend:
+                stack.extend(pend)
+            else:
+                done.add(x)
+                out.append(by[x])
+                stack.pop()
+    for k in by:
+        visit(k)
+    return np.array(out, dtype=np.int64)
+
+
+def make_case(name):
+    case = CASES[name]
+    ped_rows, ids, truth, obs = build_inputs(case)
+    cols = ["SNP%d" % i for i in range(case["n_snps"])]
+    df = pd.DataFrame(obs, index=[int(x) for x in ids], columns=cols)
+    t0 = time.time()
+    r = rh.run_correct_matrix(df, ped_rows, **case["params"])
+    dt = time.time() - t0
+    m = re.search(r"setting initial filter to (\S+) quantile threshold", r["stdout"])
+    test_p = float(m.group(1))
+    m = re.search(r"n errors pairs\+single: not rank1 excluded (\d+) passed (\d+)", r["stdout"])
+    errors_all = int(m.group(2))
+    m = re.search(r"n errors pairs: not rank1 excluded (\d+) passed (\d+)", r["stdout"])
+    pair_excluded, pair_passed = int(m.group(1)), int(m.group(2))
+    snpi = {c: i for i, c in enumerate(cols)}
+    seen = {}
+    prec = []
+    for s, d, res in r["pair_results"]:
+        occ = seen.get((s, d), 0)
+        seen[(s, d)] = occ + 1
+        if res is None:
+            continue
+        for snp in res.prob_sire:
+            prec.append([occ, s, d, snpi[snp]] + list(np.asarray(res.prob_sire[snp], dtype=float)) +
+                        list(np.asarray(res.prob_dam[snp], dtype=float)))
+    srec = []
+    for k, res in r["single_results"]:
+        if res is None:
+            continue
+        for snp in res.prob:
+            srec.append([k, snpi[snp]] + list(np.asarray(res.prob[snp], dtype=float)))
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        ped_rows=ped_rows, ids=ids, truth=truth, obs=obs, raw=r["raw"], corrected=r["corrected"],
+        test_p=np.float64(test_p), errors_all=errors_all, pair_excluded=pair_excluded, pair_passed=pair_passed,
+        pair_post=np.array(prec, dtype=np.float64).reshape(-1, 10),
+        single_post=np.array(srec, dtype=np.float64).reshape(-1, 5),
+        params=np.array([case["params"][k] for k in ("threshold_pair", "threshold_single", "back",
+                                                     "init_filter_p", "tiethreshold", "err_thresh")], dtype=np.float64))
+    print("%s: %d x %d, reference correctMatrix %.1fs, %d cells changed, errors_all=%d, test_p=%r, raw NaN=%d" % (
+        name, obs.shape[0], obs.shape[1], dt, int((r["corrected"] != obs).sum()), errors_all, test_p,
+        int(np.isnan(r["raw"].astype(float)).sum())))
+
+
+def make_kats():
+    ref = rh.load()
+    model, jad3, pdag = ref["model"], ref["jad3"], ref["pdag"]
+    rs = np.random.Generator(np.random.PCG64(2024))
+    n_cases, width = 400, 14
+    kid = np.full((n_cases, width), -1, dtype=np.int8)
+    par = np.full((n_cases, width), -1, dtype=np.int8)  # -1 = None
+    pk = np.zeros((n_cases, 3))
+    dk = np.full((n_cases, 3, width), np.nan, dtype=np.float16)
+    for c in range(n_cases):
+        n = int(rs.integers(1, width + 1))
+        ks = rs.choice([0, 1, 2, 9], size=n, p=[.3, .3, .3, .1])
+        ps = rs.choice([-1, 0, 1, 2, 9], size=n, p=[.3, .2, .2, .2, .1])
+        kid[c, :n] = ks
+        par[c, :n] = ps
+        plist = [None if p < 0 else int(p) for p in ps]
+        pk[c] = np.asarray(model.generate_probs_kids(list(ks), plist), dtype=float)
+        inc = [k in (0, 1, 2) for k in ks]
+        ks_i = [int(k) for k, i in zip(ks, inc) if i]
+        ps_i = [p for p, i in zip(plist, inc) if i]
+        for o in range(3):
+            d = model.generate_probs_differences_kids(ks_i, ps_i, o) if ks_i else []
+            dk[c, o, :len(d)] = d
+    dp = np.zeros((4, 4, 3))
+    for i, p1 in enumerate([0, 1, 2, 9]):
+        for j, p2 in enumerate([0, 1, 2, 9]):
+            for o in range(3):
+                dp[i, j, o] = model.generate_probs_differences_parent(p1, p2, o)
+    # countJointFrq + windows
+    cj = {}
+    for w in (3, 5, 7):
+        tab = rs.integers(0, 3, size=(300, w)).astype(np.uint8)
+        mask = rs.random((300, w)) < 0.97
+        import itertools
+        sv = list(itertools.product([0, 1, 2], repeat=w))
+        names = ["S%d" % i for i in range(w)]
+        res = jad3.JointAllellicDistribution.countJointFrq(tab, mask, names, sv, 1e-4)
+        cj["cj_tab_%d" % w] = tab
+        cj["cj_mask_%d" % w] = mask
+        cj["cj_val_%d" % w] = np.array([res[tuple(zip(names, v))] for v in sv])
+    wins = []
+    import contextlib
+    import io
+    for n in (5, 12):
+        names = ["SNP%d" % i for i in range(n)]
+        for sur in (1, 2, 3):
+            with contextlib.redirect_stdout(io.StringIO()):
+                j = jad3.JointAllellicDistribution("1", names, surround_size=sur)
+            for i, nm in enumerate(names):
+                win = j.getWindow(nm)
+                a = names.index(win[0]) if win else -1
+                wins.append([n, sur, i, a, a + len(win)])
+    # pedigree structure on example.fam
+    ped = pdag.PedigreeDAG.from_file("/root/reference/examples/simulate/example.fam")
+    gens = sorted((g, len(k)) for g, k in ped.generationIndex.items())
+    animals = sorted(ped.males | ped.females)
+    pick = [animals[i] for i in rs.choice(len(animals), size=120, replace=False)]
+    gen_of = {a: g for g, ks in ped.generationIndex.items() for a in ks}
+    struct = []
+    for a in pick:
+        for depth in (2, 3):
+            anc = [x for x in ped.get_parents_depth([a], depth) if x is not None]
+            if anc:
+                nodes = sorted(ped.balance_nodes(list(set([a] + list(anc)))))
+            else:
+                nodes = []
+            struct.append([a, depth, gen_of[a], len(anc), len(nodes)] + nodes + [0] * (40 - len(nodes)))
+    np.savez_compressed(os.path.join(OUT, "kats.npz"), kid=kid, par=par, probs_kids=pk, diff_kids=dk,
+                        diff_parent=dp, windows=np.array(wins), gen_sizes=np.array(gens),
+                        blanket_struct=np.array(struct, dtype=np.int64),
+                        n_animals=len(animals), n_males=len(ped.males), n_females=len(ped.females), **cj)
+    print("kats written")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    names = sys.argv[1:] or ["kats"] + list(CASES)
+    for n in names:
+        if n == "kats":
+            make_kats()
+        else:
+            make_case(n)

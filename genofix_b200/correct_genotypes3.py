@@ -1,0 +1,251 @@
+"""CorrectGenotypes with the reference's call surface (correct_genotypes3.py), driven on a B200.
+
+`correctMatrix` keeps the reference signature and semantics for `empC=None` (the only configuration
+of the reference that is internally consistent at HEAD): Mendel rank of every cell,
+rank transform + quantile filter, per-generation pair correction with sequential apply, singles.
+All of it runs as CUDA kernels through the C ABI (genofix_b200.engine); nothing falls back to the CPU.
+
+Under-specified behaviour of the reference that is fixed here (and identically in the oracle):
+  * results of a generation are applied in ascending (sire id, dam id) order (the reference applies
+    them in process-pool completion order);
+  * correctSingle's tie set is the flat set of states.
+"""
+import multiprocessing
+
+import numpy as np
+
+from .bayesnet.result import ResultPairInfer, ResultSingleInfer
+from .engine import engine_for
+from .pedigree.pedigree_dag import PedigreeDAG
+
+_DEBUG_NO_CHANGE = False
+
+
+def initializer(corrected_genotype_c, pedigree_c, probs_errors, cacheIn=None):
+    """Bind a genotype matrix / pedigree / rank matrix to the current process, like the pool
+    initializer of the reference (correct_genotypes3.py:42-50).  The static workers below read it."""
+    cur = multiprocessing.current_process()
+    cur.genotypes = corrected_genotype_c.copy()
+    cur.pedigree = pedigree_c if isinstance(pedigree_c, PedigreeDAG) else PedigreeDAG(pedigree_c)
+    if probs_errors is not None:
+        cur.probs_errors = probs_errors.copy()
+    cur.cacheIn = cacheIn if cacheIn is not None else {}
+    cur._gfx_cache = {}
+
+
+def initializerEmp(empC):
+    multiprocessing.current_process().indexemp = empC
+
+
+class CorrectGenotypes(object):
+
+    def __init__(self, chromosome2snp=None, min_cluster_size=100, elimination_order="MinNeighbors"):
+        self.chromosome2snp = chromosome2snp
+        self.elimination_order = elimination_order  # only changes float rounding in pgmpy; unused here
+        self.last_stats = None
+
+    # ------------------------------------------------------------------------------------------
+    def correctMatrix(self, genotypes, pedigree, empC, threshold_pair, threshold_single, back=2,
+                      init_filter_p=0.9, filter_e=0.7, tiethreshold=0.05, threads=1, err_thresh=1,
+                      weight_empirical=3, outputerrors=False, DEBUGDIR=None, debugreal=None):
+        """Returns a new DataFrame of corrected genotypes (the input is not modified)."""
+        import pandas as pd
+        if empC is not None:
+            raise NotImplementedError(
+                "the empirical (LD) blend is not executable in the reference at HEAD "
+                "(correct_genotypes3.py:34-40 copies empC.frequency, which jalleledist3 objects lack); "
+                "pass empC=None")
+        print("correcting genotype %s x %s on the GPU" % (len(genotypes.index), len(genotypes.columns)))
+        eng = engine_for(pedigree, np.asarray(genotypes.index, dtype=np.int64), back)
+        G = genotypes.to_numpy(dtype=np.uint8, copy=False)
+        out = eng.correct(G, threshold_pair, threshold_single, init_filter_p=init_filter_p,
+                          tiethreshold=tiethreshold, err_thresh=err_thresh)
+        self.last_stats = eng.stats
+        errors_all = int(eng.stats["corrected_per_animal"].sum())
+        print("setting initial filter to %s quantile threshold %s" % (eng.stats["test_p"], init_filter_p))
+        print("predicted errors %s of %s" % (errors_all, G.size - errors_all))
+        return pd.DataFrame(out, index=genotypes.index, columns=genotypes.columns)
+
+    # ------------------------------------------------------------------------------------------
+    # static workers of the reference; they operate on the matrix bound by initializer()
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _bound(back, need_ranks):
+        cur = multiprocessing.current_process()
+        if not hasattr(cur, "genotypes"):
+            raise RuntimeError("call initializer(genotypes, pedigree, probs_errors) first")
+        cache = cur._gfx_cache
+        key = ("eng", back)
+        if key not in cache:
+            g = cur.genotypes
+            eng = engine_for(cur.pedigree, np.asarray(g.index, dtype=np.int64), back)
+            G = g.to_numpy(dtype=np.uint8, copy=False)
+            eng._alloc(G.shape[1])
+            hin = eng.host_in.numpy()
+            hin[:, :eng.s] = G
+            hin[:, eng.s:] = 9
+            eng.codes.copy_(eng.host_in)
+            eng.load_codes_device(eng.codes)
+            eng.mendel_rank_device()
+            eng.check_status()
+            cache[key] = (eng, eng.raw_host())
+        return cache[key]
+
+    @staticmethod
+    def mendelProbsSingle(kid, back, elimination_order="MinNeighbors"):
+        """(state probabilities [S,3] f16, rank score [S,1] f16, cache) of one animal
+        (correct_genotypes3.py:85-166).  The score column is computed on the GPU for the whole bound
+        matrix once; every caller of the reference discards the first element (:585), it is returned
+        as zeros."""
+        eng, raw = CorrectGenotypes._bound(back, False)
+        cur = multiprocessing.current_process()
+        r = list(cur.genotypes.index).index(kid)
+        S = raw.shape[1]
+        return np.zeros((S, 3), dtype=np.float16), raw[r].reshape(S, 1).copy(), {}
+
+    @staticmethod
+    def _results_for(kind, key, back, tiethreshold, test_p, suspect_t):
+        from . import _lib
+        import ctypes as C
+        cur = multiprocessing.current_process()
+        if abs(suspect_t - 0.2) > 0:
+            raise NotImplementedError("suspect_t is fixed to 0.2 like the reference driver")
+        sched_back = back - 1 if kind == "pair" else back
+        if sched_back < 1:
+            raise ValueError("back too small")
+        eng, _ = CorrectGenotypes._bound(sched_back, True)
+        t = eng.torch
+        ckey = ("post", kind, sched_back, float(tiethreshold), float(test_p))
+        cache = cur._gfx_cache
+        if ckey not in cache:
+            # E table from the bound rank matrix (probs_errors holds transformed ranks already)
+            E = cur.probs_errors.to_numpy(dtype=np.float64)
+            # feed E through an identity table: raw := rank of the distinct values
+            vals, inv = np.unique(E, return_inverse=True)
+            if len(vals) > 65536:
+                raise ValueError("too many distinct rank values")
+            elut = np.full(65536, np.nan)
+            elut[:len(vals)] = vals
+            eng.host_elut.numpy()[:] = elut
+            eng.elut.copy_(eng.host_elut)
+            rawidx = t.from_numpy(inv.reshape(E.shape).astype(np.int16)).to(eng.codes.device)
+            saved_raw = eng.raw.clone()
+            eng.raw[:, :eng.s] = rawidx
+            eng.test_p = float(test_p)
+            # E for missing cells is whatever the caller put there: patch through packed_orig = no missing
+            saved_orig = eng.packed_orig.clone()
+            nomiss = t.zeros_like(eng.packed_orig)
+            try:
+                eng.packed_live.copy_(saved_orig)
+                posts = CorrectGenotypes._infer_only(eng, nomiss, kind, tiethreshold)
+            finally:
+                eng.raw.copy_(saved_raw)
+                eng.packed_orig.copy_(saved_orig)
+            cache[ckey] = posts
+        return eng, cache[ckey]
+
+    @staticmethod
+    def _infer_only(eng, orig_for_E, kind, tiethreshold):
+        """Run the inference kernels on the bound snapshot and return posteriors WITHOUT keeping the
+        applied corrections (correctPair/correctSingle only compute results)."""
+        from . import _lib
+        import ctypes as C
+        t = eng.torch
+        info = eng.schedule.info
+        out = {}
+        live = eng.packed_orig.clone()
+        pp = _lib.CorrectParams(eng.test_p, 0.2, float(tiethreshold), 0.0, 1.0)
+        tall = t.zeros(2 * eng.n, dtype=t.int32, device=eng.codes.device)
+        if kind == "pair":
+            gen_off = eng.schedule.array(1)
+            jobs = eng.schedule.array(3)
+            pairs = eng.schedule.array(0).reshape(-1, 2)
+            for g in range(info["n_generations"]):
+                nj = int(gen_off[g + 1] - gen_off[g])
+                if nj == 0:
+                    continue
+                post = t.full((nj * 2, eng.s, 3), float("nan"), dtype=t.float64, device=eng.codes.device)
+                scratch = live.clone()  # apply happens on a scratch copy: every generation sees the bound snapshot
+                _lib.check(eng.L.gfx_correct_pairs(eng.schedule.handle, g, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
+                                                   eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
+                                                   eng.result.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                ph = post.cpu().numpy()
+                res = eng.result[:2 * nj * eng.s].view(-1, eng.s).cpu().numpy()
+                for k in range(nj):
+                    pr = tuple(int(x) for x in pairs[jobs[gen_off[g] + k]])
+                    out.setdefault(pr, (ph[2 * k], ph[2 * k + 1], res[2 * k] & 0x80))
+        else:
+            ns = info["n_singles"]
+            if ns:
+                post = t.full((ns, eng.s, 3), float("nan"), dtype=t.float64, device=eng.codes.device)
+                scratch = live.clone()
+                _lib.check(eng.L.gfx_correct_singles(eng.schedule.handle, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
+                                                     eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
+                                                     eng.result.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                ph = post.cpu().numpy()
+                res = eng.result[:ns * eng.s].view(-1, eng.s).cpu().numpy()
+                for k, r in enumerate(eng.schedule.array(2)):
+                    out[int(r)] = (ph[k], res[k] & 0x80)
+        eng.check_status()
+        return out
+
+    @staticmethod
+    def correctPair(sire, dam, back=2, tiethreshold=0.1, elimination_order="MinNeighbors", test_p=0.5, suspect_t=0.2):
+        """ResultPairInfer for one mating pair from the bound snapshot (correct_genotypes3.py:169-327)."""
+        cur = multiprocessing.current_process()
+        eng, posts = CorrectGenotypes._results_for("pair", None, back, tiethreshold, test_p, suspect_t)
+        ids = list(cur.genotypes.index)
+        key = (ids.index(sire), ids.index(dam))
+        if key not in posts:
+            raise KeyError("(%s, %s) is not a mating pair of genotyped animals with a genotyped kid" % (sire, dam))
+        ps, pd_, valid = posts[key]
+        cols = list(cur.genotypes.columns)
+        sus = np.nonzero(valid)[0]
+        if len(sus) == 0:
+            return None
+        res = ResultPairInfer(sire, dam, None)
+        g = cur.genotypes
+        for j in sus:
+            snp = cols[j]
+            a, b = ps[j], pd_[j]
+            joint = np.outer(a, b)
+            mx = np.nanmax(joint) if not np.isnan(joint).all() else np.nan
+            states = [list(x) for x in np.asarray(joint >= (mx - tiethreshold)).nonzero()]
+            os_, od = g.at[sire, snp], g.at[dam, snp]
+            res.jointprobs[snp] = joint
+            res.beststate[snp] = states
+            res.bestprobs[snp] = mx
+            res.observedprob_sire[snp] = a[os_] if os_ != 9 else np.nan
+            res.observedprob_dam[snp] = b[od] if od != 9 else np.nan
+            res.bestprob_sire[snp] = [a[x] for x in states[0]]
+            res.bestprob_dam[snp] = [b[x] for x in states[1]]
+            res.prob_sire[snp] = a
+            res.prob_dam[snp] = b
+        return res
+
+    @staticmethod
+    def correctSingle(kid, back=2, tiethreshold=0.1, elimination_order="MinNeighbors", test_p=0.5, suspect_t=0.2):
+        """ResultSingleInfer for one unpaired animal (correct_genotypes3.py:330-430)."""
+        cur = multiprocessing.current_process()
+        eng, posts = CorrectGenotypes._results_for("single", None, back, tiethreshold, test_p, suspect_t)
+        ids = list(cur.genotypes.index)
+        r = ids.index(kid)
+        if r not in posts:
+            raise KeyError("%s is part of a mating pair; use correctPair" % kid)
+        p, valid = posts[r]
+        sus = np.nonzero(valid)[0]
+        if len(sus) == 0:
+            return None
+        cols = list(cur.genotypes.columns)
+        res = ResultSingleInfer(kid, None)
+        g = cur.genotypes
+        for j in sus:
+            snp = cols[j]
+            a = p[j]
+            mx = np.nanmax(a) if not np.isnan(a).all() else np.nan
+            res.beststate[snp] = np.where(a >= (mx - tiethreshold))[0]
+            res.bestprobs[snp] = mx
+            o = g.at[kid, snp]
+            res.observedprob[snp] = a[o] if o != 9 else np.nan
+            res.prob[snp] = a
+        return res

@@ -1,0 +1,314 @@
+// Exact inference on a pedigree blanket + the reference's children heuristic, host and device.
+//
+// Replaces the pgmpy VariableElimination.query call sites of correct_genotypes3.py:119-121,242-245,
+// 388-390 on the network bayesnet/model.py:173-230 builds (founders of the sub-pedigree get the
+// allele prior [1/4,1/2,1/4], every other node the 3x3x3 Mendel table of model.py:28-30), and
+// bayesnet/model.py:65-89 generate_probs_kids.
+//
+// Method (not pgmpy's): "frontier elimination".  Blanket nodes are stored parents-before-children
+// (DFS post-order from the focal animals).  Walking that order we keep ONE joint table over the
+// currently open unobserved variables; a node multiplies its Mendel factor in (adding a base-3 digit
+// if it is unobserved) and a variable is summed out right after its last child.  Hard evidence never
+// adds a digit, so with mostly-genotyped ancestors the table has 3..27 entries.  Factors that are
+// not connected to the query through unobserved variables are skipped, which is exactly pgmpy's
+// behaviour of dropping factors whose scope became empty (contradictory evidence that is d-separated
+// from the query cannot produce NaN; contradictory evidence inside the query's component gives 0/0).
+// Every unnormalised quantity is a dyadic rational that binary64 holds exactly, so the result of the
+// single final division does not depend on the elimination order.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <cuda_fp16.h>
+
+#define GFX_WMAX 6            // max simultaneously open unobserved variables
+#define GFX_TAB 729           // 3^GFX_WMAX
+#define GFX_MAXN 64           // max nodes in one blanket (bit masks are uint64)
+#define GFX_HD __host__ __device__ __forceinline__
+
+// P(kid = k | sire = s, dam = d): bayesnet/model.py:28-30, generated from allele transmission
+// probabilities s/2 and d/2 (all values are exact dyadics, identical to the table).
+GFX_HD double gfx_mendel(int k, int s, int d) {
+  const double ps = 0.5 * (double)s, pd = 0.5 * (double)d;
+  if (k == 0) return (1.0 - ps) * (1.0 - pd);
+  if (k == 2) return ps * pd;
+  return ps * (1.0 - pd) + (1.0 - ps) * pd;
+}
+GFX_HD double gfx_prior(int k) { return k == 1 ? 0.5 : 0.25; }  // model.py:24
+
+GFX_HD int gfx_pow3(int k) {
+  int r = 1;
+  for (int i = 0; i < k; ++i) r *= 3;
+  return r;
+}
+
+struct GfxBlanket {
+  int n;              // nodes, topological (parents first)
+  const int8_t* p1;   // local index of sire or -1 (both parents or none are inside the blanket)
+  const int8_t* p2;   // local index of dam  or -1
+  const int8_t* last; // local index of the node's last child inside the blanket (own index if none)
+};
+
+// Marginal of node q given hard evidence on the nodes whose bit is set in `obs` (their states in
+// code[]).  tab: scratch of GFX_TAB doubles.  Returns 0, or 1 if more than GFX_WMAX variables
+// would be open at once (out = NaN).
+__host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8_t* code, uint64_t obs,
+                                         double* tab, double out[3]) {
+  const int n = b.n;
+  obs &= ~(1ull << q);
+  // component of q in the interaction graph of unobserved variables
+  uint64_t comp = 1ull << q;
+  for (bool grew = true; grew;) {
+    grew = false;
+    for (int v = 0; v < n; ++v) {
+      uint64_t sc = 1ull << v;
+      if (b.p1[v] >= 0) sc |= (1ull << b.p1[v]) | (1ull << b.p2[v]);
+      sc &= ~obs;
+      if ((sc & comp) && (sc & ~comp)) { comp |= sc; grew = true; }
+    }
+    for (int v = n - 1; v >= 0 && grew; --v) {
+      uint64_t sc = 1ull << v;
+      if (b.p1[v] >= 0) sc |= (1ull << b.p1[v]) | (1ull << b.p2[v]);
+      sc &= ~obs;
+      if ((sc & comp) && (sc & ~comp)) comp |= sc;
+    }
+  }
+  int8_t open[GFX_WMAX];
+  int w = 0, size = 1;
+  tab[0] = 1.0;
+  for (int v = 0; v < n; ++v) {
+    uint64_t sc = 1ull << v;
+    const int a1 = b.p1[v], a2 = b.p2[v];
+    if (a1 >= 0) sc |= (1ull << a1) | (1ull << a2);
+    if (!((sc & ~obs) & comp)) continue;  // factor not connected to the query: dropped
+    // where do the parents' states come from: a digit of the table index, or the evidence
+    int s_pos = -1, d_pos = -1, s_val = 0, d_val = 0, s_str = 1, d_str = 1;
+    if (a1 >= 0) {
+      if ((obs >> a1) & 1) s_val = code[a1];
+      else { for (int k = 0; k < w; ++k) if (open[k] == a1) s_pos = k; s_str = gfx_pow3(s_pos); }
+      if ((obs >> a2) & 1) d_val = code[a2];
+      else { for (int k = 0; k < w; ++k) if (open[k] == a2) d_pos = k; d_str = gfx_pow3(d_pos); }
+    }
+    if (!((obs >> v) & 1)) {
+      if (w == GFX_WMAX) { out[0] = out[1] = out[2] = nan(""); return 1; }
+      for (int x = 2; x >= 0; --x) {
+        for (int i = 0; i < size; ++i) {
+          double f;
+          if (a1 >= 0) {
+            const int sv = s_pos >= 0 ? (i / s_str) % 3 : s_val;
+            const int dv = d_pos >= 0 ? (i / d_str) % 3 : d_val;
+            f = gfx_mendel(x, sv, dv);
+          } else {
+            f = gfx_prior(x);
+          }
+          tab[x * size + i] = tab[i] * f;
+        }
+      }
+      open[w++] = (int8_t)v;
+      size *= 3;
+    } else {
+      const int x = code[v];
+      for (int i = 0; i < size; ++i) {
+        const int sv = s_pos >= 0 ? (i / s_str) % 3 : s_val;
+        const int dv = d_pos >= 0 ? (i / d_str) % 3 : d_val;
+        tab[i] *= gfx_mendel(x, sv, dv);
+      }
+    }
+    // sum out every open variable whose last child is this node
+    for (int k = w - 1; k >= 0; --k) {
+      const int u = open[k];
+      if (u == q || b.last[u] > v) continue;
+      const int str = gfx_pow3(k);
+      const int nsize = size / 3;
+      for (int i = 0; i < nsize; ++i) {
+        const int hi = i / str, lo = i - hi * str;
+        const int src = hi * str * 3 + lo;
+        tab[i] = (tab[src] + tab[src + str]) + tab[src + 2 * str];
+      }
+      for (int m = k; m + 1 < w; ++m) open[m] = open[m + 1];
+      --w;
+      size = nsize;
+    }
+  }
+  const double s = (tab[0] + tab[1]) + tab[2];
+  out[0] = tab[0] / s;
+  out[1] = tab[1] / s;
+  out[2] = tab[2] / s;
+  tab[3] = s;  // unnormalised total, for gfx_infer_pair
+  return 0;
+}
+
+// correctPair queries [sire, dam] jointly with joint=False (correct_genotypes3.py:242-245): pgmpy
+// multiplies every remaining factor, marginalises to each variable and normalises.  The marginals
+// equal the single-variable queries unless the OTHER animal's component has P(evidence) = 0, in
+// which case the joint is all zero and both marginals are 0/0 = NaN.
+__host__ __device__ inline int gfx_infer_pair(const GfxBlanket& b, int q0, int q1, const uint8_t* code, uint64_t obs,
+                                              double* tab, double out0[3], double out1[3]) {
+  obs &= ~((1ull << q0) | (1ull << q1));
+  int bad = gfx_infer(b, q0, code, obs, tab, out0);
+  const double s0 = tab[3];
+  bad |= gfx_infer(b, q1, code, obs, tab, out1);
+  const double s1 = tab[3];
+  if (!bad && (s0 == 0.0 || s1 == 0.0)) {
+    out0[0] = out0[1] = out0[2] = nan("");
+    out1[0] = out1[1] = out1[2] = nan("");
+  }
+  return bad;
+}
+
+// ---- float16 score pieces of correct_genotypes3.py:121,126-127,149-155 -------------------------
+// numpy half arithmetic = compute in float32, round once to half.
+GFX_HD float gfx_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+GFX_HD uint16_t gfx_f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+
+// f16 bits of 2 * (nanmax(anc16) - anc16[obs]) where anc16 = float16(anc)
+GFX_HD uint16_t gfx_anc_score(const double anc[3], int obs) {
+  float f[3];
+  for (int i = 0; i < 3; ++i) f[i] = __half2float(__double2half(anc[i]));
+  float mx = nanf("");
+  for (int i = 0; i < 3; ++i)
+    if (f[i] == f[i] && !(mx >= f[i])) mx = f[i];
+  const uint16_t diff = gfx_f2h(mx - f[obs]);
+  return gfx_f2h(2.0f * gfx_h2f(diff));
+}
+// f16 bits of the summed children differences: m units of f16(1/3) = 1365/4096, summed in float32
+GFX_HD uint16_t gfx_child_score(uint32_t m) { return gfx_f2h((float)(m * 1365u) * (1.0f / 4096.0f)); }
+GFX_HD uint16_t gfx_half_add(uint16_t a, uint16_t b) { return gfx_f2h(gfx_h2f(a) + gfx_h2f(b)); }
+
+// ---- children heuristic, bayesnet/model.py:65-89 ------------------------------------------------
+// kv[((k*4 + p)*3 + a)*3 + x]: Mendel row of a child in state k, masked by the other parent's state
+// p (3 = unknown) on the sire axis a, divided by the row sum (model.py:78-84); x is the dam axis.
+__host__ __device__ inline void gfx_fill_kv(double* kv) {
+  for (int k = 0; k < 3; ++k)
+    for (int p = 0; p < 4; ++p) {
+      double row[9];
+      for (int a = 0; a < 3; ++a)
+        for (int x = 0; x < 3; ++x) row[3 * a + x] = (p < 3 && a != p) ? 0.0 : gfx_mendel(k, a, x);
+      // np.sum over 9 contiguous doubles: 8 unrolled accumulators, then the tail
+      double s = ((row[0] + row[1]) + (row[2] + row[3])) + ((row[4] + row[5]) + (row[6] + row[7]));
+      s += row[8];
+      for (int i = 0; i < 9; ++i) kv[(k * 4 + p) * 9 + i] = s > 0 ? row[i] / s : row[i];
+    }
+}
+
+// numpy's pairwise summation (loops_utils.h pairwise_sum) streamed over `n` elements that each carry
+// three values (the three dam-axis columns are summed in lock step).  next(v) yields the next element.
+template <class Next>
+__host__ __device__ inline void gfx_pw_leaf(Next& next, int n, double res[3]) {
+  double v[3];
+  if (n < 8) {
+    res[0] = res[1] = res[2] = 0.0;
+    for (int i = 0; i < n; ++i) { next(v); res[0] += v[0]; res[1] += v[1]; res[2] += v[2]; }
+    return;
+  }
+  double r[8][3];
+  for (int j = 0; j < 8; ++j) { next(v); r[j][0] = v[0]; r[j][1] = v[1]; r[j][2] = v[2]; }
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) { next(v); r[j][0] += v[0]; r[j][1] += v[1]; r[j][2] += v[2]; }
+  for (int c = 0; c < 3; ++c)
+    res[c] = ((r[0][c] + r[1][c]) + (r[2][c] + r[3][c])) + ((r[4][c] + r[5][c]) + (r[6][c] + r[7][c]));
+  for (; i < n; ++i) { next(v); res[0] += v[0]; res[1] += v[1]; res[2] += v[2]; }
+}
+
+template <class Next>
+__host__ __device__ inline void gfx_pairwise3(Next& next, int n, double res[3]) {
+  if (n <= 128) { gfx_pw_leaf(next, n, res); return; }
+  // explicit post-order walk of numpy's recursive halving (n2 = n/2 rounded down to a multiple of 8)
+  int fn[24], fstage[24];
+  double fleft[24][3];
+  int sp = 0;
+  fn[0] = n; fstage[0] = 0;
+  double val[3] = {0, 0, 0};
+  while (sp >= 0) {
+    const int m = fn[sp];
+    if (m <= 128) {
+      gfx_pw_leaf(next, m, val);
+      --sp;
+    } else if (fstage[sp] == 0) {
+      int n2 = m / 2; n2 -= n2 % 8;
+      fstage[sp] = 1;
+      fn[sp + 1] = n2; fstage[sp + 1] = 0;
+      ++sp;
+      continue;
+    } else if (fstage[sp] == 1) {
+      int n2 = m / 2; n2 -= n2 % 8;
+      fleft[sp][0] = val[0]; fleft[sp][1] = val[1]; fleft[sp][2] = val[2];
+      fstage[sp] = 2;
+      fn[sp + 1] = m - n2; fstage[sp + 1] = 0;
+      ++sp;
+      continue;
+    } else {
+      val[0] = fleft[sp][0] + val[0]; val[1] = fleft[sp][1] + val[1]; val[2] = fleft[sp][2] + val[2];
+      --sp;
+    }
+  }
+  res[0] = val[0]; res[1] = val[1]; res[2] = val[2];
+}
+
+// kid_code(i) -> state of the i-th genotyped child (0..2, anything else = not usable);
+// par_code(i) -> state of that child's other parent (0..2, anything else = unknown).
+// np.nanmean(table[:, dam_axis == x]): the fancy-indexed block is column-major, so memory order is
+// sire-axis a = 0,1,2 outermost and the usable children innermost.
+template <class KidCode, class ParCode>
+struct GfxKidStream {
+  int a, cur, nkids;
+  KidCode& kid_code;
+  ParCode& par_code;
+  const double* kv;
+  __host__ __device__ void operator()(double v[3]) {
+    for (;;) {
+      if (cur == nkids) { cur = 0; ++a; }
+      const int k = kid_code(cur);
+      if (k <= 2) {
+        int p = par_code(cur);
+        if (p > 2) p = 3;
+        const double* e = kv + (k * 4 + p) * 9 + 3 * a;
+        v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+        ++cur;
+        return;
+      }
+      ++cur;
+    }
+  }
+};
+
+// Returns false when there is no genotyped child at all (the reference's `probs = None`).
+template <class KidCode, class ParCode>
+__host__ __device__ inline bool gfx_kids_term(int nkids, KidCode kid_code, ParCode par_code, const double* kv,
+                                              double out[3]) {
+  if (nkids <= 0) return false;
+  int ninc = 0;
+  for (int i = 0; i < nkids; ++i) ninc += kid_code(i) <= 2;
+  if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return true; }
+  GfxKidStream<KidCode, ParCode> next{0, 0, nkids, kid_code, par_code, kv};
+  double tot[3];
+  gfx_pairwise3(next, 3 * ninc, tot);
+  const double cnt = (double)(3 * ninc);
+  double r0 = tot[0] / cnt, r1 = tot[1] / cnt, r2 = tot[2] / cnt;
+  const double s = (r0 + r1) + r2;
+  if (s > 0) { r0 /= s; r1 /= s; r2 /= s; }
+  out[0] = r0; out[1] = r1; out[2] = r2;
+  return true;
+}
+
+// correct_genotypes3.py:280-304 / :410-422 : product (or whichever exists), divided by its sum if > 0
+GFX_HD void gfx_combine(bool has_anc, const double anc[3], bool has_kids, const double kids[3], double p[3]) {
+  for (int i = 0; i < 3; ++i) p[i] = (has_anc && has_kids) ? anc[i] * kids[i] : (has_anc ? anc[i] : kids[i]);
+  const double s = (p[0] + p[1]) + p[2];
+  if (s > 0) { p[0] /= s; p[1] /= s; p[2] /= s; }
+}
+
+// Decision inputs of correct_genotypes3.py:741-744,809 (pairs) / :932 (singles), computed from the
+// generation-start snapshot: bits 0-2 tie set, bit 3 (max - P[obs]) >= threshold, bit 7 valid.
+GFX_HD uint8_t gfx_decision_bits(const double p[3], int obs_snapshot, double tie, double threshold) {
+  double mx = nan("");
+  for (int i = 0; i < 3; ++i)
+    if (p[i] == p[i] && !(mx >= p[i])) mx = p[i];
+  uint8_t r = 0x80;
+  const double cut = mx - tie;
+  for (int i = 0; i < 3; ++i)
+    if (p[i] >= cut) r |= (uint8_t)(1u << i);
+  const double op = obs_snapshot <= 2 ? p[obs_snapshot] : nan("");
+  if ((mx - op) >= threshold) r |= 8u;
+  return r;
+}

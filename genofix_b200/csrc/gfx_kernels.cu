@@ -1,0 +1,1004 @@
+// CUDA kernels (sm_100a) + C ABI of genofix_b200.  See include/genofix_b200.h for the contract and
+// DESIGN.md for the data layout and the roofline of each kernel.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/genofix_b200.h"
+#include "gfx_infer.cuh"
+#include "gfx_schedule.h"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define GFX_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(GFX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+#define GFX_LAUNCHED()                                                                   \
+  do {                                                                                   \
+    ++g_launches;                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                 \
+    if (e_ != cudaSuccess) return fail(GFX_E_CUDA, std::string("launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" const char* gfx_last_error(void) { return g_err.c_str(); }
+extern "C" int gfx_version(void) { return 100; }
+extern "C" int64_t gfx_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// device-side schedule
+// ------------------------------------------------------------------------------------------------
+struct gfx_schedule {
+  GfxHostSchedule h;
+  int device = 0;
+  int num_sms = 148;
+  // device copies
+  int32_t *anc6 = nullptr, *rank_blanket = nullptr, *prow = nullptr;
+  uint8_t* rank_flags = nullptr;
+  int32_t *child_off = nullptr, *child_row = nullptr, *child_other = nullptr;
+  int32_t *bl_off = nullptr, *bl_row = nullptr;
+  int8_t *bl_p1 = nullptr, *bl_p2 = nullptr, *bl_last = nullptr, *bl_q0 = nullptr, *bl_q1 = nullptr;
+  int32_t *job_row0 = nullptr, *job_row1 = nullptr, *job_bl = nullptr;        // pair jobs, all generations
+  int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr;
+  int32_t *single_row = nullptr, *single_bl = nullptr, *single_off = nullptr, *single_entry = nullptr;
+  int32_t *loopy_rows = nullptr, *trio_row = nullptr;
+  int n_loopy_rows = 0;
+  uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
+  double* kv = nullptr;        // 108 doubles, children-heuristic element table
+  int* status = nullptr;
+};
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+  *dst = nullptr;
+  const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc((void**)dst, bytes);
+  if (e != cudaSuccess) return e;
+  if (v.size()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+// Table for the plain 2-generation tree: index = 2-bit codes of S,D,SS,SD,DS,DD (3 = unobserved).
+static void build_rank_lut(std::vector<uint2>& lut) {
+  lut.resize(4096);
+  // topological order: SS SD S DS DD D K
+  const int8_t p1[7] = {-1, -1, 0, -1, -1, 3, 2};
+  const int8_t p2[7] = {-1, -1, 1, -1, -1, 4, 5};
+  const int8_t last[7] = {2, 2, 6, 5, 5, 6, 6};
+  GfxBlanket b{7, p1, p2, last};
+  double tab[GFX_TAB];
+  for (int idx = 0; idx < 4096; ++idx) {
+    const int c[6] = {idx & 3, (idx >> 2) & 3, (idx >> 4) & 3, (idx >> 6) & 3, (idx >> 8) & 3, (idx >> 10) & 3};
+    uint8_t code[7] = {(uint8_t)c[2], (uint8_t)c[3], (uint8_t)c[0], (uint8_t)c[4], (uint8_t)c[5], (uint8_t)c[1], 3};
+    uint64_t obs = 0;
+    for (int v = 0; v < 6; ++v)
+      if (code[v] < 3) obs |= 1ull << v;
+    double anc[3];
+    gfx_infer(b, 6, code, obs, tab, anc);
+    uint16_t s[3];
+    for (int o = 0; o < 3; ++o) s[o] = gfx_anc_score(anc, o);
+    lut[idx] = make_uint2((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2]);
+  }
+}
+
+extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
+  if (!s) return;
+  void* ptrs[] = {s->anc6, s->rank_blanket, s->prow, s->rank_flags, s->child_off, s->child_row, s->child_other,
+                  s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
+                  s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
+                  s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete s;
+}
+
+extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** out) {
+  if (!ped || !out) return fail(GFX_E_INVALID, "null argument");
+  *out = nullptr;
+  gfx_schedule* s = new (std::nothrow) gfx_schedule();
+  if (!s) return fail(GFX_E_NOMEM, "out of host memory");
+  std::string err;
+  int rc = gfx_build_schedule(ped, s->h, err);
+  if (rc != GFX_OK) { delete s; return fail(rc, err); }
+  GfxHostSchedule& h = s->h;
+  cudaError_t e = cudaGetDevice(&s->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device);
+  std::vector<int32_t> job_row0, job_row1, job_bl;
+  for (int32_t p : h.job_pair) {
+    job_row0.push_back(h.pair_sire_row[p]);
+    job_row1.push_back(h.pair_dam_row[p]);
+    job_bl.push_back(h.pair_blanket[p]);
+  }
+  std::vector<int32_t> single_off(h.single_row.size() + 1), single_entry(h.single_row.size());
+  for (size_t i = 0; i < h.single_row.size(); ++i) { single_off[i] = (int32_t)i; single_entry[i] = (int32_t)i; }
+  single_off[h.single_row.size()] = (int32_t)h.single_row.size();
+  std::vector<int32_t> loopy;
+  for (int r = 0; r < h.n_rows; ++r)
+    if (h.rank_flags[r] & 2) loopy.push_back(r);
+  s->n_loopy_rows = (int)loopy.size();
+  std::vector<uint2> lut;
+  build_rank_lut(lut);
+  std::vector<double> kv(108);
+  gfx_fill_kv(kv.data());
+  std::vector<int> status(1, 0);
+#define UP(field, vec) if (e == cudaSuccess) e = upload(&s->field, vec)
+  UP(anc6, h.anc6); UP(rank_blanket, h.rank_blanket); UP(prow, h.prow); UP(rank_flags, h.rank_flags);
+  UP(child_off, h.child_off); UP(child_row, h.child_row); UP(child_other, h.child_other);
+  UP(bl_off, h.bl.off); UP(bl_row, h.bl.row); UP(bl_p1, h.bl.p1); UP(bl_p2, h.bl.p2); UP(bl_last, h.bl.last);
+  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1);
+  UP(job_row0, job_row0); UP(job_row1, job_row1); UP(job_bl, job_bl);
+  UP(app_focal_row, h.app_focal_row); UP(app_focal_off, h.app_focal_off); UP(app_entry, h.app_entry);
+  UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
+  UP(single_entry, single_entry);
+  UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(rank_lut, lut); UP(kv, kv); UP(status, status);
+#undef UP
+  if (e != cudaSuccess) {
+    gfx_schedule_destroy(s);
+    return fail(GFX_E_CUDA, std::string("schedule upload: ") + cudaGetErrorString(e));
+  }
+  *out = s;
+  return GFX_OK;
+}
+
+// Host-only variant (no CUDA calls): builds the index arrays so that gfx_schedule_info / _copy can be
+// inspected on a machine without a GPU.  The handle must not be passed to any kernel entry point.
+extern "C" int gfx_schedule_create_host(const gfx_pedigree_desc* ped, gfx_schedule** out) {
+  if (!ped || !out) return fail(GFX_E_INVALID, "null argument");
+  *out = nullptr;
+  gfx_schedule* s = new (std::nothrow) gfx_schedule();
+  if (!s) return fail(GFX_E_NOMEM, "out of host memory");
+  std::string err;
+  int rc = gfx_build_schedule(ped, s->h, err);
+  if (rc != GFX_OK) { delete s; return fail(rc, err); }
+  s->device = -1;
+  *out = s;
+  return GFX_OK;
+}
+
+extern "C" int gfx_schedule_info(const gfx_schedule* s, gfx_schedule_info_t* out) {
+  if (!s || !out) return fail(GFX_E_INVALID, "null argument");
+  *out = s->h.info;
+  return GFX_OK;
+}
+
+extern "C" int gfx_schedule_copy(const gfx_schedule* s, int which, int32_t* out, int64_t cap) {
+  if (!s || !out) return fail(GFX_E_INVALID, "null argument");
+  const GfxHostSchedule& h = s->h;
+  std::vector<int32_t> tmp;
+  const std::vector<int32_t>* src = nullptr;
+  switch (which) {
+    case 0:
+      for (size_t i = 0; i < h.pair_sire_row.size(); ++i) { tmp.push_back(h.pair_sire_row[i]); tmp.push_back(h.pair_dam_row[i]); }
+      src = &tmp; break;
+    case 1: src = &h.gen_off; break;
+    case 2: src = &h.single_row; break;
+    case 3: src = &h.job_pair; break;
+    case 4: for (uint8_t f : h.rank_flags) tmp.push_back(f); src = &tmp; break;
+    default: return fail(GFX_E_INVALID, "unknown array selector");
+  }
+  if ((int64_t)src->size() > cap) return fail(GFX_E_INVALID, "output buffer too small");
+  if (!src->empty()) memcpy(out, src->data(), src->size() * sizeof(int32_t));
+  return (int)src->size();
+}
+
+extern "C" int gfx_check_device_status(const gfx_schedule* s, void* stream) {
+  if (!s) return fail(GFX_E_INVALID, "null argument");
+  int st = 0;
+  GFX_CUDA(cudaMemcpyAsync(&st, s->status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GFX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (st != 0) {
+    int zero = 0;
+    GFX_CUDA(cudaMemcpy(s->status, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX simultaneously unobserved variables");
+  }
+  return GFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack / unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack2(const uint8_t* __restrict__ codes, int64_t n, int64_t s, int64_t ld, uint32_t* __restrict__ packed,
+                        int64_t wpr, bool vec) {
+  const int64_t total = n * wpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / wpr, w = i - r * wpr;
+    const int64_t j0 = w * 16;
+    uint32_t out = 0;
+    const uint8_t* src = codes + r * ld + j0;
+    if (vec && j0 + 16 <= s) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t c = (q[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+        out |= (c > 2u ? 3u : c) << (2 * k);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        uint32_t c = 3u;
+        if (j0 + k < s) { c = src[k]; if (c > 2u) c = 3u; }
+        out |= c << (2 * k);
+      }
+    }
+    packed[i] = out;
+  }
+}
+
+__global__ void k_unpack2(const uint32_t* __restrict__ packed, int64_t n, int64_t s, int64_t wpr,
+                          uint8_t* __restrict__ codes, int64_t ld, bool vec) {
+  const int64_t total = n * wpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / wpr, w = i - r * wpr;
+    const int64_t j0 = w * 16;
+    if (j0 >= s) continue;
+    const uint32_t p = packed[i];
+    uint8_t* dst = codes + r * ld + j0;
+    if (vec && j0 + 16 <= s) {
+      uint32_t q[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t c = (p >> (2 * (4 * g + k))) & 3u;
+          o |= (c == 3u ? 9u : c) << (8 * k);
+        }
+        q[g] = o;
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
+    } else {
+      for (int k = 0; k < 16 && j0 + k < s; ++k) {
+        const uint32_t c = (p >> (2 * k)) & 3u;
+        dst[k] = (uint8_t)(c == 3u ? 9u : c);
+      }
+    }
+  }
+}
+
+static int grid_for(int64_t work_items, int threads, int num_sms, int per_sm) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static int device_sms() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+extern "C" int gfx_pack2(const uint8_t* codes, int64_t n, int64_t s, int64_t ld, uint32_t* packed, int64_t wpr, void* stream) {
+  if (!codes || !packed || n <= 0 || s <= 0 || wpr * 16 < s || ld < s) return fail(GFX_E_INVALID, "gfx_pack2: bad shape");
+  const bool vec = (ld % 16 == 0) && (((uintptr_t)codes) % 16 == 0);
+  k_pack2<<<grid_for(n * wpr, 256, device_sms(), 16), 256, 0, (cudaStream_t)stream>>>(codes, n, s, ld, packed, wpr, vec);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+extern "C" int gfx_unpack2(const uint32_t* packed, int64_t n, int64_t s, int64_t wpr, uint8_t* codes, int64_t ld, void* stream) {
+  if (!codes || !packed || n <= 0 || s <= 0 || wpr * 16 < s || ld < s) return fail(GFX_E_INVALID, "gfx_unpack2: bad shape");
+  const bool vec = (ld % 16 == 0) && (((uintptr_t)codes) % 16 == 0);
+  k_unpack2<<<grid_for(n * wpr, 256, device_sms(), 16), 256, 0, (cudaStream_t)stream>>>(packed, n, s, wpr, codes, ld, vec);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mendel rank kernel (tree blankets through the shared-memory table)
+// ------------------------------------------------------------------------------------------------
+struct RankArgs {
+  const uint32_t* packed;
+  int64_t wpr;        // words per row
+  int64_t nwords;     // words that hold SNPs: ceil(n_snps/16)
+  uint16_t* raw;
+  int64_t ld_raw;
+  int n_rows;
+  const int32_t* anc6;
+  const uint8_t* flags;
+  const int32_t* child_off;
+  const int32_t* child_row;
+  const uint2* lut;
+};
+
+__device__ __forceinline__ uint32_t ldg_word(const uint32_t* p, int64_t row, int64_t wpr, int64_t w) {
+  return row >= 0 ? __ldg(p + row * wpr + w) : 0xFFFFFFFFu;
+}
+
+// One thread = one 32-bit word = 16 SNPs of one animal.  A warp covers 32 consecutive words of a row
+// (128 B of codes in, 1 KB of scores out); blocks are persistent and stride over (row, chunk) tasks.
+__global__ void __launch_bounds__(256) k_mendel_rank(RankArgs a) {
+  extern __shared__ uint2 s_lut[];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_lut[i] = a.lut[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t chunks = (a.nwords + 31) >> 5;
+  const int64_t tasks = (int64_t)a.n_rows * chunks;
+  for (int64_t task = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < tasks;
+       task += (int64_t)gridDim.x * warps_per_block) {
+    const int64_t row = task / chunks;
+    const int64_t w = (task - row * chunks) * 32 + lane;
+    const uint8_t fl = a.flags[row];
+    if (fl & 2) continue;  // generic-engine rows are written by k_mendel_rank_generic
+    if (w >= a.nwords) continue;
+    const bool has_anc = fl & 1;
+    const uint32_t w0 = __ldg(a.packed + row * a.wpr + w);
+    uint32_t wa[6];
+    if (has_anc) {
+      const int32_t* a6 = a.anc6 + row * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) wa[k] = ldg_word(a.packed, a6[k], a.wpr, w);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) wa[k] = 0xFFFFFFFFu;
+    }
+    // observed-state masks of the focal animal, one bit per cell at even positions
+    const uint32_t lo = w0, hi = w0 >> 1;
+    const uint32_t o0 = ~(lo | hi) & 0x55555555u;        // code 0
+    const uint32_t o1 = (lo & ~hi) & 0x55555555u;        // code 1
+    const uint32_t o2 = (hi & ~lo) & 0x55555555u;        // code 2
+    // children: per cell m = sum over genotyped children of the float16 difference in units of 1/3
+    //   obs 0: 2 per child in state 2, 1 per child in state 0 ... (bayesnet/model.py:93-116 with the
+    //   other parent unknown, D7): child 0 -> [0,1,2][obs], child 1 -> 0, child 2 -> [2,1,0][obs]
+    uint32_t m16[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m16[k] = 0;
+    uint32_t anyv = 0, acc_lo = 0, acc_hi = 0;
+    int pend = 0;
+    const int c0 = a.child_off[row], c1 = a.child_off[row + 1];
+    for (int c = c0; c < c1; ++c) {
+      const uint32_t wc = __ldg(a.packed + (int64_t)a.child_row[c] * a.wpr + w);
+      const uint32_t cl = wc, ch = wc >> 1;
+      const uint32_t is0 = ~(cl | ch) & 0x55555555u;
+      const uint32_t is2 = (ch & ~cl) & 0x55555555u;
+      anyv |= ~(cl & ch) & 0x55555555u;
+      const uint32_t one = (is0 | is2) & o1;
+      const uint32_t two = (is2 & o0) | (is0 & o2);
+      const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
+      acc_lo += contrib & 0x33333333u;            // even cells, 4-bit lanes
+      acc_hi += (contrib >> 2) & 0x33333333u;     // odd cells
+      if (++pend == 7) {                          // 7 * 2 = 14 < 16: flush nibble lanes
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          m16[k] += ((acc_lo >> (4 * k)) & 0xFu) | (((acc_hi >> (4 * k)) & 0xFu) << 16);
+        acc_lo = acc_hi = 0;
+        pend = 0;
+      }
+    }
+    if (pend) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        m16[k] += ((acc_lo >> (4 * k)) & 0xFu) | (((acc_hi >> (4 * k)) & 0xFu) << 16);
+    }
+    uint32_t outw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t pair = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * k + h;
+        const uint32_t obs = (w0 >> (2 * i)) & 3u;
+        uint16_t r = 0x3C00;  // 1.0: unobserved, or neither ancestors nor usable children (:102)
+        if (obs != 3u) {
+          const bool kids = (anyv >> (2 * i)) & 1u;
+          const uint32_t m = (m16[k] >> (16 * h)) & 0xFFFFu;
+          if (has_anc) {
+            const uint32_t idx = ((wa[0] >> (2 * i)) & 3u) | (((wa[1] >> (2 * i)) & 3u) << 2) |
+                                 (((wa[2] >> (2 * i)) & 3u) << 4) | (((wa[3] >> (2 * i)) & 3u) << 6) |
+                                 (((wa[4] >> (2 * i)) & 3u) << 8) | (((wa[5] >> (2 * i)) & 3u) << 10);
+            const uint2 e = s_lut[idx];
+            const uint16_t sc = obs == 0 ? (uint16_t)(e.x & 0xFFFFu) : (obs == 1 ? (uint16_t)(e.x >> 16) : (uint16_t)(e.y & 0xFFFFu));
+            r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+          } else if (kids) {
+            r = gfx_child_score(m);
+          }
+        }
+        pair |= (uint32_t)r << (16 * h);
+      }
+      outw[k] = pair;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(a.raw + row * a.ld_raw + w * 16);
+    dst[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    dst[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic (loopy blanket) rank, pair/single inference, apply
+// ------------------------------------------------------------------------------------------------
+struct CellCtx {
+  const uint32_t* live;   // snapshot being read
+  const uint32_t* orig;   // original matrix (defines E = 1 for missing)
+  int64_t wpr;
+  const uint16_t* raw;
+  int64_t ld_raw;
+  const double* elut;
+};
+
+__device__ __forceinline__ int cell_code(const uint32_t* p, int64_t wpr, int row, int64_t j) {
+  return (int)((__ldg(p + (int64_t)row * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u);
+}
+__device__ __forceinline__ double cell_E(const CellCtx& c, int row, int64_t j) {
+  if (cell_code(c.orig, c.wpr, row, j) == 3) return 1.0;  // correct_genotypes3.py:603
+  return __ldg(c.elut + c.raw[(int64_t)row * c.ld_raw + j]);
+}
+
+struct BlanketDev {
+  const int32_t* off;
+  const int32_t* row;
+  const int8_t *p1, *p2, *last, *q0, *q1;
+};
+
+struct GenericRankArgs {
+  const uint32_t* packed;
+  int64_t wpr, n_snps;
+  uint16_t* raw;
+  int64_t ld_raw;
+  const int32_t* rows;
+  int n_rows_sel;
+  const int32_t* rank_blanket;
+  const int32_t* child_off;
+  const int32_t* child_row;
+  BlanketDev bl;
+  int* status;
+};
+
+// Rows whose blanket is not the plain tree: one thread per cell, full inference.
+__global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) {
+  const int64_t padded = ((a.n_snps + 15) / 16) * 16;
+  const int64_t total = (int64_t)a.n_rows_sel * padded;
+  double tab[GFX_TAB];
+  uint8_t code[GFX_MAXN];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int sel = (int)(i / padded);
+    const int64_t j = i - (int64_t)sel * padded;
+    const int row = a.rows[sel];
+    uint16_t r = 0x3C00;
+    const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
+    if (obs != 3) {
+      const int bid = a.rank_blanket[row];
+      const int off = a.bl.off[bid], n = a.bl.off[bid + 1] - off;
+      uint64_t om = 0;
+      for (int v = 0; v < n; ++v) {
+        const int rr = a.bl.row[off + v];
+        int c = 3;
+        if (rr >= 0) c = cell_code(a.packed, a.wpr, rr, j);
+        code[v] = (uint8_t)c;
+        if (c != 3) om |= 1ull << v;
+      }
+      GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
+      double anc[3];
+      if (gfx_infer(b, a.bl.q0[bid], code, om, tab, anc)) atomicExch(a.status, 1);
+      const uint16_t sc = gfx_anc_score(anc, obs);
+      uint32_t m = 0;
+      bool kids = false;
+      for (int c = a.child_off[row]; c < a.child_off[row + 1]; ++c) {
+        const int k = cell_code(a.packed, a.wpr, a.child_row[c], j);
+        if (k != 3) kids = true;
+        if (k == 0) m += obs;            // [0,1,2][obs]
+        else if (k == 2) m += 2 - obs;   // [2,1,0][obs]
+      }
+      r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+    }
+    a.raw[(int64_t)row * a.ld_raw + j] = r;
+  }
+}
+
+extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr,
+                               uint16_t* raw, int64_t ld_raw, void* stream) {
+  if (!s || !packed || !raw) return fail(GFX_E_INVALID, "null argument");
+  if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
+  const int64_t nwords = (n_snps + 15) / 16;
+  if (n_snps <= 0 || wpr < nwords || ld_raw < nwords * 16 || (ld_raw % 8) != 0 || (((uintptr_t)raw) % 16) != 0)
+    return fail(GFX_E_INVALID, "gfx_mendel_rank: need wpr >= ceil(s/16), ld_raw >= 16*ceil(s/16), ld_raw % 8 == 0, raw 16-byte aligned");
+  RankArgs a{packed, wpr, nwords, raw, ld_raw, s->h.n_rows, s->anc6, s->rank_flags, s->child_off, s->child_row, s->rank_lut};
+  static bool attr_set = false;
+  if (!attr_set) {
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    attr_set = true;
+  }
+  const int64_t tasks = (int64_t)s->h.n_rows * ((nwords + 31) / 32);
+  int blocks = (int)((tasks + 7) / 8);
+  const int cap = s->num_sms * 6;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_mendel_rank<<<blocks, 256, 32768, (cudaStream_t)stream>>>(a);
+  GFX_LAUNCHED();
+  if (s->n_loopy_rows > 0) {
+    GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
+                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1}, s->status};
+    const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
+    k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, (cudaStream_t)stream>>>(g);
+    GFX_LAUNCHED();
+  }
+  return GFX_OK;
+}
+
+// ---- histogram of raw scores ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rank_hist(const uint16_t* __restrict__ raw, int64_t ld_raw,
+                                                   const uint32_t* __restrict__ packed, int64_t wpr, int64_t n,
+                                                   int64_t n_snps, unsigned long long* __restrict__ hist) {
+  extern __shared__ uint32_t s_hist[];  // patterns 0 .. 0x3FFF (values in [0, 2))
+  for (int i = threadIdx.x; i < 0x4000; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int64_t nwords = (n_snps + 15) / 16;
+  const int64_t total = n * nwords;
+  unsigned long long zeros = 0, missing = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nwords, w = i - r * nwords;
+    const uint32_t pw = __ldg(packed + r * wpr + w);
+    const uint4* src = reinterpret_cast<const uint4*>(raw + r * ld_raw + w * 16);
+    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    const uint32_t q[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (w * 16 + k >= n_snps) break;
+      const uint32_t c = (pw >> (2 * k)) & 3u;
+      const uint32_t h = (q[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+      if (c == 3u) ++missing;
+      else if (h == 0u) ++zeros;
+      else if (h < 0x4000u) atomicAdd(&s_hist[h], 1u);
+      else atomicAdd(&hist[h], 1ull);
+    }
+  }
+  // warp-reduce the two hot counters
+  for (int o = 16; o > 0; o >>= 1) {
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    missing += __shfl_xor_sync(0xffffffffu, missing, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (zeros) atomicAdd(&hist[0], zeros);
+    if (missing) atomicAdd(&hist[65536], missing);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 0x4000; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+extern "C" int gfx_rank_hist(const uint16_t* raw, int64_t ld_raw, const uint32_t* packed, int64_t wpr, int64_t n,
+                             int64_t n_snps, uint64_t* hist, void* stream) {
+  if (!raw || !packed || !hist || n <= 0 || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_rank_hist: bad argument");
+  GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), (cudaStream_t)stream));
+  static bool attr_set = false;
+  if (!attr_set) {
+    GFX_CUDA(cudaFuncSetAttribute(k_rank_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_set = true;
+  }
+  const int64_t total = n * ((n_snps + 15) / 16);
+  k_rank_hist<<<grid_for(total, 256, device_sms(), 3), 256, 65536, (cudaStream_t)stream>>>(
+      raw, ld_raw, packed, wpr, n, n_snps, (unsigned long long*)hist);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ---- per-animal sum of E ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rank_rowsum(const uint16_t* __restrict__ raw, int64_t ld_raw,
+                                                     const uint32_t* __restrict__ packed, int64_t wpr, int64_t n,
+                                                     int64_t n_snps, const double* __restrict__ elut, double missing_value,
+                                                     double* __restrict__ out) {
+  // one warp per row, fixed lane-strided order + fixed shuffle tree => deterministic sums
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    double acc = 0.0;
+    for (int64_t j = lane; j < n_snps; j += 32) {
+      const uint32_t c = (__ldg(packed + r * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u;
+      acc += c == 3u ? missing_value : __ldg(elut + raw[r * ld_raw + j]);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[r] = acc;
+  }
+}
+
+extern "C" int gfx_rank_rowsum(const uint16_t* raw, int64_t ld_raw, const uint32_t* packed, int64_t wpr, int64_t n,
+                               int64_t n_snps, const double* elut, double missing_value, double* out, void* stream) {
+  if (!raw || !packed || !elut || !out || n <= 0 || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_rank_rowsum: bad argument");
+  k_rank_rowsum<<<grid_for(n * 32, 256, device_sms(), 8), 256, 0, (cudaStream_t)stream>>>(raw, ld_raw, packed, wpr, n, n_snps,
+                                                                                          elut, missing_value, out);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ---- correctPair / correctSingle -----------------------------------------------------------------
+struct InferArgs {
+  CellCtx c;
+  int64_t n_snps;
+  int nf;                 // 2 = pairs, 1 = singles
+  int n_jobs;
+  const int32_t* job_row0;
+  const int32_t* job_row1;
+  const int32_t* job_bl;
+  BlanketDev bl;
+  const int32_t* child_off;
+  const int32_t* child_row;
+  const int32_t* child_other;
+  const int32_t* prow;
+  const double* kv;
+  gfx_correct_params p;
+  uint8_t* result;        // [(job*nf + side) * n_snps + j]
+  double* post;           // optional [(job*nf + side) * n_snps + j] * 3
+  int* status;
+};
+
+struct KidCodeFn {
+  const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
+  __device__ int operator()(int i) const { return cell_code(live, wpr, rows[i], j); }
+};
+struct ParCodeFn {
+  const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
+  __device__ int operator()(int i) const { const int r = rows[i]; return r >= 0 ? cell_code(live, wpr, r, j) : 3; }
+};
+
+#define GFX_INFER_CHUNK 1024
+__global__ void __launch_bounds__(128) k_infer(InferArgs a) {
+  __shared__ int s_list[GFX_INFER_CHUNK];
+  __shared__ int s_cnt;
+  const int64_t chunks = (a.n_snps + GFX_INFER_CHUNK - 1) / GFX_INFER_CHUNK;
+  const int64_t tasks = (int64_t)a.n_jobs * chunks;
+  double tab[GFX_TAB];
+  uint8_t code[GFX_MAXN];
+  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int job = (int)(task / chunks);
+    const int64_t j0 = (task - (int64_t)job * chunks) * GFX_INFER_CHUNK;
+    const int64_t j1 = min(a.n_snps, j0 + GFX_INFER_CHUNK);
+    const int row0 = a.job_row0[job];
+    const int row1 = a.nf == 2 ? a.job_row1[job] : -1;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    // pass 1: suspect SNPs (correct_genotypes3.py:181-185 / :342)
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+      bool sus = cell_E(a.c, row0, j) >= a.p.test_p;
+      if (a.nf == 2) sus = sus || (cell_E(a.c, row1, j) >= a.p.test_p);
+      a.result[((int64_t)job * a.nf) * a.n_snps + j] = 0;
+      if (a.nf == 2) a.result[((int64_t)job * 2 + 1) * a.n_snps + j] = 0;
+      if (sus) s_list[atomicAdd(&s_cnt, 1)] = (int)(j - j0);
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    // pass 2: inference on the suspect cells
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const int64_t j = j0 + s_list[k];
+      const int rows[2] = {row0, row1};
+      int obs[2] = {3, 3};
+      double E[2] = {1.0, 1.0};
+      for (int f = 0; f < a.nf; ++f) {
+        obs[f] = cell_code(a.c.live, a.c.wpr, rows[f], j);
+        E[f] = cell_E(a.c, rows[f], j);
+      }
+      double pmax;
+      if (a.nf == 2) {
+        if (obs[0] != 3 && obs[1] != 3) pmax = E[1] > E[0] ? E[1] : E[0];
+        else if (obs[0] == 3 && obs[1] == 3) pmax = 1.0;
+        else pmax = obs[0] != 3 ? E[0] : E[1];
+      } else {
+        pmax = obs[0] != 3 ? E[0] : 1.0;
+      }
+      const double cut = pmax - a.p.suspect_t;
+      const int bid = a.job_bl[job];
+      double anc[2][3];
+      if (bid >= 0) {
+        const int off = a.bl.off[bid], n = a.bl.off[bid + 1] - off;
+        uint64_t om = 0;
+        for (int v = 0; v < n; ++v) {
+          const int rr = a.bl.row[off + v];
+          int c = 3;
+          if (rr >= 0) {
+            c = cell_code(a.c.live, a.c.wpr, rr, j);
+            if (c != 3 && cell_E(a.c, rr, j) > cut) c = 3;   // suspect node: not evidence (:230-238)
+          }
+          code[v] = (uint8_t)c;
+          if (c != 3) om |= 1ull << v;
+        }
+        const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
+        om &= ~(1ull << q0);
+        if (q1 >= 0) om &= ~(1ull << q1);
+        GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
+        const int bad = a.nf == 2 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc[0], anc[1])
+                                  : gfx_infer(b, q0, code, om, tab, anc[0]);
+        if (bad) atomicExch(a.status, 1);
+      }
+      for (int f = 0; f < a.nf; ++f) {
+        const int r = rows[f];
+        const int k0 = a.child_off[r], nk = a.child_off[r + 1] - k0;
+        double kids[3];
+        KidCodeFn kc{a.c.live, a.c.wpr, a.child_row + k0, j};
+        ParCodeFn pc{a.c.live, a.c.wpr, a.child_other + k0, j};
+        const bool has_kids = gfx_kids_term(nk, kc, pc, a.kv, kids);
+        const int64_t slot = ((int64_t)job * a.nf + f) * a.n_snps + j;
+        if (bid < 0 && !has_kids) { a.result[slot] = 0; continue; }   // lone node: no result
+        double p[3];
+        gfx_combine(bid >= 0, anc[f], has_kids, kids, p);
+        uint8_t bits = gfx_decision_bits(p, obs[f], a.p.tiethreshold, a.p.threshold);
+        // rank gate (:733-737,817 / :928-933): focal E against the max E of its own genotyped parents
+        double mr = 0.0;
+        for (int q = 0; q < 2; ++q) {
+          const int pr = a.prow[2 * r + q];
+          if (pr >= 0) { const double e = cell_E(a.c, pr, j); if (e > mr) mr = e; }
+        }
+        if (E[f] * a.p.err_thresh >= mr) bits |= 16u;
+        a.result[slot] = bits;
+        if (a.post) { a.post[slot * 3] = p[0]; a.post[slot * 3 + 1] = p[1]; a.post[slot * 3 + 2] = p[2]; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct ApplyArgs {
+  uint32_t* live;
+  int64_t wpr, nwords, n_snps;
+  int n_focal;
+  const int32_t* focal_row;
+  const int32_t* focal_off;   // n_focal+1
+  const int32_t* entry;       // job*nf + side
+  const uint8_t* result;
+  int32_t* tallies;           // [0..n_rows) applied, [n_rows..2n_rows) excluded
+  int n_rows;
+  int count_excluded;
+};
+
+// Sequential apply of a generation's results in canonical job order (correct_genotypes3.py:714-845,
+// 877-944).  One thread owns 16 SNPs of one focal animal, so writes never collide.
+__global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
+  const int64_t total = (int64_t)a.n_focal * a.nwords;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i / a.nwords);
+    const int64_t w = i - (int64_t)f * a.nwords;
+    const int row = a.focal_row[f];
+    uint32_t word = a.live[(int64_t)row * a.wpr + w];
+    const uint32_t before = word;
+    int applied = 0, excluded = 0;
+    for (int e = a.focal_off[f]; e < a.focal_off[f + 1]; ++e) {
+      const uint8_t* res = a.result + (int64_t)a.entry[e] * a.n_snps + w * 16;
+      for (int k = 0; k < 16; ++k) {
+        if (w * 16 + k >= a.n_snps) break;
+        const uint32_t b = res[k];
+        if (!(b & 0x80u)) continue;
+        const uint32_t obs = (word >> (2 * k)) & 3u;  // LIVE state
+        const bool cond = obs == 3u || (!((b >> obs) & 1u) && (b & 8u));
+        if (!cond) continue;
+        if (b & 16u) {
+          const uint32_t set = b & 7u;
+          const uint32_t nv = __popc(set) == 1 ? (uint32_t)(__ffs(set) - 1) : 3u;
+          word = (word & ~(3u << (2 * k))) | (nv << (2 * k));
+          ++applied;
+        } else {
+          ++excluded;
+        }
+      }
+    }
+    if (word != before) a.live[(int64_t)row * a.wpr + w] = word;
+    if (applied) atomicAdd(a.tallies + row, applied);
+    if (excluded && a.count_excluded) atomicAdd(a.tallies + a.n_rows + row, excluded);
+  }
+}
+
+static int run_infer_apply(const gfx_schedule* s, int nf, int n_jobs, const int32_t* job_row0, const int32_t* job_row1,
+                           const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
+                           const int32_t* entry, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
+                           const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
+                           uint8_t* result, double* post, int32_t* tallies, cudaStream_t stream) {
+  if (n_jobs <= 0) return GFX_OK;
+  InferArgs a;
+  a.c = CellCtx{live, orig, wpr, raw, ld_raw, elut};
+  a.n_snps = n_snps; a.nf = nf; a.n_jobs = n_jobs;
+  a.job_row0 = job_row0; a.job_row1 = job_row1; a.job_bl = job_bl;
+  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1};
+  a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
+  a.prow = s->prow; a.kv = s->kv; a.p = *p; a.result = result; a.post = post; a.status = s->status;
+  const int64_t tasks = (int64_t)n_jobs * ((n_snps + GFX_INFER_CHUNK - 1) / GFX_INFER_CHUNK);
+  int blocks = (int)(tasks < (int64_t)s->num_sms * 8 ? tasks : (int64_t)s->num_sms * 8);
+  k_infer<<<blocks, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  ApplyArgs ap{live, wpr, (n_snps + 15) / 16, n_snps, n_focal, focal_row, focal_off, entry, result, tallies, s->h.n_rows, nf == 2};
+  k_apply<<<grid_for((int64_t)n_focal * ap.nwords, 128, s->num_sms, 16), 128, 0, stream>>>(ap);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* live, const uint32_t* orig,
+                                 int64_t n_snps, int64_t wpr, const uint16_t* raw, int64_t ld_raw, const double* elut,
+                                 const gfx_correct_params* p, uint8_t* result, double* post, int32_t* tallies, void* stream) {
+  if (!s || !live || !orig || !raw || !elut || !p || !result || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (generation < 0 || generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
+  const int j0 = s->h.gen_off[generation], nj = s->h.gen_off[generation + 1] - j0;
+  const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
+  // focal_off holds global offsets into app_entry: pass the un-shifted entry array
+  return run_infer_apply(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
+                         s->app_focal_off + f0, s->app_entry, live, orig, n_snps, wpr, raw, ld_raw, elut, p, result, post,
+                         tallies, (cudaStream_t)stream);
+}
+
+extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
+                                   const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
+                                   uint8_t* result, double* post, int32_t* tallies, void* stream) {
+  if (!s || !live || !orig || !raw || !elut || !p || !result || !tallies) return fail(GFX_E_INVALID, "null argument");
+  const int n = (int)s->h.single_row.size();
+  return run_infer_apply(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
+                         live, orig, n_snps, wpr, raw, ld_raw, elut, p, result, post, tallies, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// trio consistency scan: bit-parallel over 16 SNPs per word
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trio_scan(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nwords,
+                                                   int64_t n_snps, const int32_t* __restrict__ trio_row, int n_trios,
+                                                   const int32_t* __restrict__ prow, long long* __restrict__ inc,
+                                                   long long* __restrict__ tested) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_trios; t += warps) {
+    const int r = trio_row[t];
+    const int64_t rs = prow[2 * r], rd = prow[2 * r + 1];
+    int n_inc = 0, n_tst = 0;
+    for (int64_t w = lane; w < nwords; w += 32) {
+      const uint32_t k = __ldg(packed + (int64_t)r * wpr + w);
+      const uint32_t s = __ldg(packed + rs * wpr + w);
+      const uint32_t d = __ldg(packed + rd * wpr + w);
+      uint32_t valid = 0x55555555u;
+      const int64_t rem = n_snps - w * 16;
+      if (rem < 16) valid = (1u << (2 * rem)) - 1u & 0x55555555u;
+      const uint32_t k0 = ~(k | (k >> 1)), k1 = k & ~(k >> 1), k2 = (k >> 1) & ~k;
+      const uint32_t s0 = ~(s | (s >> 1)), s1 = s & ~(s >> 1), s2 = (s >> 1) & ~s;
+      const uint32_t d0 = ~(d | (d >> 1)), d1 = d & ~(d >> 1), d2 = (d >> 1) & ~d;
+      const uint32_t present = (k0 | k1 | k2) & (s0 | s1 | s2) & (d0 | d1 | d2) & valid;
+      // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
+      const uint32_t bad = (k0 & (s2 | d2)) | (k2 & (s0 | d0)) | (k1 & ((s0 & d0) | (s2 & d2)));
+      n_tst += __popc(present);
+      n_inc += __popc(bad & present);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      n_inc += __shfl_xor_sync(0xffffffffu, n_inc, o);
+      n_tst += __shfl_xor_sync(0xffffffffu, n_tst, o);
+    }
+    if (lane == 0) { inc[r] = n_inc; tested[r] = n_tst; }
+  }
+}
+
+extern "C" int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
+                             int64_t* tested, void* stream) {
+  if (!s || !packed || !inc || !tested || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_trio_scan: bad argument");
+  GFX_CUDA(cudaMemsetAsync(inc, 0, sizeof(int64_t) * s->h.n_rows, (cudaStream_t)stream));
+  GFX_CUDA(cudaMemsetAsync(tested, 0, sizeof(int64_t) * s->h.n_rows, (cudaStream_t)stream));
+  const int nt = (int)s->h.trio_row.size();
+  if (nt == 0) return GFX_OK;
+  k_trio_scan<<<grid_for((int64_t)nt * 32, 256, s->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+      packed, wpr, (n_snps + 15) / 16, n_snps, s->trio_row, nt, s->prow, (long long*)inc, (long long*)tested);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LD-window joint counts
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_window_counts(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ mask,
+                                                       int64_t n, int64_t wpr, int64_t mwpr, const int32_t* __restrict__ win_start,
+                                                       const int32_t* __restrict__ win_len, int n_windows, int stride,
+                                                       uint32_t* __restrict__ counts) {
+  extern __shared__ uint32_t s_cnt[];
+  for (int wi = blockIdx.x; wi < n_windows; wi += gridDim.x) {
+    const int start = win_start[wi], len = win_len[wi];
+    const int nstates = gfx_pow3(len);
+    for (int i = threadIdx.x; i < nstates; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
+      int idx = 0;
+      bool ok = len > 0;
+      for (int c = 0; c < len; ++c) {
+        const int64_t j = start + c;
+        const uint32_t code = (__ldg(packed + r * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u;
+        if (code == 3u) { ok = false; break; }
+        if (mask && !((__ldg(mask + r * mwpr + (j >> 5)) >> (j & 31)) & 1u)) { ok = false; break; }
+        idx = idx * 3 + (int)code;
+      }
+      if (ok) atomicAdd(&s_cnt[idx], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nstates; i += blockDim.x) counts[(int64_t)wi * stride + i] = s_cnt[i];
+    __syncthreads();
+  }
+}
+
+extern "C" int gfx_window_counts(const uint32_t* packed, const uint32_t* mask, int64_t n, int64_t n_snps, int64_t wpr,
+                                 int64_t mwpr, const int32_t* win_start, const int32_t* win_len, int32_t n_windows,
+                                 int32_t stride, uint32_t* counts, void* stream) {
+  if (!packed || !win_start || !win_len || !counts || n <= 0 || n_windows <= 0 || stride <= 0)
+    return fail(GFX_E_INVALID, "gfx_window_counts: bad argument");
+  (void)n_snps;
+  const size_t smem = (size_t)stride * sizeof(uint32_t);
+  if (smem > 200 * 1024) return fail(GFX_E_INVALID, "window too wide for shared memory (surround <= 4)");
+  GFX_CUDA(cudaFuncSetAttribute(k_window_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = n_windows < device_sms() * 4 ? n_windows : device_sms() * 4;
+  k_window_counts<<<blocks, 256, smem, (cudaStream_t)stream>>>(packed, mask, n, wpr, mwpr, win_start, win_len, n_windows,
+                                                              stride, counts);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+extern "C" int gfx_founders(const gfx_pedigree_desc* ped, const uint8_t* restrict_host, int32_t* out_idx, int32_t* out_n) {
+  if (!ped || !out_idx || !out_n) return fail(GFX_E_INVALID, "null argument");
+  int n = 0;
+  for (int a = 0; a < ped->n_ped; ++a) {
+    if (restrict_host && !restrict_host[a]) continue;
+    const int32_t s = ped->sire[a], d = ped->dam[a];
+    const bool has_s = s >= 0 && (!restrict_host || restrict_host[s]);
+    const bool has_d = d >= 0 && (!restrict_host || restrict_host[d]);
+    if (!has_s || !has_d) out_idx[n++] = a;
+  }
+  *out_n = n;
+  return GFX_OK;
+}
+
+extern "C" int gfx_infer_host(int32_t n, const int8_t* p1, const int8_t* p2, const uint8_t* code, int32_t query, double* out3) {
+  if (n <= 0 || n > GFX_MAXN || !p1 || !p2 || !code || !out3 || query < 0 || query >= n)
+    return fail(GFX_E_INVALID, "gfx_infer_host: bad argument");
+  std::vector<int8_t> last(n);
+  for (int i = 0; i < n; ++i) last[i] = (int8_t)i;
+  for (int i = 0; i < n; ++i)
+    if (p1[i] >= 0) {
+      if (p1[i] >= i || p2[i] >= i || p2[i] < 0) return fail(GFX_E_INVALID, "nodes must be topologically ordered");
+      last[p1[i]] = (int8_t)i;
+      last[p2[i]] = (int8_t)i;
+    }
+  uint64_t obs = 0;
+  for (int i = 0; i < n; ++i)
+    if (code[i] < 3 && i != query) obs |= 1ull << i;
+  GfxBlanket b{n, p1, p2, last.data()};
+  std::vector<double> tab(GFX_TAB);
+  if (gfx_infer(b, query, code, obs, tab.data(), out3)) return fail(GFX_E_TOO_WIDE, "too many open variables");
+  return GFX_OK;
+}
+
+extern "C" int gfx_infer_pair_host(int32_t n, const int8_t* p1, const int8_t* p2, const uint8_t* code, int32_t q0, int32_t q1,
+                                   double* out6) {
+  if (n <= 0 || n > GFX_MAXN || !p1 || !p2 || !code || !out6 || q0 < 0 || q0 >= n || q1 < 0 || q1 >= n || q0 == q1)
+    return fail(GFX_E_INVALID, "gfx_infer_pair_host: bad argument");
+  std::vector<int8_t> last(n);
+  for (int i = 0; i < n; ++i) last[i] = (int8_t)i;
+  for (int i = 0; i < n; ++i)
+    if (p1[i] >= 0) {
+      if (p1[i] >= i || p2[i] >= i || p2[i] < 0) return fail(GFX_E_INVALID, "nodes must be topologically ordered");
+      last[p1[i]] = (int8_t)i;
+      last[p2[i]] = (int8_t)i;
+    }
+  uint64_t obs = 0;
+  for (int i = 0; i < n; ++i)
+    if (code[i] < 3) obs |= 1ull << i;
+  GfxBlanket b{n, p1, p2, last.data()};
+  std::vector<double> tab(GFX_TAB);
+  if (gfx_infer_pair(b, q0, q1, code, obs, tab.data(), out6, out6 + 3)) return fail(GFX_E_TOO_WIDE, "too many open variables");
+  return GFX_OK;
+}
+
+extern "C" int gfx_kids_term_host(int32_t n, const uint8_t* kid, const uint8_t* par, double* out3) {
+  if (n < 0 || !out3) return fail(GFX_E_INVALID, "gfx_kids_term_host: bad argument");
+  double kv[108];
+  gfx_fill_kv(kv);
+  struct K { const uint8_t* p; __host__ __device__ int operator()(int i) const { return p[i]; } };
+  K kc{kid}, pc{par};
+  if (!gfx_kids_term(n, kc, pc, kv, out3)) { out3[0] = out3[1] = out3[2] = nan(""); return 1; }
+  return GFX_OK;
+}

@@ -1,0 +1,52 @@
+// Host-side flattening of the pedigree into the index arrays the kernels consume.
+//
+// Replaces, once per (pedigree, genotyped id list, back):
+//   PedigreeDAG.get_parents_depth / balance_nodes / get_subset per animal and per pair
+//   (pedigree/pedigree_dag.py:124-168,221-231), BayesPedigreeNetworkModel.generateModel
+//   (bayesnet/model.py:173-230) and correctMatrix's bookkeeping: partner_pairs, blankets,
+//   per-generation gen_pairs, singlekids (correct_genotypes3.py:556-565,684-686,851-853).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/genofix_b200.h"
+
+struct GfxBlanketSet {
+  std::vector<int32_t> off;   // nb+1
+  std::vector<int32_t> row;   // genotype row of the node or -1
+  std::vector<int8_t> p1, p2, last;
+  std::vector<int8_t> q0, q1; // focal local indices (q1 = -1 for a single focal animal)
+  int max_nodes = 0;
+  int max_width = 0;
+  int count() const { return (int)off.size() - 1; }
+};
+
+struct GfxHostSchedule {
+  int n_ped = 0, n_rows = 0, back = 2;
+  // rank
+  std::vector<int32_t> anc6;         // n_rows*6 rows of S,D,SS,SD,DS,DD or -1
+  std::vector<uint8_t> rank_flags;   // bit0 has ancestors, bit1 needs the generic engine
+  std::vector<int32_t> rank_blanket; // blanket id (depth `back`) or -1
+  std::vector<int32_t> prow;         // n_rows*2 rows of the own parents (rank gate) or -1
+  // genotyped children CSR per row, reference iteration order
+  std::vector<int32_t> child_off, child_row, child_other;
+  // pairs
+  std::vector<int32_t> pair_sire_row, pair_dam_row, pair_blanket;
+  std::vector<int32_t> gen_off;      // n_generations+1 offsets into job_pair
+  std::vector<int32_t> job_pair;
+  // per generation apply lists: focal rows with their (job-in-generation*2 + side) entries
+  std::vector<int32_t> app_gen_off;  // n_generations+1 offsets into app_focal_row / app_focal_off
+  std::vector<int32_t> app_focal_row;
+  std::vector<int32_t> app_focal_off; // size app_focal_row.size()+1 (global offsets into app_entry)
+  std::vector<int32_t> app_entry;
+  // singles
+  std::vector<int32_t> single_row, single_blanket;
+  // trios
+  std::vector<int32_t> trio_row;     // rows with both parents genotyped
+  GfxBlanketSet bl;
+  gfx_schedule_info_t info{};
+};
+
+// Returns GFX_OK or an error code with `err` filled.
+int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::string& err);

@@ -1,0 +1,370 @@
+"""Device pipeline behind CorrectGenotypes.correctMatrix: schedule + kernels through the C ABI.
+
+PyTorch is used only for device memory, pinned host buffers and streams.  Every compute step is a
+kernel of libgenofix_b200.so; the one host-side numeric step is the rank transform table
+(log(log(x+1)+1)/max over the <= 65536 distinct float16 scores), done with numpy so that it is
+bit-identical to the reference's own numpy calls (correct_genotypes3.py:600-603).
+"""
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .pedigree.pedigree_dag import PedigreeDAG
+
+SUSPECT_T = 0.2  # hard-coded in the reference driver (correct_genotypes3.py:691,858)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("genofix_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Schedule(object):
+    """Flattened pedigree for a given list of genotyped ids (matrix row order) and look-back depth."""
+
+    def __init__(self, pedigree, ids, back=2, host_only=False):
+        if not isinstance(pedigree, PedigreeDAG):
+            raise TypeError("pedigree must be a genofix_b200 PedigreeDAG")
+        L = _lib.lib()
+        ids = np.asarray(ids, dtype=np.int64)
+        pidx = pedigree.index_of(ids)
+        if (pidx < 0).any():
+            # the reference fails with NetworkXError when a genotyped id is missing from the pedigree
+            bad = ids[pidx < 0][:5]
+            try:
+                import networkx as nx
+                raise nx.NetworkXError("The node %s is not in the digraph." % bad[0])
+            except ImportError:
+                raise KeyError(int(bad[0]))
+        n_ped = len(pedigree.ids)
+        row = np.full(n_ped, -1, dtype=np.int32)
+        row[pidx] = np.arange(len(ids), dtype=np.int32)
+        if len(np.unique(pidx)) != len(pidx):
+            raise ValueError("duplicate ids in the genotype index")
+        kid_off, kid = pedigree.children_csr_reference_order()
+        self._keep = dict(ped_id=np.ascontiguousarray(pedigree.ids, dtype=np.int64),
+                          sire=np.ascontiguousarray(pedigree.sire_idx, dtype=np.int32),
+                          dam=np.ascontiguousarray(pedigree.dam_idx, dtype=np.int32),
+                          generation=np.ascontiguousarray(pedigree.generation, dtype=np.int32),
+                          row=row, kid_off=np.ascontiguousarray(kid_off, dtype=np.int32),
+                          kid=np.ascontiguousarray(kid, dtype=np.int32))
+        k = self._keep
+        self.desc = _lib.PedigreeDesc(n_ped, len(ids), int(back), _ptr(k["ped_id"]), _ptr(k["sire"]), _ptr(k["dam"]),
+                                      _ptr(k["generation"]), _ptr(k["row"]), _ptr(k["kid_off"]), _ptr(k["kid"]))
+        self.handle = C.c_void_p()
+        fn = L.gfx_schedule_create_host if host_only else L.gfx_schedule_create
+        _lib.check(fn(C.byref(self.desc), C.byref(self.handle)))
+        info = _lib.ScheduleInfo()
+        _lib.check(L.gfx_schedule_info(self.handle, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in _lib.ScheduleInfo._fields_ if f != "reserved"}
+        self.n_rows = len(ids)
+        self.back = int(back)
+        self.ids = ids
+
+    def array(self, which):
+        cap = {0: 2 * self.info["n_pairs"], 1: self.info["n_generations"] + 1, 2: self.info["n_singles"],
+               3: self.info["n_pair_jobs"], 4: self.n_rows}[which]
+        out = np.zeros(max(cap, 1), dtype=np.int32)
+        n = _lib.check(_lib.lib().gfx_schedule_copy(self.handle, which, _ptr(out), cap))
+        return out[:n]
+
+    def founders(self, restrict_ids=None):
+        """Pedigree ids lacking a sire or a dam (gfutils/extract_founders.py:106-110)."""
+        n_ped = self.desc.n_ped
+        flags = None
+        if restrict_ids is not None:
+            flags = np.zeros(n_ped, dtype=np.uint8)
+            idx = np.searchsorted(self._keep["ped_id"], np.asarray(restrict_ids, dtype=np.int64))
+            idx = idx[(idx < n_ped)]
+            idx = idx[np.isin(self._keep["ped_id"][idx], np.asarray(restrict_ids, dtype=np.int64))]
+            flags[idx] = 1
+        out = np.zeros(n_ped, dtype=np.int32)
+        n = C.c_int32(0)
+        _lib.check(_lib.lib().gfx_founders(C.byref(self.desc), _ptr(flags) if flags is not None else None, _ptr(out),
+                                           C.byref(n)))
+        return self._keep["ped_id"][out[:n.value]]
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            _lib.lib().gfx_schedule_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------
+# rank transform + quantile on the histogram (host, numpy)
+# ---------------------------------------------------------------------------------------------------
+_ALL_HALF = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float64)
+
+
+def _lerp(a, b, t):
+    # numpy.lib._function_base_impl._lerp
+    d = b - a
+    r = a + d * t
+    if t >= 0.5:
+        r = b - d * (1 - t)
+    return r
+
+
+def weighted_quantile_linear(values, counts, q):
+    """np.quantile(x, q) (default 'linear' method) for x = values repeated counts times; values need
+    not be sorted.  Bit-identical to numpy (checked in tests/test_host_logic.py)."""
+    values = np.asarray(values, dtype=np.float64)
+    counts = np.asarray(counts, dtype=np.int64)
+    if np.isnan(values[counts > 0]).any():
+        return np.float64(np.nan)
+    order = np.argsort(values, kind="stable")
+    v = values[order]
+    cum = np.cumsum(counts[order])
+    n = int(cum[-1])
+    vi = np.float64(n - 1) * np.float64(q)
+    lo = np.floor(vi)
+    if vi >= n - 1:
+        lo_i = hi_i = n - 1
+    elif vi < 0:
+        lo_i = hi_i = 0
+    else:
+        lo_i = int(lo)
+        hi_i = lo_i + 1
+    gamma = vi - lo
+    a = v[np.searchsorted(cum, lo_i, side="right")]
+    b = v[np.searchsorted(cum, hi_i, side="right")]
+    return np.float64(_lerp(a, b, gamma))
+
+
+def rank_transform_table(hist, init_filter_p):
+    """hist: uint64[65537] from gfx_rank_hist.  Returns (elut float64[65536], test_p, n_nan_cells).
+
+    E = log(log(raw+1)+1) / nanmax(.)  with missing cells set to 1 afterwards
+    (correct_genotypes3.py:600-603); test_p = np.quantile(E, init_filter_p) (:666-667)."""
+    hist = np.asarray(hist, dtype=np.uint64)
+    counts = hist[:65536].astype(np.int64)
+    n_missing = int(hist[65536])
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e_all = np.log(np.log(_ALL_HALF + 1) + 1)
+        present = counts > 0
+        if n_missing > 0:
+            present = present.copy()
+            present[0x3C00] = True  # missing cells carry raw = 1.0 until they are overwritten with E = 1
+        m = np.nanmax(e_all[present]) if present.any() else np.float64(np.nan)
+        elut = e_all / m
+    n_nan = int(counts[np.isnan(_ALL_HALF)].sum())
+    vals = np.concatenate([elut, [1.0]])
+    cnts = np.concatenate([counts, [n_missing]])
+    keep = cnts > 0
+    test_p = weighted_quantile_linear(vals[keep], cnts[keep], init_filter_p) if keep.any() else np.float64(np.nan)
+    return elut, test_p, n_nan
+
+
+# ---------------------------------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------------------------------
+class Engine(object):
+    """One schedule + device buffers; `correct()` is the host-buffer (end-to-end) call,
+    the `*_device` methods work on resident data."""
+
+    def __init__(self, pedigree, ids, back=2):
+        self.torch = _torch()
+        self.L = _lib.lib()
+        self.schedule = Schedule(pedigree, ids, back)
+        self.n = self.schedule.n_rows
+        self.back = int(back)
+        self._shape = None
+        self.stats = {}
+
+    # ---- buffers -----------------------------------------------------------------------------
+    def _alloc(self, s):
+        if self._shape == s:
+            return
+        t = self.torch
+        dev = t.device("cuda", t.cuda.current_device())
+        n = self.n
+        self.s = int(s)
+        self.nwords = (self.s + 15) // 16
+        self.wpr = ((self.nwords + 3) // 4) * 4
+        self.ld_raw = 16 * self.wpr
+        self.ldc = ((self.s + 15) // 16) * 16
+        self.codes = t.empty((n, self.ldc), dtype=t.uint8, device=dev)
+        self.packed_orig = t.empty((n, self.wpr), dtype=t.int32, device=dev)
+        self.packed_live = t.empty((n, self.wpr), dtype=t.int32, device=dev)
+        self.raw = t.empty((n, self.ld_raw), dtype=t.int16, device=dev)
+        self.hist = t.empty(65537, dtype=t.int64, device=dev)
+        self.elut = t.empty(65536, dtype=t.float64, device=dev)
+        info = self.schedule.info
+        nres = max(2 * info["max_pairs_in_generation"], info["n_singles"], 1)
+        self.result = t.empty(nres * self.s, dtype=t.uint8, device=dev)
+        self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
+        self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
+        self.host_out = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
+        self.host_hist = t.empty(65537, dtype=t.int64, pin_memory=True)
+        self.host_elut = t.empty(65536, dtype=t.float64, pin_memory=True)
+        self._shape = s
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    # ---- resident-data steps -------------------------------------------------------------------
+    def load_codes_device(self, codes_dev):
+        """codes_dev: uint8 cuda tensor [n, >=s] (values 0,1,2,9)."""
+        _lib.check(self.L.gfx_pack2(codes_dev.data_ptr(), self.n, self.s, codes_dev.stride(0), self.packed_orig.data_ptr(),
+                                    self.wpr, self._stream()))
+
+    def use_packed(self, packed_dev, n_snps):
+        """Adopt an already packed device matrix [n, wpr] int32 (wpr as computed by `_alloc(n_snps)`)."""
+        self._alloc(n_snps)
+        if tuple(packed_dev.shape) != (self.n, self.wpr):
+            raise ValueError("packed matrix must be [%d, %d]" % (self.n, self.wpr))
+        self.packed_orig = packed_dev
+
+    def correct_resident(self, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1):
+        """Whole path on resident data: rank -> histogram -> thresholds -> pairs -> singles.
+        Result stays in self.packed_live; per-animal tallies in self.tallies."""
+        self.mendel_rank_device()
+        self.thresholds_device(init_filter_p)
+        self.correct_device(threshold_pair, threshold_single, tiethreshold, err_thresh)
+
+    def mendel_rank_device(self):
+        _lib.check(self.L.gfx_mendel_rank(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
+                                          self.raw.data_ptr(), self.ld_raw, self._stream()))
+
+    def thresholds_device(self, init_filter_p):
+        _lib.check(self.L.gfx_rank_hist(self.raw.data_ptr(), self.ld_raw, self.packed_orig.data_ptr(), self.wpr, self.n,
+                                        self.s, self.hist.data_ptr(), self._stream()))
+        self.host_hist.copy_(self.hist, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        elut, test_p, n_nan = rank_transform_table(self.host_hist.numpy().view(np.uint64), init_filter_p)
+        self.host_elut.numpy()[:] = elut
+        self.elut.copy_(self.host_elut, non_blocking=True)
+        self.test_p = float(test_p)
+        self.n_nan = n_nan
+        self.elut_host = elut
+        return self.test_p
+
+    def correct_device(self, threshold_pair, threshold_single, tiethreshold, err_thresh, keep_posteriors=False):
+        t = self.torch
+        self.packed_live.copy_(self.packed_orig)
+        self.tallies.zero_()
+        posts = {"pairs": [], "singles": None}
+        if not np.isnan(self.test_p):  # D16: NaN threshold => nothing is suspect
+            info = self.schedule.info
+            pp = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_pair), float(err_thresh))
+            gen_off = self.schedule.array(1) if keep_posteriors else None
+            for g in range(info["n_generations"]):
+                post = None
+                if keep_posteriors:
+                    nj = int(gen_off[g + 1] - gen_off[g])
+                    post = t.full((max(nj, 1) * 2, self.s, 3), float("nan"), dtype=t.float64, device=self.codes.device)
+                _lib.check(self.L.gfx_correct_pairs(
+                    self.schedule.handle, g, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
+                    self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.result.data_ptr(),
+                    post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
+                if keep_posteriors:
+                    res = self.result[:2 * max(nj, 1) * self.s].view(-1, self.s).cpu().numpy().copy()
+                    posts["pairs"].append((post.cpu().numpy(), res))
+            ps = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_single), float(err_thresh))
+            post = None
+            ns = info["n_singles"]
+            if keep_posteriors:
+                post = t.full((max(ns, 1), self.s, 3), float("nan"), dtype=t.float64, device=self.codes.device)
+            _lib.check(self.L.gfx_correct_singles(
+                self.schedule.handle, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
+                self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.result.data_ptr(),
+                post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
+            if keep_posteriors:
+                res = self.result[:max(ns, 1) * self.s].view(-1, self.s).cpu().numpy().copy()
+                posts["singles"] = (post.cpu().numpy(), res)
+        return posts
+
+    def unpack_device(self, out_codes_dev):
+        _lib.check(self.L.gfx_unpack2(self.packed_live.data_ptr(), self.n, self.s, self.wpr, out_codes_dev.data_ptr(),
+                                      out_codes_dev.stride(0), self._stream()))
+
+    def check_status(self):
+        _lib.check(self.L.gfx_check_device_status(self.schedule.handle, self._stream()))
+
+    def raw_host(self):
+        """float16 [n, s] rank matrix (what mendelProbsSingle returns per animal)."""
+        return self.raw[:, :self.s].cpu().numpy().view(np.float16)
+
+    def E_host(self):
+        """float64 [n, s] transformed ranks, missing cells = 1 (correct_genotypes3.py:600-603)."""
+        raw = self.raw[:, :self.s].cpu().numpy().view(np.uint16)
+        E = self.elut_host[raw]
+        codes = self.codes[:, :self.s].cpu().numpy()
+        E[codes > 2] = 1.0
+        return E
+
+    # ---- end-to-end on host buffers ----------------------------------------------------------------
+    def correct(self, G, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
+                keep_posteriors=False):
+        """G: uint8 [n, s] numpy (0,1,2,9).  Returns the corrected uint8 [n, s] matrix (new array)."""
+        G = np.asarray(G)
+        if G.ndim != 2 or G.shape[0] != self.n:
+            raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+        self._alloc(G.shape[1])
+        hin = self.host_in.numpy()
+        hin[:, :self.s] = G
+        if self.ldc > self.s:
+            hin[:, self.s:] = 9
+        self.codes.copy_(self.host_in, non_blocking=True)
+        self.load_codes_device(self.codes)
+        self.mendel_rank_device()
+        self.thresholds_device(init_filter_p)
+        posts = self.correct_device(threshold_pair, threshold_single, tiethreshold, err_thresh, keep_posteriors)
+        self.unpack_device(self.codes)
+        self.host_out.copy_(self.codes, non_blocking=True)
+        self.check_status()  # synchronises the stream
+        tall = self.tallies.cpu().numpy()
+        self.stats = dict(test_p=self.test_p, n_nan=self.n_nan, corrected_per_animal=tall[:self.n].copy(),
+                          excluded_per_animal=tall[self.n:].copy(), posteriors=posts)
+        return self.host_out.numpy()[:, :self.s].copy()
+
+    # ---- config 5: trio scan ---------------------------------------------------------------------------
+    def trio_scan(self, G=None):
+        t = self.torch
+        if G is not None:
+            G = np.asarray(G)
+            self._alloc(G.shape[1])
+            hin = self.host_in.numpy()
+            hin[:, :self.s] = G
+            if self.ldc > self.s:
+                hin[:, self.s:] = 9
+            self.codes.copy_(self.host_in, non_blocking=True)
+            self.load_codes_device(self.codes)
+        inc = t.empty(self.n, dtype=t.int64, device=self.codes.device)
+        tst = t.empty(self.n, dtype=t.int64, device=self.codes.device)
+        _lib.check(self.L.gfx_trio_scan(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
+                                        inc.data_ptr(), tst.data_ptr(), self._stream()))
+        return inc.cpu().numpy(), tst.cpu().numpy()
+
+
+_ENGINES = {}
+
+
+def engine_for(pedigree, ids, back):
+    """Engines are cached per (pedigree object, id list, back): building the schedule is the
+    per-pedigree set-up cost, the matrix chunks then stream through it."""
+    ids = np.asarray(ids, dtype=np.int64)
+    key = (id(pedigree), ids.tobytes(), int(back))
+    e = _ENGINES.get(key)
+    if e is None:
+        if len(_ENGINES) > 4:
+            _ENGINES.clear()
+        e = Engine(pedigree, ids, back)
+        _ENGINES[key] = e
+        e._pedigree_ref = pedigree  # keep id() stable
+    return e

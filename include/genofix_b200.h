@@ -1,0 +1,206 @@
+/*
+ * genofix_b200 -- C ABI of the B200-native Mendelian-rank / genotype-correction hot path.
+ *
+ * Drop-in boundary for GenoFix (andreaskranis/genofix).  The reference is pure Python and has no
+ * FFI; the entry points below are what a ctypes binding inside the reference's own modules would
+ * call (INTEGRATION.md shows the stubs).  Each entry point cites the reference code it replaces
+ * (paths relative to the reference's src/ directory).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GFX_E_* code on failure; the message is
+ *     available from gfx_last_error() (thread local).  No exceptions cross the ABI.
+ *   - pointers named *_dev are CUDA device pointers on the current device; *_host are host
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - genotypes on the device are 2-bit packed: animal-major rows, 16 codes per uint32 word,
+ *     SNP j of a row lives in word j/16 at bits 2*(j%16); code 0/1/2 = genotype, 3 = missing
+ *     (the reference's 9).  `wpr` = words per row (>= ceil(n_snps/16), a multiple of 4 so that rows are
+ *     16-byte aligned); padding codes must be 3.
+ *   - rank matrices are IEEE binary16 bit patterns (uint16_t), row stride `ld_raw` elements.
+ *   - handles are opaque and owned by the caller until the matching *_destroy.
+ */
+#ifndef GENOFIX_B200_H
+#define GENOFIX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFX_OK 0
+#define GFX_E_INVALID (-1)   /* bad argument                                                   */
+#define GFX_E_CUDA (-2)      /* CUDA runtime error (message has the cudaError string)          */
+#define GFX_E_PEDIGREE (-3)  /* pedigree outside the reference's domain (e.g. one known parent, */
+                             /* pedigree_dag.py:126-128 KeyError)                    */
+#define GFX_E_TOO_WIDE (-4)  /* a blanket needs more simultaneous free variables than GFX_WMAX  */
+#define GFX_E_NOMEM (-5)
+
+typedef struct gfx_schedule gfx_schedule;
+
+const char* gfx_last_error(void);
+int gfx_version(void);
+/* Number of kernels launched by this library in the calling process since load (bench `gpu_launches`). */
+int64_t gfx_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pedigree schedule: replaces PedigreeDAG indexes + per-animal get_parents_depth / get_subset /
+ * balance_nodes / generateModel (pedigree/pedigree_dag.py:124-168,188-231; bayesnet/model.py:173-230)
+ * and correctMatrix's bookkeeping (correct_genotypes3.py:556-565,684-686,851-853).
+ *
+ * All arrays are HOST arrays indexed by pedigree animal 0..n_ped-1:
+ *   ped_id      original id (canonical pair order is ascending (sire id, dam id))
+ *   sire, dam   pedigree index of the parent or -1
+ *   generation  min(pure sire-line length, pure dam-line length)   (pedigree_dag.py:197-200)
+ *   row         genotype-matrix row of the animal or -1 if not genotyped
+ *   kid_off/kid children CSR in the reference's iteration order (set(successors), see
+ *               correct_genotypes3.py:199-200); n_ped+1 offsets
+ * back = blanket depth for rank and singles; pairs use back+1 (correct_genotypes3.py:691).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_ped;
+  int32_t n_rows;
+  int32_t back;
+  const int64_t* ped_id;
+  const int32_t* sire;
+  const int32_t* dam;
+  const int32_t* generation;
+  const int32_t* row;
+  const int32_t* kid_off;
+  const int32_t* kid;
+} gfx_pedigree_desc;
+
+int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** out);
+/* Same index arrays, no device upload: for inspecting the schedule (gfx_schedule_info / _copy) on a
+ * machine without a GPU.  The handle must not be passed to a kernel entry point. */
+int gfx_schedule_create_host(const gfx_pedigree_desc* ped, gfx_schedule** out);
+void gfx_schedule_destroy(gfx_schedule* s);
+
+typedef struct {
+  int32_t n_rows;
+  int32_t n_generations;   /* max generation + 1 */
+  int32_t n_pairs;         /* distinct (sire, dam) of genotyped kids with both parents genotyped */
+  int32_t n_pair_jobs;     /* sum over generations of pairs scheduled (a pair can run twice)     */
+  int32_t n_singles;       /* genotyped animals that are in no partner pair                      */
+  int32_t n_loopy;         /* rank blankets that are not the plain 2-generation tree             */
+  int32_t n_blankets;
+  int32_t max_blanket_nodes;
+  int32_t max_width;       /* worst-case free-variable frontier over all blankets                */
+  int32_t max_pairs_in_generation;
+  int32_t n_trios;         /* genotyped animals with both parents genotyped                      */
+  int32_t reserved;
+} gfx_schedule_info_t;
+
+int gfx_schedule_info(const gfx_schedule* s, gfx_schedule_info_t* out);
+/* Copies host-side index arrays out for inspection / tests.  which: 0 = pairs (n_pairs*2 rows:
+ * sire_row, dam_row), 1 = pair jobs per generation offsets (n_generations+1), 2 = singles rows,
+ * 3 = generation pair-job list (n_pair_jobs pair indices), 4 = rank flags (n_rows). */
+int gfx_schedule_copy(const gfx_schedule* s, int which, int32_t* out_host, int64_t capacity);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2-bit packing (replaces the uint8 DataFrame the reference keeps per worker,
+ * correct_genotypes3.py:42-50; gfutils/gensrandaccess.py:38-50 yields the uint8 matrix)
+ * codes: uint8 [n, ld_codes] with values 0,1,2 and 9 (anything > 2 packs as missing).
+ * ------------------------------------------------------------------------------------------- */
+int gfx_pack2(const uint8_t* codes_dev, int64_t n, int64_t s, int64_t ld_codes,
+              uint32_t* packed_dev, int64_t wpr, void* stream);
+int gfx_unpack2(const uint32_t* packed_dev, int64_t n, int64_t s, int64_t wpr,
+                uint8_t* codes_dev, int64_t ld_codes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mendel rank ("peeling") kernel: CorrectGenotypes.mendelProbsSingle for every genotyped animal
+ * and SNP (correct_genotypes3.py:85-166 with bayesnet/model.py:93-116 and the pgmpy query of
+ * :119-121).  raw_dev receives the float16 score of :149-155 (1.0 where unobserved / lone).
+ * ------------------------------------------------------------------------------------------- */
+int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
+                    uint16_t* raw_dev, int64_t ld_raw, void* stream);
+
+/* Histogram of the raw float16 bit patterns over non-missing cells (65536 x uint64) plus the
+ * number of missing cells in hist_dev[65536]: everything the rank transform and both quantiles need
+ * (correct_genotypes3.py:593-606,666-667).  hist_dev must hold 65537 uint64 and is zeroed here. */
+int gfx_rank_hist(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* packed_dev, int64_t wpr,
+                  int64_t n, int64_t n_snps, uint64_t* hist_dev, void* stream);
+
+/* Per-animal sum over SNPs of E = elut[raw] (missing cells use missing_value):
+ * error_checker.py:193-204 / preindex.py:259-266 individualSumProbs. */
+int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* packed_dev, int64_t wpr,
+                    int64_t n, int64_t n_snps, const double* elut_dev, double missing_value,
+                    double* rowsum_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Correction: correctPair + pair apply per generation (correct_genotypes3.py:169-327,684-848) and
+ * correctSingle + single apply (:330-430,851-944).
+ *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
+ *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
+ *   packed_orig  the matrix as given (defines E[g==9] = 1, :603); packed_live is updated in place
+ *   result_dev   scratch, >= 2 * max_pairs_in_generation * n_snps bytes (pairs) / n_singles * n_snps
+ *   post_dev     optional (may be NULL): posteriors per job and SNP, 6 (pairs) or 3 (singles) doubles
+ *   tallies_dev  int32 [2 * n_rows]: [0..n) corrections applied (n_errors), [n..2n) excluded by the
+ *                rank gate (excludedNotBest); accumulated, not zeroed here
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  double test_p;        /* quantP_t, :666-667 */
+  double suspect_t;     /* 0.2, :691 */
+  double tiethreshold;
+  double threshold;     /* threshold_pair or threshold_single */
+  double err_thresh;
+} gfx_correct_params;
+
+int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* packed_live_dev,
+                      const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
+                      const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
+                      const gfx_correct_params* params, uint8_t* result_dev, double* post_dev,
+                      int32_t* tallies_dev, void* stream);
+
+int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
+                        const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
+                        const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
+                        const gfx_correct_params* params, uint8_t* result_dev, double* post_dev,
+                        int32_t* tallies_dev, void* stream);
+
+/* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); returns and clears it.
+ * Synchronises the stream. */
+int gfx_check_device_status(const gfx_schedule* s, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Empirical Mendelian-consistency scan (BASELINE config 5; trio selection of
+ * pedigree/error_checker.py:138-153): for every genotyped animal with both parents genotyped,
+ * the number of SNPs where all three calls are present (tested) and the number where
+ * P(kid | sire, dam) = 0 under bayesnet/model.py:28-30 (inconsistent).  int64 [n_rows] each.
+ * ------------------------------------------------------------------------------------------- */
+int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
+                  int64_t* inconsistent_dev, int64_t* tested_dev, void* stream);
+
+/* Founders (gfutils/extract_founders.py:106-110): HOST call.  restrict_host is NULL or n_ped flags;
+ * writes pedigree indices of animals lacking a sire or a dam inside the (restricted) pedigree. */
+int gfx_founders(const gfx_pedigree_desc* ped, const uint8_t* restrict_host, int32_t* out_idx_host,
+                 int32_t* out_n);
+
+/* ---------------------------------------------------------------------------------------------
+ * LD-window joint genotype counts (empirical/jalleledist3.py:120-141 countJointFrq, the integer
+ * part): for each of n_windows windows [win_start[i], win_start[i]+win_len[i]) count, over rows
+ * whose window cells all pass the mask (mask bit = 1, 1 bit per SNP, `mwpr` uint32 words per row,
+ * may be NULL = all pass) and are non-missing, the rows matching each of the 3^win_len state tuples
+ * (first SNP of the window is the most significant base-3 digit, itertools.product order).
+ * counts_dev: uint32 [n_windows * stride], stride >= 3^max_len.
+ * ------------------------------------------------------------------------------------------- */
+int gfx_window_counts(const uint32_t* packed_dev, const uint32_t* mask_dev, int64_t n, int64_t n_snps,
+                      int64_t wpr, int64_t mwpr, const int32_t* win_start_dev, const int32_t* win_len_dev,
+                      int32_t n_windows, int32_t stride, uint32_t* counts_dev, void* stream);
+
+/* Host-side inference on one blanket (the same routine the kernels run), for tests and for
+ * building tables: nodes in topological order, p1/p2 local parent indices or -1, code 0..2 or 3
+ * (unobserved).  out = normalised P(query | evidence) (NaN if P(evidence) = 0). */
+int gfx_infer_host(int32_t n, const int8_t* p1, const int8_t* p2, const uint8_t* code, int32_t query,
+                   double* out3);
+/* Same for the joint=False query of two animals (correctPair): out6 = P(q0|e) then P(q1|e); both are
+ * NaN when either animal's component has P(evidence) = 0, like pgmpy's normalised joint. */
+int gfx_infer_pair_host(int32_t n, const int8_t* p1, const int8_t* p2, const uint8_t* code, int32_t q0,
+                        int32_t q1, double* out6);
+/* Host-side children term (bayesnet/model.py:65-89 with numpy's summation order). kid/par: n codes,
+ * par 0..2 or anything else = unknown. */
+int gfx_kids_term_host(int32_t n, const uint8_t* kid, const uint8_t* par, double* out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+"""Parity of the CUDA path (through the C ABI) with the golden fixtures of the unmodified reference
+and with the oracle on seeded inputs.  Integer / byte results are bit-exact; posteriors are compared
+to 1e-5 relative in log space (BASELINE.json north_star) and additionally counted for bit equality."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+LOG_RTOL = 1e-5   # posteriors: |log p_gpu - log p_ref| <= 1e-5 * max(1, |log p_ref|)
+
+
+def _engine(g, back=2):
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    return Engine(ped, g["ids"], back)
+
+
+def _log_close(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if not np.array_equal(np.isnan(a), np.isnan(b)):
+        return False
+    if not np.array_equal(a == 0, b == 0):
+        return False
+    m = (a > 0) & (b > 0)
+    la, lb = np.log(a[m]), np.log(b[m])
+    return bool(np.all(np.abs(la - lb) <= LOG_RTOL * np.maximum(1.0, np.abs(lb))))
+
+
+@pytest.mark.parametrize("name", ["toy_a", "toy_b", "deep", "nan_loop", "example_fam"])
+def test_correct_matrix_matches_reference_golden(name):
+    g = load_golden(name)
+    tp, ts, back, q, tie, et = g["params"]
+    eng = _engine(g, int(back))
+    out = eng.correct(g["obs"], tp, ts, init_filter_p=q, tiethreshold=tie, err_thresh=et, keep_posteriors=True)
+    raw = eng.raw_host()
+    assert np.array_equal(raw.view(np.uint16), g["raw"].view(np.uint16)), "rank matrix not bit-exact"
+    tpv = eng.stats["test_p"]
+    assert tpv == g["test_p"] or (np.isnan(tpv) and np.isnan(g["test_p"]))
+    assert np.array_equal(out, g["corrected"]), "%d corrected calls differ" % int((out != g["corrected"]).sum())
+    assert int(eng.stats["corrected_per_animal"].sum()) == int(g["errors_all"])
+    assert int(eng.stats["excluded_per_animal"].sum()) == int(g["pair_excluded"])
+    if np.isnan(tpv):
+        return
+    # posteriors of every suspect (pair, SNP) and (single, SNP)
+    ids = [int(x) for x in g["ids"]]
+    pairs = eng.schedule.array(0).reshape(-1, 2)
+    gen_off, jobs = eng.schedule.array(1), eng.schedule.array(3)
+    mine, occ = {}, {}
+    for gen, (post, res) in enumerate(eng.stats["posteriors"]["pairs"]):
+        for k, j in enumerate(jobs[gen_off[gen]:gen_off[gen + 1]]):
+            s, d = ids[pairs[j][0]], ids[pairs[j][1]]
+            o = occ.get((s, d), 0)
+            occ[(s, d)] = o + 1
+            for snp in np.nonzero(res[2 * k] & 0x80)[0]:
+                mine[(o, s, d, int(snp))] = np.concatenate([post[2 * k, snp], post[2 * k + 1, snp]])
+    ref = {(int(x[0]), int(x[1]), int(x[2]), int(x[3])): x[4:] for x in g["pair_post"]}
+    assert set(mine) == set(ref)
+    nbit = 0
+    for k, v in ref.items():
+        assert _log_close(mine[k], v), (k, mine[k], v)
+        nbit += int(np.array_equal(mine[k], v, equal_nan=True))
+    post, res = eng.stats["posteriors"]["singles"]
+    smine = {}
+    for k, r in enumerate(eng.schedule.array(2)):
+        for snp in np.nonzero(res[k] & 0x80)[0]:
+            smine[(ids[r], int(snp))] = post[k, snp]
+    sref = {(int(x[0]), int(x[1])): x[2:] for x in g["single_post"]}
+    assert set(smine) == set(sref)
+    for k, v in sref.items():
+        assert _log_close(smine[k], v), (k, smine[k], v)
+    print("%s: %d/%d pair posteriors bit-identical" % (name, nbit, len(ref)))
+
+
+def _random_case(seed, n=400, gens=7, s=160, related=0.3, unknown=0.05, miss=0.03, drop=0.1):
+    from genofix_b200 import synth
+    rows = synth.make_pedigree(n, gens, sire_frac=0.2, dam_frac=0.5, seed=seed, related_mating_p=related,
+                               unknown_parents_frac=unknown)
+    truth = synth.gene_drop(rows, s, seed=seed)
+    obs = synth.inject_missing(synth.inject_errors(truth, 0.02, seed=seed), miss, seed=seed + 1)
+    ids = rows[:, 0].copy()
+    if drop > 0:
+        keep = np.random.default_rng(seed).random(len(ids)) >= drop
+        ids, obs = ids[keep], obs[keep]
+    return rows, ids, obs
+
+
+@pytest.mark.parametrize("seed,params", [(101, (0.5, 0.64, 2, 0.95, 0.4, 1.0)), (202, (0.5, 0.7, 2, 0.9, 0.05, 1.0)),
+                                         (303, (0.6, 0.6, 1, 0.9, 0.2, 1.0)), (404, (0.5, 0.64, 3, 0.92, 0.4, 0.9))])
+def test_correct_matrix_matches_oracle_on_seeded_inputs(seed, params):
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle.genofix_oracle import Oracle
+    rows, ids, obs = _random_case(seed, s=96 if params[2] == 3 else 160)
+    tp, ts, back, q, tie, et = params
+    o = Oracle(rows, ids).correct_matrix(obs, tp, ts, back=back, init_filter_p=q, tiethreshold=tie, err_thresh=et)
+    eng = Engine(PedigreeDAG.from_table(rows), ids, back)
+    out = eng.correct(obs, tp, ts, init_filter_p=q, tiethreshold=tie, err_thresh=et)
+    assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16))
+    assert eng.stats["test_p"] == o["test_p"]
+    assert np.array_equal(eng.E_host(), o["E"])
+    assert np.array_equal(out, o["corrected"]), int((out != o["corrected"]).sum())
+    assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
+    assert np.array_equal(eng.stats["excluded_per_animal"], o["excluded_per_animal"])
+
+
+def test_edge_shapes_and_ragged_inputs():
+    """1 SNP, 15/16/17 SNPs (word boundaries), all-missing rows and columns, a pedigree of founders only."""
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle.genofix_oracle import Oracle
+    rows, ids, obs = _random_case(7, n=120, gens=5, s=40, drop=0.0)
+    for s in (1, 15, 16, 17, 33):
+        sub = obs[:, :s].copy()
+        if s >= 15:
+            sub[:, 3] = 9
+            sub[5, :] = 9
+        o = Oracle(rows, ids).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4)
+        eng = Engine(PedigreeDAG.from_table(rows), ids, 2)
+        out = eng.correct(sub, 0.5, 0.64, init_filter_p=0.9, tiethreshold=0.4)
+        assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16)), s
+        assert np.array_equal(out, o["corrected"]), s
+    frows = np.array([[i, 0, 0, 1 + i % 2] for i in range(1, 9)])
+    fobs = np.random.default_rng(1).integers(0, 3, size=(8, 20)).astype(np.uint8)
+    eng = Engine(PedigreeDAG.from_table(frows), frows[:, 0], 2)
+    out = eng.correct(fobs, 0.5, 0.64)
+    assert np.array_equal(out, fobs) and np.all(eng.raw_host() == np.float16(1.0))
+
+
+def test_pack_unpack_roundtrip():
+    import torch
+    from genofix_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.default_rng(0)
+    for n, s in [(3, 1), (5, 16), (7, 17), (64, 1000), (33, 4097)]:
+        G = rs.choice([0, 1, 2, 9], size=(n, s)).astype(np.uint8)
+        ld = ((s + 15) // 16) * 16 if s % 2 == 0 else s
+        host = np.full((n, ld), 9, np.uint8)
+        host[:, :s] = G
+        d = torch.from_numpy(host).cuda()
+        wpr = (((s + 15) // 16 + 3) // 4) * 4
+        packed = torch.empty((n, wpr), dtype=torch.int32, device="cuda")
+        out = torch.zeros_like(d)
+        _lib.check(L.gfx_pack2(d.data_ptr(), n, s, ld, packed.data_ptr(), wpr, None))
+        _lib.check(L.gfx_unpack2(packed.data_ptr(), n, s, wpr, out.data_ptr(), ld, None))
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy()[:, :s], G)
+        p = packed.cpu().numpy().view(np.uint32)
+        j = int(rs.integers(0, s))
+        code = (p[:, j // 16] >> (2 * (j % 16))) & 3
+        assert np.array_equal(np.where(code == 3, 9, code), G[:, j])
+
+
+def test_snp_permutation_property_at_scale():
+    """Every SNP column is independent given the pedigree and the chunk-level threshold is permutation
+    invariant, so correcting a column-permuted matrix must give the column-permuted result.  Run at
+    10k animals x 4096 SNPs (BASELINE config 2 pedigree), where the oracle is too slow to be the check."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(10000, 6, seed=1234)
+    obs = synth.inject_errors(synth.gene_drop(rows, 4096, seed=1234), 0.01, seed=1234)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    a = eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    tally_a = eng.stats["corrected_per_animal"].copy()
+    perm = np.random.default_rng(5).permutation(obs.shape[1])
+    b = eng.correct(np.ascontiguousarray(obs[:, perm]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    assert np.array_equal(a[:, perm], b)
+    assert np.array_equal(tally_a, eng.stats["corrected_per_animal"])
+    changed = int((a != obs).sum())
+    assert 0 < changed < obs.size // 10
+    # a sample of the big run against the oracle: the first 6 SNP columns as their own chunk
+    from oracle.genofix_oracle import Oracle
+    sub = np.ascontiguousarray(obs[:, :6])
+    o = Oracle(rows, rows[:, 0]).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
+    c = eng.correct(sub, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16))
+    assert np.array_equal(c, o["corrected"])
+
+
+def test_trio_scan_matches_oracle():
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    rows, ids, obs = _random_case(11, n=600, gens=6, s=1003, miss=0.02, drop=0.15)
+    eng = Engine(PedigreeDAG.from_table(rows), ids, 2)
+    inc, tested = eng.trio_scan(obs)
+    ri, rt = go.trio_scan(go.OraclePedigree(rows), [int(x) for x in ids], obs)
+    assert np.array_equal(inc, ri) and np.array_equal(tested, rt)
+    assert inc.sum() > 0
+
+
+def test_window_counts_match_oracle():
+    import itertools
+    import torch
+    from genofix_b200.empirical.jalleledist3 import window_counts_device
+    from oracle import genofix_oracle as go
+    rs = np.random.default_rng(4)
+    n, s = 500, 40
+    G = rs.choice([0, 1, 2, 9], size=(n, s), p=[.32, .33, .32, .03]).astype(np.uint8)
+    mask = rs.random((n, s)) < 0.97
+    for sur in (1, 2, 3):
+        wins = [go.ld_window(s, i, sur) for i in range(s)]
+        counts = window_counts_device(G, mask, [a for a, b in wins], [b - a for a, b in wins])
+        for i, (a, b) in enumerate(wins):
+            w = b - a
+            if w == 0:
+                continue
+            ref = go.count_joint_frq(G[:, a:b], mask[:, a:b] & (G[:, a:b] != 9), w, 0.0, sum_inner_count=False)
+            vals = np.array([ref[v] for v in itertools.product([0, 1, 2], repeat=w)])
+            assert np.array_equal(counts[i, :3 ** w], vals.astype(np.int64)), (sur, i)

@@ -1,0 +1,249 @@
+"""CPU-side checks of the product's host logic: the C ABI loads and exports what include/*.h declares,
+PedigreeDAG flattening, the host copies of the device math (inference engine, children term), the
+histogram->threshold transform, and the schedule (pairs / singles / generations) against the oracle.
+No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from genofix_b200 import _lib
+from genofix_b200.engine import Schedule, rank_transform_table, weighted_quantile_linear
+from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+from oracle import genofix_oracle as go
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "genofix_b200.h")).read()
+    declared = set(re.findall(r"\b(gfx_[a-z0-9_]+)\s*\(", hdr))
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert L.gfx_version() >= 100
+
+
+def test_pedigree_structure_example_fam():
+    g = load_golden("kats")
+    ped = PedigreeDAG.from_table(load_golden("example_fam")["ped_rows"])
+    assert len(ped) == int(g["n_animals"])
+    assert len(ped.males) == int(g["n_males"]) and len(ped.females) == int(g["n_females"])
+    assert sorted((k, len(v)) for k, v in ped.generationIndex.items()) == [tuple(x) for x in g["gen_sizes"]]
+    for rec in g["blanket_struct"]:
+        a, depth, gen, nanc, nn = (int(x) for x in rec[:5])
+        anc = list(ped.get_parents_depth([a], depth))
+        assert len(anc) == nanc
+        assert ped.generation[ped._idx(a)] == gen
+        nodes = sorted(ped.balance_nodes(list(set([a] + anc)))) if anc else []
+        assert nodes == sorted(int(x) for x in rec[5:5 + nn])
+
+
+def test_pedigree_surface_matches_oracle_pedigree():
+    rows = load_golden("toy_b")["ped_rows"]
+    ped = PedigreeDAG.from_table(rows)
+    op = go.OraclePedigree(rows)
+    assert ped.males == op.males and ped.females == op.females
+    assert ped.kid2sire == op.sire and ped.kid2dam == op.dam
+    for a in op.animals:
+        assert ped.get_parents(a) == op.parents(a)
+        assert list(ped.get_kids(a)) == op.children(a)
+        assert ped.generation[ped._idx(a)] == op.generation[a]
+    off, kid = ped.children_csr_reference_order()
+    for a in op.animals:
+        i = ped._idx(a)
+        mine = [int(ped.ids[k]) for k in kid[off[i]:off[i + 1]]]
+        assert mine == list(set(op.children(a)))
+    sub = ped.get_subset([int(rows[-1, 0])] + list(ped.get_parents_depth([int(rows[-1, 0])], 2)))
+    assert set(sub.nodes) <= set(ped.nodes)
+    assert len(ped.as_ped()) == int(((rows[:, 1] > 0) & (rows[:, 2] > 0)).sum())
+
+
+def test_single_known_parent_raises_keyerror():
+    rows = np.array([[1, 0, 0, 1], [2, 0, 0, 2], [3, 1, 0, 1], [4, 1, 2, 2]])
+    ped = PedigreeDAG.from_table(rows)
+    with pytest.raises(KeyError):
+        Schedule(ped, [1, 2, 3, 4], 2, host_only=True)
+
+
+def _topo(nodes, par, focal):
+    order, done = [], set()
+    for root in list(focal) + list(nodes):
+        st = [root]
+        while st:
+            x = st[-1]
+            if x in done:
+                st.pop()
+                continue
+            pend = [p for p in par.get(x, ()) if p not in done]
+            if pend:
+                st.extend(pend)
+            else:
+                done.add(x)
+                order.append(x)
+                st.pop()
+    return order
+
+
+@pytest.mark.parametrize("fixture", ["deep", "toy_b"])
+def test_inference_engine_matches_oracle_ve(fixture):
+    """gfx_infer_host / gfx_infer_pair_host (the routine the kernels run) vs the oracle's variable
+    elimination on random evidence, loopy blankets included: bit-identical posteriors."""
+    L = _lib.lib()
+    ped = go.OraclePedigree(load_golden(fixture)["ped_rows"])
+    rs = np.random.default_rng(5)
+    animals = sorted(ped.animals)
+    n_checked = n_nan = 0
+    for trial in range(1500):
+        a = int(rs.choice(animals))
+        if trial % 2 == 0:
+            focal, depth = [a], int(rs.integers(1, 4))
+        else:
+            s, d = ped.parents(a)
+            if s is None:
+                continue
+            focal, depth = [s, d], int(rs.integers(2, 4))
+        if not ped.ancestors(focal, depth):
+            continue
+        nodes, par = ped.blanket(focal, depth)
+        if any(f not in par for f in focal):
+            continue
+        order = _topo(nodes, par, focal)
+        pos = {v: i for i, v in enumerate(order)}
+        n = len(order)
+        p1 = np.full(n, -1, np.int8)
+        p2 = np.full(n, -1, np.int8)
+        for k, (s_, d_) in par.items():
+            p1[pos[k]], p2[pos[k]] = pos[s_], pos[d_]
+        pobs = rs.choice([0.3, 0.7, 0.95])
+        ev = {x: int(rs.integers(0, 3)) for x in order if x not in focal and rs.random() < pobs}
+        code = np.full(n, 3, np.uint8)
+        for x, v in ev.items():
+            code[pos[x]] = v
+        ref = go.blanket_marginals(nodes, par, focal, ev)
+        out = np.zeros(6)
+        vp = lambda arr: arr.ctypes.data_as(C.c_void_p)  # noqa: E731
+        if len(focal) == 1:
+            rc = L.gfx_infer_host(n, vp(p1), vp(p2), vp(code), pos[focal[0]], vp(out))
+        else:
+            rc = L.gfx_infer_pair_host(n, vp(p1), vp(p2), vp(code), pos[focal[0]], pos[focal[1]], vp(out))
+        if rc == _lib.GFX_E_TOO_WIDE:
+            continue
+        assert rc == 0
+        for i, q in enumerate(focal):
+            assert np.array_equal(out[3 * i:3 * i + 3], ref[q], equal_nan=True), (focal, ev)
+            n_nan += int(np.isnan(ref[q]).any())
+        n_checked += 1
+    assert n_checked > 500 and n_nan > 0
+
+
+def test_oracle_ve_matches_bruteforce():
+    ped = go.OraclePedigree(load_golden("deep")["ped_rows"])
+    rs = np.random.default_rng(9)
+    animals = sorted(ped.animals)
+    done = 0
+    for _ in range(400):
+        a = int(rs.choice(animals))
+        if not ped.ancestors([a], 2):
+            continue
+        nodes, par = ped.blanket([a], 2)
+        ev = {x: int(rs.integers(0, 3)) for x in nodes if x != a and rs.random() < 0.6}
+        r1 = go.blanket_marginals(nodes, par, [a], ev)[a]
+        r2 = go.blanket_marginals_bruteforce(nodes, par, [a], ev)[a]
+        assert np.allclose(r1, r2, rtol=1e-12, atol=0, equal_nan=True)
+        done += 1
+    assert done > 100
+
+
+def test_children_term_matches_numpy_for_long_litters():
+    """gfx_kids_term_host vs the oracle's numpy code for up to 400 children (exercises numpy's
+    pairwise-summation blocks of 128 and the recursive halving)."""
+    L = _lib.lib()
+    rs = np.random.default_rng(3)
+    for n in [1, 2, 5, 7, 8, 9, 15, 16, 17, 40, 42, 43, 44, 64, 85, 86, 100, 127, 128, 129, 200, 257, 400]:
+        for _ in range(6):
+            ks = rs.choice([0, 1, 2, 9], size=n, p=[.3, .3, .3, .1]).astype(np.uint8)
+            ps = rs.choice([0, 1, 2, 9], size=n).astype(np.uint8)
+            ref = np.asarray(go.probs_kids(list(ks), [None if p == 9 else int(p) for p in ps]), dtype=float)
+            out = np.zeros(3)
+            k3 = np.where(ks > 2, 3, ks).astype(np.uint8)
+            p3 = np.where(ps > 2, 3, ps).astype(np.uint8)
+            rc = L.gfx_kids_term_host(n, k3.ctypes.data_as(C.c_void_p), p3.ctypes.data_as(C.c_void_p),
+                                      out.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            assert np.array_equal(out, ref), (n, out, ref)
+
+
+def test_weighted_quantile_is_numpy_quantile():
+    rs = np.random.default_rng(0)
+    for _ in range(300):
+        k = int(rs.integers(1, 12))
+        vals = rs.choice(np.round(rs.random(40), 3), size=k, replace=False)
+        cnt = rs.integers(1, 50, size=k)
+        x = np.repeat(vals, cnt)
+        for q in (0.0, 0.5, 0.9, 0.95, 0.99, 1.0, float(rs.random())):
+            assert weighted_quantile_linear(vals, cnt, q) == np.quantile(x, q)
+
+
+@pytest.mark.parametrize("name", ["toy_a", "toy_b", "deep", "example_fam", "nan_loop"])
+def test_transform_table_matches_reference_threshold(name):
+    """Histogram of the golden rank matrix -> E table and quantile == what the reference printed."""
+    g = load_golden(name)
+    raw = g["raw"].view(np.uint16)
+    obs = g["obs"]
+    hist = np.zeros(65537, dtype=np.uint64)
+    np.add.at(hist, raw[obs != 9].astype(np.int64), 1)
+    hist[65536] = int((obs == 9).sum())
+    q = g["params"][3]
+    elut, test_p, n_nan = rank_transform_table(hist, q)
+    assert test_p == g["test_p"] or (np.isnan(test_p) and np.isnan(g["test_p"]))
+    E, tp = go.Oracle.transform(g["raw"], obs, q)
+    mine = elut[raw]
+    mine[obs == 9] = 1.0
+    assert np.array_equal(mine, E, equal_nan=True)
+    assert n_nan == int(np.isnan(g["raw"].astype(float))[obs != 9].sum())
+
+
+@pytest.mark.parametrize("name", ["toy_a", "toy_b", "deep", "example_fam"])
+def test_schedule_matches_oracle_bookkeeping(name):
+    """pairs / per-generation jobs / singles of the native schedule vs correct_genotypes3.py:556,684-686,851-853."""
+    g = load_golden(name)
+    ids = [int(x) for x in g["ids"]]
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    s = Schedule(ped, ids, 2, host_only=True)
+    op = go.OraclePedigree(g["ped_rows"])
+    rowset = set(ids)
+    pairs = set()
+    for k in ids:
+        sd = op.parents(k)
+        if sd[0] is not None and sd[1] is not None:
+            pairs.add(sd)
+    sched_pairs = sorted(p for p in pairs if p[0] in rowset and p[1] in rowset)
+    mine = [(ids[a], ids[b]) for a, b in s.array(0).reshape(-1, 2)]
+    assert mine == sched_pairs
+    gen_off, jobs = s.array(1), s.array(3)
+    for gen in range(s.info["n_generations"]):
+        members = op.generation_index.get(gen, set())
+        want = [p for p in sched_pairs if p[0] in members or p[1] in members]
+        got = [mine[j] for j in jobs[gen_off[gen]:gen_off[gen + 1]]]
+        assert got == want
+    paired = set(x for p in pairs for x in p)
+    assert sorted(ids[r] for r in s.array(2)) == sorted(k for k in ids if k not in paired)
+    assert s.info["n_trios"] == sum(1 for k in ids if op.parents(k)[0] in rowset and op.parents(k)[1] in rowset)
+    assert sorted(s.founders()) == go.founders(op)
+    some = ids[::3]
+    assert sorted(s.founders(some)) == go.founders(op, some)
+
+
+def test_chunking_known_answers():
+    """genofix.py:207-210 chunk(): SURVEY appendix B.2."""
+    from genofix_b200.chunking import chunk
+    def spans(L, n, s):
+        b = 2 * s + 1
+        return [(c[0], c[-1], len(c)) for c in chunk(list(range(L)), n, b, b)]
+    assert spans(100, 1000, 4) == [(0, 99, 100)]
+    assert spans(2500, 1000, 4) == [(0, 1008, 1009), (1000, 2008, 1009), (2000, 2499, 500)]
+    assert spans(25, 10, 1) == [(0, 12, 13), (10, 24, 15), (20, 24, 5)]
+    assert spans(23, 10, 3) == [(0, 22, 23), (10, 22, 13)]

@@ -1,0 +1,78 @@
+"""The oracle restatement against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+oracle/make_golden.py in the build container).  Bit-exact: rank matrix, threshold, corrected calls,
+error counts and every posterior."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle.genofix_oracle import Oracle
+
+CASES = ["toy_a", "toy_b", "deep", "nan_loop", "example_fam"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference(name):
+    g = load_golden(name)
+    tp, ts, back, q, tie, et = g["params"]
+    o = Oracle(g["ped_rows"], g["ids"])
+    r = o.correct_matrix(g["obs"], tp, ts, back=int(back), init_filter_p=q, tiethreshold=tie, err_thresh=et,
+                         keep_posteriors=True)
+    assert np.array_equal(r["raw"].view(np.uint16), g["raw"].view(np.uint16))
+    assert r["test_p"] == g["test_p"] or (np.isnan(r["test_p"]) and np.isnan(g["test_p"]))
+    assert np.array_equal(r["corrected"], g["corrected"])
+    assert int(r["corrected_per_animal"].sum()) == int(g["errors_all"])
+    occ, mine = {}, {}
+    for (gen, s, d) in sorted(r["pair_posteriors"].keys()):
+        k = occ.get((s, d), 0)
+        occ[(s, d)] = k + 1
+        for j, (ps, pd_, _a, _b) in r["pair_posteriors"][(gen, s, d)].items():
+            mine[(k, s, d, j)] = np.concatenate([ps, pd_])
+    ref = {(int(x[0]), int(x[1]), int(x[2]), int(x[3])): x[4:] for x in g["pair_post"]}
+    assert set(mine) == set(ref)
+    for k, v in ref.items():
+        assert np.array_equal(mine[k], v, equal_nan=True)
+    smine = {(k, j): v[0] for k, res in r["single_posteriors"].items() for j, v in res.items()}
+    sref = {(int(x[0]), int(x[1])): x[2:] for x in g["single_post"]}
+    assert set(smine) == set(sref)
+    for k, v in sref.items():
+        assert np.array_equal(smine[k], v, equal_nan=True)
+
+
+def test_nan_case_is_really_nan():
+    g = load_golden("nan_loop")
+    assert np.isnan(g["raw"].astype(float)).sum() == 3
+    assert np.isnan(g["test_p"])
+    assert np.array_equal(g["corrected"], g["obs"])
+
+
+def test_kats_model_functions():
+    from oracle import genofix_oracle as go
+    g = load_golden("kats")
+    for c in range(len(g["kid"])):
+        n = int((g["kid"][c] >= 0).sum())
+        ks = list(g["kid"][c, :n])
+        ps = [None if p < 0 else int(p) for p in g["par"][c, :n]]
+        assert np.array_equal(np.asarray(go.probs_kids(ks, ps), dtype=float), g["probs_kids"][c])
+    # commented examples inside the reference (bayesnet/model.py:91,136-142)
+    assert np.allclose(go.probs_kids([1, 0, 1, 0, 1], [2, 2, 2, 2, 2]), [2 / 3, 1 / 3, 0])
+    assert go.probs_differences_parent(2, 2, 1) == 1.0
+    assert go.probs_differences_parent(1, 1, 0) == 0.25
+    assert go.probs_differences_parent(2, 9, 0) == 0.5
+    assert go.probs_differences_parent(9, 2, 0) == 0.5
+    assert go.probs_differences_parent(9, 9, 1) == 0
+    for i, p1 in enumerate([0, 1, 2, 9]):
+        for j, p2 in enumerate([0, 1, 2, 9]):
+            for o in range(3):
+                assert go.probs_differences_parent(p1, p2, o) == g["diff_parent"][i, j, o]
+
+
+def test_kats_empirical_counts_and_windows():
+    from oracle import genofix_oracle as go
+    g = load_golden("kats")
+    for w in (3, 5, 7):
+        res = go.count_joint_frq(g["cj_tab_%d" % w], g["cj_mask_%d" % w], w, 1e-4)
+        import itertools
+        vals = np.array([res[v] for v in itertools.product([0, 1, 2], repeat=w)])
+        assert np.array_equal(vals, g["cj_val_%d" % w])
+    for n, sur, i, a, b in g["windows"]:
+        assert go.ld_window(int(n), int(i), int(sur)) == (int(a), int(b))

@@ -20,8 +20,10 @@
 #include <math.h>
 #include <cuda_fp16.h>
 
-#define GFX_WMAX 6            // max simultaneously open unobserved variables
+#define GFX_WMAX 6            // open unobserved variables the per-thread table holds (fast path)
 #define GFX_TAB 729           // 3^GFX_WMAX
+#define GFX_WMAX_BIG 9        // rare wide blankets rerun on a pooled global-memory table
+#define GFX_TAB_BIG 19683     // 3^GFX_WMAX_BIG
 #define GFX_MAXN 64           // max nodes in one blanket (bit masks are uint64)
 #define GFX_HD __host__ __device__ __forceinline__
 
@@ -51,8 +53,14 @@ struct GfxBlanket {
 // Marginal of node q given hard evidence on the nodes whose bit is set in `obs` (their states in
 // code[]).  tab: scratch of GFX_TAB doubles.  Returns 0, or 1 if more than GFX_WMAX variables
 // would be open at once (out = NaN).
+//
+// Three reductions keep the table small without changing the (exact, dyadic) unnormalised values:
+//   * only factors connected to q through unobserved variables are used (pgmpy drops the others);
+//   * barren nodes -- unobserved, not q, no evidence below them -- are skipped: their factor sums to 1;
+//   * an unobserved founder with a single remaining child is folded into that child's factor
+//     (sum_p prior(p) T(x | p, .)) instead of opening a digit for it.
 __host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8_t* code, uint64_t obs,
-                                         double* tab, double out[3]) {
+                                         double* tab, double out[3], int wmax = GFX_WMAX) {
   const int n = b.n;
   obs &= ~(1ull << q);
   // component of q in the interaction graph of unobserved variables
@@ -72,51 +80,80 @@ __host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8
       if ((sc & comp) && (sc & ~comp)) comp |= sc;
     }
   }
-  int8_t open[GFX_WMAX];
-  int w = 0, size = 1;
-  tab[0] = 1.0;
-  for (int v = 0; v < n; ++v) {
+  // needed factors: connected to q and not barren (reverse topological sweep)
+  uint64_t need = 1ull << q, inc = 0;
+  int8_t nkids[GFX_MAXN], dlast[GFX_MAXN];
+  for (int v = 0; v < n; ++v) { nkids[v] = 0; dlast[v] = (int8_t)v; }
+  for (int v = n - 1; v >= 0; --v) {
     uint64_t sc = 1ull << v;
     const int a1 = b.p1[v], a2 = b.p2[v];
     if (a1 >= 0) sc |= (1ull << a1) | (1ull << a2);
-    if (!((sc & ~obs) & comp)) continue;  // factor not connected to the query: dropped
-    // where do the parents' states come from: a digit of the table index, or the evidence
-    int s_pos = -1, d_pos = -1, s_val = 0, d_val = 0, s_str = 1, d_str = 1;
+    if (!((sc & ~obs) & comp)) continue;
+    inc |= 1ull << v;
+    if ((obs >> v) & 1) need |= 1ull << v;  // evidence that touches the component
+    if (!((need >> v) & 1)) continue;
     if (a1 >= 0) {
-      if ((obs >> a1) & 1) s_val = code[a1];
+      need |= (1ull << a1) | (1ull << a2);
+      ++nkids[a1]; ++nkids[a2];
+      if (dlast[a1] < v) dlast[a1] = (int8_t)v;
+      if (dlast[a2] < v) dlast[a2] = (int8_t)v;
+    }
+  }
+  need &= inc;  // observed parents were marked too; their own factors count only if connected
+  int8_t open[GFX_WMAX_BIG];
+  int w = 0, size = 1;
+  uint64_t folded = 0;
+  tab[0] = 1.0;
+  for (int v = 0; v < n; ++v) {
+    if (!((need >> v) & 1)) continue;
+    const int a1 = b.p1[v], a2 = b.p2[v];
+    const bool v_obs = (obs >> v) & 1;
+    if (a1 < 0) {
+      if (v_obs) continue;                       // prior of an observed founder: scalar, dropped
+      if (v != q && nkids[v] == 1) { folded |= 1ull << v; continue; }
+    } else if (v_obs && ((obs >> a1) & 1) && ((obs >> a2) & 1)) {
+      continue;                                  // fully observed trio: scalar, dropped
+    }
+    // where do the parents' states come from: evidence, a digit of the table index, or a folded prior
+    int s_pos = -1, d_pos = -1, s_lo = 0, s_hi = 0, d_lo = 0, d_hi = 0, s_str = 1, d_str = 1;
+    bool s_fold = false, d_fold = false;
+    if (a1 >= 0) {
+      if ((obs >> a1) & 1) s_lo = s_hi = code[a1];
+      else if ((folded >> a1) & 1) { s_fold = true; s_lo = 0; s_hi = 2; }
       else { for (int k = 0; k < w; ++k) if (open[k] == a1) s_pos = k; s_str = gfx_pow3(s_pos); }
-      if ((obs >> a2) & 1) d_val = code[a2];
+      if ((obs >> a2) & 1) d_lo = d_hi = code[a2];
+      else if ((folded >> a2) & 1) { d_fold = true; d_lo = 0; d_hi = 2; }
       else { for (int k = 0; k < w; ++k) if (open[k] == a2) d_pos = k; d_str = gfx_pow3(d_pos); }
     }
-    if (!((obs >> v) & 1)) {
-      if (w == GFX_WMAX) { out[0] = out[1] = out[2] = nan(""); return 1; }
-      for (int x = 2; x >= 0; --x) {
-        for (int i = 0; i < size; ++i) {
-          double f;
-          if (a1 >= 0) {
-            const int sv = s_pos >= 0 ? (i / s_str) % 3 : s_val;
-            const int dv = d_pos >= 0 ? (i / d_str) % 3 : d_val;
-            f = gfx_mendel(x, sv, dv);
-          } else {
-            f = gfx_prior(x);
-          }
-          tab[x * size + i] = tab[i] * f;
-        }
-      }
-      open[w++] = (int8_t)v;
-      size *= 3;
-    } else {
-      const int x = code[v];
+    const int x_lo = v_obs ? code[v] : 0, x_hi = v_obs ? code[v] : 2;
+    if (!v_obs && w == wmax) { out[0] = out[1] = out[2] = nan(""); return 1; }
+    for (int x = x_hi; x >= x_lo; --x) {
       for (int i = 0; i < size; ++i) {
-        const int sv = s_pos >= 0 ? (i / s_str) % 3 : s_val;
-        const int dv = d_pos >= 0 ? (i / d_str) % 3 : d_val;
-        tab[i] *= gfx_mendel(x, sv, dv);
+        double f;
+        if (a1 >= 0) {
+          int sl = s_lo, sh = s_hi, dl = d_lo, dh = d_hi;
+          if (s_pos >= 0) sl = sh = (i / s_str) % 3;
+          if (d_pos >= 0) dl = dh = (i / d_str) % 3;
+          f = 0.0;
+          for (int sv = sl; sv <= sh; ++sv)
+            for (int dv = dl; dv <= dh; ++dv) {
+              double t = gfx_mendel(x, sv, dv);
+              if (s_fold) t *= gfx_prior(sv);
+              if (d_fold) t *= gfx_prior(dv);
+              f += t;
+            }
+        } else {
+          f = gfx_prior(x);
+        }
+        if (v_obs) tab[i] *= f;
+        else tab[x * size + i] = tab[i] * f;
       }
     }
-    // sum out every open variable whose last child is this node
+    if (!v_obs) { open[w++] = (int8_t)v; size *= 3; }
+    // sum out every open variable whose last needed child is this node
     for (int k = w - 1; k >= 0; --k) {
       const int u = open[k];
-      if (u == q || b.last[u] > v) continue;
+      if (u == q || dlast[u] > v) continue;
       const int str = gfx_pow3(k);
       const int nsize = size / 3;
       for (int i = 0; i < nsize; ++i) {
@@ -142,11 +179,11 @@ __host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8
 // equal the single-variable queries unless the OTHER animal's component has P(evidence) = 0, in
 // which case the joint is all zero and both marginals are 0/0 = NaN.
 __host__ __device__ inline int gfx_infer_pair(const GfxBlanket& b, int q0, int q1, const uint8_t* code, uint64_t obs,
-                                              double* tab, double out0[3], double out1[3]) {
+                                              double* tab, double out0[3], double out1[3], int wmax = GFX_WMAX) {
   obs &= ~((1ull << q0) | (1ull << q1));
-  int bad = gfx_infer(b, q0, code, obs, tab, out0);
+  int bad = gfx_infer(b, q0, code, obs, tab, out0, wmax);
   const double s0 = tab[3];
-  bad |= gfx_infer(b, q1, code, obs, tab, out1);
+  bad |= gfx_infer(b, q1, code, obs, tab, out1, wmax);
   const double s1 = tab[3];
   if (!bad && (s0 == 0.0 || s1 == 0.0)) {
     out0[0] = out0[1] = out0[2] = nan("");

@@ -15,6 +15,8 @@
 #include "gfx_infer.cuh"
 #include "gfx_schedule.h"
 
+#define GFX_BIG_SLOTS 64
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -63,6 +65,8 @@ struct gfx_schedule {
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
   double* kv = nullptr;        // 108 doubles, children-heuristic element table
   int* status = nullptr;
+  double* big_pool = nullptr;  // GFX_BIG_SLOTS tables of GFX_TAB_BIG doubles for rare wide blankets
+  int* big_flags = nullptr;
 };
 
 template <class T>
@@ -103,7 +107,8 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
   void* ptrs[] = {s->anc6, s->rank_blanket, s->prow, s->rank_flags, s->child_off, s->child_row, s->child_other,
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
-                  s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status};
+                  s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
+                  s->big_pool, s->big_flags};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -149,6 +154,9 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(single_entry, single_entry);
   UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(rank_lut, lut); UP(kv, kv); UP(status, status);
 #undef UP
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * GFX_BIG_SLOTS);
+  if (e == cudaSuccess) e = cudaMemset(s->big_flags, 0, sizeof(int) * GFX_BIG_SLOTS);
   if (e != cudaSuccess) {
     gfx_schedule_destroy(s);
     return fail(GFX_E_CUDA, std::string("schedule upload: ") + cudaGetErrorString(e));
@@ -206,7 +214,7 @@ extern "C" int gfx_check_device_status(const gfx_schedule* s, void* stream) {
   if (st != 0) {
     int zero = 0;
     GFX_CUDA(cudaMemcpy(s->status, &zero, sizeof(int), cudaMemcpyHostToDevice));
-    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX simultaneously unobserved variables");
+    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX_BIG (9) simultaneously unobserved variables");
   }
   return GFX_OK;
 }
@@ -447,7 +455,27 @@ struct BlanketDev {
   const int32_t* off;
   const int32_t* row;
   const int8_t *p1, *p2, *last, *q0, *q1;
+  double* big_pool;
+  int* big_flags;
 };
+
+// Inference with the per-thread table; the rare blanket that needs more than GFX_WMAX open variables
+// borrows one of GFX_BIG_SLOTS global tables (holders never wait on each other, so spinning is safe).
+__device__ __noinline__ int infer_big(const GfxBlanket& b, int q0, int q1, const uint8_t* code, uint64_t om,
+                                      const BlanketDev& bl, double* anc0, double* anc1) {
+  int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) % GFX_BIG_SLOTS);
+  for (;;) {
+    if (atomicCAS(bl.big_flags + slot, 0, 1) == 0) break;
+    slot = (slot + 1) % GFX_BIG_SLOTS;
+    __nanosleep(200);
+  }
+  double* tab = bl.big_pool + (size_t)slot * GFX_TAB_BIG;
+  const int bad = q1 >= 0 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc0, anc1, GFX_WMAX_BIG)
+                          : gfx_infer(b, q0, code, om, tab, anc0, GFX_WMAX_BIG);
+  __threadfence();
+  atomicExch(bl.big_flags + slot, 0);
+  return bad;
+}
 
 struct GenericRankArgs {
   const uint32_t* packed;
@@ -488,7 +516,8 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
       }
       GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
       double anc[3];
-      if (gfx_infer(b, a.bl.q0[bid], code, om, tab, anc)) atomicExch(a.status, 1);
+      if (gfx_infer(b, a.bl.q0[bid], code, om, tab, anc) && infer_big(b, a.bl.q0[bid], -1, code, om, a.bl, anc, anc))
+        atomicExch(a.status, 1);
       const uint16_t sc = gfx_anc_score(anc, obs);
       uint32_t m = 0;
       bool kids = false;
@@ -526,7 +555,7 @@ extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, in
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
-                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1}, s->status};
+                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags}, s->status};
     const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
     k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, (cudaStream_t)stream>>>(g);
     GFX_LAUNCHED();
@@ -713,8 +742,9 @@ __global__ void __launch_bounds__(128) k_infer(InferArgs a) {
         om &= ~(1ull << q0);
         if (q1 >= 0) om &= ~(1ull << q1);
         GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
-        const int bad = a.nf == 2 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc[0], anc[1])
-                                  : gfx_infer(b, q0, code, om, tab, anc[0]);
+        int bad = a.nf == 2 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc[0], anc[1])
+                            : gfx_infer(b, q0, code, om, tab, anc[0]);
+        if (bad) bad = infer_big(b, q0, a.nf == 2 ? q1 : -1, code, om, a.bl, anc[0], anc[1]);
         if (bad) atomicExch(a.status, 1);
       }
       for (int f = 0; f < a.nf; ++f) {
@@ -803,7 +833,7 @@ static int run_infer_apply(const gfx_schedule* s, int nf, int n_jobs, const int3
   a.c = CellCtx{live, orig, wpr, raw, ld_raw, elut};
   a.n_snps = n_snps; a.nf = nf; a.n_jobs = n_jobs;
   a.job_row0 = job_row0; a.job_row1 = job_row1; a.job_bl = job_bl;
-  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1};
+  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags};
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.result = result; a.post = post; a.status = s->status;
   const int64_t tasks = (int64_t)n_jobs * ((n_snps + GFX_INFER_CHUNK - 1) / GFX_INFER_CHUNK);
@@ -967,8 +997,8 @@ extern "C" int gfx_infer_host(int32_t n, const int8_t* p1, const int8_t* p2, con
   for (int i = 0; i < n; ++i)
     if (code[i] < 3 && i != query) obs |= 1ull << i;
   GfxBlanket b{n, p1, p2, last.data()};
-  std::vector<double> tab(GFX_TAB);
-  if (gfx_infer(b, query, code, obs, tab.data(), out3)) return fail(GFX_E_TOO_WIDE, "too many open variables");
+  std::vector<double> tab(GFX_TAB_BIG);
+  if (gfx_infer(b, query, code, obs, tab.data(), out3, GFX_WMAX_BIG)) return fail(GFX_E_TOO_WIDE, "too many open variables");
   return GFX_OK;
 }
 
@@ -988,8 +1018,9 @@ extern "C" int gfx_infer_pair_host(int32_t n, const int8_t* p1, const int8_t* p2
   for (int i = 0; i < n; ++i)
     if (code[i] < 3) obs |= 1ull << i;
   GfxBlanket b{n, p1, p2, last.data()};
-  std::vector<double> tab(GFX_TAB);
-  if (gfx_infer_pair(b, q0, q1, code, obs, tab.data(), out6, out6 + 3)) return fail(GFX_E_TOO_WIDE, "too many open variables");
+  std::vector<double> tab(GFX_TAB_BIG);
+  if (gfx_infer_pair(b, q0, q1, code, obs, tab.data(), out6, out6 + 3, GFX_WMAX_BIG))
+    return fail(GFX_E_TOO_WIDE, "too many open variables");
   return GFX_OK;
 }
 

@@ -301,11 +301,13 @@ class Engine(object):
         return self.raw[:, :self.s].cpu().numpy().view(np.float16)
 
     def E_host(self):
-        """float64 [n, s] transformed ranks, missing cells = 1 (correct_genotypes3.py:600-603)."""
+        """float64 [n, s] transformed ranks, missing cells of the input = 1 (correct_genotypes3.py:600-603)."""
         raw = self.raw[:, :self.s].cpu().numpy().view(np.uint16)
         E = self.elut_host[raw]
-        codes = self.codes[:, :self.s].cpu().numpy()
-        E[codes > 2] = 1.0
+        p = self.packed_orig.cpu().numpy().view(np.uint32)
+        j = np.arange(self.s)
+        codes = (p[:, j // 16] >> (2 * (j % 16)).astype(np.uint32)) & 3
+        E[codes == 3] = 1.0
         return E
 
     # ---- end-to-end on host buffers ----------------------------------------------------------------

@@ -18,6 +18,13 @@ def _engine(g, back=2):
     return Engine(ped, g["ids"], back)
 
 
+def _same_f16(a, b):
+    """bit-exact float16 comparison; NaN payloads are not significant"""
+    a, b = np.asarray(a), np.asarray(b)
+    an, bn = np.isnan(a.astype(np.float32)), np.isnan(b.astype(np.float32))
+    return bool(np.array_equal(an, bn) and np.array_equal(a.view(np.uint16)[~an], b.view(np.uint16)[~bn]))
+
+
 def _log_close(a, b):
     a, b = np.asarray(a, float), np.asarray(b, float)
     if not np.array_equal(np.isnan(a), np.isnan(b)):
@@ -36,7 +43,7 @@ def test_correct_matrix_matches_reference_golden(name):
     eng = _engine(g, int(back))
     out = eng.correct(g["obs"], tp, ts, init_filter_p=q, tiethreshold=tie, err_thresh=et, keep_posteriors=True)
     raw = eng.raw_host()
-    assert np.array_equal(raw.view(np.uint16), g["raw"].view(np.uint16)), "rank matrix not bit-exact"
+    assert _same_f16(raw, g["raw"]), "rank matrix not bit-exact"
     tpv = eng.stats["test_p"]
     assert tpv == g["test_p"] or (np.isnan(tpv) and np.isnan(g["test_p"]))
     assert np.array_equal(out, g["corrected"]), "%d corrected calls differ" % int((out != g["corrected"]).sum())
@@ -88,19 +95,20 @@ def _random_case(seed, n=400, gens=7, s=160, related=0.3, unknown=0.05, miss=0.0
 
 
 @pytest.mark.parametrize("seed,params", [(101, (0.5, 0.64, 2, 0.95, 0.4, 1.0)), (202, (0.5, 0.7, 2, 0.9, 0.05, 1.0)),
-                                         (303, (0.6, 0.6, 1, 0.9, 0.2, 1.0)), (404, (0.5, 0.64, 3, 0.92, 0.4, 0.9))])
+                                         (303, (0.6, 0.6, 1, 0.9, 0.2, 1.0)), (404, (0.5, 0.64, 3, 0.92, 0.4, 0.9)),
+                                         (505, (0.5, 0.64, 3, 0.9, 0.4, 1.0))])
 def test_correct_matrix_matches_oracle_on_seeded_inputs(seed, params):
     from genofix_b200.engine import Engine
     from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
     from oracle.genofix_oracle import Oracle
-    rows, ids, obs = _random_case(seed, s=96 if params[2] == 3 else 160)
+    rows, ids, obs = _random_case(seed, s=96 if params[2] == 3 else 160, miss=0.0 if seed == 505 else 0.03)
     tp, ts, back, q, tie, et = params
     o = Oracle(rows, ids).correct_matrix(obs, tp, ts, back=back, init_filter_p=q, tiethreshold=tie, err_thresh=et)
     eng = Engine(PedigreeDAG.from_table(rows), ids, back)
     out = eng.correct(obs, tp, ts, init_filter_p=q, tiethreshold=tie, err_thresh=et)
-    assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16))
-    assert eng.stats["test_p"] == o["test_p"]
-    assert np.array_equal(eng.E_host(), o["E"])
+    assert _same_f16(eng.raw_host(), o["raw"])
+    assert eng.stats["test_p"] == o["test_p"] or (np.isnan(eng.stats["test_p"]) and np.isnan(o["test_p"]))
+    assert np.array_equal(eng.E_host(), o["E"], equal_nan=True)
     assert np.array_equal(out, o["corrected"]), int((out != o["corrected"]).sum())
     assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
     assert np.array_equal(eng.stats["excluded_per_animal"], o["excluded_per_animal"])
@@ -120,7 +128,7 @@ def test_edge_shapes_and_ragged_inputs():
         o = Oracle(rows, ids).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4)
         eng = Engine(PedigreeDAG.from_table(rows), ids, 2)
         out = eng.correct(sub, 0.5, 0.64, init_filter_p=0.9, tiethreshold=0.4)
-        assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16)), s
+        assert _same_f16(eng.raw_host(), o["raw"]), s
         assert np.array_equal(out, o["corrected"]), s
     frows = np.array([[i, 0, 0, 1 + i % 2] for i in range(1, 9)])
     fobs = np.random.default_rng(1).integers(0, 3, size=(8, 20)).astype(np.uint8)
@@ -176,7 +184,7 @@ def test_snp_permutation_property_at_scale():
     sub = np.ascontiguousarray(obs[:, :6])
     o = Oracle(rows, rows[:, 0]).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
     c = eng.correct(sub, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
-    assert np.array_equal(eng.raw_host().view(np.uint16), o["raw"].view(np.uint16))
+    assert _same_f16(eng.raw_host(), o["raw"])
     assert np.array_equal(c, o["corrected"])
 
 

@@ -164,28 +164,26 @@ class CorrectGenotypes(object):
                 nj = int(gen_off[g + 1] - gen_off[g])
                 if nj == 0:
                     continue
-                post = t.full((nj * 2, eng.s, 3), float("nan"), dtype=t.float64, device=eng.codes.device)
+                post = t.full((nj * 2, eng.s, 3), -1.0, dtype=t.float64, device=eng.codes.device)
                 scratch = live.clone()  # apply happens on a scratch copy: every generation sees the bound snapshot
                 _lib.check(eng.L.gfx_correct_pairs(eng.schedule.handle, g, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
                                                    eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
-                                                   eng.result.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                                                   eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()
-                res = eng.result[:2 * nj * eng.s].view(-1, eng.s).cpu().numpy()
                 for k in range(nj):
                     pr = tuple(int(x) for x in pairs[jobs[gen_off[g] + k]])
-                    out.setdefault(pr, (ph[2 * k], ph[2 * k + 1], res[2 * k] & 0x80))
+                    out.setdefault(pr, (ph[2 * k], ph[2 * k + 1], ph[2 * k, :, 0] != -1.0))
         else:
             ns = info["n_singles"]
             if ns:
-                post = t.full((ns, eng.s, 3), float("nan"), dtype=t.float64, device=eng.codes.device)
+                post = t.full((ns, eng.s, 3), -1.0, dtype=t.float64, device=eng.codes.device)
                 scratch = live.clone()
                 _lib.check(eng.L.gfx_correct_singles(eng.schedule.handle, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
                                                      eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
-                                                     eng.result.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                                                     eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()
-                res = eng.result[:ns * eng.s].view(-1, eng.s).cpu().numpy()
                 for k, r in enumerate(eng.schedule.array(2)):
-                    out[int(r)] = (ph[k], res[k] & 0x80)
+                    out[int(r)] = (ph[k], ph[k, :, 0] != -1.0)
         eng.check_status()
         return out
 

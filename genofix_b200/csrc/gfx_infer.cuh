@@ -50,15 +50,149 @@ struct GfxBlanket {
   const int8_t* last; // local index of the node's last child inside the blanket (own index if none)
 };
 
-// Marginal of node q given hard evidence on the nodes whose bit is set in `obs` (their states in
-// code[]).  tab: scratch of GFX_TAB doubles.  Returns 0, or 1 if more than GFX_WMAX variables
-// would be open at once (out = NaN).
+GFX_HD int gfx_lowbit(uint64_t m) {
+#ifdef __CUDA_ARCH__
+  return __ffsll((long long)m) - 1;
+#else
+  return __builtin_ctzll(m);
+#endif
+}
+GFX_HD int gfx_highbit(uint64_t m) {
+#ifdef __CUDA_ARCH__
+  return 63 - __clzll((long long)m);
+#else
+  return 63 - __builtin_clzll(m);
+#endif
+}
+
+// Core of the inference: sum-product over the component `comp` of the query q (bit mask of the
+// unobserved variables connected to q), visiting only the candidate factors in `cand` (any superset
+// of comp and the children of comp; nodes outside are never referenced, so code[] / obs only need
+// to be valid for comp, its children and their parents).
 //
 // Three reductions keep the table small without changing the (exact, dyadic) unnormalised values:
 //   * only factors connected to q through unobserved variables are used (pgmpy drops the others);
 //   * barren nodes -- unobserved, not q, no evidence below them -- are skipped: their factor sums to 1;
 //   * an unobserved founder with a single remaining child is folded into that child's factor
 //     (sum_p prior(p) T(x | p, .)) instead of opening a digit for it.
+// Returns 0, or 1 if more than `wmax` variables would be open at once (out = NaN).
+// tab[3] receives the unnormalised total P(evidence in the component).
+__host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const uint8_t* code, uint64_t obs,
+                                             uint64_t comp, uint64_t cand, double* tab, double out[3], int wmax) {
+  // needed factors: connected to q and not barren (reverse topological sweep)
+  uint64_t need = 1ull << q, inc = 0;
+  int8_t nkids[GFX_MAXN], dlast[GFX_MAXN];
+  for (uint64_t m = cand; m;) {
+    const int v = gfx_highbit(m);
+    m &= ~(1ull << v);
+    nkids[v] = 0;
+    dlast[v] = (int8_t)v;
+    const int a1 = b.p1[v];
+    if (a1 >= 0) { nkids[a1] = 0; nkids[b.p2[v]] = 0; dlast[a1] = (int8_t)a1; dlast[b.p2[v]] = (int8_t)b.p2[v]; }
+  }
+  for (uint64_t m = cand; m;) {
+    const int v = gfx_highbit(m);
+    m &= ~(1ull << v);
+    uint64_t sc = 1ull << v;
+    const int a1 = b.p1[v], a2 = b.p2[v];
+    if (a1 >= 0) sc |= (1ull << a1) | (1ull << a2);
+    if (!((sc & ~obs) & comp)) continue;
+    inc |= 1ull << v;
+    if ((obs >> v) & 1) need |= 1ull << v;  // evidence that touches the component
+    if (!((need >> v) & 1)) continue;
+    if (a1 >= 0) {
+      need |= (1ull << a1) | (1ull << a2);
+      ++nkids[a1]; ++nkids[a2];
+      if (dlast[a1] < v) dlast[a1] = (int8_t)v;
+      if (dlast[a2] < v) dlast[a2] = (int8_t)v;
+    }
+  }
+  need &= inc;  // observed parents were marked too; their own factors count only if connected
+  int8_t open[GFX_WMAX_BIG];
+  int w = 0, size = 1;
+  uint64_t folded = 0;
+  tab[0] = 1.0;
+  for (uint64_t m = need; m;) {
+    const int v = gfx_lowbit(m);
+    m &= m - 1;
+    const int a1 = b.p1[v], a2 = b.p2[v];
+    const bool v_obs = (obs >> v) & 1;
+    if (a1 < 0) {
+      if (v_obs) continue;                       // prior of an observed founder: scalar, dropped
+      if (v != q && nkids[v] == 1) { folded |= 1ull << v; continue; }
+    }
+    // where do the parents' states come from: evidence, a digit of the table index, or a folded prior
+    int s_pos = -1, d_pos = -1, s_val = 0, d_val = 0, s_str = 1, d_str = 1;
+    bool s_fold = false, d_fold = false;
+    if (a1 >= 0) {
+      if ((obs >> a1) & 1) s_val = code[a1];
+      else if ((folded >> a1) & 1) s_fold = true;
+      else { for (int k = 0; k < w; ++k) if (open[k] == a1) s_pos = k; s_str = gfx_pow3(s_pos); }
+      if ((obs >> a2) & 1) d_val = code[a2];
+      else if ((folded >> a2) & 1) d_fold = true;
+      else { for (int k = 0; k < w; ++k) if (open[k] == a2) d_pos = k; d_str = gfx_pow3(d_pos); }
+    }
+    // g[x][a][b]: factor value for parent digits a, b (index 0 where the parent is not a digit)
+    const int na = s_pos >= 0 ? 3 : 1, nb = d_pos >= 0 ? 3 : 1;
+    const int x_lo = v_obs ? code[v] : 0, x_hi = v_obs ? code[v] : 2;
+    double g[27];
+    for (int x = x_lo; x <= x_hi; ++x)
+      for (int a = 0; a < na; ++a)
+        for (int c = 0; c < nb; ++c) {
+          double f;
+          if (a1 < 0) {
+            f = gfx_prior(x);
+          } else {
+            const int sl = s_pos >= 0 ? a : (s_fold ? 0 : s_val), sh = s_pos >= 0 ? a : (s_fold ? 2 : s_val);
+            const int dl = d_pos >= 0 ? c : (d_fold ? 0 : d_val), dh = d_pos >= 0 ? c : (d_fold ? 2 : d_val);
+            f = 0.0;
+            for (int sv = sl; sv <= sh; ++sv)
+              for (int dv = dl; dv <= dh; ++dv) {
+                double t = gfx_mendel(x, sv, dv);
+                if (s_fold) t *= gfx_prior(sv);
+                if (d_fold) t *= gfx_prior(dv);
+                f += t;
+              }
+          }
+          g[(x * 3 + a) * 3 + c] = f;
+        }
+    if (!v_obs && w == wmax) { out[0] = out[1] = out[2] = nan(""); return 1; }
+    for (int x = x_hi; x >= x_lo; --x) {
+      for (int i = 0; i < size; ++i) {
+        const int a = s_pos >= 0 ? (i / s_str) % 3 : 0;
+        const int c = d_pos >= 0 ? (i / d_str) % 3 : 0;
+        const double f = g[(x * 3 + a) * 3 + c];
+        if (v_obs) tab[i] *= f;
+        else tab[x * size + i] = tab[i] * f;
+      }
+    }
+    if (!v_obs) { open[w++] = (int8_t)v; size *= 3; }
+    // sum out every open variable whose last needed child is this node
+    for (int k = w - 1; k >= 0; --k) {
+      const int u = open[k];
+      if (u == q || dlast[u] > v) continue;
+      const int str = gfx_pow3(k);
+      const int nsize = size / 3;
+      for (int i = 0; i < nsize; ++i) {
+        const int hi = i / str, lo = i - hi * str;
+        const int src = hi * str * 3 + lo;
+        tab[i] = (tab[src] + tab[src + str]) + tab[src + 2 * str];
+      }
+      for (int mm = k; mm + 1 < w; ++mm) open[mm] = open[mm + 1];
+      --w;
+      size = nsize;
+    }
+  }
+  const double s = (tab[0] + tab[1]) + tab[2];
+  out[0] = tab[0] / s;
+  out[1] = tab[1] / s;
+  out[2] = tab[2] / s;
+  tab[3] = s;
+  return 0;
+}
+
+// Marginal of node q given hard evidence on the nodes whose bit is set in `obs` (their states in
+// code[]), every node's status known up front.  tab: scratch of 3^wmax doubles (>= 4).
 __host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8_t* code, uint64_t obs,
                                          double* tab, double out[3], int wmax = GFX_WMAX) {
   const int n = b.n;
@@ -80,98 +214,8 @@ __host__ __device__ inline int gfx_infer(const GfxBlanket& b, int q, const uint8
       if ((sc & comp) && (sc & ~comp)) comp |= sc;
     }
   }
-  // needed factors: connected to q and not barren (reverse topological sweep)
-  uint64_t need = 1ull << q, inc = 0;
-  int8_t nkids[GFX_MAXN], dlast[GFX_MAXN];
-  for (int v = 0; v < n; ++v) { nkids[v] = 0; dlast[v] = (int8_t)v; }
-  for (int v = n - 1; v >= 0; --v) {
-    uint64_t sc = 1ull << v;
-    const int a1 = b.p1[v], a2 = b.p2[v];
-    if (a1 >= 0) sc |= (1ull << a1) | (1ull << a2);
-    if (!((sc & ~obs) & comp)) continue;
-    inc |= 1ull << v;
-    if ((obs >> v) & 1) need |= 1ull << v;  // evidence that touches the component
-    if (!((need >> v) & 1)) continue;
-    if (a1 >= 0) {
-      need |= (1ull << a1) | (1ull << a2);
-      ++nkids[a1]; ++nkids[a2];
-      if (dlast[a1] < v) dlast[a1] = (int8_t)v;
-      if (dlast[a2] < v) dlast[a2] = (int8_t)v;
-    }
-  }
-  need &= inc;  // observed parents were marked too; their own factors count only if connected
-  int8_t open[GFX_WMAX_BIG];
-  int w = 0, size = 1;
-  uint64_t folded = 0;
-  tab[0] = 1.0;
-  for (int v = 0; v < n; ++v) {
-    if (!((need >> v) & 1)) continue;
-    const int a1 = b.p1[v], a2 = b.p2[v];
-    const bool v_obs = (obs >> v) & 1;
-    if (a1 < 0) {
-      if (v_obs) continue;                       // prior of an observed founder: scalar, dropped
-      if (v != q && nkids[v] == 1) { folded |= 1ull << v; continue; }
-    } else if (v_obs && ((obs >> a1) & 1) && ((obs >> a2) & 1)) {
-      continue;                                  // fully observed trio: scalar, dropped
-    }
-    // where do the parents' states come from: evidence, a digit of the table index, or a folded prior
-    int s_pos = -1, d_pos = -1, s_lo = 0, s_hi = 0, d_lo = 0, d_hi = 0, s_str = 1, d_str = 1;
-    bool s_fold = false, d_fold = false;
-    if (a1 >= 0) {
-      if ((obs >> a1) & 1) s_lo = s_hi = code[a1];
-      else if ((folded >> a1) & 1) { s_fold = true; s_lo = 0; s_hi = 2; }
-      else { for (int k = 0; k < w; ++k) if (open[k] == a1) s_pos = k; s_str = gfx_pow3(s_pos); }
-      if ((obs >> a2) & 1) d_lo = d_hi = code[a2];
-      else if ((folded >> a2) & 1) { d_fold = true; d_lo = 0; d_hi = 2; }
-      else { for (int k = 0; k < w; ++k) if (open[k] == a2) d_pos = k; d_str = gfx_pow3(d_pos); }
-    }
-    const int x_lo = v_obs ? code[v] : 0, x_hi = v_obs ? code[v] : 2;
-    if (!v_obs && w == wmax) { out[0] = out[1] = out[2] = nan(""); return 1; }
-    for (int x = x_hi; x >= x_lo; --x) {
-      for (int i = 0; i < size; ++i) {
-        double f;
-        if (a1 >= 0) {
-          int sl = s_lo, sh = s_hi, dl = d_lo, dh = d_hi;
-          if (s_pos >= 0) sl = sh = (i / s_str) % 3;
-          if (d_pos >= 0) dl = dh = (i / d_str) % 3;
-          f = 0.0;
-          for (int sv = sl; sv <= sh; ++sv)
-            for (int dv = dl; dv <= dh; ++dv) {
-              double t = gfx_mendel(x, sv, dv);
-              if (s_fold) t *= gfx_prior(sv);
-              if (d_fold) t *= gfx_prior(dv);
-              f += t;
-            }
-        } else {
-          f = gfx_prior(x);
-        }
-        if (v_obs) tab[i] *= f;
-        else tab[x * size + i] = tab[i] * f;
-      }
-    }
-    if (!v_obs) { open[w++] = (int8_t)v; size *= 3; }
-    // sum out every open variable whose last needed child is this node
-    for (int k = w - 1; k >= 0; --k) {
-      const int u = open[k];
-      if (u == q || dlast[u] > v) continue;
-      const int str = gfx_pow3(k);
-      const int nsize = size / 3;
-      for (int i = 0; i < nsize; ++i) {
-        const int hi = i / str, lo = i - hi * str;
-        const int src = hi * str * 3 + lo;
-        tab[i] = (tab[src] + tab[src + str]) + tab[src + 2 * str];
-      }
-      for (int m = k; m + 1 < w; ++m) open[m] = open[m + 1];
-      --w;
-      size = nsize;
-    }
-  }
-  const double s = (tab[0] + tab[1]) + tab[2];
-  out[0] = tab[0] / s;
-  out[1] = tab[1] / s;
-  out[2] = tab[2] / s;
-  tab[3] = s;  // unnormalised total, for gfx_infer_pair
-  return 0;
+  const uint64_t all = n >= 64 ? ~0ull : ((1ull << n) - 1);
+  return gfx_eliminate(b, q, code, obs, comp, all, tab, out, wmax);
 }
 
 // correctPair queries [sire, dam] jointly with joint=False (correct_genotypes3.py:242-245): pgmpy
@@ -309,6 +353,15 @@ struct GfxKidStream {
   }
 };
 
+// mean over the 3*ninc entries of each dam-axis column, then divide by the Python sum (model.py:85-88)
+GFX_HD void gfx_kids_finish(const double tot[3], int ninc, double out[3]) {
+  const double cnt = (double)(3 * ninc);
+  double r0 = tot[0] / cnt, r1 = tot[1] / cnt, r2 = tot[2] / cnt;
+  const double s = (r0 + r1) + r2;
+  if (s > 0) { r0 /= s; r1 /= s; r2 /= s; }
+  out[0] = r0; out[1] = r1; out[2] = r2;
+}
+
 // Returns false when there is no genotyped child at all (the reference's `probs = None`).
 template <class KidCode, class ParCode>
 __host__ __device__ inline bool gfx_kids_term(int nkids, KidCode kid_code, ParCode par_code, const double* kv,
@@ -320,12 +373,28 @@ __host__ __device__ inline bool gfx_kids_term(int nkids, KidCode kid_code, ParCo
   GfxKidStream<KidCode, ParCode> next{0, 0, nkids, kid_code, par_code, kv};
   double tot[3];
   gfx_pairwise3(next, 3 * ninc, tot);
-  const double cnt = (double)(3 * ninc);
-  double r0 = tot[0] / cnt, r1 = tot[1] / cnt, r2 = tot[2] / cnt;
-  const double s = (r0 + r1) + r2;
-  if (s > 0) { r0 /= s; r1 /= s; r2 /= s; }
-  out[0] = r0; out[1] = r1; out[2] = r2;
+  gfx_kids_finish(tot, ninc, out);
   return true;
+}
+
+// Same sum over a compacted list of usable children: cls[i] = 4 * state + other-parent class.
+struct GfxClsStream {
+  int a, cur, ninc;
+  const uint8_t* cls;
+  const double* kv;
+  __host__ __device__ void operator()(double v[3]) {
+    if (cur == ninc) { cur = 0; ++a; }
+    const double* e = kv + (int)cls[cur] * 9 + 3 * a;
+    v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+    ++cur;
+  }
+};
+__host__ __device__ inline void gfx_kids_term_cls(int ninc, const uint8_t* cls, const double* kv, double out[3]) {
+  if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return; }
+  GfxClsStream next{0, 0, ninc, cls, kv};
+  double tot[3];
+  gfx_pairwise3(next, 3 * ninc, tot);
+  gfx_kids_finish(tot, ninc, out);
 }
 
 // correct_genotypes3.py:280-304 / :410-422 : product (or whichever exists), divided by its sum if > 0

@@ -57,6 +57,7 @@ struct gfx_schedule {
   int32_t *child_off = nullptr, *child_row = nullptr, *child_other = nullptr;
   int32_t *bl_off = nullptr, *bl_row = nullptr;
   int8_t *bl_p1 = nullptr, *bl_p2 = nullptr, *bl_last = nullptr, *bl_q0 = nullptr, *bl_q1 = nullptr;
+  uint64_t* bl_kid = nullptr;
   int32_t *job_row0 = nullptr, *job_row1 = nullptr, *job_bl = nullptr;        // pair jobs, all generations
   int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr;
   int32_t *single_row = nullptr, *single_bl = nullptr, *single_off = nullptr, *single_entry = nullptr;
@@ -108,7 +109,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags};
+                  s->big_pool, s->big_flags, s->bl_kid};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -147,7 +148,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(anc6, h.anc6); UP(rank_blanket, h.rank_blanket); UP(prow, h.prow); UP(rank_flags, h.rank_flags);
   UP(child_off, h.child_off); UP(child_row, h.child_row); UP(child_other, h.child_other);
   UP(bl_off, h.bl.off); UP(bl_row, h.bl.row); UP(bl_p1, h.bl.p1); UP(bl_p2, h.bl.p2); UP(bl_last, h.bl.last);
-  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1);
+  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1); UP(bl_kid, h.bl.kidmask);
   UP(job_row0, job_row0); UP(job_row1, job_row1); UP(job_bl, job_bl);
   UP(app_focal_row, h.app_focal_row); UP(app_focal_off, h.app_focal_off); UP(app_entry, h.app_entry);
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
@@ -459,22 +460,83 @@ struct BlanketDev {
   int* big_flags;
 };
 
-// Inference with the per-thread table; the rare blanket that needs more than GFX_WMAX open variables
-// borrows one of GFX_BIG_SLOTS global tables (holders never wait on each other, so spinning is safe).
-__device__ __noinline__ int infer_big(const GfxBlanket& b, int q0, int q1, const uint8_t* code, uint64_t om,
-                                      const BlanketDev& bl, double* anc0, double* anc1) {
-  int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) % GFX_BIG_SLOTS);
-  for (;;) {
-    if (atomicCAS(bl.big_flags + slot, 0, 1) == 0) break;
-    slot = (slot + 1) % GFX_BIG_SLOTS;
-    __nanosleep(200);
+// Evidence is gathered lazily, walking outwards from the query only through unobserved nodes: the
+// usual case (both parents observed and not suspect) touches two rows instead of the whole blanket.
+struct LazyBlanket {
+  const CellCtx& c;
+  const int32_t* rows;
+  const int8_t* p1;
+  const int8_t* p2;
+  const uint64_t* kid;
+  int n;
+  int64_t j;
+  double cut;
+  bool filter;            // false: plain evidence (rank), true: drop suspect nodes (correct)
+  __device__ int status(int t) const {
+    const int r = rows[t];
+    if (r < 0) return 3;
+    const int cd = cell_code(c.live, c.wpr, r, j);
+    if (cd == 3) return 3;
+    if (filter && cell_E(c, r, j) > cut) return 3;   // suspect node: not evidence (:230-238)
+    return cd;
   }
-  double* tab = bl.big_pool + (size_t)slot * GFX_TAB_BIG;
-  const int bad = q1 >= 0 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc0, anc1, GFX_WMAX_BIG)
-                          : gfx_infer(b, q0, code, om, tab, anc0, GFX_WMAX_BIG);
-  __threadfence();
-  atomicExch(bl.big_flags + slot, 0);
-  return bad;
+};
+
+// Marginal of q (qother: the second focal animal of a pair, forced unobserved, or -1).
+// *total = unnormalised P(evidence in the component).
+__device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, uint8_t* code,
+                                       double* tab, double out[3], double* total) {
+  uint64_t known = 1ull << q, obs = 0, comp = 1ull << q, queue = 1ull << q, cand = 0;
+  if (qother >= 0) known |= 1ull << qother;
+  while (queue) {
+    const int u = gfx_lowbit(queue);
+    queue &= queue - 1;
+    uint64_t touch = 0;
+    if (L.p1[u] >= 0) touch |= (1ull << L.p1[u]) | (1ull << L.p2[u]);
+    const uint64_t km = L.kid[u];
+    touch |= km;
+    cand |= km;
+    for (uint64_t m = km; m; m &= m - 1) {
+      const int k = gfx_lowbit(m);
+      touch |= (1ull << L.p1[k]) | (1ull << L.p2[k]);
+    }
+    for (uint64_t m = touch & ~known; m; m &= m - 1) {
+      const int t = gfx_lowbit(m);
+      const int st = L.status(t);
+      code[t] = (uint8_t)st;
+      if (st != 3) obs |= 1ull << t;
+    }
+    known |= touch;
+    const uint64_t add = touch & ~obs & ~comp;
+    comp |= add;
+    queue |= add;
+  }
+  cand |= comp;
+  if (comp == (1ull << q) && L.kid[q] == 0 && L.p1[q] >= 0) {
+    // both parents observed, nothing below: the Mendel column, already normalised
+    const int sv = code[L.p1[q]], dv = code[L.p2[q]];
+    out[0] = gfx_mendel(0, sv, dv); out[1] = gfx_mendel(1, sv, dv); out[2] = gfx_mendel(2, sv, dv);
+    *total = 1.0;
+    return 0;
+  }
+  GfxBlanket b{L.n, L.p1, L.p2, nullptr};
+  int bad = gfx_eliminate(b, q, code, obs, comp, cand, tab, out, GFX_WMAX);
+  if (bad) {
+    int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) % GFX_BIG_SLOTS);
+    for (;;) {
+      if (atomicCAS(bl.big_flags + slot, 0, 1) == 0) break;
+      slot = (slot + 1) % GFX_BIG_SLOTS;
+      __nanosleep(200);
+    }
+    double* big = bl.big_pool + (size_t)slot * GFX_TAB_BIG;
+    bad = gfx_eliminate(b, q, code, obs, comp, cand, big, out, GFX_WMAX_BIG);
+    *total = big[3];
+    __threadfence();
+    atomicExch(bl.big_flags + slot, 0);
+    return bad;
+  }
+  *total = tab[3];
+  return 0;
 }
 
 struct GenericRankArgs {
@@ -488,6 +550,7 @@ struct GenericRankArgs {
   const int32_t* child_off;
   const int32_t* child_row;
   BlanketDev bl;
+  const uint64_t* bl_kid;
   int* status;
 };
 
@@ -505,19 +568,11 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
     const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
     if (obs != 3) {
       const int bid = a.rank_blanket[row];
-      const int off = a.bl.off[bid], n = a.bl.off[bid + 1] - off;
-      uint64_t om = 0;
-      for (int v = 0; v < n; ++v) {
-        const int rr = a.bl.row[off + v];
-        int c = 3;
-        if (rr >= 0) c = cell_code(a.packed, a.wpr, rr, j);
-        code[v] = (uint8_t)c;
-        if (c != 3) om |= 1ull << v;
-      }
-      GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
-      double anc[3];
-      if (gfx_infer(b, a.bl.q0[bid], code, om, tab, anc) && infer_big(b, a.bl.q0[bid], -1, code, om, a.bl, anc, anc))
-        atomicExch(a.status, 1);
+      const int off = a.bl.off[bid];
+      CellCtx cc{a.packed, a.packed, a.wpr, nullptr, 0, nullptr};
+      LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0.0, false};
+      double anc[3], tot;
+      if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot)) atomicExch(a.status, 1);
       const uint16_t sc = gfx_anc_score(anc, obs);
       uint32_t m = 0;
       bool kids = false;
@@ -555,7 +610,8 @@ extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, in
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
-                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags}, s->status};
+                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags},
+                      s->bl_kid, s->status};
     const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
     k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, (cudaStream_t)stream>>>(g);
     GFX_LAUNCHED();
@@ -648,224 +704,218 @@ extern "C" int gfx_rank_rowsum(const uint16_t* raw, int64_t ld_raw, const uint32
   return GFX_OK;
 }
 
-// ---- correctPair / correctSingle -----------------------------------------------------------------
-struct InferArgs {
-  CellCtx c;
+// ---- correctPair / correctSingle + apply, fused per focal animal -----------------------------------
+//
+// One warp owns 32 consecutive SNPs of one focal animal of the generation and walks that animal's
+// jobs (mating pairs it takes part in, canonical order).  Everything except the animal's own cell is
+// read from the generation-start snapshot, exactly like the reference's workers
+// (correct_genotypes3.py:687-689); the own cell is carried in a register and updated job after job,
+// like the serial apply loop (:714-845).  The children term of the focal animal does not depend on
+// the mate, so it is evaluated at most once per (animal, SNP).
+struct FocalArgs {
+  CellCtx c;              // c.live = snapshot
+  uint32_t* live;         // matrix being corrected
   int64_t n_snps;
   int nf;                 // 2 = pairs, 1 = singles
-  int n_jobs;
+  int n_focal;
+  const int32_t* focal_row;
+  const int32_t* focal_off;
+  const int32_t* entry;   // job * nf + side
   const int32_t* job_row0;
   const int32_t* job_row1;
   const int32_t* job_bl;
   BlanketDev bl;
+  const uint64_t* bl_kid;
   const int32_t* child_off;
   const int32_t* child_row;
   const int32_t* child_other;
   const int32_t* prow;
   const double* kv;
   gfx_correct_params p;
-  uint8_t* result;        // [(job*nf + side) * n_snps + j]
   double* post;           // optional [(job*nf + side) * n_snps + j] * 3
+  int32_t* tallies;
+  int n_rows;
   int* status;
 };
 
-struct KidCodeFn {
-  const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
-  __device__ int operator()(int i) const { return cell_code(live, wpr, rows[i], j); }
-};
-struct ParCodeFn {
-  const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
-  __device__ int operator()(int i) const { const int r = rows[i]; return r >= 0 ? cell_code(live, wpr, r, j) : 3; }
-};
+#define GFX_KIDS_LOCAL 160
+// children term of `row` at SNP j from the snapshot (bayesnet/model.py:65-89); false = no genotyped child
+__device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
+                                           int64_t j, const double* kv, double out[3]) {
+  if (nk <= 0) return false;
+  if (nk <= GFX_KIDS_LOCAL) {
+    uint8_t cls[GFX_KIDS_LOCAL];
+    int ninc = 0;
+    for (int i = 0; i < nk; ++i) {
+      const int k = cell_code(c.live, c.wpr, child_row[i], j);
+      if (k > 2) continue;
+      const int o = child_other[i];
+      const int pc = o >= 0 ? cell_code(c.live, c.wpr, o, j) : 3;
+      cls[ninc++] = (uint8_t)(k * 4 + pc);
+    }
+    gfx_kids_term_cls(ninc, cls, kv, out);
+    return true;
+  }
+  struct KC { const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
+    __device__ int operator()(int i) const { return cell_code(live, wpr, rows[i], j); } };
+  struct PC { const uint32_t* live; int64_t wpr; const int32_t* rows; int64_t j;
+    __device__ int operator()(int i) const { const int r = rows[i]; return r >= 0 ? cell_code(live, wpr, r, j) : 3; } };
+  KC kc{c.live, c.wpr, child_row, j};
+  PC pc{c.live, c.wpr, child_other, j};
+  return gfx_kids_term(nk, kc, pc, kv, out);
+}
 
-#define GFX_INFER_CHUNK 1024
-__global__ void __launch_bounds__(128) k_infer(InferArgs a) {
-  __shared__ int s_list[GFX_INFER_CHUNK];
-  __shared__ int s_cnt;
-  const int64_t chunks = (a.n_snps + GFX_INFER_CHUNK - 1) / GFX_INFER_CHUNK;
-  const int64_t tasks = (int64_t)a.n_jobs * chunks;
+__global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int64_t groups = (a.n_snps + 31) >> 5;
+  const int64_t tasks = (int64_t)a.n_focal * groups;
   double tab[GFX_TAB];
   uint8_t code[GFX_MAXN];
-  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int job = (int)(task / chunks);
-    const int64_t j0 = (task - (int64_t)job * chunks) * GFX_INFER_CHUNK;
-    const int64_t j1 = min(a.n_snps, j0 + GFX_INFER_CHUNK);
-    const int row0 = a.job_row0[job];
-    const int row1 = a.nf == 2 ? a.job_row1[job] : -1;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    // pass 1: suspect SNPs (correct_genotypes3.py:181-185 / :342)
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-      bool sus = cell_E(a.c, row0, j) >= a.p.test_p;
-      if (a.nf == 2) sus = sus || (cell_E(a.c, row1, j) >= a.p.test_p);
-      a.result[((int64_t)job * a.nf) * a.n_snps + j] = 0;
-      if (a.nf == 2) a.result[((int64_t)job * 2 + 1) * a.n_snps + j] = 0;
-      if (sus) s_list[atomicAdd(&s_cnt, 1)] = (int)(j - j0);
-    }
-    __syncthreads();
-    const int cnt = s_cnt;
-    // pass 2: inference on the suspect cells
-    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const int64_t j = j0 + s_list[k];
-      const int rows[2] = {row0, row1};
-      int obs[2] = {3, 3};
-      double E[2] = {1.0, 1.0};
-      for (int f = 0; f < a.nf; ++f) {
-        obs[f] = cell_code(a.c.live, a.c.wpr, rows[f], j);
-        E[f] = cell_E(a.c, rows[f], j);
-      }
-      double pmax;
-      if (a.nf == 2) {
-        if (obs[0] != 3 && obs[1] != 3) pmax = E[1] > E[0] ? E[1] : E[0];
-        else if (obs[0] == 3 && obs[1] == 3) pmax = 1.0;
-        else pmax = obs[0] != 3 ? E[0] : E[1];
-      } else {
-        pmax = obs[0] != 3 ? E[0] : 1.0;
-      }
-      const double cut = pmax - a.p.suspect_t;
-      const int bid = a.job_bl[job];
-      double anc[2][3];
-      if (bid >= 0) {
-        const int off = a.bl.off[bid], n = a.bl.off[bid + 1] - off;
-        uint64_t om = 0;
-        for (int v = 0; v < n; ++v) {
-          const int rr = a.bl.row[off + v];
-          int c = 3;
-          if (rr >= 0) {
-            c = cell_code(a.c.live, a.c.wpr, rr, j);
-            if (c != 3 && cell_E(a.c, rr, j) > cut) c = 3;   // suspect node: not evidence (:230-238)
-          }
-          code[v] = (uint8_t)c;
-          if (c != 3) om |= 1ull << v;
-        }
-        const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
-        om &= ~(1ull << q0);
-        if (q1 >= 0) om &= ~(1ull << q1);
-        GfxBlanket b{n, a.bl.p1 + off, a.bl.p2 + off, a.bl.last + off};
-        int bad = a.nf == 2 ? gfx_infer_pair(b, q0, q1, code, om, tab, anc[0], anc[1])
-                            : gfx_infer(b, q0, code, om, tab, anc[0]);
-        if (bad) bad = infer_big(b, q0, a.nf == 2 ? q1 : -1, code, om, a.bl, anc[0], anc[1]);
-        if (bad) atomicExch(a.status, 1);
-      }
-      for (int f = 0; f < a.nf; ++f) {
-        const int r = rows[f];
-        const int k0 = a.child_off[r], nk = a.child_off[r + 1] - k0;
-        double kids[3];
-        KidCodeFn kc{a.c.live, a.c.wpr, a.child_row + k0, j};
-        ParCodeFn pc{a.c.live, a.c.wpr, a.child_other + k0, j};
-        const bool has_kids = gfx_kids_term(nk, kc, pc, a.kv, kids);
-        const int64_t slot = ((int64_t)job * a.nf + f) * a.n_snps + j;
-        if (bid < 0 && !has_kids) { a.result[slot] = 0; continue; }   // lone node: no result
-        double p[3];
-        gfx_combine(bid >= 0, anc[f], has_kids, kids, p);
-        uint8_t bits = gfx_decision_bits(p, obs[f], a.p.tiethreshold, a.p.threshold);
-        // rank gate (:733-737,817 / :928-933): focal E against the max E of its own genotyped parents
-        double mr = 0.0;
-        for (int q = 0; q < 2; ++q) {
-          const int pr = a.prow[2 * r + q];
-          if (pr >= 0) { const double e = cell_E(a.c, pr, j); if (e > mr) mr = e; }
-        }
-        if (E[f] * a.p.err_thresh >= mr) bits |= 16u;
-        a.result[slot] = bits;
-        if (a.post) { a.post[slot * 3] = p[0]; a.post[slot * 3 + 1] = p[1]; a.post[slot * 3 + 2] = p[2]; }
-      }
-    }
-    __syncthreads();
-  }
-}
-
-struct ApplyArgs {
-  uint32_t* live;
-  int64_t wpr, nwords, n_snps;
-  int n_focal;
-  const int32_t* focal_row;
-  const int32_t* focal_off;   // n_focal+1
-  const int32_t* entry;       // job*nf + side
-  const uint8_t* result;
-  int32_t* tallies;           // [0..n_rows) applied, [n_rows..2n_rows) excluded
-  int n_rows;
-  int count_excluded;
-};
-
-// Sequential apply of a generation's results in canonical job order (correct_genotypes3.py:714-845,
-// 877-944).  One thread owns 16 SNPs of one focal animal, so writes never collide.
-__global__ void __launch_bounds__(128) k_apply(ApplyArgs a) {
-  const int64_t total = (int64_t)a.n_focal * a.nwords;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int f = (int)(i / a.nwords);
-    const int64_t w = i - (int64_t)f * a.nwords;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < tasks; task += (int64_t)gridDim.x * wpb) {
+    const int f = (int)(task / groups);
+    const int64_t j = (task - (int64_t)f * groups) * 32 + lane;
+    if (j >= a.n_snps) continue;
     const int row = a.focal_row[f];
-    uint32_t word = a.live[(int64_t)row * a.wpr + w];
-    const uint32_t before = word;
+    const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
+    int cur = obs0;                                          // live state, updated job after job
+    const double Ef = cell_E(a.c, row, j);
+    bool gate_done = false, gate = false, kids_done = false, has_kids = false;
+    double kids[3] = {0, 0, 0};
     int applied = 0, excluded = 0;
     for (int e = a.focal_off[f]; e < a.focal_off[f + 1]; ++e) {
-      const uint8_t* res = a.result + (int64_t)a.entry[e] * a.n_snps + w * 16;
-      for (int k = 0; k < 16; ++k) {
-        if (w * 16 + k >= a.n_snps) break;
-        const uint32_t b = res[k];
-        if (!(b & 0x80u)) continue;
-        const uint32_t obs = (word >> (2 * k)) & 3u;  // LIVE state
-        const bool cond = obs == 3u || (!((b >> obs) & 1u) && (b & 8u));
-        if (!cond) continue;
-        if (b & 16u) {
-          const uint32_t set = b & 7u;
-          const uint32_t nv = __popc(set) == 1 ? (uint32_t)(__ffs(set) - 1) : 3u;
-          word = (word & ~(3u << (2 * k))) | (nv << (2 * k));
-          ++applied;
-        } else {
-          ++excluded;
+      const int ent = a.entry[e];
+      const int job = a.nf == 2 ? (ent >> 1) : ent;
+      const int side = a.nf == 2 ? (ent & 1) : 0;
+      int mrow = -1, obs_m = 3;
+      double Em = 1.0;
+      bool sus = Ef >= a.p.test_p;                            // :181-185 / :342
+      if (a.nf == 2) {
+        mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+        Em = cell_E(a.c, mrow, j);
+        sus = sus || (Em >= a.p.test_p);
+      }
+      if (!sus) continue;
+      double pmax;                                            // :220-228 / :374-376
+      if (a.nf == 2) {
+        obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
+        const double Es = side == 0 ? Ef : Em, Ed = side == 0 ? Em : Ef;
+        if (obs0 != 3 && obs_m != 3) pmax = Ed > Es ? Ed : Es;
+        else if (obs0 == 3 && obs_m == 3) pmax = 1.0;
+        else pmax = obs0 != 3 ? Ef : Em;
+      } else {
+        pmax = obs0 != 3 ? Ef : 1.0;
+      }
+      const int bid = a.job_bl[job];
+      double anc[3] = {0, 0, 0};
+      if (bid >= 0) {
+        const int off = a.bl.off[bid];
+        LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
+                       pmax - a.p.suspect_t, true};
+        const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
+        const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
+        double tot_me = 1.0, tot_ot = 1.0;
+        int bad = query_lazy(LB, a.bl, qme, qot, code, tab, anc, &tot_me);
+        if (qot >= 0) {
+          // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0
+          double tmp[3];
+          bad |= query_lazy(LB, a.bl, qot, qme, code, tab, tmp, &tot_ot);
+          if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
         }
+        if (bad) atomicExch(a.status, 1);
+      }
+      if (!kids_done) {
+        const int k0 = a.child_off[row];
+        has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, a.child_off[row + 1] - k0, j, a.kv, kids);
+        kids_done = true;
+      }
+      if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
+      double p[3];
+      gfx_combine(bid >= 0, anc, has_kids, kids, p);
+      const uint32_t bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
+      if (a.post) {
+        double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+      }
+      // decision on the LIVE state (:809-824 / :932-938)
+      const bool cond = cur == 3 || (!((bits >> cur) & 1u) && (bits & 8u));
+      if (!cond) continue;
+      if (!gate_done) {                                       // rank gate (:733-737,817 / :928-933)
+        double mr = 0.0;
+        for (int k = 0; k < 2; ++k) {
+          const int pr = a.prow[2 * row + k];
+          if (pr >= 0) { const double ev = cell_E(a.c, pr, j); if (ev > mr) mr = ev; }
+        }
+        gate = Ef * a.p.err_thresh >= mr;
+        gate_done = true;
+      }
+      if (gate) {
+        const uint32_t set = bits & 7u;
+        cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
+        ++applied;
+      } else {
+        ++excluded;
       }
     }
-    if (word != before) a.live[(int64_t)row * a.wpr + w] = word;
+    if (cur != obs0) {
+      uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
+      const int sh = 2 * (int)(j & 15);
+      atomicAnd(wp, ~(3u << sh));
+      atomicOr(wp, (uint32_t)cur << sh);
+    }
     if (applied) atomicAdd(a.tallies + row, applied);
-    if (excluded && a.count_excluded) atomicAdd(a.tallies + a.n_rows + row, excluded);
+    if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
   }
 }
 
-static int run_infer_apply(const gfx_schedule* s, int nf, int n_jobs, const int32_t* job_row0, const int32_t* job_row1,
-                           const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
-                           const int32_t* entry, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
-                           const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                           uint8_t* result, double* post, int32_t* tallies, cudaStream_t stream) {
-  if (n_jobs <= 0) return GFX_OK;
-  InferArgs a;
-  a.c = CellCtx{live, orig, wpr, raw, ld_raw, elut};
-  a.n_snps = n_snps; a.nf = nf; a.n_jobs = n_jobs;
+static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t* job_row0, const int32_t* job_row1,
+                       const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
+                       const int32_t* entry, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
+                       const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
+                       uint32_t* snapshot, double* post, int32_t* tallies, cudaStream_t stream) {
+  if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
+  GFX_CUDA(cudaMemcpyAsync(snapshot, live, sizeof(uint32_t) * (size_t)s->h.n_rows * wpr, cudaMemcpyDeviceToDevice, stream));
+  FocalArgs a;
+  a.c = CellCtx{snapshot, orig, wpr, raw, ld_raw, elut};
+  a.live = live;
+  a.n_snps = n_snps; a.nf = nf; a.n_focal = n_focal;
+  a.focal_row = focal_row; a.focal_off = focal_off; a.entry = entry;
   a.job_row0 = job_row0; a.job_row1 = job_row1; a.job_bl = job_bl;
   a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags};
+  a.bl_kid = s->bl_kid;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
-  a.prow = s->prow; a.kv = s->kv; a.p = *p; a.result = result; a.post = post; a.status = s->status;
-  const int64_t tasks = (int64_t)n_jobs * ((n_snps + GFX_INFER_CHUNK - 1) / GFX_INFER_CHUNK);
-  int blocks = (int)(tasks < (int64_t)s->num_sms * 8 ? tasks : (int64_t)s->num_sms * 8);
-  k_infer<<<blocks, 128, 0, stream>>>(a);
-  GFX_LAUNCHED();
-  ApplyArgs ap{live, wpr, (n_snps + 15) / 16, n_snps, n_focal, focal_row, focal_off, entry, result, tallies, s->h.n_rows, nf == 2};
-  k_apply<<<grid_for((int64_t)n_focal * ap.nwords, 128, s->num_sms, 16), 128, 0, stream>>>(ap);
+  a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
+  const int64_t tasks = (int64_t)n_focal * ((n_snps + 31) / 32);
+  int64_t blocks = (tasks + 3) / 4;
+  const int64_t cap = (int64_t)s->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  k_correct<<<(int)blocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   return GFX_OK;
 }
 
 extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* live, const uint32_t* orig,
                                  int64_t n_snps, int64_t wpr, const uint16_t* raw, int64_t ld_raw, const double* elut,
-                                 const gfx_correct_params* p, uint8_t* result, double* post, int32_t* tallies, void* stream) {
-  if (!s || !live || !orig || !raw || !elut || !p || !result || !tallies) return fail(GFX_E_INVALID, "null argument");
+                                 const gfx_correct_params* p, uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
+  if (!s || !live || !orig || !raw || !elut || !p || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   if (generation < 0 || generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
   const int j0 = s->h.gen_off[generation], nj = s->h.gen_off[generation + 1] - j0;
   const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
-  return run_infer_apply(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
-                         s->app_focal_off + f0, s->app_entry, live, orig, n_snps, wpr, raw, ld_raw, elut, p, result, post,
-                         tallies, (cudaStream_t)stream);
+  return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
+                     s->app_focal_off + f0, s->app_entry, live, orig, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post,
+                     tallies, (cudaStream_t)stream);
 }
 
 extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
                                    const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                                   uint8_t* result, double* post, int32_t* tallies, void* stream) {
-  if (!s || !live || !orig || !raw || !elut || !p || !result || !tallies) return fail(GFX_E_INVALID, "null argument");
+                                   uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
+  if (!s || !live || !orig || !raw || !elut || !p || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   const int n = (int)s->h.single_row.size();
-  return run_infer_apply(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
-                         live, orig, n_snps, wpr, raw, ld_raw, elut, p, result, post, tallies, (cudaStream_t)stream);
+  return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
+                     live, orig, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post, tallies, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -106,6 +106,7 @@ struct Builder {
     bs.p1.resize(base + n);
     bs.p2.resize(base + n);
     bs.last.resize(base + n);
+    bs.kidmask.resize(base + n, 0);
     for (int i = 0; i < n; ++i) {
       const int32_t k = order[i];
       bs.row[base + i] = ped->row[k];
@@ -121,6 +122,8 @@ struct Builder {
       if (bs.p1[base + i] >= 0) {
         bs.last[base + bs.p1[base + i]] = std::max<int8_t>(bs.last[base + bs.p1[base + i]], (int8_t)i);
         bs.last[base + bs.p2[base + i]] = std::max<int8_t>(bs.last[base + bs.p2[base + i]], (int8_t)i);
+        bs.kidmask[base + bs.p1[base + i]] |= 1ull << i;
+        bs.kidmask[base + bs.p2[base + i]] |= 1ull << i;
       }
     }
     // worst-case frontier width (nothing observed)

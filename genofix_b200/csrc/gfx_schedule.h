@@ -16,6 +16,7 @@ struct GfxBlanketSet {
   std::vector<int32_t> off;   // nb+1
   std::vector<int32_t> row;   // genotype row of the node or -1
   std::vector<int8_t> p1, p2, last;
+  std::vector<uint64_t> kidmask;  // per node: bit mask of its children inside the blanket
   std::vector<int8_t> q0, q1; // focal local indices (q1 = -1 for a single focal animal)
   int max_nodes = 0;
   int max_width = 0;

@@ -14,6 +14,7 @@ from . import _lib
 from .pedigree.pedigree_dag import PedigreeDAG
 
 SUSPECT_T = 0.2  # hard-coded in the reference driver (correct_genotypes3.py:691,858)
+POST_SENTINEL = -1.0  # posterior buffers are prefilled with it; evaluated cells hold probabilities or NaN
 
 
 def _torch():
@@ -204,9 +205,7 @@ class Engine(object):
         self.raw = t.empty((n, self.ld_raw), dtype=t.int16, device=dev)
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
-        info = self.schedule.info
-        nres = max(2 * info["max_pairs_in_generation"], info["n_singles"], 1)
-        self.result = t.empty(nres * self.s, dtype=t.uint8, device=dev)
+        self.snapshot = t.empty((n, self.wpr), dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
         self.host_out = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
@@ -267,26 +266,26 @@ class Engine(object):
                 post = None
                 if keep_posteriors:
                     nj = int(gen_off[g + 1] - gen_off[g])
-                    post = t.full((max(nj, 1) * 2, self.s, 3), float("nan"), dtype=t.float64, device=self.codes.device)
+                    post = t.full((max(nj, 1) * 2, self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
                 _lib.check(self.L.gfx_correct_pairs(
                     self.schedule.handle, g, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
-                    self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.result.data_ptr(),
+                    self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(),
                     post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
                 if keep_posteriors:
-                    res = self.result[:2 * max(nj, 1) * self.s].view(-1, self.s).cpu().numpy().copy()
-                    posts["pairs"].append((post.cpu().numpy(), res))
+                    ph = post.cpu().numpy()
+                    posts["pairs"].append((ph, ph[:, :, 0] != POST_SENTINEL))
             ps = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_single), float(err_thresh))
             post = None
             ns = info["n_singles"]
             if keep_posteriors:
-                post = t.full((max(ns, 1), self.s, 3), float("nan"), dtype=t.float64, device=self.codes.device)
+                post = t.full((max(ns, 1), self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
             _lib.check(self.L.gfx_correct_singles(
                 self.schedule.handle, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
-                self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.result.data_ptr(),
+                self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.snapshot.data_ptr(),
                 post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
             if keep_posteriors:
-                res = self.result[:max(ns, 1) * self.s].view(-1, self.s).cpu().numpy().copy()
-                posts["singles"] = (post.cpu().numpy(), res)
+                ph = post.cpu().numpy()
+                posts["singles"] = (ph, ph[:, :, 0] != POST_SENTINEL)
         return posts
 
     def unpack_device(self, out_codes_dev):

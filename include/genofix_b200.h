@@ -132,8 +132,11 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
  *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
  *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
  *   packed_orig  the matrix as given (defines E[g==9] = 1, :603); packed_live is updated in place
- *   result_dev   scratch, >= 2 * max_pairs_in_generation * n_snps bytes (pairs) / n_singles * n_snps
- *   post_dev     optional (may be NULL): posteriors per job and SNP, 6 (pairs) or 3 (singles) doubles
+ *   snapshot_dev scratch of n_rows * wpr uint32: receives the generation-start snapshot every worker of
+ *                the reference reads (:687-689); neighbours are read from it, only the focal cell is live
+ *   post_dev     optional (may be NULL): posterior of every evaluated (job, side, SNP), 3 doubles at
+ *                [((job * sides + side) * n_snps + snp) * 3]; cells that were not evaluated are left
+ *                untouched (prefill with a sentinel)
  *   tallies_dev  int32 [2 * n_rows]: [0..n) corrections applied (n_errors), [n..2n) excluded by the
  *                rank gate (excludedNotBest); accumulated, not zeroed here
  * ------------------------------------------------------------------------------------------- */
@@ -148,13 +151,13 @@ typedef struct {
 int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* packed_live_dev,
                       const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
                       const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
-                      const gfx_correct_params* params, uint8_t* result_dev, double* post_dev,
+                      const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
                       int32_t* tallies_dev, void* stream);
 
 int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
                         const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
                         const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
-                        const gfx_correct_params* params, uint8_t* result_dev, double* post_dev,
+                        const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
                         int32_t* tallies_dev, void* stream);
 
 /* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); returns and clears it.

@@ -111,17 +111,15 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
   int8_t open[GFX_WMAX_BIG];
   int w = 0, size = 1;
   uint64_t folded = 0;
+  double fv[GFX_MAXN * 3];  // belief vectors of folded nodes (only touched entries are used)
   tab[0] = 1.0;
   for (uint64_t m = need; m;) {
     const int v = gfx_lowbit(m);
     m &= m - 1;
     const int a1 = b.p1[v], a2 = b.p2[v];
     const bool v_obs = (obs >> v) & 1;
-    if (a1 < 0) {
-      if (v_obs) continue;                       // prior of an observed founder: scalar, dropped
-      if (v != q && nkids[v] == 1) { folded |= 1ull << v; continue; }
-    }
-    // where do the parents' states come from: evidence, a digit of the table index, or a folded prior
+    if (a1 < 0 && v_obs) continue;               // prior of an observed founder: scalar, dropped
+    // where do the parents' states come from: evidence, a folded belief vector, or a table digit
     int s_pos = -1, d_pos = -1, s_val = 0, d_val = 0, s_str = 1, d_str = 1;
     bool s_fold = false, d_fold = false;
     if (a1 >= 0) {
@@ -149,13 +147,20 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
             for (int sv = sl; sv <= sh; ++sv)
               for (int dv = dl; dv <= dh; ++dv) {
                 double t = gfx_mendel(x, sv, dv);
-                if (s_fold) t *= gfx_prior(sv);
-                if (d_fold) t *= gfx_prior(dv);
+                if (s_fold) t *= fv[a1 * 3 + sv];
+                if (d_fold) t *= fv[a2 * 3 + dv];
                 f += t;
               }
           }
           g[(x * 3 + a) * 3 + c] = f;
         }
+    // an unobserved node with a single remaining child whose own factor involves no table digit is
+    // carried as a belief vector (plain peeling) instead of opening a digit
+    if (!v_obs && v != q && nkids[v] == 1 && s_pos < 0 && d_pos < 0) {
+      fv[v * 3 + 0] = g[0]; fv[v * 3 + 1] = g[9]; fv[v * 3 + 2] = g[18];
+      folded |= 1ull << v;
+      continue;
+    }
     if (!v_obs && w == wmax) { out[0] = out[1] = out[2] = nan(""); return 1; }
     for (int x = x_hi; x >= x_lo; --x) {
       for (int i = 0; i < size; ++i) {

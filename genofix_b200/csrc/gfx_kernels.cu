@@ -765,106 +765,128 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
   return gfx_kids_term(nk, kc, pc, kv, out);
 }
 
+#define GFX_CORRECT_CHUNK 1024
 __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int64_t groups = (a.n_snps + 31) >> 5;
-  const int64_t tasks = (int64_t)a.n_focal * groups;
+  __shared__ int s_list[GFX_CORRECT_CHUNK];
+  __shared__ int s_cnt;
+  const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
+  const int64_t tasks = (int64_t)a.n_focal * chunks;
   double tab[GFX_TAB];
   uint8_t code[GFX_MAXN];
-  for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < tasks; task += (int64_t)gridDim.x * wpb) {
-    const int f = (int)(task / groups);
-    const int64_t j = (task - (int64_t)f * groups) * 32 + lane;
-    if (j >= a.n_snps) continue;
+  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int f = (int)(task / chunks);
+    const int64_t j0 = (task - (int64_t)f * chunks) * GFX_CORRECT_CHUNK;
+    const int64_t j1 = min(a.n_snps, j0 + (int64_t)GFX_CORRECT_CHUNK);
     const int row = a.focal_row[f];
-    const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
-    int cur = obs0;                                          // live state, updated job after job
-    const double Ef = cell_E(a.c, row, j);
-    bool gate_done = false, gate = false, kids_done = false, has_kids = false;
-    double kids[3] = {0, 0, 0};
-    int applied = 0, excluded = 0;
-    for (int e = a.focal_off[f]; e < a.focal_off[f + 1]; ++e) {
-      const int ent = a.entry[e];
-      const int job = a.nf == 2 ? (ent >> 1) : ent;
-      const int side = a.nf == 2 ? (ent & 1) : 0;
-      int mrow = -1, obs_m = 3;
-      double Em = 1.0;
-      bool sus = Ef >= a.p.test_p;                            // :181-185 / :342
-      if (a.nf == 2) {
-        mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
-        Em = cell_E(a.c, mrow, j);
-        sus = sus || (Em >= a.p.test_p);
-      }
-      if (!sus) continue;
-      double pmax;                                            // :220-228 / :374-376
-      if (a.nf == 2) {
-        obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
-        const double Es = side == 0 ? Ef : Em, Ed = side == 0 ? Em : Ef;
-        if (obs0 != 3 && obs_m != 3) pmax = Ed > Es ? Ed : Es;
-        else if (obs0 == 3 && obs_m == 3) pmax = 1.0;
-        else pmax = obs0 != 3 ? Ef : Em;
-      } else {
-        pmax = obs0 != 3 ? Ef : 1.0;
-      }
-      const int bid = a.job_bl[job];
-      double anc[3] = {0, 0, 0};
-      if (bid >= 0) {
-        const int off = a.bl.off[bid];
-        LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
-                       pmax - a.p.suspect_t, true};
-        const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
-        const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
-        double tot_me = 1.0, tot_ot = 1.0;
-        int bad = query_lazy(LB, a.bl, qme, qot, code, tab, anc, &tot_me);
-        if (qot >= 0) {
-          // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0
-          double tmp[3];
-          bad |= query_lazy(LB, a.bl, qot, qme, code, tab, tmp, &tot_ot);
-          if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
+    const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342)
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+      bool sus = cell_E(a.c, row, j) >= a.p.test_p;
+      if (a.nf == 2)
+        for (int e = e0; e < e1 && !sus; ++e) {
+          const int ent = a.entry[e];
+          const int mrow = (ent & 1) == 0 ? a.job_row1[ent >> 1] : a.job_row0[ent >> 1];
+          sus = cell_E(a.c, mrow, j) >= a.p.test_p;
         }
-        if (bad) atomicExch(a.status, 1);
-      }
-      if (!kids_done) {
-        const int k0 = a.child_off[row];
-        has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, a.child_off[row + 1] - k0, j, a.kv, kids);
-        kids_done = true;
-      }
-      if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
-      double p[3];
-      gfx_combine(bid >= 0, anc, has_kids, kids, p);
-      const uint32_t bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
-      if (a.post) {
-        double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
-        o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-      }
-      // decision on the LIVE state (:809-824 / :932-938)
-      const bool cond = cur == 3 || (!((bits >> cur) & 1u) && (bits & 8u));
-      if (!cond) continue;
-      if (!gate_done) {                                       // rank gate (:733-737,817 / :928-933)
-        double mr = 0.0;
-        for (int k = 0; k < 2; ++k) {
-          const int pr = a.prow[2 * row + k];
-          if (pr >= 0) { const double ev = cell_E(a.c, pr, j); if (ev > mr) mr = ev; }
+      if (sus) s_list[atomicAdd(&s_cnt, 1)] = (int)(j - j0);
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    // pass 2: the suspect cells, one thread each, jobs in canonical order
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+      const int64_t j = j0 + s_list[k];
+      const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
+      int cur = obs0;                                          // live state, updated job after job
+      const double Ef = cell_E(a.c, row, j);
+      bool gate_done = false, gate = false, kids_done = false, has_kids = false;
+      double kids[3] = {0, 0, 0};
+      int applied = 0, excluded = 0;
+      for (int e = e0; e < e1; ++e) {
+        const int ent = a.entry[e];
+        const int job = a.nf == 2 ? (ent >> 1) : ent;
+        const int side = a.nf == 2 ? (ent & 1) : 0;
+        int mrow = -1, obs_m = 3;
+        double Em = 1.0;
+        bool sus = Ef >= a.p.test_p;
+        if (a.nf == 2) {
+          mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+          Em = cell_E(a.c, mrow, j);
+          sus = sus || (Em >= a.p.test_p);
         }
-        gate = Ef * a.p.err_thresh >= mr;
-        gate_done = true;
+        if (!sus) continue;
+        double pmax;                                            // :220-228 / :374-376
+        if (a.nf == 2) {
+          obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
+          const double Es = side == 0 ? Ef : Em, Ed = side == 0 ? Em : Ef;
+          if (obs0 != 3 && obs_m != 3) pmax = Ed > Es ? Ed : Es;
+          else if (obs0 == 3 && obs_m == 3) pmax = 1.0;
+          else pmax = obs0 != 3 ? Ef : Em;
+        } else {
+          pmax = obs0 != 3 ? Ef : 1.0;
+        }
+        const int bid = a.job_bl[job];
+        double anc[3] = {0, 0, 0};
+        if (bid >= 0) {
+          const int off = a.bl.off[bid];
+          LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
+                         pmax - a.p.suspect_t, true};
+          const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
+          const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
+          double tot_me = 1.0, tot_ot = 1.0;
+          int bad = query_lazy(LB, a.bl, qme, qot, code, tab, anc, &tot_me);
+          if (qot >= 0) {
+            // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0
+            double tmp[3];
+            bad |= query_lazy(LB, a.bl, qot, qme, code, tab, tmp, &tot_ot);
+            if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
+          }
+          if (bad) atomicExch(a.status, 1);
+        }
+        if (!kids_done) {
+          const int k0 = a.child_off[row];
+          has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, a.child_off[row + 1] - k0, j, a.kv, kids);
+          kids_done = true;
+        }
+        if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
+        double p[3];
+        gfx_combine(bid >= 0, anc, has_kids, kids, p);
+        const uint32_t bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
+        if (a.post) {
+          double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
+          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        }
+        // decision on the LIVE state (:809-824 / :932-938)
+        const bool cond = cur == 3 || (!((bits >> cur) & 1u) && (bits & 8u));
+        if (!cond) continue;
+        if (!gate_done) {                                       // rank gate (:733-737,817 / :928-933)
+          double mr = 0.0;
+          for (int q = 0; q < 2; ++q) {
+            const int pr = a.prow[2 * row + q];
+            if (pr >= 0) { const double ev = cell_E(a.c, pr, j); if (ev > mr) mr = ev; }
+          }
+          gate = Ef * a.p.err_thresh >= mr;
+          gate_done = true;
+        }
+        if (gate) {
+          const uint32_t set = bits & 7u;
+          cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
+          ++applied;
+        } else {
+          ++excluded;
+        }
       }
-      if (gate) {
-        const uint32_t set = bits & 7u;
-        cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
-        ++applied;
-      } else {
-        ++excluded;
+      if (cur != obs0) {
+        uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
+        const int sh = 2 * (int)(j & 15);
+        atomicAnd(wp, ~(3u << sh));
+        atomicOr(wp, (uint32_t)cur << sh);
       }
+      if (applied) atomicAdd(a.tallies + row, applied);
+      if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
     }
-    if (cur != obs0) {
-      uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
-      const int sh = 2 * (int)(j & 15);
-      atomicAnd(wp, ~(3u << sh));
-      atomicOr(wp, (uint32_t)cur << sh);
-    }
-    if (applied) atomicAdd(a.tallies + row, applied);
-    if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
+    __syncthreads();
   }
 }
 
@@ -885,8 +907,8 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.bl_kid = s->bl_kid;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
-  const int64_t tasks = (int64_t)n_focal * ((n_snps + 31) / 32);
-  int64_t blocks = (tasks + 3) / 4;
+  const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
+  int64_t blocks = tasks;
   const int64_t cap = (int64_t)s->num_sms * 16;
   if (blocks > cap) blocks = cap;
   k_correct<<<(int)blocks, 128, 0, stream>>>(a);

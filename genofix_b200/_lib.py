@@ -18,8 +18,8 @@ GFX_E_NOMEM = -5
 EXPORTS = [
     "gfx_last_error", "gfx_version", "gfx_launch_count", "gfx_schedule_create", "gfx_schedule_create_host",
     "gfx_schedule_destroy", "gfx_schedule_info", "gfx_schedule_copy", "gfx_pack2", "gfx_unpack2",
-    "gfx_mendel_rank", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_correct_pairs", "gfx_correct_singles",
-    "gfx_check_device_status", "gfx_trio_scan", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
+    "gfx_mendel_rank", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
+    "gfx_check_device_status", "gfx_debug_counters", "gfx_trio_scan", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
     "gfx_kids_term_host",
 ]
 
@@ -33,12 +33,13 @@ class PedigreeDesc(C.Structure):
 class ScheduleInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "n_rows", "n_generations", "n_pairs", "n_pair_jobs", "n_singles", "n_loopy", "n_blankets",
-        "max_blanket_nodes", "max_width", "max_pairs_in_generation", "n_trios", "reserved")]
+        "max_blanket_nodes", "max_width", "max_pairs_in_generation", "n_trios", "n_lone")]
 
 
 class CorrectParams(C.Structure):
     _fields_ = [("test_p", C.c_double), ("suspect_t", C.c_double), ("tiethreshold", C.c_double),
-                ("threshold", C.c_double), ("err_thresh", C.c_double)]
+                ("threshold", C.c_double), ("err_thresh", C.c_double), ("cutraw_dev", C.c_void_p),
+                ("tp_raw", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class GfxError(RuntimeError):
@@ -74,9 +75,11 @@ def lib():
     L.gfx_mendel_rank.argtypes = [vp, vp, i64, i64, vp, i64, vp]
     L.gfx_rank_hist.argtypes = [vp, i64, vp, i64, i64, i64, vp, vp]
     L.gfx_rank_rowsum.argtypes = [vp, i64, vp, i64, i64, i64, vp, C.c_double, vp, vp]
-    L.gfx_correct_pairs.argtypes = [vp, i32, vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
-    L.gfx_correct_singles.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
+    L.gfx_correct_pairs.argtypes = [vp, i32, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
+    L.gfx_correct_singles.argtypes = [vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
+    L.gfx_build_cut_table.argtypes = [vp, C.c_double, C.c_double, vp, C.POINTER(C.c_uint32)]
     L.gfx_check_device_status.argtypes = [vp, vp]
+    L.gfx_debug_counters.argtypes = [vp, C.c_int, vp]
     L.gfx_trio_scan.argtypes = [vp, vp, i64, i64, vp, vp, vp]
     L.gfx_founders.argtypes = [C.POINTER(PedigreeDesc), vp, vp, C.POINTER(i32)]
     L.gfx_window_counts.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, i32, i32, vp, vp]

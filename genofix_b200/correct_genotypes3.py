@@ -154,7 +154,11 @@ class CorrectGenotypes(object):
         info = eng.schedule.info
         out = {}
         live = eng.packed_orig.clone()
-        pp = _lib.CorrectParams(eng.test_p, 0.2, float(tiethreshold), 0.0, 1.0)
+        tp_raw = C.c_uint32(0)
+        _lib.check(eng.L.gfx_build_cut_table(eng.host_elut.data_ptr(), float(eng.test_p), 0.2, eng.host_cutraw.data_ptr(),
+                                             C.byref(tp_raw)))
+        eng.cutraw.copy_(eng.host_cutraw)
+        pp = _lib.CorrectParams(eng.test_p, 0.2, float(tiethreshold), 0.0, 1.0, eng.cutraw.data_ptr(), int(tp_raw.value), 0)
         tall = t.zeros(2 * eng.n, dtype=t.int32, device=eng.codes.device)
         if kind == "pair":
             gen_off = eng.schedule.array(1)
@@ -166,7 +170,7 @@ class CorrectGenotypes(object):
                     continue
                 post = t.full((nj * 2, eng.s, 3), -1.0, dtype=t.float64, device=eng.codes.device)
                 scratch = live.clone()  # apply happens on a scratch copy: every generation sees the bound snapshot
-                _lib.check(eng.L.gfx_correct_pairs(eng.schedule.handle, g, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
+                _lib.check(eng.L.gfx_correct_pairs(eng.schedule.handle, g, scratch.data_ptr(), eng.s,
                                                    eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
                                                    eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()
@@ -178,7 +182,7 @@ class CorrectGenotypes(object):
             if ns:
                 post = t.full((ns, eng.s, 3), -1.0, dtype=t.float64, device=eng.codes.device)
                 scratch = live.clone()
-                _lib.check(eng.L.gfx_correct_singles(eng.schedule.handle, scratch.data_ptr(), orig_for_E.data_ptr(), eng.s,
+                _lib.check(eng.L.gfx_correct_singles(eng.schedule.handle, scratch.data_ptr(), eng.s,
                                                      eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
                                                      eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()

@@ -58,14 +58,17 @@ struct gfx_schedule {
   int32_t *bl_off = nullptr, *bl_row = nullptr;
   int8_t *bl_p1 = nullptr, *bl_p2 = nullptr, *bl_last = nullptr, *bl_q0 = nullptr, *bl_q1 = nullptr;
   uint64_t* bl_kid = nullptr;
+  uint8_t* bl_tree = nullptr;
   int32_t *job_row0 = nullptr, *job_row1 = nullptr, *job_bl = nullptr;        // pair jobs, all generations
   int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr;
   int32_t *single_row = nullptr, *single_bl = nullptr, *single_off = nullptr, *single_entry = nullptr;
   int32_t *loopy_rows = nullptr, *trio_row = nullptr;
   int n_loopy_rows = 0;
+  int debug = 0;
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
   double* kv = nullptr;        // 108 doubles, children-heuristic element table
   int* status = nullptr;
+  unsigned long long* counters = nullptr;  // 16 diagnostic counters (gfx_debug_counters)
   double* big_pool = nullptr;  // GFX_BIG_SLOTS tables of GFX_TAB_BIG doubles for rare wide blankets
   int* big_flags = nullptr;
 };
@@ -109,7 +112,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid};
+                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -148,7 +151,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(anc6, h.anc6); UP(rank_blanket, h.rank_blanket); UP(prow, h.prow); UP(rank_flags, h.rank_flags);
   UP(child_off, h.child_off); UP(child_row, h.child_row); UP(child_other, h.child_other);
   UP(bl_off, h.bl.off); UP(bl_row, h.bl.row); UP(bl_p1, h.bl.p1); UP(bl_p2, h.bl.p2); UP(bl_last, h.bl.last);
-  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1); UP(bl_kid, h.bl.kidmask);
+  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1); UP(bl_kid, h.bl.kidmask); UP(bl_tree, h.bl.tree);
   UP(job_row0, job_row0); UP(job_row1, job_row1); UP(job_bl, job_bl);
   UP(app_focal_row, h.app_focal_row); UP(app_focal_off, h.app_focal_off); UP(app_entry, h.app_entry);
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
@@ -158,6 +161,8 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * GFX_BIG_SLOTS);
   if (e == cudaSuccess) e = cudaMemset(s->big_flags, 0, sizeof(int) * GFX_BIG_SLOTS);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess) e = cudaMemset(s->counters, 0, sizeof(unsigned long long) * 16);
   if (e != cudaSuccess) {
     gfx_schedule_destroy(s);
     return fail(GFX_E_CUDA, std::string("schedule upload: ") + cudaGetErrorString(e));
@@ -205,6 +210,14 @@ extern "C" int gfx_schedule_copy(const gfx_schedule* s, int which, int32_t* out,
   if ((int64_t)src->size() > cap) return fail(GFX_E_INVALID, "output buffer too small");
   if (!src->empty()) memcpy(out, src->data(), src->size() * sizeof(int32_t));
   return (int)src->size();
+}
+
+extern "C" int gfx_debug_counters(gfx_schedule* s, int enable, uint64_t* out16_host) {
+  if (!s || s->device < 0) return fail(GFX_E_INVALID, "bad schedule");
+  if (out16_host) GFX_CUDA(cudaMemcpy(out16_host, s->counters, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost));
+  GFX_CUDA(cudaMemset(s->counters, 0, sizeof(uint64_t) * 16));
+  s->debug = enable;
+  return GFX_OK;
 }
 
 extern "C" int gfx_check_device_status(const gfx_schedule* s, void* stream) {
@@ -436,21 +449,23 @@ __global__ void __launch_bounds__(256) k_mendel_rank(RankArgs a) {
 // generic (loopy blanket) rank, pair/single inference, apply
 // ------------------------------------------------------------------------------------------------
 struct CellCtx {
-  const uint32_t* live;   // snapshot being read
-  const uint32_t* orig;   // original matrix (defines E = 1 for missing)
+  const uint32_t* live;   // packed matrix being read (the generation-start snapshot in the correct kernels)
   int64_t wpr;
-  const uint16_t* raw;
+  const uint16_t* raw;    // float16 scores; 0xFFFF marks a cell that was missing in the input (E = 1, :603)
   int64_t ld_raw;
-  const double* elut;
+  const double* elut;     // E per raw pattern (only the rank gate needs the values themselves)
+  const uint16_t* cutraw; // per pmax pattern (65536 = "E is 1"): first raw pattern whose E > pmax - suspect_t
+  uint32_t tp_raw;        // first raw pattern whose E >= test_p
 };
 
 __device__ __forceinline__ int cell_code(const uint32_t* p, int64_t wpr, int row, int64_t j) {
   return (int)((__ldg(p + (int64_t)row * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u);
 }
-__device__ __forceinline__ double cell_E(const CellCtx& c, int row, int64_t j) {
-  if (cell_code(c.orig, c.wpr, row, j) == 3) return 1.0;  // correct_genotypes3.py:603
-  return __ldg(c.elut + c.raw[(int64_t)row * c.ld_raw + j]);
+// raw pattern of a cell, 0xFFFF if it was missing in the input; patterns of non-negative halves order like values
+__device__ __forceinline__ uint32_t cell_rx(const CellCtx& c, int row, int64_t j) {
+  return __ldg(c.raw + (int64_t)row * c.ld_raw + j);
 }
+__device__ __forceinline__ double rx_E(const CellCtx& c, uint32_t rx) { return rx == 0xFFFFu ? 1.0 : __ldg(c.elut + rx); }
 
 struct BlanketDev {
   const int32_t* off;
@@ -458,7 +473,11 @@ struct BlanketDev {
   const int8_t *p1, *p2, *last, *q0, *q1;
   double* big_pool;
   int* big_flags;
+  unsigned long long* counters;
 };
+// diagnostic counters: 0 queries, 1 answered from the two parents, 2 eliminations, 3 big-table reruns,
+// 4 nodes touched, 5 suspect cells, 6 job evaluations, 7 children visited
+#define GFX_COUNT(bl, k, v) do { if ((bl).counters) atomicAdd((bl).counters + (k), (unsigned long long)(v)); } while (0)
 
 // Evidence is gathered lazily, walking outwards from the query only through unobserved nodes: the
 // usual case (both parents observed and not suspect) touches two rows instead of the whole blanket.
@@ -470,20 +489,61 @@ struct LazyBlanket {
   const uint64_t* kid;
   int n;
   int64_t j;
-  double cut;
+  uint32_t cut;           // raw pattern from which a node is "suspect" and dropped from the evidence
   bool filter;            // false: plain evidence (rank), true: drop suspect nodes (correct)
-  __device__ int status(int t) const {
-    const int r = rows[t];
+  __device__ __forceinline__ int status(int t) const {
+    const int r = __ldg(rows + t);
     if (r < 0) return 3;
     const int cd = cell_code(c.live, c.wpr, r, j);
     if (cd == 3) return 3;
-    if (filter && cell_E(c, r, j) > cut) return 3;   // suspect node: not evidence (:230-238)
+    if (filter && cell_rx(c, r, j) >= cut) return 3;   // suspect node: not evidence (:230-238)
     return cd;
   }
 };
 
+// Plain peeling for tree-shaped ancestry: belief of node t from its ancestors, evidence fetched on the
+// way.  Returns false as soon as an unobserved node has more than one child inside the blanket (a loop
+// or evidence below it): the caller then runs the general elimination.  T(x|s,d) factorises over the
+// transmitted alleles, so the contraction needs the two "transmits 0" / "transmits 1" masses only.
+template <int D>
+__device__ __forceinline__ bool peel(const LazyBlanket& L, int t, int qother, double& b0, double& b1, double& b2) {
+  const int st = t == qother ? 3 : L.status(t);
+  if (st != 3) { b0 = st == 0 ? 1.0 : 0.0; b1 = st == 1 ? 1.0 : 0.0; b2 = st == 2 ? 1.0 : 0.0; return true; }
+  const int a1 = L.p1[t];
+  if (a1 < 0) { b0 = 0.25; b1 = 0.5; b2 = 0.25; return true; }
+  if constexpr (D == 0) {
+    return false;
+  } else {
+    if (__popcll(L.kid[t]) != 1) return false;
+    double s0, s1, s2, d0, d1, d2;
+    if (!peel<D - 1>(L, a1, qother, s0, s1, s2)) return false;
+    if (!peel<D - 1>(L, L.p2[t], qother, d0, d1, d2)) return false;
+    const double sa = s0 + 0.5 * s1, sb = 0.5 * s1 + s2, da = d0 + 0.5 * d1, db = 0.5 * d1 + d2;
+    b0 = sa * da; b2 = sb * db; b1 = sa * db + sb * da;
+    return true;
+  }
+}
+__device__ __noinline__ bool peel_query(const LazyBlanket& L, int q, int qother, double out[3]) {
+  if (L.kid[q] != 0 || L.p1[q] < 0) return false;
+  double s0, s1, s2, d0, d1, d2;
+  if (!peel<3>(L, L.p1[q], qother, s0, s1, s2)) return false;
+  if (!peel<3>(L, L.p2[q], qother, d0, d1, d2)) return false;
+  const double sa = s0 + 0.5 * s1, sb = 0.5 * s1 + s2, da = d0 + 0.5 * d1, db = 0.5 * d1 + d2;
+  out[0] = sa * da; out[2] = sb * db; out[1] = sa * db + sb * da;   // sums to exactly 1
+  return true;
+}
+
 // Marginal of q (qother: the second focal animal of a pair, forced unobserved, or -1).
 // *total = unnormalised P(evidence in the component).
+__device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, uint8_t* code,
+                                       double* tab, double out[3], double* total);
+// general query with its own scratch (kept out of line so the common path stays small)
+__device__ __noinline__ int query_general(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, double out[3],
+                                          double* total) {
+  double tab[GFX_TAB];
+  uint8_t code[GFX_MAXN];
+  return query_lazy(L, bl, q, qother, code, tab, out, total);
+}
 __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, uint8_t* code,
                                        double* tab, double out[3], double* total) {
   uint64_t known = 1ull << q, obs = 0, comp = 1ull << q, queue = 1ull << q, cand = 0;
@@ -512,7 +572,10 @@ __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& b
     queue |= add;
   }
   cand |= comp;
+  GFX_COUNT(bl, 0, 1);
+  GFX_COUNT(bl, 4, __popcll(known));
   if (comp == (1ull << q) && L.kid[q] == 0 && L.p1[q] >= 0) {
+    GFX_COUNT(bl, 1, 1);
     // both parents observed, nothing below: the Mendel column, already normalised
     const int sv = code[L.p1[q]], dv = code[L.p2[q]];
     out[0] = gfx_mendel(0, sv, dv); out[1] = gfx_mendel(1, sv, dv); out[2] = gfx_mendel(2, sv, dv);
@@ -521,7 +584,9 @@ __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& b
   }
   GfxBlanket b{L.n, L.p1, L.p2, nullptr};
   int bad = gfx_eliminate(b, q, code, obs, comp, cand, tab, out, GFX_WMAX);
+  GFX_COUNT(bl, 2, 1);
   if (bad) {
+    GFX_COUNT(bl, 3, 1);
     int slot = (int)((blockIdx.x * blockDim.x + threadIdx.x) % GFX_BIG_SLOTS);
     for (;;) {
       if (atomicCAS(bl.big_flags + slot, 0, 1) == 0) break;
@@ -569,8 +634,8 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
     if (obs != 3) {
       const int bid = a.rank_blanket[row];
       const int off = a.bl.off[bid];
-      CellCtx cc{a.packed, a.packed, a.wpr, nullptr, 0, nullptr};
-      LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0.0, false};
+      CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
+      LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
       double anc[3], tot;
       if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot)) atomicExch(a.status, 1);
       const uint16_t sc = gfx_anc_score(anc, obs);
@@ -610,7 +675,7 @@ extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, in
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
-                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags},
+                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr},
                       s->bl_kid, s->status};
     const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
     k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, (cudaStream_t)stream>>>(g);
@@ -620,7 +685,7 @@ extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, in
 }
 
 // ---- histogram of raw scores ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rank_hist(const uint16_t* __restrict__ raw, int64_t ld_raw,
+__global__ void __launch_bounds__(256) k_rank_hist(uint16_t* __restrict__ raw, int64_t ld_raw,
                                                    const uint32_t* __restrict__ packed, int64_t wpr, int64_t n,
                                                    int64_t n_snps, unsigned long long* __restrict__ hist) {
   extern __shared__ uint32_t s_hist[];  // patterns 0 .. 0x3FFF (values in [0, 2))
@@ -633,14 +698,14 @@ __global__ void __launch_bounds__(256) k_rank_hist(const uint16_t* __restrict__ 
     const int64_t r = i / nwords, w = i - r * nwords;
     const uint32_t pw = __ldg(packed + r * wpr + w);
     const uint4* src = reinterpret_cast<const uint4*>(raw + r * ld_raw + w * 16);
-    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    const uint4 v0 = src[0], v1 = src[1];
     const uint32_t q[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       if (w * 16 + k >= n_snps) break;
       const uint32_t c = (pw >> (2 * k)) & 3u;
       const uint32_t h = (q[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-      if (c == 3u) ++missing;
+      if (c == 3u) { ++missing; raw[r * ld_raw + w * 16 + k] = 0xFFFFu; }  // E = 1 by definition (:603)
       else if (h == 0u) ++zeros;
       else if (h < 0x4000u) atomicAdd(&s_hist[h], 1u);
       else atomicAdd(&hist[h], 1ull);
@@ -660,7 +725,7 @@ __global__ void __launch_bounds__(256) k_rank_hist(const uint16_t* __restrict__ 
     if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
 }
 
-extern "C" int gfx_rank_hist(const uint16_t* raw, int64_t ld_raw, const uint32_t* packed, int64_t wpr, int64_t n,
+extern "C" int gfx_rank_hist(uint16_t* raw, int64_t ld_raw, const uint32_t* packed, int64_t wpr, int64_t n,
                              int64_t n_snps, uint64_t* hist, void* stream) {
   if (!raw || !packed || !hist || n <= 0 || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_rank_hist: bad argument");
   GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), (cudaStream_t)stream));
@@ -726,6 +791,7 @@ struct FocalArgs {
   const int32_t* job_bl;
   BlanketDev bl;
   const uint64_t* bl_kid;
+  const uint8_t* bl_tree;
   const int32_t* child_off;
   const int32_t* child_row;
   const int32_t* child_other;
@@ -737,6 +803,42 @@ struct FocalArgs {
   int n_rows;
   int* status;
 };
+
+// Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
+// numpy's 8-accumulator block sum run straight from them (one leaf of the pairwise scheme).
+#define GFX_KIDS_FAST 42
+struct NibStream {
+  unsigned long long pk0, pk1, pk2;
+  int a, cur, ninc;
+  const double* kv;
+  __device__ __forceinline__ void operator()(double v[3]) {
+    if (cur == ninc) { cur = 0; ++a; }
+    const unsigned long long w = cur < 16 ? pk0 : (cur < 32 ? pk1 : pk2);
+    const int cls = (int)((w >> ((cur & 15) * 4)) & 15ull);
+    const double* e = kv + cls * 9 + 3 * a;
+    v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
+    ++cur;
+  }
+};
+__device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
+                                               int64_t j, const double* kv, double out[3]) {
+  unsigned long long pk0 = 0, pk1 = 0, pk2 = 0;
+  int ninc = 0;
+  for (int i = 0; i < nk; ++i) {
+    const int k = cell_code(c.live, c.wpr, __ldg(child_row + i), j);
+    if (k > 2) continue;
+    const int o = __ldg(child_other + i);
+    const int pc = o >= 0 ? cell_code(c.live, c.wpr, o, j) : 3;
+    const unsigned long long v = (unsigned long long)(k * 4 + pc) << ((ninc & 15) * 4);
+    if (ninc < 16) pk0 |= v; else if (ninc < 32) pk1 |= v; else pk2 |= v;
+    ++ninc;
+  }
+  if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return; }
+  NibStream next{pk0, pk1, pk2, 0, 0, ninc, kv};
+  double tot[3];
+  gfx_pw_leaf(next, 3 * ninc, tot);
+  gfx_kids_finish(tot, ninc, out);
+}
 
 #define GFX_KIDS_LOCAL 160
 // children term of `row` at SNP j from the snapshot (bayesnet/model.py:65-89); false = no genotyped child
@@ -769,10 +871,11 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
   __shared__ int s_list[GFX_CORRECT_CHUNK];
   __shared__ int s_cnt;
+  __shared__ double s_kv[108];
+  for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
   const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
   const int64_t tasks = (int64_t)a.n_focal * chunks;
-  double tab[GFX_TAB];
-  uint8_t code[GFX_MAXN];
+  const uint32_t tp = a.c.tp_raw;
   for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
     const int f = (int)(task / chunks);
     const int64_t j0 = (task - (int64_t)f * chunks) * GFX_CORRECT_CHUNK;
@@ -781,14 +884,15 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
     const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342)
+    // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342); E >= test_p is a
+    // comparison of raw patterns because E is monotone in the score
     for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-      bool sus = cell_E(a.c, row, j) >= a.p.test_p;
+      bool sus = cell_rx(a.c, row, j) >= tp;
       if (a.nf == 2)
         for (int e = e0; e < e1 && !sus; ++e) {
           const int ent = a.entry[e];
           const int mrow = (ent & 1) == 0 ? a.job_row1[ent >> 1] : a.job_row0[ent >> 1];
-          sus = cell_E(a.c, mrow, j) >= a.p.test_p;
+          sus = cell_rx(a.c, mrow, j) >= tp;
         }
       if (sus) s_list[atomicAdd(&s_cnt, 1)] = (int)(j - j0);
     }
@@ -799,55 +903,62 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
       const int64_t j = j0 + s_list[k];
       const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
       int cur = obs0;                                          // live state, updated job after job
-      const double Ef = cell_E(a.c, row, j);
+      const uint32_t rxf = cell_rx(a.c, row, j);
+      const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
       bool gate_done = false, gate = false, kids_done = false, has_kids = false;
       double kids[3] = {0, 0, 0};
       int applied = 0, excluded = 0;
+      GFX_COUNT(a.bl, 5, 1);
       for (int e = e0; e < e1; ++e) {
         const int ent = a.entry[e];
         const int job = a.nf == 2 ? (ent >> 1) : ent;
         const int side = a.nf == 2 ? (ent & 1) : 0;
-        int mrow = -1, obs_m = 3;
-        double Em = 1.0;
-        bool sus = Ef >= a.p.test_p;
+        bool sus = rxf >= tp;
+        uint32_t pidx;                                          // pattern of pmax (:220-228 / :374-376)
         if (a.nf == 2) {
-          mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
-          Em = cell_E(a.c, mrow, j);
-          sus = sus || (Em >= a.p.test_p);
-        }
-        if (!sus) continue;
-        double pmax;                                            // :220-228 / :374-376
-        if (a.nf == 2) {
-          obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
-          const double Es = side == 0 ? Ef : Em, Ed = side == 0 ? Em : Ef;
-          if (obs0 != 3 && obs_m != 3) pmax = Ed > Es ? Ed : Es;
-          else if (obs0 == 3 && obs_m == 3) pmax = 1.0;
-          else pmax = obs0 != 3 ? Ef : Em;
+          const int mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+          const uint32_t rxm = cell_rx(a.c, mrow, j);
+          sus = sus || (rxm >= tp);
+          if (!sus) continue;
+          const uint32_t idxm = rxm == 0xFFFFu ? 65536u : rxm;
+          const int obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
+          if (obs0 != 3 && obs_m != 3) pidx = idxf > idxm ? idxf : idxm;
+          else if (obs0 == 3 && obs_m == 3) pidx = 65536u;
+          else pidx = obs0 != 3 ? idxf : idxm;
         } else {
-          pmax = obs0 != 3 ? Ef : 1.0;
+          if (!sus) continue;
+          pidx = obs0 != 3 ? idxf : 65536u;
         }
+        GFX_COUNT(a.bl, 6, 1);
         const int bid = a.job_bl[job];
         double anc[3] = {0, 0, 0};
         if (bid >= 0) {
           const int off = a.bl.off[bid];
           LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
-                         pmax - a.p.suspect_t, true};
+                         (uint32_t)__ldg(a.c.cutraw + pidx), true};
           const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
           const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
+          const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
+          bool done = peel_query(LB, qme, qot, anc);
           double tot_me = 1.0, tot_ot = 1.0;
-          int bad = query_lazy(LB, a.bl, qme, qot, code, tab, anc, &tot_me);
-          if (qot >= 0) {
-            // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0
+          int bad = 0;
+          if (done) { GFX_COUNT(a.bl, 1, 1); }
+          else bad = query_general(LB, a.bl, qme, qot, anc, &tot_me);
+          if (qot >= 0 && !((tree >> (side ^ 1)) & 1u)) {
+            // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
+            // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
             double tmp[3];
-            bad |= query_lazy(LB, a.bl, qot, qme, code, tab, tmp, &tot_ot);
-            if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
+            if (!peel_query(LB, qot, qme, tmp)) bad |= query_general(LB, a.bl, qot, qme, tmp, &tot_ot);
           }
+          if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
           if (bad) atomicExch(a.status, 1);
         }
         if (!kids_done) {
-          const int k0 = a.child_off[row];
-          has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, a.child_off[row + 1] - k0, j, a.kv, kids);
+          const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+          if (nk > 0 && nk <= GFX_KIDS_FAST) { kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, kids); has_kids = true; }
+          else has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
           kids_done = true;
+          GFX_COUNT(a.bl, 7, nk);
         }
         if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
         double p[3];
@@ -864,9 +975,9 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
           double mr = 0.0;
           for (int q = 0; q < 2; ++q) {
             const int pr = a.prow[2 * row + q];
-            if (pr >= 0) { const double ev = cell_E(a.c, pr, j); if (ev > mr) mr = ev; }
+            if (pr >= 0) { const double ev = rx_E(a.c, cell_rx(a.c, pr, j)); if (ev > mr) mr = ev; }
           }
-          gate = Ef * a.p.err_thresh >= mr;
+          gate = rx_E(a.c, rxf) * a.p.err_thresh >= mr;
           gate_done = true;
         }
         if (gate) {
@@ -892,19 +1003,20 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
 
 static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t* job_row0, const int32_t* job_row1,
                        const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
-                       const int32_t* entry, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
+                       const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
                        const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
                        uint32_t* snapshot, double* post, int32_t* tallies, cudaStream_t stream) {
   if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
   GFX_CUDA(cudaMemcpyAsync(snapshot, live, sizeof(uint32_t) * (size_t)s->h.n_rows * wpr, cudaMemcpyDeviceToDevice, stream));
   FocalArgs a;
-  a.c = CellCtx{snapshot, orig, wpr, raw, ld_raw, elut};
+  a.c = CellCtx{snapshot, wpr, raw, ld_raw, elut, p->cutraw_dev, p->tp_raw};
   a.live = live;
   a.n_snps = n_snps; a.nf = nf; a.n_focal = n_focal;
   a.focal_row = focal_row; a.focal_off = focal_off; a.entry = entry;
   a.job_row0 = job_row0; a.job_row1 = job_row1; a.job_bl = job_bl;
-  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags};
+  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr};
   a.bl_kid = s->bl_kid;
+  a.bl_tree = s->bl_tree;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
@@ -916,28 +1028,28 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   return GFX_OK;
 }
 
-extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* live, const uint32_t* orig,
+extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* live,
                                  int64_t n_snps, int64_t wpr, const uint16_t* raw, int64_t ld_raw, const double* elut,
                                  const gfx_correct_params* p, uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
-  if (!s || !live || !orig || !raw || !elut || !p || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (!s || !live || !raw || !elut || !p || !p->cutraw_dev || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   if (generation < 0 || generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
   const int j0 = s->h.gen_off[generation], nj = s->h.gen_off[generation + 1] - j0;
   const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
   return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
-                     s->app_focal_off + f0, s->app_entry, live, orig, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post,
+                     s->app_focal_off + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post,
                      tallies, (cudaStream_t)stream);
 }
 
-extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, const uint32_t* orig, int64_t n_snps, int64_t wpr,
+extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_t n_snps, int64_t wpr,
                                    const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
                                    uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
-  if (!s || !live || !orig || !raw || !elut || !p || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (!s || !live || !raw || !elut || !p || !p->cutraw_dev || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   const int n = (int)s->h.single_row.size();
   return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
-                     live, orig, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post, tallies, (cudaStream_t)stream);
+                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post, tallies, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1040,6 +1152,26 @@ extern "C" int gfx_window_counts(const uint32_t* packed, const uint32_t* mask, i
 // ------------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------------
+extern "C" int gfx_build_cut_table(const double* elut, double test_p, double suspect_t, uint16_t* cutraw, uint32_t* tp_raw) {
+  if (!elut || !cutraw || !tp_raw) return fail(GFX_E_INVALID, "null argument");
+  // finite non-negative half patterns 0 .. 0x7C00 order like their values and E is monotone in the score
+  const uint32_t top = 0x7C00u;  // +inf: never reached by a score, used as "no pattern qualifies"
+  uint32_t t = top + 1;
+  for (uint32_t p = 0; p <= top; ++p)
+    if (elut[p] >= test_p) { t = p; break; }
+  *tp_raw = t;
+  // cutraw[r] = first pattern whose E > E(r) - suspect_t; two-pointer sweep (both sides monotone)
+  uint32_t q = 0;
+  for (uint32_t r = 0; r <= 65536u; ++r) {
+    if (r > top && r < 65536u) { cutraw[r] = (uint16_t)(top + 1); continue; }  // NaN / negative patterns: unused
+    const double cut = (r == 65536u ? 1.0 : elut[r]) - suspect_t;
+    if (r == 65536u) q = 0;
+    while (q <= top && !(elut[q] > cut)) ++q;
+    cutraw[r] = (uint16_t)q;
+  }
+  return GFX_OK;
+}
+
 extern "C" int gfx_founders(const gfx_pedigree_desc* ped, const uint8_t* restrict_host, int32_t* out_idx, int32_t* out_n) {
   if (!ped || !out_idx || !out_n) return fail(GFX_E_INVALID, "null argument");
   int n = 0;

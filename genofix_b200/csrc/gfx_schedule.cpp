@@ -146,6 +146,23 @@ struct Builder {
     bs.q0.push_back((int8_t)local[focal[0]]);
     bs.q1.push_back(nf > 1 ? (int8_t)local[focal[1]] : (int8_t)-1);
     bs.off.push_back((int32_t)(base + n));
+    {
+      uint8_t tr = 0;
+      for (int fi = 0; fi < nf; ++fi) {
+        const int qf = local[focal[fi]];
+        bool ok = bs.kidmask[base + qf] == 0 && bs.p1[base + qf] >= 0;
+        std::vector<int> stk;
+        if (ok) { stk.push_back(bs.p1[base + qf]); stk.push_back(bs.p2[base + qf]); }
+        while (ok && !stk.empty()) {
+          const int u = stk.back();
+          stk.pop_back();
+          if (__builtin_popcountll(bs.kidmask[base + u]) != 1) { ok = false; break; }
+          if (bs.p1[base + u] >= 0) { stk.push_back(bs.p1[base + u]); stk.push_back(bs.p2[base + u]); }
+        }
+        if (ok) tr |= (uint8_t)(1u << fi);
+      }
+      bs.tree.push_back(tr);
+    }
     if (plain) {
       bool extra = false;
       for (int32_t k : last_level)
@@ -188,7 +205,7 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
   out.rank_flags.assign(nr, 0);
   out.rank_blanket.assign(nr, -1);
   out.prow.assign((size_t)nr * 2, -1);
-  int n_loopy = 0, n_trios = 0;
+  int n_loopy = 0, n_trios = 0, n_lone = 0;
   for (int r = 0; r < nr; ++r) {
     const int32_t a = ped_of_row[r];
     const int32_t s = ped->sire[a], d = ped->dam[a];
@@ -297,6 +314,9 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
   for (int r = 0; r < nr; ++r) {
     const int32_t a = ped_of_row[r];
     if (paired[a]) continue;
+    // an animal with neither a blanket nor genotyped children can never yield a result
+    // (correct_genotypes3.py:417-419 returns None for it): leave it out of the job list
+    if (out.rank_blanket[r] < 0 && out.child_off[r + 1] == out.child_off[r]) { ++n_lone; continue; }
     out.single_row.push_back(r);
     out.single_blanket.push_back(out.rank_blanket[r]);
   }
@@ -313,5 +333,6 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
   I.max_width = out.bl.max_width;
   I.max_pairs_in_generation = max_jobs;
   I.n_trios = n_trios;
+  I.n_lone = n_lone;
   return GFX_OK;
 }

@@ -18,6 +18,7 @@ struct GfxBlanketSet {
   std::vector<int8_t> p1, p2, last;
   std::vector<uint64_t> kidmask;  // per node: bit mask of its children inside the blanket
   std::vector<int8_t> q0, q1; // focal local indices (q1 = -1 for a single focal animal)
+  std::vector<uint8_t> tree;  // bit f: the ancestry of focal f is a plain tree (every ancestor has one child in the blanket)
   int max_nodes = 0;
   int max_width = 0;
   int count() const { return (int)off.size() - 1; }

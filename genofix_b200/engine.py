@@ -65,7 +65,7 @@ class Schedule(object):
         _lib.check(fn(C.byref(self.desc), C.byref(self.handle)))
         info = _lib.ScheduleInfo()
         _lib.check(L.gfx_schedule_info(self.handle, C.byref(info)))
-        self.info = {f: getattr(info, f) for f, _ in _lib.ScheduleInfo._fields_ if f != "reserved"}
+        self.info = {f: getattr(info, f) for f, _ in _lib.ScheduleInfo._fields_}
         self.n_rows = len(ids)
         self.back = int(back)
         self.ids = ids
@@ -211,6 +211,8 @@ class Engine(object):
         self.host_out = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
         self.host_hist = t.empty(65537, dtype=t.int64, pin_memory=True)
         self.host_elut = t.empty(65536, dtype=t.float64, pin_memory=True)
+        self.cutraw = t.empty(65537, dtype=t.int16, device=dev)
+        self.host_cutraw = t.empty(65537, dtype=t.int16, pin_memory=True)
         self._shape = s
 
     def _stream(self):
@@ -248,6 +250,11 @@ class Engine(object):
         elut, test_p, n_nan = rank_transform_table(self.host_hist.numpy().view(np.uint64), init_filter_p)
         self.host_elut.numpy()[:] = elut
         self.elut.copy_(self.host_elut, non_blocking=True)
+        tp_raw = C.c_uint32(0)
+        _lib.check(self.L.gfx_build_cut_table(self.host_elut.data_ptr(), float(test_p), SUSPECT_T,
+                                              self.host_cutraw.data_ptr(), C.byref(tp_raw)))
+        self.cutraw.copy_(self.host_cutraw, non_blocking=True)
+        self.tp_raw = int(tp_raw.value)
         self.test_p = float(test_p)
         self.n_nan = n_nan
         self.elut_host = elut
@@ -260,7 +267,8 @@ class Engine(object):
         posts = {"pairs": [], "singles": None}
         if not np.isnan(self.test_p):  # D16: NaN threshold => nothing is suspect
             info = self.schedule.info
-            pp = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_pair), float(err_thresh))
+            pp = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_pair), float(err_thresh),
+                                    self.cutraw.data_ptr(), self.tp_raw, 0)
             gen_off = self.schedule.array(1) if keep_posteriors else None
             for g in range(info["n_generations"]):
                 post = None
@@ -268,19 +276,20 @@ class Engine(object):
                     nj = int(gen_off[g + 1] - gen_off[g])
                     post = t.full((max(nj, 1) * 2, self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
                 _lib.check(self.L.gfx_correct_pairs(
-                    self.schedule.handle, g, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
+                    self.schedule.handle, g, self.packed_live.data_ptr(), self.s, self.wpr,
                     self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(),
                     post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
                 if keep_posteriors:
                     ph = post.cpu().numpy()
                     posts["pairs"].append((ph, ph[:, :, 0] != POST_SENTINEL))
-            ps = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_single), float(err_thresh))
+            ps = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_single), float(err_thresh),
+                                    self.cutraw.data_ptr(), self.tp_raw, 0)
             post = None
             ns = info["n_singles"]
             if keep_posteriors:
                 post = t.full((max(ns, 1), self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
             _lib.check(self.L.gfx_correct_singles(
-                self.schedule.handle, self.packed_live.data_ptr(), self.packed_orig.data_ptr(), self.s, self.wpr,
+                self.schedule.handle, self.packed_live.data_ptr(), self.s, self.wpr,
                 self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.snapshot.data_ptr(),
                 post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
             if keep_posteriors:
@@ -296,13 +305,16 @@ class Engine(object):
         _lib.check(self.L.gfx_check_device_status(self.schedule.handle, self._stream()))
 
     def raw_host(self):
-        """float16 [n, s] rank matrix (what mendelProbsSingle returns per animal)."""
-        return self.raw[:, :self.s].cpu().numpy().view(np.float16)
+        """float16 [n, s] rank matrix (what mendelProbsSingle returns per animal).  gfx_rank_hist marks
+        missing cells with 0xFFFF; their score is 1.0 (correct_genotypes3.py:102)."""
+        r = self.raw[:, :self.s].cpu().numpy().view(np.uint16).copy()
+        r[r == 0xFFFF] = 0x3C00
+        return r.view(np.float16)
 
     def E_host(self):
         """float64 [n, s] transformed ranks, missing cells of the input = 1 (correct_genotypes3.py:600-603)."""
         raw = self.raw[:, :self.s].cpu().numpy().view(np.uint16)
-        E = self.elut_host[raw]
+        E = self.elut_host[np.where(raw == 0xFFFF, 0x3C00, raw)]
         p = self.packed_orig.cpu().numpy().view(np.uint32)
         j = np.arange(self.s)
         codes = (p[:, j // 16] >> (2 * (j % 16)).astype(np.uint32)) & 3

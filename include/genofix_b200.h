@@ -87,7 +87,7 @@ typedef struct {
   int32_t max_width;       /* worst-case free-variable frontier over all blankets                */
   int32_t max_pairs_in_generation;
   int32_t n_trios;         /* genotyped animals with both parents genotyped                      */
-  int32_t reserved;
+  int32_t n_lone;          /* unpaired animals with neither ancestors nor genotyped children (never corrected) */
 } gfx_schedule_info_t;
 
 int gfx_schedule_info(const gfx_schedule* s, gfx_schedule_info_t* out);
@@ -116,8 +116,10 @@ int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n
 
 /* Histogram of the raw float16 bit patterns over non-missing cells (65536 x uint64) plus the
  * number of missing cells in hist_dev[65536]: everything the rank transform and both quantiles need
- * (correct_genotypes3.py:593-606,666-667).  hist_dev must hold 65537 uint64 and is zeroed here. */
-int gfx_rank_hist(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* packed_dev, int64_t wpr,
+ * (correct_genotypes3.py:593-606,666-667).  hist_dev must hold 65537 uint64 and is zeroed here.
+ * Side effect: the score of every missing cell (always 1.0, :102) is replaced by the marker 0xFFFF,
+ * which the correction kernels read as "E = 1" (:603). */
+int gfx_rank_hist(uint16_t* raw_dev, int64_t ld_raw, const uint32_t* packed_dev, int64_t wpr,
                   int64_t n, int64_t n_snps, uint64_t* hist_dev, void* stream);
 
 /* Per-animal sum over SNPs of E = elut[raw] (missing cells use missing_value):
@@ -131,7 +133,7 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
  * correctSingle + single apply (:330-430,851-944).
  *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
  *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
- *   packed_orig  the matrix as given (defines E[g==9] = 1, :603); packed_live is updated in place
+ *   raw_dev      scores after gfx_rank_hist (missing cells marked 0xFFFF); packed_live is updated in place
  *   snapshot_dev scratch of n_rows * wpr uint32: receives the generation-start snapshot every worker of
  *                the reference reads (:687-689); neighbours are read from it, only the focal cell is live
  *   post_dev     optional (may be NULL): posterior of every evaluated (job, side, SNP), 3 doubles at
@@ -146,19 +148,34 @@ typedef struct {
   double tiethreshold;
   double threshold;     /* threshold_pair or threshold_single */
   double err_thresh;
+  const uint16_t* cutraw_dev; /* 65537 entries from gfx_build_cut_table, on the device */
+  uint32_t tp_raw;            /* from gfx_build_cut_table */
+  uint32_t reserved;
 } gfx_correct_params;
 
+/* HOST helper: E is monotone in the float16 score, so both rank comparisons of correctPair/correctSingle
+ * become comparisons of raw bit patterns.  tp_raw = first pattern with E >= test_p (:181-185,342);
+ * cutraw[r] = first pattern whose E > E(r) - suspect_t (:230,378), r = 65536 standing for E = 1.
+ * elut_host: the 65536-entry table that is also uploaded as elut_dev. */
+int gfx_build_cut_table(const double* elut_host, double test_p, double suspect_t, uint16_t* cutraw_host,
+                        uint32_t* tp_raw);
+
 int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* packed_live_dev,
-                      const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
+                      int64_t n_snps, int64_t wpr,
                       const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
                       const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
                       int32_t* tallies_dev, void* stream);
 
 int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
-                        const uint32_t* packed_orig_dev, int64_t n_snps, int64_t wpr,
+                        int64_t n_snps, int64_t wpr,
                         const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
                         const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
                         int32_t* tallies_dev, void* stream);
+
+/* Diagnostics: reads and clears 16 device counters (queries, parent-only answers, eliminations, big-table
+ * reruns, nodes touched, suspect cells, job evaluations, children visited, ...) and switches counting
+ * on (enable = 1) or off.  Counting is off by default; it serialises on atomics. */
+int gfx_debug_counters(gfx_schedule* s, int enable, uint64_t* out16_host);
 
 /* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); returns and clears it.
  * Synchronises the stream. */

@@ -509,12 +509,12 @@ template <int D>
 __device__ __forceinline__ bool peel(const LazyBlanket& L, int t, int qother, double& b0, double& b1, double& b2) {
   const int st = t == qother ? 3 : L.status(t);
   if (st != 3) { b0 = st == 0 ? 1.0 : 0.0; b1 = st == 1 ? 1.0 : 0.0; b2 = st == 2 ? 1.0 : 0.0; return true; }
+  if (__popcll(L.kid[t]) != 1) return false;   // an unobserved node shared by two branches couples them
   const int a1 = L.p1[t];
   if (a1 < 0) { b0 = 0.25; b1 = 0.5; b2 = 0.25; return true; }
   if constexpr (D == 0) {
     return false;
   } else {
-    if (__popcll(L.kid[t]) != 1) return false;
     double s0, s1, s2, d0, d1, d2;
     if (!peel<D - 1>(L, a1, qother, s0, s1, s2)) return false;
     if (!peel<D - 1>(L, L.p2[t], qother, d0, d1, d2)) return false;
@@ -802,6 +802,8 @@ struct FocalArgs {
   int32_t* tallies;
   int n_rows;
   int* status;
+  uint32_t* deferred;     // 1 bit per (focal, SNP): cell needs the general kernel; dwords words per focal
+  int64_t dwords;
 };
 
 // Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
@@ -868,7 +870,124 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 }
 
 #define GFX_CORRECT_CHUNK 1024
-__global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
+
+// All jobs of one suspect (focal animal, SNP) cell, in canonical order.  GENERAL = false is the lean
+// instantiation: ancestor terms by plain peeling only; it returns false (nothing written) as soon as a
+// job needs the general elimination, and the cell is redone by the GENERAL = true instantiation.
+template <bool GENERAL>
+__device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s_kv, int row, int e0, int e1, int64_t j) {
+  const uint32_t tp = a.c.tp_raw;
+  const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
+  int cur = obs0;                                          // live state, updated job after job
+  const uint32_t rxf = cell_rx(a.c, row, j);
+  const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
+  bool gate_done = false, gate = false, kids_done = false, has_kids = false;
+  double kids[3] = {0, 0, 0};
+  int applied = 0, excluded = 0;
+  GFX_COUNT(a.bl, 5, 1);
+  for (int e = e0; e < e1; ++e) {
+    const int ent = a.entry[e];
+    const int job = a.nf == 2 ? (ent >> 1) : ent;
+    const int side = a.nf == 2 ? (ent & 1) : 0;
+    bool sus = rxf >= tp;
+    uint32_t pidx;                                          // pattern of pmax (:220-228 / :374-376)
+    if (a.nf == 2) {
+      const int mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+      const uint32_t rxm = cell_rx(a.c, mrow, j);
+      sus = sus || (rxm >= tp);
+      if (!sus) continue;
+      const uint32_t idxm = rxm == 0xFFFFu ? 65536u : rxm;
+      const int obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
+      if (obs0 != 3 && obs_m != 3) pidx = idxf > idxm ? idxf : idxm;
+      else if (obs0 == 3 && obs_m == 3) pidx = 65536u;
+      else pidx = obs0 != 3 ? idxf : idxm;
+    } else {
+      if (!sus) continue;
+      pidx = obs0 != 3 ? idxf : 65536u;
+    }
+    GFX_COUNT(a.bl, 6, 1);
+    const int bid = a.job_bl[job];
+    double anc[3] = {0, 0, 0};
+    if (bid >= 0) {
+      const int off = a.bl.off[bid];
+      LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
+                     (uint32_t)__ldg(a.c.cutraw + pidx), true};
+      const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
+      const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
+      const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
+      double tot_me = 1.0, tot_ot = 1.0;
+      if (!peel_query(LB, qme, qot, anc)) {
+        if constexpr (!GENERAL) return false;
+        else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
+      } else {
+        GFX_COUNT(a.bl, 1, 1);
+      }
+      if (qot >= 0 && !((tree >> (side ^ 1)) & 1u)) {
+        // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
+        // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
+        double tmp[3];
+        if (!peel_query(LB, qot, qme, tmp)) {
+          if constexpr (!GENERAL) return false;
+          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
+        }
+      }
+      if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
+    }
+    if (!kids_done) {
+      const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+      if (nk > 0 && nk <= GFX_KIDS_FAST) {
+        kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, kids);
+        has_kids = true;
+      } else if (nk > 0) {
+        if constexpr (!GENERAL) return false;
+        else has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
+      }
+      kids_done = true;
+      GFX_COUNT(a.bl, 7, nk);
+    }
+    if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
+    double p[3];
+    gfx_combine(bid >= 0, anc, has_kids, kids, p);
+    const uint32_t bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
+    if (a.post) {
+      double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
+      o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+    }
+    // decision on the LIVE state (:809-824 / :932-938)
+    const bool cond = cur == 3 || (!((bits >> cur) & 1u) && (bits & 8u));
+    if (!cond) continue;
+    if (!gate_done) {                                       // rank gate (:733-737,817 / :928-933)
+      double mr = 0.0;
+      for (int q = 0; q < 2; ++q) {
+        const int pr = a.prow[2 * row + q];
+        if (pr >= 0) { const double ev = rx_E(a.c, cell_rx(a.c, pr, j)); if (ev > mr) mr = ev; }
+      }
+      gate = rx_E(a.c, rxf) * a.p.err_thresh >= mr;
+      gate_done = true;
+    }
+    if (gate) {
+      const uint32_t set = bits & 7u;
+      cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
+      ++applied;
+    } else {
+      ++excluded;
+    }
+  }
+  if (cur != obs0) {
+    uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
+    const int sh = 2 * (int)(j & 15);
+    atomicAnd(wp, ~(3u << sh));
+    atomicOr(wp, (uint32_t)cur << sh);
+  }
+  if (applied) atomicAdd(a.tallies + row, applied);
+  if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
+  return true;
+}
+
+// Lean kernel: one block per (focal animal, 1024-SNP chunk); suspect SNPs are compacted first so that
+// every thread of pass 2 has a cell.  Cells that need the general path are flagged in `deferred`
+// (1 bit per (focal, SNP)) and left untouched.
+__global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
   __shared__ int s_list[GFX_CORRECT_CHUNK];
   __shared__ int s_cnt;
   __shared__ double s_kv[108];
@@ -883,6 +1002,7 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
     const int row = a.focal_row[f];
     const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
     if (threadIdx.x == 0) s_cnt = 0;
+    if (threadIdx.x < GFX_CORRECT_CHUNK / 32) a.deferred[(int64_t)f * a.dwords + (j0 >> 5) + threadIdx.x] = 0u;
     __syncthreads();
     // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342); E >= test_p is a
     // comparison of raw patterns because E is monotone in the score
@@ -898,104 +1018,42 @@ __global__ void __launch_bounds__(128) k_correct(FocalArgs a) {
     }
     __syncthreads();
     const int cnt = s_cnt;
-    // pass 2: the suspect cells, one thread each, jobs in canonical order
     for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
       const int64_t j = j0 + s_list[k];
-      const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
-      int cur = obs0;                                          // live state, updated job after job
-      const uint32_t rxf = cell_rx(a.c, row, j);
-      const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
-      bool gate_done = false, gate = false, kids_done = false, has_kids = false;
-      double kids[3] = {0, 0, 0};
-      int applied = 0, excluded = 0;
-      GFX_COUNT(a.bl, 5, 1);
-      for (int e = e0; e < e1; ++e) {
-        const int ent = a.entry[e];
-        const int job = a.nf == 2 ? (ent >> 1) : ent;
-        const int side = a.nf == 2 ? (ent & 1) : 0;
-        bool sus = rxf >= tp;
-        uint32_t pidx;                                          // pattern of pmax (:220-228 / :374-376)
-        if (a.nf == 2) {
-          const int mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
-          const uint32_t rxm = cell_rx(a.c, mrow, j);
-          sus = sus || (rxm >= tp);
-          if (!sus) continue;
-          const uint32_t idxm = rxm == 0xFFFFu ? 65536u : rxm;
-          const int obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
-          if (obs0 != 3 && obs_m != 3) pidx = idxf > idxm ? idxf : idxm;
-          else if (obs0 == 3 && obs_m == 3) pidx = 65536u;
-          else pidx = obs0 != 3 ? idxf : idxm;
-        } else {
-          if (!sus) continue;
-          pidx = obs0 != 3 ? idxf : 65536u;
-        }
-        GFX_COUNT(a.bl, 6, 1);
-        const int bid = a.job_bl[job];
-        double anc[3] = {0, 0, 0};
-        if (bid >= 0) {
-          const int off = a.bl.off[bid];
-          LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
-                         (uint32_t)__ldg(a.c.cutraw + pidx), true};
-          const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
-          const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
-          const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
-          bool done = peel_query(LB, qme, qot, anc);
-          double tot_me = 1.0, tot_ot = 1.0;
-          int bad = 0;
-          if (done) { GFX_COUNT(a.bl, 1, 1); }
-          else bad = query_general(LB, a.bl, qme, qot, anc, &tot_me);
-          if (qot >= 0 && !((tree >> (side ^ 1)) & 1u)) {
-            // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
-            // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
-            double tmp[3];
-            if (!peel_query(LB, qot, qme, tmp)) bad |= query_general(LB, a.bl, qot, qme, tmp, &tot_ot);
-          }
-          if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
-          if (bad) atomicExch(a.status, 1);
-        }
-        if (!kids_done) {
-          const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
-          if (nk > 0 && nk <= GFX_KIDS_FAST) { kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, kids); has_kids = true; }
-          else has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
-          kids_done = true;
-          GFX_COUNT(a.bl, 7, nk);
-        }
-        if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
-        double p[3];
-        gfx_combine(bid >= 0, anc, has_kids, kids, p);
-        const uint32_t bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
-        if (a.post) {
-          double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
-          o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
-        }
-        // decision on the LIVE state (:809-824 / :932-938)
-        const bool cond = cur == 3 || (!((bits >> cur) & 1u) && (bits & 8u));
-        if (!cond) continue;
-        if (!gate_done) {                                       // rank gate (:733-737,817 / :928-933)
-          double mr = 0.0;
-          for (int q = 0; q < 2; ++q) {
-            const int pr = a.prow[2 * row + q];
-            if (pr >= 0) { const double ev = rx_E(a.c, cell_rx(a.c, pr, j)); if (ev > mr) mr = ev; }
-          }
-          gate = rx_E(a.c, rxf) * a.p.err_thresh >= mr;
-          gate_done = true;
-        }
-        if (gate) {
-          const uint32_t set = bits & 7u;
-          cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
-          ++applied;
-        } else {
-          ++excluded;
-        }
+      if (!correct_cell<false>(a, s_kv, row, e0, e1, j))
+        atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+    }
+    __syncthreads();
+  }
+}
+
+// General kernel: the deferred cells only.
+__global__ void __launch_bounds__(128) k_correct_general(FocalArgs a) {
+  __shared__ int s_list[GFX_CORRECT_CHUNK];
+  __shared__ int s_cnt;
+  __shared__ double s_kv[108];
+  for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
+  const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
+  const int64_t tasks = (int64_t)a.n_focal * chunks;
+  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
+    const int f = (int)(task / chunks);
+    const int64_t j0 = (task - (int64_t)f * chunks) * GFX_CORRECT_CHUNK;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (threadIdx.x < GFX_CORRECT_CHUNK / 32) {
+      uint32_t m = a.deferred[(int64_t)f * a.dwords + (j0 >> 5) + threadIdx.x];
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        s_list[atomicAdd(&s_cnt, 1)] = threadIdx.x * 32 + b;
       }
-      if (cur != obs0) {
-        uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
-        const int sh = 2 * (int)(j & 15);
-        atomicAnd(wp, ~(3u << sh));
-        atomicOr(wp, (uint32_t)cur << sh);
-      }
-      if (applied) atomicAdd(a.tallies + row, applied);
-      if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt) {
+      const int row = a.focal_row[f];
+      const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
+      for (int k = threadIdx.x; k < cnt; k += blockDim.x) correct_cell<true>(a, s_kv, row, e0, e1, j0 + s_list[k]);
     }
     __syncthreads();
   }
@@ -1019,11 +1077,16 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.bl_tree = s->bl_tree;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
+  // scratch layout: [snapshot: n_rows * wpr words][deferred bitmap: n_focal * dwords words], n_focal <= n_rows
+  a.dwords = ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK) * (GFX_CORRECT_CHUNK / 32);
+  a.deferred = snapshot + (size_t)s->h.n_rows * wpr;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
   int64_t blocks = tasks;
-  const int64_t cap = (int64_t)s->num_sms * 16;
+  const int64_t cap = (int64_t)s->num_sms * 24;
   if (blocks > cap) blocks = cap;
   k_correct<<<(int)blocks, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_correct_general<<<(int)blocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   return GFX_OK;
 }

@@ -205,7 +205,7 @@ class Engine(object):
         self.raw = t.empty((n, self.ld_raw), dtype=t.int16, device=dev)
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
-        self.snapshot = t.empty((n, self.wpr), dtype=t.int32, device=dev)
+        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)), dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
         self.host_out = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)

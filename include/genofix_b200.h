@@ -134,8 +134,9 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
  *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
  *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
  *   raw_dev      scores after gfx_rank_hist (missing cells marked 0xFFFF); packed_live is updated in place
- *   snapshot_dev scratch of n_rows * wpr uint32: receives the generation-start snapshot every worker of
- *                the reference reads (:687-689); neighbours are read from it, only the focal cell is live
+ *   snapshot_dev scratch of n_rows * (wpr + 32 * ceil(n_snps / 1024)) uint32: the generation-start snapshot every
+ *                worker of the reference reads (:687-689) -- neighbours are read from it, only the focal cell
+ *                is live -- followed by a bitmap of the cells deferred to the general-elimination kernel
  *   post_dev     optional (may be NULL): posterior of every evaluated (job, side, SNP), 3 doubles at
  *                [((job * sides + side) * n_snps + snp) * 3]; cells that were not evaluated are left
  *                untouched (prefill with a sentinel)

@@ -75,8 +75,8 @@ def lib():
     L.gfx_mendel_rank.argtypes = [vp, vp, i64, i64, vp, i64, vp]
     L.gfx_rank_hist.argtypes = [vp, i64, vp, i64, i64, i64, vp, vp]
     L.gfx_rank_rowsum.argtypes = [vp, i64, vp, i64, i64, i64, vp, C.c_double, vp, vp]
-    L.gfx_correct_pairs.argtypes = [vp, i32, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
-    L.gfx_correct_singles.argtypes = [vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, vp, vp, vp]
+    L.gfx_correct_pairs.argtypes = [vp, i32, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
+    L.gfx_correct_singles.argtypes = [vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
     L.gfx_build_cut_table.argtypes = [vp, C.c_double, C.c_double, vp, C.POINTER(C.c_uint32)]
     L.gfx_check_device_status.argtypes = [vp, vp]
     L.gfx_debug_counters.argtypes = [vp, C.c_int, vp]

@@ -172,7 +172,7 @@ class CorrectGenotypes(object):
                 scratch = live.clone()  # apply happens on a scratch copy: every generation sees the bound snapshot
                 _lib.check(eng.L.gfx_correct_pairs(eng.schedule.handle, g, scratch.data_ptr(), eng.s,
                                                    eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
-                                                   eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                                                   eng.snapshot.data_ptr(), eng.snapshot.numel(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()
                 for k in range(nj):
                     pr = tuple(int(x) for x in pairs[jobs[gen_off[g] + k]])
@@ -184,7 +184,7 @@ class CorrectGenotypes(object):
                 scratch = live.clone()
                 _lib.check(eng.L.gfx_correct_singles(eng.schedule.handle, scratch.data_ptr(), eng.s,
                                                      eng.wpr, eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp),
-                                                     eng.snapshot.data_ptr(), post.data_ptr(), tall.data_ptr(), eng._stream()))
+                                                     eng.snapshot.data_ptr(), eng.snapshot.numel(), post.data_ptr(), tall.data_ptr(), eng._stream()))
                 ph = post.cpu().numpy()
                 for k, r in enumerate(eng.schedule.array(2)):
                     out[int(r)] = (ph[k], ph[k, :, 0] != -1.0)

@@ -802,8 +802,11 @@ struct FocalArgs {
   int32_t* tallies;
   int n_rows;
   int* status;
-  uint32_t* deferred;     // 1 bit per (focal, SNP): cell needs the general kernel; dwords words per focal
-  int64_t dwords;
+  uint32_t* deferred;     // overflow bitmap, 1 bit per (focal, SNP): cell needs the general kernel
+  int64_t dwords;         // bitmap words per focal animal
+  unsigned long long* wl_count;  // deferred cells so far
+  uint2* wl;              // work list of deferred (focal, snp) cells
+  unsigned long long wl_cap;
 };
 
 // Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
@@ -1020,18 +1023,37 @@ __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
     const int cnt = s_cnt;
     for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
       const int64_t j = j0 + s_list[k];
-      if (!correct_cell<false>(a, s_kv, row, e0, e1, j))
-        atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+      if (!correct_cell<false>(a, s_kv, row, e0, e1, j)) {
+        const unsigned long long slot = atomicAdd(a.wl_count, 1ull);
+        if (slot < a.wl_cap) a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
+        else atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+      }
     }
     __syncthreads();
   }
 }
 
-// General kernel: the deferred cells only.
+// General kernel: the deferred cells, one thread each, straight from the global work list.
 __global__ void __launch_bounds__(128) k_correct_general(FocalArgs a) {
+  __shared__ double s_kv[108];
+  for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
+  __syncthreads();
+  unsigned long long n = *a.wl_count;
+  if (n > a.wl_cap) n = a.wl_cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 c = a.wl[i];
+    const int f = (int)c.x;
+    correct_cell<true>(a, s_kv, a.focal_row[f], a.focal_off[f], a.focal_off[f + 1], (int64_t)c.y);
+  }
+}
+
+// Only when the work list overflowed: the remaining deferred cells from the bitmap.
+__global__ void __launch_bounds__(128) k_correct_general_overflow(FocalArgs a) {
   __shared__ int s_list[GFX_CORRECT_CHUNK];
   __shared__ int s_cnt;
   __shared__ double s_kv[108];
+  if (*a.wl_count <= a.wl_cap) return;
   for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
   const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
   const int64_t tasks = (int64_t)a.n_focal * chunks;
@@ -1063,8 +1085,12 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
                        const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
                        const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
                        const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                       uint32_t* snapshot, double* post, int32_t* tallies, cudaStream_t stream) {
+                       uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, cudaStream_t stream) {
   if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
+  const int64_t dwords = ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK) * (GFX_CORRECT_CHUNK / 32);
+  const int64_t fixed = (int64_t)s->h.n_rows * wpr + (int64_t)s->h.n_rows * dwords + 4;
+  if (scratch_words < fixed + 2 * 1024)
+    return fail(GFX_E_INVALID, "scratch too small: need n_rows * (wpr + 32 * ceil(n_snps / 1024)) + 4 words plus the work list");
   GFX_CUDA(cudaMemcpyAsync(snapshot, live, sizeof(uint32_t) * (size_t)s->h.n_rows * wpr, cudaMemcpyDeviceToDevice, stream));
   FocalArgs a;
   a.c = CellCtx{snapshot, wpr, raw, ld_raw, elut, p->cutraw_dev, p->tp_raw};
@@ -1077,23 +1103,32 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.bl_tree = s->bl_tree;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
-  // scratch layout: [snapshot: n_rows * wpr words][deferred bitmap: n_focal * dwords words], n_focal <= n_rows
-  a.dwords = ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK) * (GFX_CORRECT_CHUNK / 32);
+  // scratch layout: [snapshot: n_rows * wpr][overflow bitmap: n_rows * dwords][count: 4][work list: the rest]
+  a.dwords = dwords;
   a.deferred = snapshot + (size_t)s->h.n_rows * wpr;
+  uint32_t* tail = a.deferred + (size_t)s->h.n_rows * dwords;
+  tail += (4 - (((uintptr_t)tail / 4) & 3)) & 3;   // 16-byte alignment for the counter / list
+  a.wl_count = (unsigned long long*)tail;
+  a.wl = (uint2*)(tail + 4);
+  a.wl_cap = (unsigned long long)((snapshot + scratch_words - (tail + 4)) / 2);
+  GFX_CUDA(cudaMemsetAsync(a.wl_count, 0, 16, stream));
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
   int64_t blocks = tasks;
   const int64_t cap = (int64_t)s->num_sms * 24;
   if (blocks > cap) blocks = cap;
   k_correct<<<(int)blocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
-  k_correct_general<<<(int)blocks, 128, 0, stream>>>(a);
+  k_correct_general<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_correct_general_overflow<<<(int)blocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   return GFX_OK;
 }
 
 extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* live,
                                  int64_t n_snps, int64_t wpr, const uint16_t* raw, int64_t ld_raw, const double* elut,
-                                 const gfx_correct_params* p, uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
+                                 const gfx_correct_params* p, uint32_t* snapshot, int64_t scratch_words, double* post,
+                                 int32_t* tallies, void* stream) {
   if (!s || !live || !raw || !elut || !p || !p->cutraw_dev || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   if (generation < 0 || generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
@@ -1101,18 +1136,18 @@ extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint
   const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
   return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
-                     s->app_focal_off + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post,
-                     tallies, (cudaStream_t)stream);
+                     s->app_focal_off + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words,
+                     post, tallies, (cudaStream_t)stream);
 }
 
 extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_t n_snps, int64_t wpr,
                                    const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                                   uint32_t* snapshot, double* post, int32_t* tallies, void* stream) {
+                                   uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, void* stream) {
   if (!s || !live || !raw || !elut || !p || !p->cutraw_dev || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   const int n = (int)s->h.single_row.size();
   return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
-                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, post, tallies, (cudaStream_t)stream);
+                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -205,7 +205,9 @@ class Engine(object):
         self.raw = t.empty((n, self.ld_raw), dtype=t.int16, device=dev)
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
-        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)), dtype=t.int32, device=dev)
+        # snapshot + overflow bitmap + work list of deferred cells (up to 1/8 of the cells, 2 words each)
+        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 8 + max(4096, n * self.s // 4),
+                                dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
         self.host_out = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
@@ -277,7 +279,7 @@ class Engine(object):
                     post = t.full((max(nj, 1) * 2, self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
                 _lib.check(self.L.gfx_correct_pairs(
                     self.schedule.handle, g, self.packed_live.data_ptr(), self.s, self.wpr,
-                    self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(),
+                    self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(), self.snapshot.numel(),
                     post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
                 if keep_posteriors:
                     ph = post.cpu().numpy()
@@ -290,7 +292,7 @@ class Engine(object):
                 post = t.full((max(ns, 1), self.s, 3), POST_SENTINEL, dtype=t.float64, device=self.codes.device)
             _lib.check(self.L.gfx_correct_singles(
                 self.schedule.handle, self.packed_live.data_ptr(), self.s, self.wpr,
-                self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.snapshot.data_ptr(),
+                self.raw.data_ptr(), self.ld_raw, self.elut.data_ptr(), C.byref(ps), self.snapshot.data_ptr(), self.snapshot.numel(),
                 post.data_ptr() if post is not None else None, self.tallies.data_ptr(), self._stream()))
             if keep_posteriors:
                 ph = post.cpu().numpy()

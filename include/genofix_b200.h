@@ -134,9 +134,10 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
  *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
  *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
  *   raw_dev      scores after gfx_rank_hist (missing cells marked 0xFFFF); packed_live is updated in place
- *   snapshot_dev scratch of n_rows * (wpr + 32 * ceil(n_snps / 1024)) uint32: the generation-start snapshot every
- *                worker of the reference reads (:687-689) -- neighbours are read from it, only the focal cell
- *                is live -- followed by a bitmap of the cells deferred to the general-elimination kernel
+ *   scratch_dev  scratch_words uint32, at least n_rows * (wpr + 32 * ceil(n_snps / 1024)) + 4 + 2048: the
+ *                generation-start snapshot every worker of the reference reads (:687-689) -- neighbours are
+ *                read from it, only the focal cell is live --, an overflow bitmap, and whatever is left as
+ *                the work list (2 words per cell) of cells deferred to the general-elimination kernel
  *   post_dev     optional (may be NULL): posterior of every evaluated (job, side, SNP), 3 doubles at
  *                [((job * sides + side) * n_snps + snp) * 3]; cells that were not evaluated are left
  *                untouched (prefill with a sentinel)
@@ -164,14 +165,14 @@ int gfx_build_cut_table(const double* elut_host, double test_p, double suspect_t
 int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint32_t* packed_live_dev,
                       int64_t n_snps, int64_t wpr,
                       const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
-                      const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
-                      int32_t* tallies_dev, void* stream);
+                      const gfx_correct_params* params, uint32_t* scratch_dev, int64_t scratch_words,
+                      double* post_dev, int32_t* tallies_dev, void* stream);
 
 int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
                         int64_t n_snps, int64_t wpr,
                         const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev,
-                        const gfx_correct_params* params, uint32_t* snapshot_dev, double* post_dev,
-                        int32_t* tallies_dev, void* stream);
+                        const gfx_correct_params* params, uint32_t* scratch_dev, int64_t scratch_words,
+                        double* post_dev, int32_t* tallies_dev, void* stream);
 
 /* Diagnostics: reads and clears 16 device counters (queries, parent-only answers, eliminations, big-table
  * reruns, nodes touched, suspect cells, job evaluations, children visited, ...) and switches counting

@@ -21,14 +21,14 @@ pp = _lib.CorrectParams(eng.test_p, 0.2, 0.4, 0.5, 1.0, eng.cutraw.data_ptr(), e
 for g in range(eng.schedule.info["n_generations"]):
     torch.cuda.synchronize(); t = time.time()
     _lib.check(L.gfx_correct_pairs(eng.schedule.handle, g, eng.packed_live.data_ptr(), eng.s, eng.wpr,
-               eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp), eng.snapshot.data_ptr(), None, eng.tallies.data_ptr(), None))
+               eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(pp), eng.snapshot.data_ptr(), eng.snapshot.numel(), None, eng.tallies.data_ptr(), None))
     torch.cuda.synchronize(); dt = time.time() - t
     _lib.check(L.gfx_debug_counters(eng.schedule.handle, 1, cnt.ctypes.data_as(C.c_void_p)))
     print("gen", g, "%.1f ms (with counters)" % (dt * 1e3), dict(zip(names, [int(x) for x in cnt[:8]])))
 ps = _lib.CorrectParams(eng.test_p, 0.2, 0.4, 0.64, 1.0, eng.cutraw.data_ptr(), eng.tp_raw, 0)
 torch.cuda.synchronize(); t = time.time()
 _lib.check(L.gfx_correct_singles(eng.schedule.handle, eng.packed_live.data_ptr(), eng.s, eng.wpr,
-           eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(ps), eng.snapshot.data_ptr(), None, eng.tallies.data_ptr(), None))
+           eng.raw.data_ptr(), eng.ld_raw, eng.elut.data_ptr(), C.byref(ps), eng.snapshot.data_ptr(), eng.snapshot.numel(), None, eng.tallies.data_ptr(), None))
 torch.cuda.synchronize(); dt = time.time() - t
 _lib.check(L.gfx_debug_counters(eng.schedule.handle, 0, cnt.ctypes.data_as(C.c_void_p)))
 print("singles %.1f ms" % (dt * 1e3), dict(zip(names, [int(x) for x in cnt[:8]])))

@@ -130,45 +130,47 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
       else if ((folded >> a2) & 1) d_fold = true;
       else { for (int k = 0; k < w; ++k) if (open[k] == a2) d_pos = k; d_str = gfx_pow3(d_pos); }
     }
-    // g[x][a][b]: factor value for parent digits a, b (index 0 where the parent is not a digit)
+    // T(x | s, d) factorises over the transmitted alleles: with al(.) = P(parent passes allele 0) and
+    // be(.) = P(passes allele 1), T(0|.) = al_s al_d, T(2|.) = be_s be_d, T(1|.) = al_s be_d + be_s al_d.
+    // Per parent these masses come from the evidence, from a folded belief vector, or from a table digit.
+    double sa[3], sb[3], da[3], db[3];
     const int na = s_pos >= 0 ? 3 : 1, nb = d_pos >= 0 ? 3 : 1;
+    if (a1 >= 0) {
+      if (s_pos >= 0) { sa[0] = 1.0; sa[1] = 0.5; sa[2] = 0.0; sb[0] = 0.0; sb[1] = 0.5; sb[2] = 1.0; }
+      else if (s_fold) { sa[0] = fv[a1 * 3] + 0.5 * fv[a1 * 3 + 1]; sb[0] = 0.5 * fv[a1 * 3 + 1] + fv[a1 * 3 + 2]; }
+      else { sa[0] = 1.0 - 0.5 * s_val; sb[0] = 0.5 * s_val; }
+      if (d_pos >= 0) { da[0] = 1.0; da[1] = 0.5; da[2] = 0.0; db[0] = 0.0; db[1] = 0.5; db[2] = 1.0; }
+      else if (d_fold) { da[0] = fv[a2 * 3] + 0.5 * fv[a2 * 3 + 1]; db[0] = 0.5 * fv[a2 * 3 + 1] + fv[a2 * 3 + 2]; }
+      else { da[0] = 1.0 - 0.5 * d_val; db[0] = 0.5 * d_val; }
+    }
     const int x_lo = v_obs ? code[v] : 0, x_hi = v_obs ? code[v] : 2;
-    double g[27];
-    for (int x = x_lo; x <= x_hi; ++x)
-      for (int a = 0; a < na; ++a)
-        for (int c = 0; c < nb; ++c) {
-          double f;
-          if (a1 < 0) {
-            f = gfx_prior(x);
-          } else {
-            const int sl = s_pos >= 0 ? a : (s_fold ? 0 : s_val), sh = s_pos >= 0 ? a : (s_fold ? 2 : s_val);
-            const int dl = d_pos >= 0 ? c : (d_fold ? 0 : d_val), dh = d_pos >= 0 ? c : (d_fold ? 2 : d_val);
-            f = 0.0;
-            for (int sv = sl; sv <= sh; ++sv)
-              for (int dv = dl; dv <= dh; ++dv) {
-                double t = gfx_mendel(x, sv, dv);
-                if (s_fold) t *= fv[a1 * 3 + sv];
-                if (d_fold) t *= fv[a2 * 3 + dv];
-                f += t;
-              }
-          }
-          g[(x * 3 + a) * 3 + c] = f;
-        }
     // an unobserved node with a single remaining child whose own factor involves no table digit is
     // carried as a belief vector (plain peeling) instead of opening a digit
     if (!v_obs && v != q && nkids[v] == 1 && s_pos < 0 && d_pos < 0) {
-      fv[v * 3 + 0] = g[0]; fv[v * 3 + 1] = g[9]; fv[v * 3 + 2] = g[18];
+      if (a1 < 0) { fv[v * 3] = 0.25; fv[v * 3 + 1] = 0.5; fv[v * 3 + 2] = 0.25; }
+      else {
+        fv[v * 3] = sa[0] * da[0];
+        fv[v * 3 + 1] = sa[0] * db[0] + sb[0] * da[0];
+        fv[v * 3 + 2] = sb[0] * db[0];
+      }
       folded |= 1ull << v;
       continue;
     }
     if (!v_obs && w == wmax) { out[0] = out[1] = out[2] = nan(""); return 1; }
     for (int x = x_hi; x >= x_lo; --x) {
+      // digits of the two parents advance with the running index: no divisions
+      int ia = 0, ca = 0, ib = 0, cb = 0;
       for (int i = 0; i < size; ++i) {
-        const int a = s_pos >= 0 ? (i / s_str) % 3 : 0;
-        const int c = d_pos >= 0 ? (i / d_str) % 3 : 0;
-        const double f = g[(x * 3 + a) * 3 + c];
+        double f;
+        if (a1 < 0) f = gfx_prior(x);
+        else {
+          const int a = na == 3 ? ia : 0, c = nb == 3 ? ib : 0;
+          f = x == 0 ? sa[a] * da[c] : (x == 2 ? sb[a] * db[c] : sa[a] * db[c] + sb[a] * da[c]);
+        }
         if (v_obs) tab[i] *= f;
         else tab[x * size + i] = tab[i] * f;
+        if (++ca == s_str) { ca = 0; ia = ia == 2 ? 0 : ia + 1; }
+        if (++cb == d_str) { cb = 0; ib = ib == 2 ? 0 : ib + 1; }
       }
     }
     if (!v_obs) { open[w++] = (int8_t)v; size *= 3; }
@@ -178,10 +180,10 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
       if (u == q || dlast[u] > v) continue;
       const int str = gfx_pow3(k);
       const int nsize = size / 3;
-      for (int i = 0; i < nsize; ++i) {
-        const int hi = i / str, lo = i - hi * str;
-        const int src = hi * str * 3 + lo;
+      for (int i = 0, src = 0, lo = 0; i < nsize; ++i) {
         tab[i] = (tab[src] + tab[src + str]) + tab[src + 2 * str];
+        ++src;
+        if (++lo == str) { lo = 0; src += 2 * str; }
       }
       for (int mm = k; mm + 1 < w; ++mm) open[mm] = open[mm + 1];
       --w;

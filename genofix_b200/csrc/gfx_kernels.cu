@@ -811,14 +811,15 @@ struct FocalArgs {
 
 // Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
 // numpy's 8-accumulator block sum run straight from them (one leaf of the pairwise scheme).
-#define GFX_KIDS_FAST 42
+#define GFX_KIDS_FAST 96
 struct NibStream {
-  unsigned long long pk0, pk1, pk2;
+  unsigned long long pk0, pk1, pk2, pk3, pk4, pk5;
   int a, cur, ninc;
   const double* kv;
   __device__ __forceinline__ void operator()(double v[3]) {
     if (cur == ninc) { cur = 0; ++a; }
-    const unsigned long long w = cur < 16 ? pk0 : (cur < 32 ? pk1 : pk2);
+    const int r = cur >> 4;
+    const unsigned long long w = r == 0 ? pk0 : (r == 1 ? pk1 : (r == 2 ? pk2 : (r == 3 ? pk3 : (r == 4 ? pk4 : pk5))));
     const int cls = (int)((w >> ((cur & 15) * 4)) & 15ull);
     const double* e = kv + cls * 9 + 3 * a;
     v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
@@ -827,7 +828,7 @@ struct NibStream {
 };
 __device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
                                                int64_t j, const double* kv, double out[3]) {
-  unsigned long long pk0 = 0, pk1 = 0, pk2 = 0;
+  unsigned long long pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, pk4 = 0, pk5 = 0;
   int ninc = 0;
   for (int i = 0; i < nk; ++i) {
     const int k = cell_code(c.live, c.wpr, __ldg(child_row + i), j);
@@ -835,13 +836,16 @@ __device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* 
     const int o = __ldg(child_other + i);
     const int pc = o >= 0 ? cell_code(c.live, c.wpr, o, j) : 3;
     const unsigned long long v = (unsigned long long)(k * 4 + pc) << ((ninc & 15) * 4);
-    if (ninc < 16) pk0 |= v; else if (ninc < 32) pk1 |= v; else pk2 |= v;
+    const int r = ninc >> 4;
+    if (r == 0) pk0 |= v; else if (r == 1) pk1 |= v; else if (r == 2) pk2 |= v;
+    else if (r == 3) pk3 |= v; else if (r == 4) pk4 |= v; else pk5 |= v;
     ++ninc;
   }
   if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return; }
-  NibStream next{pk0, pk1, pk2, 0, 0, ninc, kv};
+  NibStream next{pk0, pk1, pk2, pk3, pk4, pk5, 0, 0, ninc, kv};
   double tot[3];
-  gfx_pw_leaf(next, 3 * ninc, tot);
+  if (3 * ninc <= 128) gfx_pw_leaf(next, 3 * ninc, tot);
+  else gfx_pairwise3(next, 3 * ninc, tot);
   gfx_kids_finish(tot, ninc, out);
 }
 

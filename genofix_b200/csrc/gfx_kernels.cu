@@ -60,7 +60,8 @@ struct gfx_schedule {
   uint64_t* bl_kid = nullptr;
   uint8_t* bl_tree = nullptr;
   int32_t *job_row0 = nullptr, *job_row1 = nullptr, *job_bl = nullptr;        // pair jobs, all generations
-  int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr;
+  int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr, *app_order = nullptr;
+  int32_t* single_order = nullptr;
   int32_t *single_row = nullptr, *single_bl = nullptr, *single_off = nullptr, *single_entry = nullptr;
   int32_t *loopy_rows = nullptr, *trio_row = nullptr;
   int n_loopy_rows = 0;
@@ -112,7 +113,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree};
+                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -156,6 +157,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(app_focal_row, h.app_focal_row); UP(app_focal_off, h.app_focal_off); UP(app_entry, h.app_entry);
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
   UP(single_entry, single_entry);
+  UP(app_order, h.app_order); UP(single_order, h.single_order);
   UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(rank_lut, lut); UP(kv, kv); UP(status, status);
 #undef UP
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
@@ -805,6 +807,8 @@ struct FocalArgs {
   uint32_t* deferred;     // overflow bitmap, 1 bit per (focal, SNP): cell needs the general kernel
   int64_t dwords;         // bitmap words per focal animal
   unsigned long long* wl_count;  // deferred cells so far
+  unsigned long long* task_count; // next (animal, chunk) task of the lean kernel
+  const int32_t* focal_order;    // focal indices, heaviest first
   uint2* wl;              // work list of deferred (focal, snp) cells
   unsigned long long wl_cap;
 };
@@ -812,37 +816,40 @@ struct FocalArgs {
 // Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
 // numpy's 8-accumulator block sum run straight from them (one leaf of the pairwise scheme).
 #define GFX_KIDS_FAST 96
+#define GFX_KIDS_WORDS (GFX_KIDS_FAST / 8)
+// classes of the usable children, 4 bits each, in shared memory: word w of thread t at cls[w * 128 + t]
 struct NibStream {
-  unsigned long long pk0, pk1, pk2, pk3, pk4, pk5;
+  const uint32_t* cls;   // already offset by the thread index
+  uint32_t word;
   int a, cur, ninc;
   const double* kv;
   __device__ __forceinline__ void operator()(double v[3]) {
     if (cur == ninc) { cur = 0; ++a; }
-    const int r = cur >> 4;
-    const unsigned long long w = r == 0 ? pk0 : (r == 1 ? pk1 : (r == 2 ? pk2 : (r == 3 ? pk3 : (r == 4 ? pk4 : pk5))));
-    const int cls = (int)((w >> ((cur & 15) * 4)) & 15ull);
-    const double* e = kv + cls * 9 + 3 * a;
+    if ((cur & 7) == 0) word = cls[(cur >> 3) * 128];
+    const int c = (int)((word >> ((cur & 7) * 4)) & 15u);
+    const double* e = kv + c * 9 + 3 * a;
     v[0] = e[0]; v[1] = e[1]; v[2] = e[2];
     ++cur;
   }
 };
 __device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
-                                               int64_t j, const double* kv, double out[3]) {
-  unsigned long long pk0 = 0, pk1 = 0, pk2 = 0, pk3 = 0, pk4 = 0, pk5 = 0;
+                                               int64_t j, const double* kv, uint32_t* cls, double out[3]) {
   int ninc = 0;
+  uint32_t word = 0;
+  const int64_t wo = j >> 4;
+  const int sh = 2 * (int)(j & 15);
   for (int i = 0; i < nk; ++i) {
-    const int k = cell_code(c.live, c.wpr, __ldg(child_row + i), j);
+    const int k = (int)((__ldg(c.live + (int64_t)__ldg(child_row + i) * c.wpr + wo) >> sh) & 3u);
     if (k > 2) continue;
     const int o = __ldg(child_other + i);
-    const int pc = o >= 0 ? cell_code(c.live, c.wpr, o, j) : 3;
-    const unsigned long long v = (unsigned long long)(k * 4 + pc) << ((ninc & 15) * 4);
-    const int r = ninc >> 4;
-    if (r == 0) pk0 |= v; else if (r == 1) pk1 |= v; else if (r == 2) pk2 |= v;
-    else if (r == 3) pk3 |= v; else if (r == 4) pk4 |= v; else pk5 |= v;
+    const int pc = o >= 0 ? (int)((__ldg(c.live + (int64_t)o * c.wpr + wo) >> sh) & 3u) : 3;
+    word |= (uint32_t)(k * 4 + pc) << ((ninc & 7) * 4);
     ++ninc;
+    if ((ninc & 7) == 0) { cls[((ninc >> 3) - 1) * 128] = word; word = 0; }
   }
+  if (ninc & 7) cls[(ninc >> 3) * 128] = word;
   if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return; }
-  NibStream next{pk0, pk1, pk2, pk3, pk4, pk5, 0, 0, ninc, kv};
+  NibStream next{cls, 0u, 0, 0, ninc, kv};
   double tot[3];
   if (3 * ninc <= 128) gfx_pw_leaf(next, 3 * ninc, tot);
   else gfx_pairwise3(next, 3 * ninc, tot);
@@ -882,7 +889,8 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 // instantiation: ancestor terms by plain peeling only; it returns false (nothing written) as soon as a
 // job needs the general elimination, and the cell is redone by the GENERAL = true instantiation.
 template <bool GENERAL>
-__device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s_kv, int row, int e0, int e1, int64_t j) {
+__device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s_kv, uint32_t* s_cls, int row, int e0, int e1,
+                                             int64_t j) {
   const uint32_t tp = a.c.tp_raw;
   const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
   int cur = obs0;                                          // live state, updated job after job
@@ -943,7 +951,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
     if (!kids_done) {
       const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
       if (nk > 0 && nk <= GFX_KIDS_FAST) {
-        kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, kids);
+        kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, s_cls, kids);
         has_kids = true;
       } else if (nk > 0) {
         if constexpr (!GENERAL) return false;
@@ -991,55 +999,66 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
   return true;
 }
 
-// Lean kernel: one block per (focal animal, 1024-SNP chunk); suspect SNPs are compacted first so that
-// every thread of pass 2 has a cell.  Cells that need the general path are flagged in `deferred`
-// (1 bit per (focal, SNP)) and left untouched.
+// Lean kernel.  A warp takes (focal animal, 256-SNP chunk) tasks from a global counter -- animals are
+// ordered heaviest first, so the many-mate sires do not end up as the tail --, compacts the suspect
+// SNPs of the chunk with ballots and then runs one cell per lane.  Cells that need the general path
+// go to the work list (or, if that is full, the overflow bitmap) untouched.
+#define GFX_LEAN_CHUNK 256
 __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
-  __shared__ int s_list[GFX_CORRECT_CHUNK];
-  __shared__ int s_cnt;
+  __shared__ uint8_t s_list[4][GFX_LEAN_CHUNK];
   __shared__ double s_kv[108];
+  __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
   for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
-  const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t chunks = (a.n_snps + GFX_LEAN_CHUNK - 1) / GFX_LEAN_CHUNK;
   const int64_t tasks = (int64_t)a.n_focal * chunks;
   const uint32_t tp = a.c.tp_raw;
-  for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
-    const int f = (int)(task / chunks);
-    const int64_t j0 = (task - (int64_t)f * chunks) * GFX_CORRECT_CHUNK;
-    const int64_t j1 = min(a.n_snps, j0 + (int64_t)GFX_CORRECT_CHUNK);
+  for (;;) {
+    unsigned long long task = 0;
+    if (lane == 0) task = atomicAdd(a.task_count, 1ull);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if ((int64_t)task >= tasks) break;
+    const int f = a.focal_order[task / chunks];
+    const int64_t j0 = (int64_t)(task % chunks) * GFX_LEAN_CHUNK;
     const int row = a.focal_row[f];
     const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
-    if (threadIdx.x == 0) s_cnt = 0;
-    if (threadIdx.x < GFX_CORRECT_CHUNK / 32) a.deferred[(int64_t)f * a.dwords + (j0 >> 5) + threadIdx.x] = 0u;
-    __syncthreads();
     // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342); E >= test_p is a
     // comparison of raw patterns because E is monotone in the score
-    for (int64_t j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
-      bool sus = cell_rx(a.c, row, j) >= tp;
-      if (a.nf == 2)
-        for (int e = e0; e < e1 && !sus; ++e) {
-          const int ent = a.entry[e];
-          const int mrow = (ent & 1) == 0 ? a.job_row1[ent >> 1] : a.job_row0[ent >> 1];
-          sus = cell_rx(a.c, mrow, j) >= tp;
-        }
-      if (sus) s_list[atomicAdd(&s_cnt, 1)] = (int)(j - j0);
+    int cnt = 0;
+    for (int t = 0; t < GFX_LEAN_CHUNK / 32; ++t) {
+      const int64_t j = j0 + t * 32 + lane;
+      bool sus = false;
+      if (j < a.n_snps) {
+        sus = cell_rx(a.c, row, j) >= tp;
+        if (a.nf == 2)
+          for (int e = e0; e < e1 && !sus; ++e) {
+            const int ent = a.entry[e];
+            const int mrow = (ent & 1) == 0 ? a.job_row1[ent >> 1] : a.job_row0[ent >> 1];
+            sus = cell_rx(a.c, mrow, j) >= tp;
+          }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, sus);
+      if (sus) s_list[wib][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(t * 32 + lane);
+      cnt += __popc(m);
     }
-    __syncthreads();
-    const int cnt = s_cnt;
-    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const int64_t j = j0 + s_list[k];
-      if (!correct_cell<false>(a, s_kv, row, e0, e1, j)) {
+    __syncwarp();
+    for (int k = lane; k < cnt; k += 32) {
+      const int64_t j = j0 + s_list[wib][k];
+      if (!correct_cell<false>(a, s_kv, s_cls + threadIdx.x, row, e0, e1, j)) {
         const unsigned long long slot = atomicAdd(a.wl_count, 1ull);
         if (slot < a.wl_cap) a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
         else atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
 // General kernel: the deferred cells, one thread each, straight from the global work list.
 __global__ void __launch_bounds__(128) k_correct_general(FocalArgs a) {
   __shared__ double s_kv[108];
+  __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
   for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
   __syncthreads();
   unsigned long long n = *a.wl_count;
@@ -1048,7 +1067,7 @@ __global__ void __launch_bounds__(128) k_correct_general(FocalArgs a) {
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const uint2 c = a.wl[i];
     const int f = (int)c.x;
-    correct_cell<true>(a, s_kv, a.focal_row[f], a.focal_off[f], a.focal_off[f + 1], (int64_t)c.y);
+    correct_cell<true>(a, s_kv, s_cls + threadIdx.x, a.focal_row[f], a.focal_off[f], a.focal_off[f + 1], (int64_t)c.y);
   }
 }
 
@@ -1057,6 +1076,7 @@ __global__ void __launch_bounds__(128) k_correct_general_overflow(FocalArgs a) {
   __shared__ int s_list[GFX_CORRECT_CHUNK];
   __shared__ int s_cnt;
   __shared__ double s_kv[108];
+  __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
   if (*a.wl_count <= a.wl_cap) return;
   for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
   const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
@@ -1079,7 +1099,8 @@ __global__ void __launch_bounds__(128) k_correct_general_overflow(FocalArgs a) {
     if (cnt) {
       const int row = a.focal_row[f];
       const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
-      for (int k = threadIdx.x; k < cnt; k += blockDim.x) correct_cell<true>(a, s_kv, row, e0, e1, j0 + s_list[k]);
+      for (int k = threadIdx.x; k < cnt; k += blockDim.x)
+        correct_cell<true>(a, s_kv, s_cls + threadIdx.x, row, e0, e1, j0 + s_list[k]);
     }
     __syncthreads();
   }
@@ -1087,7 +1108,7 @@ __global__ void __launch_bounds__(128) k_correct_general_overflow(FocalArgs a) {
 
 static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t* job_row0, const int32_t* job_row1,
                        const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
-                       const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
+                       const int32_t* focal_order, const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
                        const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
                        uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, cudaStream_t stream) {
   if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
@@ -1115,12 +1136,17 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.wl_count = (unsigned long long*)tail;
   a.wl = (uint2*)(tail + 4);
   a.wl_cap = (unsigned long long)((snapshot + scratch_words - (tail + 4)) / 2);
-  GFX_CUDA(cudaMemsetAsync(a.wl_count, 0, 16, stream));
+  GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(tail + 4)) - (char*)a.deferred, stream));  // bitmap + counters
+  a.task_count = a.wl_count + 1;
+  a.focal_order = focal_order;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
   int64_t blocks = tasks;
   const int64_t cap = (int64_t)s->num_sms * 24;
   if (blocks > cap) blocks = cap;
-  k_correct<<<(int)blocks, 128, 0, stream>>>(a);
+  const int64_t wtasks = (int64_t)n_focal * ((n_snps + GFX_LEAN_CHUNK - 1) / GFX_LEAN_CHUNK);
+  int64_t lblocks = (wtasks + 3) / 4;
+  if (lblocks > (int64_t)s->num_sms * 6) lblocks = (int64_t)s->num_sms * 6;
+  k_correct<<<(int)lblocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_general<<<s->num_sms * 8, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
@@ -1140,7 +1166,7 @@ extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint
   const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
   return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
-                     s->app_focal_off + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words,
+                     s->app_focal_off + f0, s->app_order + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words,
                      post, tallies, (cudaStream_t)stream);
 }
 
@@ -1150,7 +1176,8 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
   if (!s || !live || !raw || !elut || !p || !p->cutraw_dev || !snapshot || !tallies) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   const int n = (int)s->h.single_row.size();
-  return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_entry,
+  return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_order,
+                     s->single_entry,
                      live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, (cudaStream_t)stream);
 }
 

@@ -310,6 +310,18 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
     }
     if (!ent.empty()) out.app_focal_off.push_back((int32_t)out.app_entry.size());
     out.app_gen_off[g + 1] = (int32_t)out.app_focal_row.size();
+    // heaviest animals first: cost ~ jobs * (blanket walk) + genotyped children
+    {
+      const int f0 = out.app_gen_off[g], nf = out.app_gen_off[g + 1] - f0;
+      std::vector<std::pair<int64_t, int32_t>> wgt(nf);
+      for (int i = 0; i < nf; ++i) {
+        const int32_t r = out.app_focal_row[f0 + i];
+        const int64_t jobs = out.app_focal_off[f0 + i + 1] - out.app_focal_off[f0 + i];
+        wgt[i] = {-(jobs * 12 + (out.child_off[r + 1] - out.child_off[r])), i};
+      }
+      std::sort(wgt.begin(), wgt.end());
+      for (int i = 0; i < nf; ++i) out.app_order.push_back(wgt[i].second);
+    }
   }
   for (int r = 0; r < nr; ++r) {
     const int32_t a = ped_of_row[r];
@@ -321,6 +333,16 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
     out.single_blanket.push_back(out.rank_blanket[r]);
   }
 
+  {
+    const int ns = (int)out.single_row.size();
+    std::vector<std::pair<int64_t, int32_t>> wgt(ns);
+    for (int i = 0; i < ns; ++i) {
+      const int32_t r = out.single_row[i];
+      wgt[i] = {-(int64_t)(out.child_off[r + 1] - out.child_off[r]), i};
+    }
+    std::sort(wgt.begin(), wgt.end());
+    for (int i = 0; i < ns; ++i) out.single_order.push_back(wgt[i].second);
+  }
   gfx_schedule_info_t& I = out.info;
   I.n_rows = nr;
   I.n_generations = ng;

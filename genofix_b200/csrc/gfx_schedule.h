@@ -42,8 +42,9 @@ struct GfxHostSchedule {
   std::vector<int32_t> app_focal_row;
   std::vector<int32_t> app_focal_off; // size app_focal_row.size()+1 (global offsets into app_entry)
   std::vector<int32_t> app_entry;
+  std::vector<int32_t> app_order;     // per generation: focal indices (local to the generation), heaviest first
   // singles
-  std::vector<int32_t> single_row, single_blanket;
+  std::vector<int32_t> single_row, single_blanket, single_order;
   // trios
   std::vector<int32_t> trio_row;     // rows with both parents genotyped
   GfxBlanketSet bl;

@@ -507,30 +507,49 @@ struct LazyBlanket {
 // way.  Returns false as soon as an unobserved node has more than one child inside the blanket (a loop
 // or evidence below it): the caller then runs the general elimination.  T(x|s,d) factorises over the
 // transmitted alleles, so the contraction needs the two "transmits 0" / "transmits 1" masses only.
-template <int D>
-__device__ __forceinline__ bool peel(const LazyBlanket& L, int t, int qother, double& b0, double& b1, double& b2) {
-  const int st = t == qother ? 3 : L.status(t);
-  if (st != 3) { b0 = st == 0 ? 1.0 : 0.0; b1 = st == 1 ? 1.0 : 0.0; b2 = st == 2 ? 1.0 : 0.0; return true; }
-  if (__popcll(L.kid[t]) != 1) return false;   // an unobserved node shared by two branches couples them
-  const int a1 = L.p1[t];
-  if (a1 < 0) { b0 = 0.25; b1 = 0.5; b2 = 0.25; return true; }
-  if constexpr (D == 0) {
-    return false;
-  } else {
-    double s0, s1, s2, d0, d1, d2;
-    if (!peel<D - 1>(L, a1, qother, s0, s1, s2)) return false;
-    if (!peel<D - 1>(L, L.p2[t], qother, d0, d1, d2)) return false;
-    const double sa = s0 + 0.5 * s1, sb = 0.5 * s1 + s2, da = d0 + 0.5 * d1, db = 0.5 * d1 + d2;
-    b0 = sa * da; b2 = sb * db; b1 = sa * db + sb * da;
-    return true;
+// (explicit stack instead of recursion: depth <= 5 levels of unobserved ancestors, else the general path)
+__device__ __noinline__ bool peel(const LazyBlanket& L, int root, int qother, double* out) {
+  int8_t node[6], stage[6];
+  double sv[6][3];
+  double r0 = 0, r1 = 0, r2 = 0;
+  int sp = 0;
+  node[0] = (int8_t)root;
+  stage[0] = 0;
+  while (sp >= 0) {
+    const int t = node[sp];
+    if (stage[sp] == 0) {
+      const int st = t == qother ? 3 : L.status(t);
+      if (st != 3) { r0 = st == 0 ? 1.0 : 0.0; r1 = st == 1 ? 1.0 : 0.0; r2 = st == 2 ? 1.0 : 0.0; --sp; continue; }
+      if (__popcll(L.kid[t]) != 1) return false;   // an unobserved node shared by two branches couples them
+      const int a1 = L.p1[t];
+      if (a1 < 0) { r0 = 0.25; r1 = 0.5; r2 = 0.25; --sp; continue; }
+      if (sp == 5) return false;
+      stage[sp] = 1;
+      node[sp + 1] = (int8_t)a1;
+      stage[sp + 1] = 0;
+      ++sp;
+    } else if (stage[sp] == 1) {
+      sv[sp][0] = r0; sv[sp][1] = r1; sv[sp][2] = r2;
+      stage[sp] = 2;
+      node[sp + 1] = L.p2[t];
+      stage[sp + 1] = 0;
+      ++sp;
+    } else {
+      const double sa = sv[sp][0] + 0.5 * sv[sp][1], sb = 0.5 * sv[sp][1] + sv[sp][2];
+      const double da = r0 + 0.5 * r1, db = 0.5 * r1 + r2;
+      r0 = sa * da; r2 = sb * db; r1 = sa * db + sb * da;
+      --sp;
+    }
   }
+  out[0] = r0; out[1] = r1; out[2] = r2;
+  return true;
 }
-__device__ __noinline__ bool peel_query(const LazyBlanket& L, int q, int qother, double out[3]) {
+__device__ __forceinline__ bool peel_query(const LazyBlanket& L, int q, int qother, double out[3]) {
   if (L.kid[q] != 0 || L.p1[q] < 0) return false;
-  double s0, s1, s2, d0, d1, d2;
-  if (!peel<3>(L, L.p1[q], qother, s0, s1, s2)) return false;
-  if (!peel<3>(L, L.p2[q], qother, d0, d1, d2)) return false;
-  const double sa = s0 + 0.5 * s1, sb = 0.5 * s1 + s2, da = d0 + 0.5 * d1, db = 0.5 * d1 + d2;
+  double s[3], d[3];
+  if (!peel(L, L.p1[q], qother, s)) return false;
+  if (!peel(L, L.p2[q], qother, d)) return false;
+  const double sa = s[0] + 0.5 * s[1], sb = 0.5 * s[1] + s[2], da = d[0] + 0.5 * d[1], db = 0.5 * d[1] + d[2];
   out[0] = sa * da; out[2] = sb * db; out[1] = sa * db + sb * da;   // sums to exactly 1
   return true;
 }
@@ -896,10 +915,22 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
   int cur = obs0;                                          // live state, updated job after job
   const uint32_t rxf = cell_rx(a.c, row, j);
   const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
-  bool gate_done = false, gate = false, kids_done = false, has_kids = false;
+  bool gate_done = false, gate = false, has_kids = false;
   double kids[3] = {0, 0, 0};
   int applied = 0, excluded = 0;
   GFX_COUNT(a.bl, 5, 1);
+  {
+    // children term: the same for every job of this animal, evaluated once with the warp converged
+    const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+    if (nk > 0 && nk <= GFX_KIDS_FAST) {
+      kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, s_cls, kids);
+      has_kids = true;
+    } else if (nk > 0) {
+      if constexpr (!GENERAL) return false;
+      else has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
+    }
+    GFX_COUNT(a.bl, 7, nk);
+  }
   for (int e = e0; e < e1; ++e) {
     const int ent = a.entry[e];
     const int job = a.nf == 2 ? (ent >> 1) : ent;
@@ -948,18 +979,6 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
       }
       if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
     }
-    if (!kids_done) {
-      const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
-      if (nk > 0 && nk <= GFX_KIDS_FAST) {
-        kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, s_cls, kids);
-        has_kids = true;
-      } else if (nk > 0) {
-        if constexpr (!GENERAL) return false;
-        else has_kids = kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
-      }
-      kids_done = true;
-      GFX_COUNT(a.bl, 7, nk);
-    }
     if (bid < 0 && !has_kids) continue;                     // lone node: no result (:287-288 / :417-419)
     double p[3];
     gfx_combine(bid >= 0, anc, has_kids, kids, p);
@@ -1003,7 +1022,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
 // ordered heaviest first, so the many-mate sires do not end up as the tail --, compacts the suspect
 // SNPs of the chunk with ballots and then runs one cell per lane.  Cells that need the general path
 // go to the work list (or, if that is full, the overflow bitmap) untouched.
-#define GFX_LEAN_CHUNK 256
+#define GFX_LEAN_CHUNK 128
 __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
   __shared__ uint8_t s_list[4][GFX_LEAN_CHUNK];
   __shared__ double s_kv[108];
@@ -1043,12 +1062,26 @@ __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
       cnt += __popc(m);
     }
     __syncwarp();
-    for (int k = lane; k < cnt; k += 32) {
-      const int64_t j = j0 + s_list[wib][k];
-      if (!correct_cell<false>(a, s_kv, s_cls + threadIdx.x, row, e0, e1, j)) {
-        const unsigned long long slot = atomicAdd(a.wl_count, 1ull);
-        if (slot < a.wl_cap) a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
-        else atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+    for (int k0 = 0; k0 < cnt; k0 += 32) {
+      const int k = k0 + lane;
+      int64_t j = 0;
+      bool defer = false;
+      if (k < cnt) {
+        j = j0 + s_list[wib][k];
+        defer = !correct_cell<false>(a, s_kv, s_cls + threadIdx.x, row, e0, e1, j);
+      }
+      // deferred cells of a warp take consecutive work-list slots, so the general kernel sees runs of
+      // cells of the same animal
+      const uint32_t m = __ballot_sync(0xffffffffu, defer);
+      if (m) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.wl_count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) {
+          const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+          if (slot < a.wl_cap) a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
+          else atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+        }
       }
     }
     __syncwarp();

@@ -544,6 +544,103 @@ __device__ __noinline__ bool peel(const LazyBlanket& L, int root, int qother, do
   out[0] = r0; out[1] = r1; out[2] = r2;
   return true;
 }
+// Extended peeling: the same upward recursion, but an unobserved node may have further children inside
+// the blanket as long as they are observed (their Mendel factor becomes a likelihood on the node, with
+// the other parent's belief obtained the same way) or are childless and unobserved (barren).  Exact as
+// long as no unobserved node is reached twice; otherwise `ok` is cleared and the caller falls back to
+// the general elimination.  Beliefs are unnormalised: their sum is P(evidence in the component).
+#define GFX_XPEEL_DEPTH 16
+// Iterative form (explicit frames, no device recursion).  Returns false when the general path is needed.
+__device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, uint64_t& visited, int root, int root_from,
+                                       double* out) {
+  int8_t f_node[GFX_XPEEL_DEPTH], f_from[GFX_XPEEL_DEPTH], f_stage[GFX_XPEEL_DEPTH], f_sk[GFX_XPEEL_DEPTH];
+  uint64_t f_m[GFX_XPEEL_DEPTH];
+  double f_b[GFX_XPEEL_DEPTH][3], f_s[GFX_XPEEL_DEPTH][3];
+  double r0 = 0, r1 = 0, r2 = 0;
+  int sp = 0;
+  f_node[0] = (int8_t)root; f_from[0] = (int8_t)root_from; f_stage[0] = 0;
+  while (sp >= 0) {
+    const int t = f_node[sp];
+    const int stage = f_stage[sp];
+    if (stage == 0) {
+      const int st = (t == q || t == qother) ? 3 : L.status(t);
+      if (st != 3) { r0 = st == 0 ? 1.0 : 0.0; r1 = st == 1 ? 1.0 : 0.0; r2 = st == 2 ? 1.0 : 0.0; --sp; continue; }
+      if ((visited >> t) & 1) return false;
+      visited |= 1ull << t;
+      const int a1 = L.p1[t];
+      if (a1 < 0) {
+        f_b[sp][0] = 0.25; f_b[sp][1] = 0.5; f_b[sp][2] = 0.25;
+        f_m[sp] = L.kid[t] & ~(1ull << f_from[sp]);
+        f_stage[sp] = 3;
+      } else {
+        if (sp + 1 >= GFX_XPEEL_DEPTH) return false;
+        f_stage[sp] = 1;
+        f_node[sp + 1] = (int8_t)a1; f_from[sp + 1] = (int8_t)t; f_stage[sp + 1] = 0;
+        ++sp;
+      }
+    } else if (stage == 1) {
+      f_s[sp][0] = r0; f_s[sp][1] = r1; f_s[sp][2] = r2;
+      f_stage[sp] = 2;
+      f_node[sp + 1] = L.p2[t]; f_from[sp + 1] = (int8_t)t; f_stage[sp + 1] = 0;
+      ++sp;
+    } else if (stage == 2) {
+      const double sa = f_s[sp][0] + 0.5 * f_s[sp][1], sb = 0.5 * f_s[sp][1] + f_s[sp][2];
+      const double da = r0 + 0.5 * r1, db = 0.5 * r1 + r2;
+      f_b[sp][0] = sa * da; f_b[sp][2] = sb * db; f_b[sp][1] = sa * db + sb * da;
+      f_m[sp] = L.kid[t] & ~(1ull << f_from[sp]);
+      f_stage[sp] = 3;
+    } else {
+      if (stage == 4) {
+        // likelihood of the observed child for x = 0, 1, 2 (x passes allele 0 with probability 1, 1/2, 0)
+        const double oa = r0 + 0.5 * r1, ob = 0.5 * r1 + r2;
+        const int sk = f_sk[sp];
+        if (sk == 0)      { f_b[sp][0] *= oa;  f_b[sp][1] *= 0.5 * oa;            f_b[sp][2] *= 0.0; }
+        else if (sk == 2) { f_b[sp][0] *= 0.0; f_b[sp][1] *= 0.5 * ob;            f_b[sp][2] *= ob; }
+        else              { f_b[sp][0] *= ob;  f_b[sp][1] *= 0.5 * ob + 0.5 * oa; f_b[sp][2] *= oa; }
+        f_stage[sp] = 3;
+      }
+      bool pushed = false;
+      uint64_t m = f_m[sp];
+      while (m) {
+        const int k = gfx_lowbit(m);
+        m &= m - 1;
+        const int sk = (k == q || k == qother) ? 3 : L.status(k);
+        if (sk == 3) {
+          if (L.kid[k] != 0) return false;   // evidence may sit below it: general path
+          continue;                          // childless and unobserved: barren, sums to 1
+        }
+        if (sp + 1 >= GFX_XPEEL_DEPTH) return false;
+        f_m[sp] = m;
+        f_sk[sp] = (int8_t)sk;
+        f_stage[sp] = 4;
+        f_node[sp + 1] = L.p1[k] == t ? L.p2[k] : L.p1[k];
+        f_from[sp + 1] = (int8_t)k;
+        f_stage[sp + 1] = 0;
+        ++sp;
+        pushed = true;
+        break;
+      }
+      if (!pushed) { r0 = f_b[sp][0]; r1 = f_b[sp][1]; r2 = f_b[sp][2]; --sp; }
+    }
+  }
+  out[0] = r0; out[1] = r1; out[2] = r2;
+  return true;
+}
+// out = normalised marginal, *total = unnormalised sum (0 => the reference's joint is 0/0)
+__device__ __noinline__ bool xpeel_query(const LazyBlanket& L, int q, int qother, double out[3], double* total) {
+  if (L.kid[q] != 0 || L.p1[q] < 0) return false;
+  uint64_t visited = 1ull << q;
+  double s[3], d[3];
+  if (!belief_up(L, q, qother, visited, L.p1[q], q, s)) return false;
+  if (!belief_up(L, q, qother, visited, L.p2[q], q, d)) return false;
+  const double sa = s[0] + 0.5 * s[1], sb = 0.5 * s[1] + s[2], da = d[0] + 0.5 * d[1], db = 0.5 * d[1] + d[2];
+  const double u0 = sa * da, u2 = sb * db, u1 = sa * db + sb * da;
+  const double t = (u0 + u1) + u2;
+  out[0] = u0 / t; out[1] = u1 / t; out[2] = u2 / t;
+  *total = t;
+  return true;
+}
+
 __device__ __forceinline__ bool peel_query(const LazyBlanket& L, int q, int qother, double out[3]) {
   if (L.kid[q] != 0 || L.p1[q] < 0) return false;
   double s[3], d[3];
@@ -963,7 +1060,8 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
       const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
       double tot_me = 1.0, tot_ot = 1.0;
       if (!peel_query(LB, qme, qot, anc)) {
-        if constexpr (!GENERAL) return false;
+        if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
+        else if constexpr (!GENERAL) return false;
         else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
       } else {
         GFX_COUNT(a.bl, 1, 1);
@@ -972,7 +1070,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
         // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
         // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
         double tmp[3];
-        if (!peel_query(LB, qot, qme, tmp)) {
+        if (!peel_query(LB, qot, qme, tmp) && !xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (!GENERAL) return false;
           else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
         }

@@ -59,6 +59,8 @@ struct gfx_schedule {
   int8_t *bl_p1 = nullptr, *bl_p2 = nullptr, *bl_last = nullptr, *bl_q0 = nullptr, *bl_q1 = nullptr;
   uint64_t* bl_kid = nullptr;
   uint8_t* bl_tree = nullptr;
+  int32_t* bl_slotrow = nullptr;
+  uint16_t* bl_slotbad = nullptr;
   int32_t *job_row0 = nullptr, *job_row1 = nullptr, *job_bl = nullptr;        // pair jobs, all generations
   int32_t *app_focal_row = nullptr, *app_focal_off = nullptr, *app_entry = nullptr, *app_order = nullptr;
   int32_t* single_order = nullptr;
@@ -113,7 +115,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order};
+                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -152,7 +154,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(anc6, h.anc6); UP(rank_blanket, h.rank_blanket); UP(prow, h.prow); UP(rank_flags, h.rank_flags);
   UP(child_off, h.child_off); UP(child_row, h.child_row); UP(child_other, h.child_other);
   UP(bl_off, h.bl.off); UP(bl_row, h.bl.row); UP(bl_p1, h.bl.p1); UP(bl_p2, h.bl.p2); UP(bl_last, h.bl.last);
-  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1); UP(bl_kid, h.bl.kidmask); UP(bl_tree, h.bl.tree);
+  UP(bl_q0, h.bl.q0); UP(bl_q1, h.bl.q1); UP(bl_kid, h.bl.kidmask); UP(bl_tree, h.bl.tree); UP(bl_slotrow, h.bl.slotrow); UP(bl_slotbad, h.bl.slotbad);
   UP(job_row0, job_row0); UP(job_row1, job_row1); UP(job_bl, job_bl);
   UP(app_focal_row, h.app_focal_row); UP(app_focal_off, h.app_focal_off); UP(app_entry, h.app_entry);
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
@@ -544,6 +546,55 @@ __device__ __noinline__ bool peel(const LazyBlanket& L, int root, int qother, do
   out[0] = r0; out[1] = r1; out[2] = r2;
   return true;
 }
+// Plain peeling on the precomputed ancestor slots of a focal animal (3 levels, level order).  The evidence
+// of the first two levels (6 rows) is fetched in one batch of independent loads, the third level only
+// under unobserved grand-parents.  A node passes allele 0 with probability al = 1 - c/2 when observed with
+// state c, 1/2 when it is an unobserved founder of the blanket, and the mean of its parents' al otherwise
+// (all exact dyadics), so P(q) = [al_S al_D, al_S be_D + be_S al_D, be_S be_D].  Returns false when an
+// unobserved node on the way has several children in the blanket (bit in `bad`): not a tree there.
+__device__ __forceinline__ int slot_status(const CellCtx& c, int r, int64_t wo, int sh, int64_t j, uint32_t cut) {
+  if (r < 0) return r == -3 ? 4 : 3;
+  const int cd = (int)((__ldg(c.live + (int64_t)r * c.wpr + wo) >> sh) & 3u);
+  const uint32_t rx = __ldg(c.raw + (int64_t)r * c.ld_raw + j);
+  return (cd == 3 || rx >= cut) ? 3 : cd;
+}
+__device__ __forceinline__ bool slot_peel(const CellCtx& c, const int32_t* __restrict__ srow, uint32_t bad, int64_t j,
+                                          uint32_t cut, double out[3]) {
+  if (bad & 0x8000u) return false;
+  const int64_t wo = j >> 4;
+  const int sh = 2 * (int)(j & 15);
+  int st[6];
+#pragma unroll
+  for (int s = 0; s < 6; ++s) st[s] = slot_status(c, __ldg(srow + s), wo, sh, j, cut);
+  double al[2];
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    if (st[f] <= 2) { al[f] = 1.0 - 0.5 * st[f]; continue; }
+    if ((bad >> f) & 1u) return false;
+    double a2[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int s2 = 2 * f + 2 + g;
+      const int t2 = st[s2];
+      if (t2 <= 2) { a2[g] = 1.0 - 0.5 * t2; continue; }
+      if (t2 == 4) { a2[g] = -1.0; continue; }          // no parents: f is a founder of the blanket
+      if ((bad >> s2) & 1u) return false;
+      const int u0 = slot_status(c, __ldg(srow + 2 * s2 + 2), wo, sh, j, cut);
+      const int u1 = slot_status(c, __ldg(srow + 2 * s2 + 3), wo, sh, j, cut);
+      if (u0 == 4) { a2[g] = 0.5; continue; }           // unobserved founder
+      if ((u0 == 3 && ((bad >> (2 * s2 + 2)) & 1u)) || (u1 == 3 && ((bad >> (2 * s2 + 3)) & 1u))) return false;
+      const double x0 = u0 <= 2 ? 1.0 - 0.5 * u0 : 0.5, x1 = u1 <= 2 ? 1.0 - 0.5 * u1 : 0.5;
+      a2[g] = 0.5 * (x0 + x1);
+    }
+    al[f] = a2[0] < 0.0 ? 0.5 : 0.5 * (a2[0] + a2[1]);
+  }
+  const double be0 = 1.0 - al[0], be1 = 1.0 - al[1];
+  out[0] = al[0] * al[1];
+  out[2] = be0 * be1;
+  out[1] = al[0] * be1 + be0 * al[1];
+  return true;
+}
+
 // Extended peeling: the same upward recursion, but an unobserved node may have further children inside
 // the blanket as long as they are observed (their Mendel factor becomes a likelihood on the node, with
 // the other parent's belief obtained the same way) or are childless and unobserved (barren).  Exact as
@@ -910,6 +961,8 @@ struct FocalArgs {
   BlanketDev bl;
   const uint64_t* bl_kid;
   const uint8_t* bl_tree;
+  const int32_t* bl_slotrow;
+  const uint16_t* bl_slotbad;
   const int32_t* child_off;
   const int32_t* child_row;
   const int32_t* child_other;
@@ -1059,7 +1112,8 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
       const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
       const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
       double tot_me = 1.0, tot_ot = 1.0;
-      if (!peel_query(LB, qme, qot, anc)) {
+      const int sme = a.nf == 2 ? side : 0;
+      if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
         if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
         else if constexpr (!GENERAL) return false;
         else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
@@ -1070,7 +1124,8 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
         // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
         // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
         double tmp[3];
-        if (!peel_query(LB, qot, qme, tmp) && !xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
+        if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp) &&
+            !xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (!GENERAL) return false;
           else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
         }
@@ -1257,6 +1312,8 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr};
   a.bl_kid = s->bl_kid;
   a.bl_tree = s->bl_tree;
+  a.bl_slotrow = s->bl_slotrow;
+  a.bl_slotbad = s->bl_slotbad;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
   // scratch layout: [snapshot: n_rows * wpr][overflow bitmap: n_rows * dwords][count: 4][work list: the rest]

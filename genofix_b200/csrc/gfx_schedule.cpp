@@ -163,6 +163,34 @@ struct Builder {
       }
       bs.tree.push_back(tr);
     }
+    for (int fi = 0; fi < 2; ++fi) {
+      int32_t srow[14];
+      int snode[14];
+      for (int i = 0; i < 14; ++i) { srow[i] = -3; snode[i] = -1; }
+      uint16_t bad = 0;
+      if (fi >= nf) bad = 0x8000;
+      else {
+        const int qf = local[focal[fi]];
+        const int qo = nf > 1 ? local[focal[1 - fi]] : -1;
+        if (bs.kidmask[base + qf] != 0 || bs.p1[base + qf] < 0) bad = 0x8000;
+        else {
+          snode[0] = bs.p1[base + qf];
+          snode[1] = bs.p2[base + qf];
+          for (int sl = 0; sl < 14; ++sl) {
+            const int u = snode[sl];
+            if (u < 0) continue;
+            srow[sl] = u == qo ? -2 : (bs.row[base + u] >= 0 ? bs.row[base + u] : -1);
+            if (__builtin_popcountll(bs.kidmask[base + u]) != 1) bad |= (uint16_t)(1u << sl);
+            if (bs.p1[base + u] >= 0) {
+              if (sl < 6) { snode[2 * sl + 2] = bs.p1[base + u]; snode[2 * sl + 3] = bs.p2[base + u]; }
+              else bad |= (uint16_t)(1u << sl);   // parents beyond the slot tree
+            }
+          }
+        }
+      }
+      for (int i = 0; i < 14; ++i) bs.slotrow.push_back(srow[i]);
+      bs.slotbad.push_back(bad);
+    }
     if (plain) {
       bool extra = false;
       for (int32_t k : last_level)

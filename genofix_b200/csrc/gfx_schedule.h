@@ -18,6 +18,12 @@ struct GfxBlanketSet {
   std::vector<int8_t> p1, p2, last;
   std::vector<uint64_t> kidmask;  // per node: bit mask of its children inside the blanket
   std::vector<int8_t> q0, q1; // focal local indices (q1 = -1 for a single focal animal)
+  // ancestor slots of each focal animal in level order (slot 0/1 = sire/dam, slots 2s+2 / 2s+3 = parents of slot s):
+  // genotype row, -1 = node without genotype, -2 = the other focal animal, -3 = no such node
+  std::vector<int32_t> slotrow;   // count() * 2 * 14
+  // bit s: the node at slot s must not be unobserved for plain peeling (several children in the blanket, or
+  // parents beyond the slot tree); bit 15: plain peeling never applies to this focal animal
+  std::vector<uint16_t> slotbad;  // count() * 2
   std::vector<uint8_t> tree;  // bit f: the ancestry of focal f is a plain tree (every ancestor has one child in the blanket)
   int max_nodes = 0;
   int max_width = 0;

@@ -6,7 +6,10 @@ import gzip
 import sys
 from argparse import ArgumentParser
 
-import _bootstrap  # noqa: F401
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # src/ (the reference sets PYTHONPATH=src)
+import _bootstrap  # noqa: F401,E402
 import numpy as np
 from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
 

@@ -14,7 +14,10 @@ import sys
 import time
 from argparse import ArgumentParser
 
-import _bootstrap  # noqa: F401
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # src/ (the reference sets PYTHONPATH=src)
+import _bootstrap  # noqa: F401,E402
 import numpy as np
 import pandas as pd
 

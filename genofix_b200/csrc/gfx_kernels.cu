@@ -494,7 +494,8 @@ struct LazyBlanket {
   int n;
   int64_t j;
   uint32_t cut;           // raw pattern from which a node is "suspect" and dropped from the evidence
-  bool filter;            // false: plain evidence (rank), true: drop suspect nodes (correct)
+  bool filter;
+  unsigned long long* dbg = nullptr;            // false: plain evidence (rank), true: drop suspect nodes (correct)
   __device__ __forceinline__ int status(int t) const {
     const int r = __ldg(rows + t);
     if (r < 0) return 3;
@@ -558,14 +559,18 @@ __device__ __forceinline__ int slot_status(const CellCtx& c, int r, int64_t wo, 
   const uint32_t rx = __ldg(c.raw + (int64_t)r * c.ld_raw + j);
   return (cd == 3 || rx >= cut) ? 3 : cd;
 }
-__device__ __forceinline__ bool slot_peel(const CellCtx& c, const int32_t* __restrict__ srow, uint32_t bad, int64_t j,
+__device__ __noinline__ bool slot_peel(const CellCtx& c, const int32_t* __restrict__ srow, uint32_t bad, int64_t j,
                                           uint32_t cut, double out[3]) {
   if (bad & 0x8000u) return false;
   const int64_t wo = j >> 4;
   const int sh = 2 * (int)(j & 15);
   int st[6];
+  st[0] = slot_status(c, __ldg(srow + 0), wo, sh, j, cut);
+  st[1] = slot_status(c, __ldg(srow + 1), wo, sh, j, cut);
+  // second level only under an unobserved parent (both parents' grand-parents in one batch)
+  const bool need2 = st[0] > 2 || st[1] > 2;
 #pragma unroll
-  for (int s = 0; s < 6; ++s) st[s] = slot_status(c, __ldg(srow + s), wo, sh, j, cut);
+  for (int s = 2; s < 6; ++s) st[s] = need2 ? slot_status(c, __ldg(srow + s), wo, sh, j, cut) : 4;
   double al[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
@@ -601,27 +606,41 @@ __device__ __forceinline__ bool slot_peel(const CellCtx& c, const int32_t* __res
 // long as no unobserved node is reached twice; otherwise `ok` is cleared and the caller falls back to
 // the general elimination.  Beliefs are unnormalised: their sum is P(evidence in the component).
 #define GFX_XPEEL_DEPTH 16
-// Iterative form (explicit frames, no device recursion).  Returns false when the general path is needed.
+// Iterative form (explicit frames, no device recursion) of sum-product message passing on the part of the
+// blanket that is a tree around the query.  Two kinds of frames:
+//   UP(t, from):  belief of the unobserved node t from its ancestors, times the messages of its other
+//                 children (everything except the child `from` we came through);
+//   DOWN(k):      product of the messages of all children of the unobserved node k, plus a flag telling
+//                 whether any evidence sits below k (if not, k is barren: its factor sums to 1 and the
+//                 whole branch -- including the child's other parent -- is dropped, as pgmpy does).
+// A child c of node v with other parent o sends  m(x_v) = sum_cx P(cx | x_v, o) D_c(cx)  where D_c is the
+// indicator of its state when observed and DOWN(c) otherwise; P(cx | x, o) only needs o's allele masses.
+// Returns false when the general path is needed (a node reached twice, or too deep).
 __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, uint64_t& visited, int root, int root_from,
                                        double* out) {
-  int8_t f_node[GFX_XPEEL_DEPTH], f_from[GFX_XPEEL_DEPTH], f_stage[GFX_XPEEL_DEPTH], f_sk[GFX_XPEEL_DEPTH];
+  int8_t f_node[GFX_XPEEL_DEPTH], f_from[GFX_XPEEL_DEPTH], f_stage[GFX_XPEEL_DEPTH], f_sk[GFX_XPEEL_DEPTH],
+      f_kid[GFX_XPEEL_DEPTH], f_flag[GFX_XPEEL_DEPTH];
   uint64_t f_m[GFX_XPEEL_DEPTH];
   double f_b[GFX_XPEEL_DEPTH][3], f_s[GFX_XPEEL_DEPTH][3];
   double r0 = 0, r1 = 0, r2 = 0;
+  bool rflag = false;
   int sp = 0;
   f_node[0] = (int8_t)root; f_from[0] = (int8_t)root_from; f_stage[0] = 0;
+  // stages: 0 enter UP, 1 sire belief back, 2 dam belief back, 3 child loop, 4 other parent of an observed child
+  // back, 5 DOWN(child) back, 6 other parent of an unobserved child back, 7 enter DOWN
   while (sp >= 0) {
     const int t = f_node[sp];
     const int stage = f_stage[sp];
     if (stage == 0) {
       const int st = (t == q || t == qother) ? 3 : L.status(t);
       if (st != 3) { r0 = st == 0 ? 1.0 : 0.0; r1 = st == 1 ? 1.0 : 0.0; r2 = st == 2 ? 1.0 : 0.0; --sp; continue; }
-      if ((visited >> t) & 1) return false;
+      if ((visited >> t) & 1) { if (L.dbg) atomicAdd(L.dbg + 9, 1ull); return false; }
       visited |= 1ull << t;
       const int a1 = L.p1[t];
       if (a1 < 0) {
         f_b[sp][0] = 0.25; f_b[sp][1] = 0.5; f_b[sp][2] = 0.25;
         f_m[sp] = L.kid[t] & ~(1ull << f_from[sp]);
+        f_flag[sp] = 0;
         f_stage[sp] = 3;
       } else {
         if (sp + 1 >= GFX_XPEEL_DEPTH) return false;
@@ -639,16 +658,43 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
       const double da = r0 + 0.5 * r1, db = 0.5 * r1 + r2;
       f_b[sp][0] = sa * da; f_b[sp][2] = sb * db; f_b[sp][1] = sa * db + sb * da;
       f_m[sp] = L.kid[t] & ~(1ull << f_from[sp]);
+      f_flag[sp] = 0;
+      f_stage[sp] = 3;
+    } else if (stage == 7) {
+      if ((visited >> t) & 1) { if (L.dbg) atomicAdd(L.dbg + 9, 1ull); return false; }
+      visited |= 1ull << t;
+      f_b[sp][0] = 1.0; f_b[sp][1] = 1.0; f_b[sp][2] = 1.0;
+      f_m[sp] = L.kid[t];
+      f_flag[sp] = 0;
       f_stage[sp] = 3;
     } else {
-      if (stage == 4) {
-        // likelihood of the observed child for x = 0, 1, 2 (x passes allele 0 with probability 1, 1/2, 0)
+      if (stage == 4 || stage == 6) {
+        // message of the child whose other parent's belief just came back: o passes allele 0 / 1 with oa / ob
         const double oa = r0 + 0.5 * r1, ob = 0.5 * r1 + r2;
-        const int sk = f_sk[sp];
-        if (sk == 0)      { f_b[sp][0] *= oa;  f_b[sp][1] *= 0.5 * oa;            f_b[sp][2] *= 0.0; }
-        else if (sk == 2) { f_b[sp][0] *= 0.0; f_b[sp][1] *= 0.5 * ob;            f_b[sp][2] *= ob; }
-        else              { f_b[sp][0] *= ob;  f_b[sp][1] *= 0.5 * ob + 0.5 * oa; f_b[sp][2] *= oa; }
+        double d0, d1, d2;   // D_c: indicator of the observed state, or the saved DOWN(c)
+        if (stage == 4) { const int sk = f_sk[sp]; d0 = sk == 0 ? 1.0 : 0.0; d1 = sk == 1 ? 1.0 : 0.0; d2 = sk == 2 ? 1.0 : 0.0; }
+        else { d0 = f_s[sp][0]; d1 = f_s[sp][1]; d2 = f_s[sp][2]; }
+        // x passes allele 0 with xa = 1, 1/2, 0:  P(c=0|x,o) = xa oa, P(c=2|x,o) = xb ob, P(c=1|x,o) = xa ob + xb oa
+        const double m0 = oa * d0 + ob * d1;                                   // x = 0
+        const double m1 = 0.5 * oa * d0 + (0.5 * ob + 0.5 * oa) * d1 + 0.5 * ob * d2;  // x = 1
+        const double m2 = oa * d1 + ob * d2;                                   // x = 2
+        f_b[sp][0] *= m0; f_b[sp][1] *= m1; f_b[sp][2] *= m2;
         f_stage[sp] = 3;
+      } else if (stage == 5) {
+        if (rflag) {
+          // evidence below the child: keep its DOWN vector, fetch the other parent's belief
+          if (sp + 1 >= GFX_XPEEL_DEPTH) return false;
+          f_s[sp][0] = r0; f_s[sp][1] = r1; f_s[sp][2] = r2;
+          f_flag[sp] = 1;
+          const int k = f_kid[sp];
+          f_stage[sp] = 6;
+          f_node[sp + 1] = L.p1[k] == t ? L.p2[k] : L.p1[k];
+          f_from[sp + 1] = (int8_t)k;
+          f_stage[sp + 1] = 0;
+          ++sp;
+          continue;
+        }
+        f_stage[sp] = 3;   // barren branch: dropped
       }
       bool pushed = false;
       uint64_t m = f_m[sp];
@@ -656,22 +702,28 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
         const int k = gfx_lowbit(m);
         m &= m - 1;
         const int sk = (k == q || k == qother) ? 3 : L.status(k);
-        if (sk == 3) {
-          if (L.kid[k] != 0) return false;   // evidence may sit below it: general path
-          continue;                          // childless and unobserved: barren, sums to 1
-        }
+        if (sk == 3 && L.kid[k] == 0) continue;   // childless and unobserved: barren, sums to 1
         if (sp + 1 >= GFX_XPEEL_DEPTH) return false;
         f_m[sp] = m;
-        f_sk[sp] = (int8_t)sk;
-        f_stage[sp] = 4;
-        f_node[sp + 1] = L.p1[k] == t ? L.p2[k] : L.p1[k];
-        f_from[sp + 1] = (int8_t)k;
-        f_stage[sp + 1] = 0;
+        f_kid[sp] = (int8_t)k;
+        if (sk != 3) {
+          f_sk[sp] = (int8_t)sk;
+          f_flag[sp] = 1;
+          f_stage[sp] = 4;
+          f_node[sp + 1] = L.p1[k] == t ? L.p2[k] : L.p1[k];
+          f_from[sp + 1] = (int8_t)k;
+          f_stage[sp + 1] = 0;
+        } else {
+          f_stage[sp] = 5;
+          f_node[sp + 1] = (int8_t)k;
+          f_from[sp + 1] = (int8_t)t;
+          f_stage[sp + 1] = 7;
+        }
         ++sp;
         pushed = true;
         break;
       }
-      if (!pushed) { r0 = f_b[sp][0]; r1 = f_b[sp][1]; r2 = f_b[sp][2]; --sp; }
+      if (!pushed) { r0 = f_b[sp][0]; r1 = f_b[sp][1]; r2 = f_b[sp][2]; rflag = f_flag[sp] != 0; --sp; }
     }
   }
   out[0] = r0; out[1] = r1; out[2] = r2;
@@ -679,7 +731,7 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
 }
 // out = normalised marginal, *total = unnormalised sum (0 => the reference's joint is 0/0)
 __device__ __noinline__ bool xpeel_query(const LazyBlanket& L, int q, int qother, double out[3], double* total) {
-  if (L.kid[q] != 0 || L.p1[q] < 0) return false;
+  if (L.kid[q] != 0 || L.p1[q] < 0) { if (L.dbg) atomicAdd(L.dbg + 11, 1ull); return false; }
   uint64_t visited = 1ull << q;
   double s[3], d[3];
   if (!belief_up(L, q, qother, visited, L.p1[q], q, s)) return false;
@@ -1001,8 +1053,32 @@ struct NibStream {
     ++cur;
   }
 };
-__device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
-                                               int64_t j, const double* kv, uint32_t* cls, double out[3]) {
+// one copy of numpy's block sum for the whole kernel (instruction-cache footprint matters here)
+__device__ __noinline__ void nib_leaf(NibStream& next, int n, double* res) { gfx_pw_leaf(next, n, res); }
+__device__ __noinline__ void nib_pairwise(NibStream& next, int n, double* res) {
+  if (n <= 128) { nib_leaf(next, n, res); return; }
+  int fn[16], fstage[16];
+  double fleft[16][3];
+  int sp = 0;
+  fn[0] = n; fstage[0] = 0;
+  double val[3] = {0, 0, 0};
+  while (sp >= 0) {
+    const int m = fn[sp];
+    if (m <= 128) { nib_leaf(next, m, val); --sp; continue; }
+    int n2 = m / 2; n2 -= n2 % 8;
+    if (fstage[sp] == 0) { fstage[sp] = 1; fn[sp + 1] = n2; fstage[sp + 1] = 0; ++sp; }
+    else if (fstage[sp] == 1) {
+      fleft[sp][0] = val[0]; fleft[sp][1] = val[1]; fleft[sp][2] = val[2];
+      fstage[sp] = 2; fn[sp + 1] = m - n2; fstage[sp + 1] = 0; ++sp;
+    } else {
+      val[0] = fleft[sp][0] + val[0]; val[1] = fleft[sp][1] + val[1]; val[2] = fleft[sp][2] + val[2];
+      --sp;
+    }
+  }
+  res[0] = val[0]; res[1] = val[1]; res[2] = val[2];
+}
+__device__ __noinline__ void kids_term_fast(const CellCtx& c, const int32_t* child_row, const int32_t* child_other, int nk,
+                                            int64_t j, const double* kv, uint32_t* cls, double out[3]) {
   int ninc = 0;
   uint32_t word = 0;
   const int64_t wo = j >> 4;
@@ -1020,8 +1096,7 @@ __device__ __forceinline__ void kids_term_fast(const CellCtx& c, const int32_t* 
   if (ninc == 0) { out[0] = out[1] = out[2] = 1.0 / 3.0; return; }
   NibStream next{cls, 0u, 0, 0, ninc, kv};
   double tot[3];
-  if (3 * ninc <= 128) gfx_pw_leaf(next, 3 * ninc, tot);
-  else gfx_pairwise3(next, 3 * ninc, tot);
+  nib_pairwise(next, 3 * ninc, tot);
   gfx_kids_finish(tot, ninc, out);
 }
 
@@ -1107,7 +1182,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
     if (bid >= 0) {
       const int off = a.bl.off[bid];
       LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
-                     (uint32_t)__ldg(a.c.cutraw + pidx), true};
+                     (uint32_t)__ldg(a.c.cutraw + pidx), true, a.bl.counters};
       const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
       const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
       const uint32_t tree = a.bl_tree[bid];                 // bit s: ancestry of focal s is a plain tree
@@ -1191,6 +1266,8 @@ __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
     if (lane == 0) task = atomicAdd(a.task_count, 1ull);
     task = __shfl_sync(0xffffffffu, task, 0);
     if ((int64_t)task >= tasks) break;
+    // animal-major task order, heaviest animals first: the long tasks of the many-mate sires start at once
+    // (measured: chunk-major order is 40 % slower because the last chunk's heavy tasks start late)
     const int f = a.focal_order[task / chunks];
     const int64_t j0 = (int64_t)(task % chunks) * GFX_LEAN_CHUNK;
     const int row = a.focal_row[f];

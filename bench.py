@@ -162,6 +162,7 @@ def run_cuda(args):
     torch.cuda.synchronize()
     tall = torch.zeros(args.animals, dtype=torch.int32, device=dev)
     rank_events = []
+    phase_events = []   # (name, start, end) CUDA events on the launching stream
 
     def step_resident(record):
         tall.zero_()
@@ -175,8 +176,17 @@ def run_cuda(args):
                 rank_events.append((e0, e1, (b - a)))
             else:
                 eng.mendel_rank_device()
+            if record:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
             eng.thresholds_device(PARAMS["init_filter_p"])
+            if record:
+                ev[1].record()
             eng.correct_device(PARAMS["threshold_pair"], PARAMS["threshold_single"], PARAMS["tiethreshold"], PARAMS["err_thresh"])
+            if record:
+                ev[2].record()
+                phase_events.append(("hist_thresholds", ev[0], ev[1]))
+                phase_events.append(("correct_pairs_singles", ev[1], ev[2]))
             tall.add_(eng.tallies[:eng.n])
         if world > 1:
             dist.all_reduce(tall)   # the one collective: per-animal error tallies
@@ -246,10 +256,23 @@ def run_cuda(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "rank_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
+    phases = {}
+    for name, e0, e1 in phase_events:
+        phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1)
+    phases["mendel_rank"] = sum(rk_ms)
+    phase_share = {k: v / ms for k, v in phases.items()}
     roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
-                    kernel="k_mendel_rank (+ k_mendel_rank_generic for loopy blankets)",
+                    kernel="k_mendel_rank (+ k_mendel_rank_generic for loopy blankets): the HBM-bound peeling kernel "
+                           "BASELINE.json's north_star names",
+                    algorithmic_bytes_per_cell=RANK_BYTES_PER_CELL,
                     peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                    share_of_step=sum(rk_ms) / ms)
+                    share_of_step=sum(rk_ms) / ms,
+                    note="the step is dominated by the correction kernels (k_correct, k_correct_general), which are "
+                         "instruction/latency bound: phase shares in phase_share, launch list in profiles/",
+                    correct_kernels=dict(share_of_step=phase_share.get("correct_pairs_singles"),
+                                         algorithmic_bytes_per_cell=2.5,
+                                         achieved_gbs=args.animals * args.snps * args.steps * 2.5 /
+                                         (phases.get("correct_pairs_singles", float("nan")) / 1e3) / 1e9))
     sm = [float(s[0]) for s in samples if s[0].replace(".", "").isdigit()]
     reasons = []
     for name, idx in (("hw_slowdown", 2), ("hw_thermal_slowdown", 3), ("sw_thermal_slowdown", 4), ("sw_power_cap", 5)):
@@ -272,7 +295,8 @@ def run_cuda(args):
                                    % (args.animals * args.chunk / 4 / 1e6, args.animals * args.chunk * 2 / 1e6), **PARAMS),
                     e2e=dict(value=e2e_value, unit="cells/s", h2d_bytes_per_step=int(args.animals * args.snps),
                              d2h_bytes_per_step=int(args.animals * args.snps), ms_per_step=e2e_ms / args.steps),
-                    gpu_launches=launches, roofline=roofline, clocks=clocks, corrected_cells_per_step=corrected_total)
+                    gpu_launches=launches, roofline=roofline, phase_share=phase_share, clocks=clocks,
+                    corrected_cells_per_step=corrected_total)
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
 #include <string>
@@ -1029,9 +1030,15 @@ struct FocalArgs {
   int64_t dwords;         // bitmap words per focal animal
   unsigned long long* wl_count;  // deferred cells so far
   unsigned long long* task_count; // next (animal, chunk) task of the lean kernel
+  unsigned long long* item_count; // deferred jobs so far
   const int32_t* focal_order;    // focal indices, heaviest first
-  uint2* wl;              // work list of deferred (focal, snp) cells
-  unsigned long long wl_cap;
+  uint2* wl;              // per deferred cell: (focal, snp)
+  uint2* st;              // per deferred cell: x = live state | first unresolved job << 8, y = applied | excluded << 16
+  double* skids;          // per deferred cell: children term (3) + flag
+  uint8_t* sbits;         // per deferred cell: decision bits of every job (0xFF = to be computed), row stride maxj
+  uint2* items;           // deferred jobs: (cell slot, job index within the animal)
+  unsigned long long wl_cap, item_cap;
+  int maxj;
 };
 
 // Children term for litters of up to 42 genotyped children: classes packed 4 bits each in registers,
@@ -1132,6 +1139,165 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 // All jobs of one suspect (focal animal, SNP) cell, in canonical order.  GENERAL = false is the lean
 // instantiation: ancestor terms by plain peeling only; it returns false (nothing written) as soon as a
 // job needs the general elimination, and the cell is redone by the GENERAL = true instantiation.
+// Posterior of ONE job of a cell, reduced to the decision bits of gfx_decision_bits (0 = the job is not
+// suspect at this SNP or yields no result).  Independent of the live state, so jobs of a cell can be
+// evaluated in any order / by different threads; only the apply walk below is sequential.
+// GENERAL = false: slot peeling only, returns false when the job needs tree message passing or the general
+// elimination.
+template <bool GENERAL>
+__device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, int64_t j, int obs0, uint32_t rxf,
+                                         bool has_kids, const double* kids, uint32_t* bits_out) {
+  const uint32_t tp = a.c.tp_raw;
+  const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
+  const int job = a.nf == 2 ? (ent >> 1) : ent;
+  const int side = a.nf == 2 ? (ent & 1) : 0;
+  *bits_out = 0;
+  bool sus = rxf >= tp;                                     // :181-185 / :342
+  uint32_t pidx;                                            // pattern of pmax (:220-228 / :374-376)
+  if (a.nf == 2) {
+    const int mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+    const uint32_t rxm = cell_rx(a.c, mrow, j);
+    sus = sus || (rxm >= tp);
+    if (!sus) return true;
+    const uint32_t idxm = rxm == 0xFFFFu ? 65536u : rxm;
+    const int obs_m = cell_code(a.c.live, a.c.wpr, mrow, j);
+    if (obs0 != 3 && obs_m != 3) pidx = idxf > idxm ? idxf : idxm;
+    else if (obs0 == 3 && obs_m == 3) pidx = 65536u;
+    else pidx = obs0 != 3 ? idxf : idxm;
+  } else {
+    if (!sus) return true;
+    pidx = obs0 != 3 ? idxf : 65536u;
+  }
+  GFX_COUNT(a.bl, 6, 1);
+  const int bid = a.job_bl[job];
+  double anc[3] = {0, 0, 0};
+  if (bid >= 0) {
+    const int off = a.bl.off[bid];
+    LazyBlanket LB{a.c, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j,
+                   (uint32_t)__ldg(a.c.cutraw + pidx), true, a.bl.counters};
+    const int q0 = a.bl.q0[bid], q1 = a.bl.q1[bid];
+    const int qme = side == 0 ? q0 : q1, qot = a.nf == 2 ? (side == 0 ? q1 : q0) : -1;
+    const uint32_t tree = a.bl_tree[bid];                   // bit s: ancestry of focal s is a plain tree
+    double tot_me = 1.0, tot_ot = 1.0;
+    const int sme = a.nf == 2 ? side : 0;
+    if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
+      if constexpr (!GENERAL) return false;
+      else if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
+      else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
+    } else {
+      GFX_COUNT(a.bl, 1, 1);
+    }
+    if (qot >= 0 && !((tree >> (side ^ 1)) & 1u)) {
+      // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
+      // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
+      double tmp[3];
+      if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
+        if constexpr (!GENERAL) return false;
+        else if (!xpeel_query(LB, qot, qme, tmp, &tot_ot) && query_general(LB, a.bl, qot, qme, tmp, &tot_ot))
+          atomicExch(a.status, 1);
+      }
+    }
+    if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
+  }
+  if (bid < 0 && !has_kids) return true;                    // lone node: no result (:287-288 / :417-419)
+  double p[3];
+  gfx_combine(bid >= 0, anc, has_kids, kids, p);
+  *bits_out = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
+  if (a.post) {
+    double* o = a.post + ((int64_t)ent * a.n_snps + j) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  }
+  return true;
+}
+
+// The serial apply step of one job on the live state (:809-824 / :932-938) with the lazily evaluated
+// rank gate (:733-737,817 / :928-933).
+struct ApplyState {
+  int cur, applied, excluded;
+  bool gate_done, gate;
+};
+__device__ __forceinline__ void apply_bits(const FocalArgs& a, int row, int64_t j, uint32_t rxf, uint32_t bits, ApplyState& S) {
+  if (!bits) return;
+  const bool cond = S.cur == 3 || (!((bits >> S.cur) & 1u) && (bits & 8u));
+  if (!cond) return;
+  if (!S.gate_done) {
+    double mr = 0.0;
+    for (int q = 0; q < 2; ++q) {
+      const int pr = a.prow[2 * row + q];
+      if (pr >= 0) { const double ev = rx_E(a.c, cell_rx(a.c, pr, j)); if (ev > mr) mr = ev; }
+    }
+    S.gate = rx_E(a.c, rxf) * a.p.err_thresh >= mr;
+    S.gate_done = true;
+  }
+  if (S.gate) {
+    const uint32_t set = bits & 7u;
+    S.cur = __popc(set) == 1 ? (__ffs(set) - 1) : 3;
+    ++S.applied;
+  } else {
+    ++S.excluded;
+  }
+}
+__device__ __forceinline__ void write_cell(const FocalArgs& a, int row, int64_t j, int obs0, const ApplyState& S) {
+  if (S.cur != obs0) {
+    uint32_t* wp = a.live + (int64_t)row * a.c.wpr + (j >> 4);
+    const int sh = 2 * (int)(j & 15);
+    atomicAnd(wp, ~(3u << sh));
+    atomicOr(wp, (uint32_t)S.cur << sh);
+  }
+  if (S.applied) atomicAdd(a.tallies + row, S.applied);
+  if (S.excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, S.excluded);
+}
+
+// Lean per-cell walk.  Jobs are evaluated with slot peeling and applied in order; from the first job that
+// needs more, the cell gets a slot in the deferred list: its state is parked, the remaining easy jobs
+// still deposit their bits there, the hard jobs become items for k_correct_jobs, and k_correct_apply
+// finishes the walk.  Returns false if the whole cell must go to the fallback kernel (no slot left,
+// huge litter), in which case nothing has been written.
+__device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv, uint32_t* s_cls, int f, int row, int e0, int e1,
+                                          int64_t j) {
+  const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
+  const uint32_t rxf = cell_rx(a.c, row, j);
+  bool has_kids = false;
+  double kids[3] = {0, 0, 0};
+  GFX_COUNT(a.bl, 5, 1);
+  {
+    // children term: the same for every job of this animal, evaluated once with the warp converged
+    const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+    if (nk > GFX_KIDS_FAST) return false;
+    if (nk > 0) { kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, s_cls, kids); has_kids = true; }
+    GFX_COUNT(a.bl, 7, nk);
+  }
+  ApplyState S{obs0, 0, 0, false, false};
+  bool parked = false;
+  unsigned long long slot = 0;
+  int first = 0;
+  for (int e = e0; e < e1; ++e) {
+    uint32_t bits;
+    const bool ok = job_bits<false>(a, row, a.entry[e], j, obs0, rxf, has_kids, kids, &bits);
+    if (ok && !parked) { apply_bits(a, row, j, rxf, bits, S); continue; }
+    if (!parked) {
+      if (e1 - e0 > a.maxj) return false;
+      slot = atomicAdd(a.wl_count, 1ull);
+      if (slot >= a.wl_cap) return false;
+      parked = true;
+      first = e - e0;
+    }
+    if (ok) { a.sbits[slot * a.maxj + (e - e0)] = (uint8_t)bits; continue; }
+    a.sbits[slot * a.maxj + (e - e0)] = 0xFF;
+    const unsigned long long it = atomicAdd(a.item_count, 1ull);
+    if (it < a.item_cap) a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0));
+    else first |= 0x8000;   // no room for the job item: the cell is redone by the fallback kernel
+  }
+  if (!parked) { write_cell(a, row, j, obs0, S); return true; }
+  a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
+  a.st[slot] = make_uint2((uint32_t)S.cur | ((uint32_t)(first & 0x7FFF) << 8) | ((first & 0x8000) ? 0x80000000u : 0u) |
+                              (S.gate_done ? 0x40000000u : 0u) | (S.gate ? 0x20000000u : 0u),
+                          (uint32_t)S.applied | ((uint32_t)S.excluded << 16));
+  double* kd = a.skids + slot * 4;
+  kd[0] = kids[0]; kd[1] = kids[1]; kd[2] = kids[2]; kd[3] = has_kids ? 1.0 : 0.0;
+  return (first & 0x8000) == 0;
+}
+
 template <bool GENERAL>
 __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s_kv, uint32_t* s_cls, int row, int e0, int e1,
                                              int64_t j) {
@@ -1298,39 +1464,62 @@ __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
       bool defer = false;
       if (k < cnt) {
         j = j0 + s_list[wib][k];
-        defer = !correct_cell<false>(a, s_kv, s_cls + threadIdx.x, row, e0, e1, j);
+        defer = !lean_cell(a, s_kv, s_cls + threadIdx.x, f, row, e0, e1, j);
       }
-      // deferred cells of a warp take consecutive work-list slots, so the general kernel sees runs of
-      // cells of the same animal
-      const uint32_t m = __ballot_sync(0xffffffffu, defer);
-      if (m) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.wl_count, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (defer) {
-          const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-          if (slot < a.wl_cap) a.wl[slot] = make_uint2((uint32_t)f, (uint32_t)j);
-          else atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
-        }
+      // (rare) whole cell to the fallback kernel through the bitmap
+      if (defer) {
+        atomicOr(a.deferred + (int64_t)f * a.dwords + (j >> 5), 1u << (j & 31));
+        atomicAdd(a.wl_count + 3, 1ull);
       }
     }
     __syncwarp();
   }
 }
 
-// General kernel: the deferred cells, one thread each, straight from the global work list.
-__global__ void __launch_bounds__(128) k_correct_general(FocalArgs a) {
-  __shared__ double s_kv[108];
-  __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
-  for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
-  __syncthreads();
+// Deferred jobs, one thread each: tree message passing, then the general elimination.
+__global__ void __launch_bounds__(128) k_correct_jobs(FocalArgs a) {
+  unsigned long long n = *a.item_count;
+  if (n > a.item_cap) n = a.item_cap;
+  unsigned long long ncell = *a.wl_count;
+  if (ncell > a.wl_cap) ncell = a.wl_cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 it = a.items[i];
+    if (it.x >= ncell) continue;
+    const uint2 c = a.wl[it.x];
+    const int f = (int)c.x;
+    const int64_t j = (int64_t)c.y;
+    const int row = a.focal_row[f];
+    const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);
+    const uint32_t rxf = cell_rx(a.c, row, j);
+    const double* kd = a.skids + (unsigned long long)it.x * 4;
+    const double kids[3] = {kd[0], kd[1], kd[2]};
+    uint32_t bits;
+    job_bits<true>(a, row, a.entry[a.focal_off[f] + (int)it.y], j, obs0, rxf, kd[3] != 0.0, kids, &bits);
+    a.sbits[(unsigned long long)it.x * a.maxj + it.y] = (uint8_t)bits;
+  }
+}
+
+// Finishes the serial walk of every parked cell once all its jobs have bits.
+__global__ void __launch_bounds__(128) k_correct_apply(FocalArgs a) {
   unsigned long long n = *a.wl_count;
   if (n > a.wl_cap) n = a.wl_cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 st = a.st[i];
+    if (st.x & 0x80000000u) continue;   // redone by the fallback kernel
     const uint2 c = a.wl[i];
     const int f = (int)c.x;
-    correct_cell<true>(a, s_kv, s_cls + threadIdx.x, a.focal_row[f], a.focal_off[f], a.focal_off[f + 1], (int64_t)c.y);
+    const int64_t j = (int64_t)c.y;
+    const int row = a.focal_row[f];
+    const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
+    const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);
+    const uint32_t rxf = cell_rx(a.c, row, j);
+    ApplyState S{(int)(st.x & 0xFFu), (int)(st.y & 0xFFFFu), (int)(st.y >> 16), (st.x & 0x40000000u) != 0,
+                 (st.x & 0x20000000u) != 0};
+    const int first = (int)((st.x >> 8) & 0x7FFFu);
+    for (int e = e0 + first; e < e1; ++e) apply_bits(a, row, j, rxf, a.sbits[i * a.maxj + (e - e0)], S);
+    write_cell(a, row, j, obs0, S);
   }
 }
 
@@ -1340,7 +1529,7 @@ __global__ void __launch_bounds__(128) k_correct_general_overflow(FocalArgs a) {
   __shared__ int s_cnt;
   __shared__ double s_kv[108];
   __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
-  if (*a.wl_count <= a.wl_cap) return;
+  if (a.wl_count[3] == 0) return;   // no cell was sent to the fallback
   for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
   const int64_t chunks = (a.n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK;
   const int64_t tasks = (int64_t)a.n_focal * chunks;
@@ -1373,12 +1562,12 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
                        const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
                        const int32_t* focal_order, const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
                        const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                       uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, cudaStream_t stream) {
+                       uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, int maxj, cudaStream_t stream) {
   if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
   const int64_t dwords = ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK) * (GFX_CORRECT_CHUNK / 32);
   const int64_t fixed = (int64_t)s->h.n_rows * wpr + (int64_t)s->h.n_rows * dwords + 4;
-  if (scratch_words < fixed + 2 * 1024)
-    return fail(GFX_E_INVALID, "scratch too small: need n_rows * (wpr + 32 * ceil(n_snps / 1024)) + 4 words plus the work list");
+  if (scratch_words < fixed + 64 * 1024)
+    return fail(GFX_E_INVALID, "scratch too small: need n_rows * (wpr + 32 * ceil(n_snps / 1024)) words plus >= 256 KB of lists");
   GFX_CUDA(cudaMemcpyAsync(snapshot, live, sizeof(uint32_t) * (size_t)s->h.n_rows * wpr, cudaMemcpyDeviceToDevice, stream));
   FocalArgs a;
   a.c = CellCtx{snapshot, wpr, raw, ld_raw, elut, p->cutraw_dev, p->tp_raw};
@@ -1393,15 +1582,29 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.bl_slotbad = s->bl_slotbad;
   a.child_off = s->child_off; a.child_row = s->child_row; a.child_other = s->child_other;
   a.prow = s->prow; a.kv = s->kv; a.p = *p; a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows; a.status = s->status;
-  // scratch layout: [snapshot: n_rows * wpr][overflow bitmap: n_rows * dwords][count: 4][work list: the rest]
+  // scratch layout: [snapshot: n_rows * wpr][fallback bitmap: n_rows * dwords][4 counters][parked cells: children
+  // terms, (focal, snp), state, job items, decision bits]
   a.dwords = dwords;
   a.deferred = snapshot + (size_t)s->h.n_rows * wpr;
   uint32_t* tail = a.deferred + (size_t)s->h.n_rows * dwords;
-  tail += (4 - (((uintptr_t)tail / 4) & 3)) & 3;   // 16-byte alignment for the counter / list
+  tail += (4 - (((uintptr_t)tail / 4) & 3)) & 3;   // 16-byte alignment
   a.wl_count = (unsigned long long*)tail;
-  a.wl = (uint2*)(tail + 4);
-  a.wl_cap = (unsigned long long)((snapshot + scratch_words - (tail + 4)) / 2);
-  GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(tail + 4)) - (char*)a.deferred, stream));  // bitmap + counters
+  a.item_count = a.wl_count + 2;
+  const int maxj_p = ((maxj + 7) / 8) * 8;
+  char* base = (char*)(tail + 8);
+  const int64_t avail = (char*)(snapshot + scratch_words) - base;
+  const int64_t per_slot = 32 + 8 + 8 + 16 + maxj_p;
+  const int64_t scap = avail > 0 ? avail / per_slot : 0;
+  if (scap < 1024) return fail(GFX_E_INVALID, "scratch too small for the deferred-cell lists");
+  a.skids = (double*)base;                       base += scap * 32;
+  a.wl = (uint2*)base;                           base += scap * 8;
+  a.st = (uint2*)base;                           base += scap * 8;
+  a.items = (uint2*)base;                        base += scap * 16;
+  a.sbits = (uint8_t*)base;
+  a.wl_cap = (unsigned long long)scap;
+  a.item_cap = (unsigned long long)scap * 2;
+  a.maxj = maxj_p;
+  GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(tail + 8)) - (char*)a.deferred, stream));  // bitmap + counters
   a.task_count = a.wl_count + 1;
   a.focal_order = focal_order;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
@@ -1413,7 +1616,9 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   if (lblocks > (int64_t)s->num_sms * 6) lblocks = (int64_t)s->num_sms * 6;
   k_correct<<<(int)lblocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
-  k_correct_general<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  k_correct_jobs<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_correct_apply<<<s->num_sms * 4, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_general_overflow<<<(int)blocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
@@ -1429,10 +1634,13 @@ extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint
   if (generation < 0 || generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
   const int j0 = s->h.gen_off[generation], nj = s->h.gen_off[generation + 1] - j0;
   const int f0 = s->h.app_gen_off[generation], nfoc = s->h.app_gen_off[generation + 1] - f0;
+  int maxj = 1;
+  for (int i = 0; i < nfoc; ++i)
+    maxj = std::max(maxj, s->h.app_focal_off[f0 + i + 1] - s->h.app_focal_off[f0 + i]);
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
   return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
                      s->app_focal_off + f0, s->app_order + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words,
-                     post, tallies, (cudaStream_t)stream);
+                     post, tallies, maxj, (cudaStream_t)stream);
 }
 
 extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_t n_snps, int64_t wpr,
@@ -1443,7 +1651,7 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
   const int n = (int)s->h.single_row.size();
   return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_order,
                      s->single_entry,
-                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, (cudaStream_t)stream);
+                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, 1, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

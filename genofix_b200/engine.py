@@ -205,8 +205,8 @@ class Engine(object):
         self.raw = t.empty((n, self.ld_raw), dtype=t.int16, device=dev)
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
-        # snapshot + overflow bitmap + work list of deferred cells (up to 1/8 of the cells, 2 words each)
-        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 8 + max(4096, n * self.s // 4),
+        # snapshot + fallback bitmap + lists of parked cells / deferred jobs (~76 bytes per parked cell)
+        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 16 + max(1 << 18, n * self.s // 4),
                                 dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)

@@ -134,10 +134,11 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
  *   elut_dev     65536 doubles: transformed rank E for every raw bit pattern (built by the host
  *                with numpy so log() matches the reference bit for bit); missing cells are E = 1
  *   raw_dev      scores after gfx_rank_hist (missing cells marked 0xFFFF); packed_live is updated in place
- *   scratch_dev  scratch_words uint32, at least n_rows * (wpr + 32 * ceil(n_snps / 1024)) + 4 + 2048: the
+ *   scratch_dev  scratch_words uint32, at least n_rows * (wpr + 32 * ceil(n_snps / 1024)) + 65552: the
  *                generation-start snapshot every worker of the reference reads (:687-689) -- neighbours are
- *                read from it, only the focal cell is live --, an overflow bitmap, and whatever is left as
- *                the work list (2 words per cell) of cells deferred to the general-elimination kernel
+ *                read from it, only the focal cell is live --, a fallback bitmap, and whatever is left for the
+ *                lists of parked cells and deferred jobs (about 80 bytes per cell whose ancestry needs more
+ *                than plain peeling; cells that do not fit are redone by a slower whole-cell kernel)
  *   post_dev     optional (may be NULL): posterior of every evaluated (job, side, SNP), 3 doubles at
  *                [((job * sides + side) * n_snps + snp) * 3]; cells that were not evaluated are left
  *                untouched (prefill with a sentinel)

@@ -907,57 +907,71 @@ extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, in
 }
 
 // ---- histogram of raw scores ----------------------------------------------------------------------
+// Scores are multiples of float16(1/3) and float16(1/4)-ish units, so a handful of patterns carry almost
+// all the mass: zeros and the four hottest patterns are counted in registers, patterns in [0x3000, 0x5000)
+// (values 0.125 .. 32) in a 32 KB shared-memory histogram, anything else (NaN, tiny, huge) in global memory.
+#define GFX_HIST_LO 0x3000u
+#define GFX_HIST_N 0x2000u
 __global__ void __launch_bounds__(256) k_rank_hist(uint16_t* __restrict__ raw, int64_t ld_raw,
                                                    const uint32_t* __restrict__ packed, int64_t wpr, int64_t n,
                                                    int64_t n_snps, unsigned long long* __restrict__ hist) {
-  extern __shared__ uint32_t s_hist[];  // patterns 0 .. 0x3FFF (values in [0, 2))
-  for (int i = threadIdx.x; i < 0x4000; i += blockDim.x) s_hist[i] = 0;
+  __shared__ uint32_t s_hist[GFX_HIST_N];
+  for (int i = threadIdx.x; i < (int)GFX_HIST_N; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const int64_t nwords = (n_snps + 15) / 16;
   const int64_t total = n * nwords;
-  unsigned long long zeros = 0, missing = 0;
+  const uint32_t H0 = 0x3555u, H1 = 0x3955u, H2 = 0x3800u, H3 = 0x3C00u;   // 1/3, 2/3, 1/2, 1
+  uint32_t zeros = 0, missing = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nwords, w = i - r * nwords;
     const uint32_t pw = __ldg(packed + r * wpr + w);
     const uint4* src = reinterpret_cast<const uint4*>(raw + r * ld_raw + w * 16);
     const uint4 v0 = src[0], v1 = src[1];
     const uint32_t q[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const int lim = (int)min((int64_t)16, n_snps - w * 16);
+    uint32_t miss_mask = pw & (pw >> 1) & 0x55555555u;   // code 3
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      if (w * 16 + k >= n_snps) break;
-      const uint32_t c = (pw >> (2 * k)) & 3u;
+      if (k >= lim) break;
       const uint32_t h = (q[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-      if (c == 3u) { ++missing; raw[r * ld_raw + w * 16 + k] = 0xFFFFu; }  // E = 1 by definition (:603)
+      if ((miss_mask >> (2 * k)) & 1u) { ++missing; raw[r * ld_raw + w * 16 + k] = 0xFFFFu; }  // E = 1 by definition (:603)
       else if (h == 0u) ++zeros;
-      else if (h < 0x4000u) atomicAdd(&s_hist[h], 1u);
+      else if (h == H0) ++c0;
+      else if (h == H1) ++c1;
+      else if (h == H2) ++c2;
+      else if (h == H3) ++c3;
+      else if (h - GFX_HIST_LO < GFX_HIST_N) atomicAdd(&s_hist[h - GFX_HIST_LO], 1u);
       else atomicAdd(&hist[h], 1ull);
     }
   }
-  // warp-reduce the two hot counters
+  // warp-reduce the register counters
   for (int o = 16; o > 0; o >>= 1) {
     zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
     missing += __shfl_xor_sync(0xffffffffu, missing, o);
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    if (zeros) atomicAdd(&hist[0], zeros);
-    if (missing) atomicAdd(&hist[65536], missing);
+    if (zeros) atomicAdd(&hist[0], (unsigned long long)zeros);
+    if (missing) atomicAdd(&hist[65536], (unsigned long long)missing);
+    if (c0) atomicAdd(&s_hist[H0 - GFX_HIST_LO], c0);
+    if (c1) atomicAdd(&s_hist[H1 - GFX_HIST_LO], c1);
+    if (c2) atomicAdd(&s_hist[H2 - GFX_HIST_LO], c2);
+    if (c3) atomicAdd(&s_hist[H3 - GFX_HIST_LO], c3);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 0x4000; i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+  for (int i = threadIdx.x; i < (int)GFX_HIST_N; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[GFX_HIST_LO + i], (unsigned long long)s_hist[i]);
 }
 
 extern "C" int gfx_rank_hist(uint16_t* raw, int64_t ld_raw, const uint32_t* packed, int64_t wpr, int64_t n,
                              int64_t n_snps, uint64_t* hist, void* stream) {
   if (!raw || !packed || !hist || n <= 0 || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_rank_hist: bad argument");
   GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), (cudaStream_t)stream));
-  static bool attr_set = false;
-  if (!attr_set) {
-    GFX_CUDA(cudaFuncSetAttribute(k_rank_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    attr_set = true;
-  }
   const int64_t total = n * ((n_snps + 15) / 16);
-  k_rank_hist<<<grid_for(total, 256, device_sms(), 3), 256, 65536, (cudaStream_t)stream>>>(
+  k_rank_hist<<<grid_for(total, 256, device_sms(), 6), 256, 0, (cudaStream_t)stream>>>(
       raw, ld_raw, packed, wpr, n, n_snps, (unsigned long long*)hist);
   GFX_LAUNCHED();
   return GFX_OK;

@@ -28,6 +28,27 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+_POOL = None
+
+
+def _parallel_copy(dst, src, threads=8):
+    """dst[...] = src for large 2-D arrays, row blocks on a few threads (numpy releases the GIL while copying):
+    staging a 100 MB chunk through pinned memory is otherwise the longest step of the end-to-end call."""
+    global _POOL
+    n = dst.shape[0]
+    if dst.size < (1 << 22) or n < threads:
+        dst[...] = src
+        return
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=threads)
+    step = (n + threads - 1) // threads
+
+    def work(i):
+        dst[i:i + step] = src[i:i + step]
+    list(_POOL.map(work, range(0, n, step)))
+
+
 class Schedule(object):
     """Flattened pedigree for a given list of genotyped ids (matrix row order) and look-back depth."""
 
@@ -332,7 +353,7 @@ class Engine(object):
             raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
         self._alloc(G.shape[1])
         hin = self.host_in.numpy()
-        hin[:, :self.s] = G
+        _parallel_copy(hin[:, :self.s], G)
         if self.ldc > self.s:
             hin[:, self.s:] = 9
         self.codes.copy_(self.host_in, non_blocking=True)
@@ -346,7 +367,9 @@ class Engine(object):
         tall = self.tallies.cpu().numpy()
         self.stats = dict(test_p=self.test_p, n_nan=self.n_nan, corrected_per_animal=tall[:self.n].copy(),
                           excluded_per_animal=tall[self.n:].copy(), posteriors=posts)
-        return self.host_out.numpy()[:, :self.s].copy()
+        out = np.empty((self.n, self.s), dtype=np.uint8)
+        _parallel_copy(out, self.host_out.numpy()[:, :self.s])
+        return out
 
     # ---- config 5: trio scan ---------------------------------------------------------------------------
     def trio_scan(self, G=None):

@@ -222,3 +222,57 @@ def test_window_counts_match_oracle():
             ref = go.count_joint_frq(G[:, a:b], mask[:, a:b] & (G[:, a:b] != 9), w, 0.0, sum_inner_count=False)
             vals = np.array([ref[v] for v in itertools.product([0, 1, 2], repeat=w)])
             assert np.array_equal(counts[i, :3 ** w], vals.astype(np.int64)), (sur, i)
+
+
+def test_config4_deep_loopy_pedigree_matches_oracle():
+    """BASELINE config 4 shape: 15 generations, few sires (inbreeding loops at depth 2/3), 10 % of the
+    non-founders with both parents unknown, 5 % missing calls."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle.genofix_oracle import Oracle
+    rows = synth.make_pedigree(1500, 15, sire_frac=0.06, dam_frac=0.3, seed=44, related_mating_p=0.25,
+                               unknown_parents_frac=0.1)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 48, seed=44), 0.01, seed=44), 0.05, seed=45)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    assert eng.schedule.info["n_loopy"] > 50          # the loopy-blanket paths are really exercised
+    out = eng.correct(obs, 0.5, 0.64, init_filter_p=0.9, tiethreshold=0.4)
+    o = Oracle(rows, rows[:, 0]).correct_matrix(obs, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4)
+    assert _same_f16(eng.raw_host(), o["raw"])
+    assert eng.stats["test_p"] == o["test_p"] or (np.isnan(eng.stats["test_p"]) and np.isnan(o["test_p"]))
+    assert np.array_equal(out, o["corrected"])
+    assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
+
+
+def test_config3_scale_permutation_property():
+    """BASELINE config 3 pedigree (100k animals, 10 generations) on a 1024-SNP slice: column permutation
+    commutes with correction, tallies are permutation invariant, and the rank kernel agrees with the
+    schedule-independent trio scan on which trios are Mendel-consistent."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(100000, 10, seed=1234)
+    obs = synth.inject_errors(synth.gene_drop(rows, 1024, seed=7), 0.01, seed=7)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    a = eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    ta = eng.stats["corrected_per_animal"].copy()
+    raw_a = eng.raw_host().copy()
+    perm = np.random.default_rng(3).permutation(obs.shape[1])
+    b = eng.correct(np.ascontiguousarray(obs[:, perm]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    assert np.array_equal(a[:, perm], b)
+    assert np.array_equal(ta, eng.stats["corrected_per_animal"])
+    assert np.array_equal(raw_a[:, perm].view(np.uint16), eng.raw_host().view(np.uint16))
+    inc, tested = eng.trio_scan(obs)
+    # a Mendel-inconsistent trio cell always has a positive score
+    ped = eng.schedule._keep
+    row_of = ped["row"]
+    has = (ped["sire"] >= 0) & (ped["dam"] >= 0)
+    kid_rows = row_of[has]
+    s_rows, d_rows = row_of[ped["sire"][has]], row_of[ped["dam"][has]]
+    sel = np.random.default_rng(1).choice(len(kid_rows), 2000, replace=False)
+    k, s, d = obs[kid_rows[sel]], obs[s_rows[sel]], obs[d_rows[sel]]
+    T = np.array([[1, .5, 0, .5, .25, 0, 0, 0, 0], [0, .5, 1, .5, .5, .5, 1, .5, 0], [0, 0, 0, 0, .25, .5, 0, .5, 1]]).reshape(3, 3, 3)
+    bad = T[k, s, d] == 0
+    assert np.array_equal(inc[kid_rows[sel]], bad.sum(axis=1))
+    assert np.all(raw_a[kid_rows[sel]][bad].astype(np.float32) > 0)
+    assert 0 < int((a != obs).sum()) < obs.size // 10

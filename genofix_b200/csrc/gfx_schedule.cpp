@@ -257,6 +257,23 @@ int gfx_build_schedule(const gfx_pedigree_desc* ped, GfxHostSchedule& out, std::
     }
   }
 
+  // trios grouped by family (same sire and dam), families of one sire adjacent: the scan kernel stages the
+  // parents' rows once per family and the sire's row stays cache-hot across his families
+  {
+    std::vector<int32_t>& tr = out.trio_row;
+    std::sort(tr.begin(), tr.end(), [&](int32_t x, int32_t y) {
+      const int32_t sx = out.prow[2 * x], sy = out.prow[2 * y];
+      if (sx != sy) return sx < sy;
+      const int32_t dx = out.prow[2 * x + 1], dy = out.prow[2 * y + 1];
+      if (dx != dy) return dx < dy;
+      return x < y;
+    });
+    out.fam_off.push_back(0);
+    for (size_t i = 1; i <= tr.size(); ++i)
+      if (i == tr.size() || out.prow[2 * tr[i]] != out.prow[2 * tr[i - 1]] || out.prow[2 * tr[i] + 1] != out.prow[2 * tr[i - 1] + 1])
+        out.fam_off.push_back((int32_t)i);
+  }
+
   // ---- genotyped children CSR, reference iteration order ----------------------------------------
   out.child_off.assign(nr + 1, 0);
   for (int r = 0; r < nr; ++r) {

@@ -52,7 +52,8 @@ struct GfxHostSchedule {
   // singles
   std::vector<int32_t> single_row, single_blanket, single_order;
   // trios
-  std::vector<int32_t> trio_row;     // rows with both parents genotyped
+  std::vector<int32_t> trio_row;     // rows with both parents genotyped, grouped by (sire, dam) family
+  std::vector<int32_t> fam_off;      // family f owns trio_row[fam_off[f] .. fam_off[f+1]); families ordered by sire
   GfxBlanketSet bl;
   gfx_schedule_info_t info{};
 };

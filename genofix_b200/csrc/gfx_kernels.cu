@@ -48,6 +48,12 @@ extern "C" int64_t gfx_launch_count(void) { return g_launches.load(); }
 // ------------------------------------------------------------------------------------------------
 // device-side schedule
 // ------------------------------------------------------------------------------------------------
+// per-row record of the rank kernel, heaviest rows (most children) first: one 32-byte load per task
+struct RankRow {
+  int32_t row, c0, nk, fl;   // fl: bit0 has ancestors, bit1 loopy blanket
+  int32_t rS, rD, pad0, pad1;
+};
+
 struct gfx_schedule {
   GfxHostSchedule h;
   int device = 0;
@@ -70,6 +76,10 @@ struct gfx_schedule {
   int n_loopy_rows = 0;
   int debug = 0;
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
+  uint32_t* rank_lut6 = nullptr;     // 64 entries (obs | sire << 2 | dam << 4): score | class << 16
+  uint16_t* rank_class_sc = nullptr; // score of each of the <= 8 classes
+  unsigned int* rank_ctr = nullptr;  // task counter of k_mendel_rank
+  RankRow* rank_rows = nullptr;  // per-row records, heaviest first
   double* kv = nullptr;        // 108 doubles, children-heuristic element table
   int* status = nullptr;
   unsigned long long* counters = nullptr;  // 16 diagnostic counters (gfx_debug_counters)
@@ -110,13 +120,51 @@ static void build_rank_lut(std::vector<uint2>& lut) {
   }
 }
 
+// Fast table of the rank kernel.  With both parents observed the grand-parents are d-separated from the focal
+// animal, so the ancestor score depends on (obs, sire, dam) only: idx6 = obs | sire << 2 | dam << 4.  This is
+// CHECKED here against all 256 grand-parent variants of the full table.  Distinct scores get a class id
+// (class 0 = score 0) for the (class, m) histogram; obs = 3 maps to the marker 0xFFFF.
+static bool build_rank_fast(const std::vector<uint2>& lut, std::vector<uint32_t>& lut6, std::vector<uint16_t>& class_sc,
+                            std::string& err) {
+  lut6.assign(64, 0);
+  class_sc.assign(8, 0);
+  int ncls = 1;
+  auto pick = [](const uint2& e, int obs) -> uint16_t {
+    return obs == 0 ? (uint16_t)(e.x & 0xFFFFu) : (obs == 1 ? (uint16_t)(e.x >> 16) : (uint16_t)(e.y & 0xFFFFu));
+  };
+  for (int idx = 0; idx < 64; ++idx) {
+    const int obs = idx & 3, sv = (idx >> 2) & 3, dv = (idx >> 4) & 3;
+    uint16_t sc;
+    if (obs == 3) sc = 0xFFFFu;
+    else if (sv == 3 || dv == 3) continue;   // not reachable on the fast path
+    else {
+      sc = pick(lut[sv | (dv << 2) | 0xFF0], obs);
+      for (int gp = 0; gp < 256; ++gp)
+        if (pick(lut[sv | (dv << 2) | (gp << 4)], obs) != sc) { err = "rank table depends on grand-parents below observed parents"; return false; }
+      // exactness precondition of the packed-half path (half add == float32 add + one rounding):
+      // finite scores are non-negative multiples of 2^-13 below 16
+      const float f = gfx_h2f(sc);
+      if (f == f && (f < 0.f || f >= 16.f || f * 8192.f != (float)(int)(f * 8192.f))) { err = "rank table score outside the exact range"; return false; }
+    }
+    int c = -1;
+    for (int i = 0; i < ncls; ++i) if (class_sc[i] == sc) c = i;
+    if (c < 0) {
+      if (ncls == 8) { err = "more than 8 distinct scores in the fast rank table"; return false; }
+      class_sc[ncls] = sc;
+      c = ncls++;
+    }
+    lut6[idx] = (uint32_t)sc | ((uint32_t)c << 16);
+  }
+  return true;
+}
+
 extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
   if (!s) return;
   void* ptrs[] = {s->anc6, s->rank_blanket, s->prow, s->rank_flags, s->child_off, s->child_row, s->child_other,
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off};
+                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc, s->rank_ctr, s->rank_rows};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -148,6 +196,23 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   s->n_loopy_rows = (int)loopy.size();
   std::vector<uint2> lut;
   build_rank_lut(lut);
+  std::vector<uint32_t> lut6;
+  std::vector<uint16_t> class_sc;
+  if (!build_rank_fast(lut, lut6, class_sc, err)) { delete s; return fail(GFX_E_INVALID, err); }
+  std::vector<unsigned int> rank_ctr(4, 0u);
+  std::vector<RankRow> rank_rows(h.n_rows);
+  {
+    std::vector<int32_t> order(h.n_rows);
+    for (int r = 0; r < h.n_rows; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+      return h.child_off[x + 1] - h.child_off[x] > h.child_off[y + 1] - h.child_off[y];
+    });
+    for (int i = 0; i < h.n_rows; ++i) {
+      const int r = order[i];
+      rank_rows[i] = RankRow{r, h.child_off[r], h.child_off[r + 1] - h.child_off[r], h.rank_flags[r],
+                             h.anc6[(size_t)r * 6], h.anc6[(size_t)r * 6 + 1], 0, 0};
+    }
+  }
   std::vector<double> kv(108);
   gfx_fill_kv(kv.data());
   std::vector<int> status(1, 0);
@@ -161,7 +226,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
   UP(single_entry, single_entry);
   UP(app_order, h.app_order); UP(single_order, h.single_order);
-  UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(kv, kv); UP(status, status);
+  UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(rank_lut6, lut6); UP(rank_class_sc, class_sc); UP(rank_ctr, rank_ctr); UP(rank_rows, rank_rows); UP(kv, kv); UP(status, status);
 #undef UP
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * GFX_BIG_SLOTS);
@@ -331,122 +396,380 @@ extern "C" int gfx_unpack2(const uint32_t* packed, int64_t n, int64_t s, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Mendel rank kernel (tree blankets through the shared-memory table)
+// Mendel rank kernel, fused with the histogram of the scores
 // ------------------------------------------------------------------------------------------------
+// One thread = one packed word = 16 SNPs of one animal; a warp takes (row, 128-word chunk) tasks from a global
+// counter and covers 32 consecutive words per iteration (128 B of codes in, 1 KB of scores out).
+//
+// Fast path (both parents genotyped and observed in all 16 cells of the word): the grand-parents are
+// d-separated, the score is a function of (obs, sire, dam).  The three words are transposed with 15 bitwise
+// operations into bytes obs | sire << 2 | dam << 4, one per cell, and looked up in a LANE-PRIVATE table
+// s_fast[idx6][lane] -- address formed by one PRMT, no bank conflicts.  The children term (m units of
+// float16(1/3), counted bit-parallel) is added with packed-half arithmetic: child = fma(1024 + m, c, -1024 c)
+// (one rounding, = float16(m * 1365 / 4096)), score = child + anc (half add of multiples of 2^-13 below 2^10
+// is float32 add + one rounding: what numpy does).
+// The histogram is fused: cells without children are counted per idx6 in lane-private counters next to the
+// table entry, cells with children per (score class, m) -- both conflict-free -- and mapped to float16
+// patterns when the block retires.  Anything else (missing parent cells, ragged last word, m >= 32, founders
+// with missing data) goes through the per-cell slow path with the full 4096-entry table.
 struct RankArgs {
   const uint32_t* packed;
   int64_t wpr;        // words per row
-  int64_t nwords;     // words that hold SNPs: ceil(n_snps/16)
+  int nwords;         // words that hold SNPs: ceil(n_snps/16)
+  int64_t n_snps;
   uint16_t* raw;
   int64_t ld_raw;
   int n_rows;
   const int32_t* anc6;
-  const uint8_t* flags;
-  const int32_t* child_off;
+  const RankRow* rows;
   const int32_t* child_row;
   const uint2* lut;
+  const uint32_t* lut6;
+  const uint16_t* class_sc;
+  unsigned long long* hist;   // 65537 bins or nullptr (HIST = false)
+  unsigned int* task_ctr;
+  uint32_t chunks;            // R2_CHUNK_WORDS-word chunks per row
 };
+
+#define R2_THREADS 1024
+#define R2_CHUNK_WORDS 64
+#define R2_CM_OFF 0u          // u32 [8 classes][32 m][32 lanes]
+#define R2_FAST_OFF 32768u    // u32 [64 idx6][64]: lanes 0..31 table entries, 32..63 counters
+#define R2_BINS_OFF 49152u    // u32 [8192] patterns 0x3000..0x4FFF
+#define R2_LUT_OFF 81920u     // uint2 [4096] full table (slow path)
+#define R2_SMEM (81920u + 32768u)
+#define R2_BIN_LO 0x3000u
+#define R2_BIN_N 0x2000u
 
 __device__ __forceinline__ uint32_t ldg_word(const uint32_t* p, int64_t row, int64_t wpr, int64_t w) {
   return row >= 0 ? __ldg(p + row * wpr + w) : 0xFFFFFFFFu;
 }
+__device__ __forceinline__ __half2 r2_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t r2_u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ void r2_store(uint16_t* dst, const uint32_t* o) {
+  __stcs(reinterpret_cast<uint4*>(dst), make_uint4(o[0], o[1], o[2], o[3]));
+  __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(o[4], o[5], o[6], o[7]));
+}
 
-// One thread = one 32-bit word = 16 SNPs of one animal.  A warp covers 32 consecutive words of a row
-// (128 B of codes in, 1 KB of scores out); blocks are persistent and stride over (row, chunk) tasks.
-__global__ void __launch_bounds__(256) k_mendel_rank(RankArgs a) {
-  extern __shared__ uint2 s_lut[];
-  for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_lut[i] = a.lut[i];
+// children of a row at word w: per cell m = sum over genotyped children of the float16 difference in units of
+// 1/3 (bayesnet/model.py:93-116 with the other parent unknown, D7): child 0 -> [0,1,2][obs], child 1 -> 0,
+// child 2 -> [2,1,0][obs].  m16[k] = m(cell 2k) | m(cell 2k+1) << 16; anyv bit 2i: cell i has a genotyped child.
+// Counted bit-parallel: 2-bit contributions -> nibble lanes (7 children) -> byte lanes (17 flushes) -> 16-bit lanes.
+__device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, int64_t w, uint32_t w0, uint32_t m16[8],
+                                            uint32_t& anyv) {
+  const uint32_t lo = w0, hi = w0 >> 1;
+  const uint32_t o0 = ~(lo | hi) & 0x55555555u;
+  const uint32_t o1 = (lo & ~hi) & 0x55555555u;
+  const uint32_t o2 = (hi & ~lo) & 0x55555555u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m16[k] = 0;
+  uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1
+  uint32_t bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;   // byte t: cells 4t, 4t + 2, 4t + 1, 4t + 3
+  int pend = 0, pend8 = 0;
+  anyv = 0;
+  for (int c = c0; c < c1; ++c) {
+    const uint32_t wc = __ldg(a.packed + (int64_t)__ldg(a.child_row + c) * a.wpr + w);
+    const uint32_t cl = wc, ch = wc >> 1;
+    const uint32_t is0 = ~(cl | ch) & 0x55555555u;
+    const uint32_t is2 = (ch & ~cl) & 0x55555555u;
+    anyv |= ~(cl & ch);
+    const uint32_t one = (is0 | is2) & o1;
+    const uint32_t two = (is2 & o0) | (is0 & o2);
+    const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
+    acc_lo += contrib & 0x33333333u;
+    acc_hi += (contrib >> 2) & 0x33333333u;
+    if (++pend == 7) {                          // 7 * 2 = 14 < 16
+      bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
+      bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+      acc_lo = acc_hi = 0;
+      pend = 0;
+      if (++pend8 == 17) {                      // 17 * 14 = 238 < 256
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+          m16[2 * t + 1] += __byte_perm(bl1, bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+        }
+        bl0 = bl1 = bh0 = bh1 = 0;
+        pend8 = 0;
+      }
+    }
+  }
+  bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
+  bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    // halves: low = byte t of bl, high = byte t of bh
+    m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+    m16[2 * t + 1] += __byte_perm(bl1, bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+  }
+  anyv &= 0x55555555u;
+}
+
+// histogram of one word's final patterns (words whose cells do not fit the lane-private counters)
+__device__ __noinline__ void r2_hist_patterns(unsigned long long* hist, uint32_t* s_bins, const uint32_t outw[8], uint32_t miss,
+                                              int lim, uint32_t& zeros, uint32_t& nmiss) {
+#pragma unroll 1
+  for (int i = 0; i < lim; ++i) {
+    const uint32_t r = (outw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+    if ((miss >> (2 * i)) & 1u) ++nmiss;
+    else if (r == 0u) ++zeros;
+    else if (r - R2_BIN_LO < R2_BIN_N) atomicAdd(&s_bins[r - R2_BIN_LO], 1u);
+    else atomicAdd(&hist[r], 1ull);
+  }
+}
+
+// Per-cell path with the full table; handles every case (and is the definition the fast path is tested against).
+template <bool HIST>
+__device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t row, int64_t w, uint32_t w0, bool has_anc,
+                                          int c0, int c1, uint32_t& zeros, uint32_t& nmiss) {
+  const uint2* s_lut = reinterpret_cast<const uint2*>(smem + R2_LUT_OFF);
+  uint32_t wa[6];
+  if (has_anc) {
+    const int32_t* a6 = a.anc6 + row * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) wa[k] = ldg_word(a.packed, __ldg(a6 + k), a.wpr, w);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) wa[k] = 0xFFFFFFFFu;
+  }
+  uint32_t m16[8], anyv;
+  r2_children(a, c0, c1, w, w0, m16, anyv);
+  const int lim = (int)min((int64_t)16, a.n_snps - w * 16);
+  uint32_t outw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t pair = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * k + h;
+      const uint32_t obs = (w0 >> (2 * i)) & 3u;
+      uint32_t r = 0x3C00u;  // 1.0: unobserved, or neither ancestors nor usable children (:102)
+      if (obs != 3u) {
+        const bool kids = (anyv >> (2 * i)) & 1u;
+        const uint32_t m = (m16[k] >> (16 * h)) & 0xFFFFu;
+        if (has_anc) {
+          const uint32_t idx = ((wa[0] >> (2 * i)) & 3u) | (((wa[1] >> (2 * i)) & 3u) << 2) |
+                               (((wa[2] >> (2 * i)) & 3u) << 4) | (((wa[3] >> (2 * i)) & 3u) << 6) |
+                               (((wa[4] >> (2 * i)) & 3u) << 8) | (((wa[5] >> (2 * i)) & 3u) << 10);
+          const uint2 e = s_lut[idx];
+          const uint16_t sc = obs == 0 ? (uint16_t)(e.x & 0xFFFFu) : (obs == 1 ? (uint16_t)(e.x >> 16) : (uint16_t)(e.y & 0xFFFFu));
+          r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+        } else if (kids) {
+          r = gfx_child_score(m);
+        }
+      } else if (HIST) {
+        r = 0xFFFFu;   // E = 1 by definition (:603)
+      }
+      pair |= r << (16 * h);
+    }
+    outw[k] = pair;
+  }
+  if (HIST)
+    r2_hist_patterns(a.hist, reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF), outw, w0 & (w0 >> 1) & 0x55555555u, lim, zeros, nmiss);
+  r2_store(a.raw + row * a.ld_raw + w * 16, outw);
+}
+
+template <bool HIST>
+__global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
+  extern __shared__ __align__(16) char smem[];
+  {
+    uint2* s_lut = reinterpret_cast<uint2*>(smem + R2_LUT_OFF);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_lut[i] = a.lut[i];
+    uint32_t* s_fast = reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF);
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int idx = i >> 6, l = i & 63;
+      uint32_t v = 0;
+      if (l < 32) {
+        const uint32_t e = a.lut6[idx];
+        uint32_t sc = e & 0xFFFFu;
+        if (!HIST && sc == 0xFFFFu) sc = 0x3C00u;   // plain mode: unobserved cells score 1.0 (:102)
+        v = sc | ((R2_CM_OFF + (e >> 16) * 4096u + (uint32_t)l * 4u) << 16);
+      }
+      s_fast[i] = v;
+    }
+    uint32_t* s_z = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < (int)(R2_FAST_OFF / 4); i += blockDim.x) s_z[i] = 0;                 // (class, m) counters
+    uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF);
+    for (int i = threadIdx.x; i < (int)R2_BIN_N; i += blockDim.x) s_bins[i] = 0;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int64_t chunks = (a.nwords + 31) >> 5;
-  const int64_t tasks = (int64_t)a.n_rows * chunks;
-  for (int64_t task = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < tasks;
-       task += (int64_t)gridDim.x * warps_per_block) {
-    const int64_t row = task / chunks;
-    const int64_t w = (task - row * chunks) * 32 + lane;
-    const uint8_t fl = a.flags[row];
-    if (fl & 2) continue;  // generic-engine rows are written by k_mendel_rank_generic
-    if (w >= a.nwords) continue;
-    const bool has_anc = fl & 1;
-    const uint32_t w0 = __ldg(a.packed + row * a.wpr + w);
-    uint32_t wa[6];
-    if (has_anc) {
-      const int32_t* a6 = a.anc6 + row * 6;
+  const uint32_t lane4 = (uint32_t)lane * 4u;
+  const uint32_t tasks = (uint32_t)a.n_rows * a.chunks;
+  const __half2 C3 = r2_h2(0x35553555u);    // float16(1/3) = 1365 / 4096
+  const __half2 K3 = r2_h2(0xDD55DD55u);    // -1024 * float16(1/3) = -341.25
+  uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF);
+  uint32_t zeros = 0, ones = 0, nmiss = 0;
+  uint32_t task = 0;
+  if (lane == 0) task = atomicAdd(a.task_ctr, 1u);
+  task = __shfl_sync(0xffffffffu, task, 0);
+  while (task < tasks) {
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(a.task_ctr, 1u);   // in flight while this task is processed
+    // task order: chunk-major inside a row record, records heaviest first
+    const uint32_t rec = task / a.chunks;
+    const int wbeg = (int)(task - rec * a.chunks) * R2_CHUNK_WORDS;
+    const int wend = min(wbeg + R2_CHUNK_WORDS, a.nwords);
+    const int4 q0 = __ldg(reinterpret_cast<const int4*>(a.rows + rec));
+    const int4 q1 = __ldg(reinterpret_cast<const int4*>(a.rows + rec) + 1);
+    const int row = q0.x, c0 = q0.y, c1 = q0.y + q0.z;
+    const bool has_anc = q0.w & 1, loopy = q0.w & 2;
+    const int rS = q1.x, rD = q1.y;
+    const bool parents_ok = has_anc && rS >= 0 && rD >= 0;
+    if (!(loopy && !parents_ok)) {   // else: every word of this row belongs to k_mendel_rank_generic
+      const uint32_t* prow0 = a.packed + (int64_t)row * a.wpr;
+      const uint32_t* prowS = a.packed + (int64_t)(parents_ok ? rS : row) * a.wpr;
+      const uint32_t* prowD = a.packed + (int64_t)(parents_ok ? rD : row) * a.wpr;
+      int w = wbeg + lane;
+      uint32_t n0 = 0, nS = 0, nD = 0;
+      if (w < wend) { n0 = __ldg(prow0 + w); nS = __ldg(prowS + w); nD = __ldg(prowD + w); }
+      for (; w < wend; w += 32) {
+        const uint32_t w0 = n0, wS = nS, wD = nD;
+        if (w + 32 < wend) { n0 = __ldg(prow0 + w + 32); nS = __ldg(prowS + w + 32); nD = __ldg(prowD + w + 32); }
+        uint16_t* dst = a.raw + (int64_t)row * a.ld_raw + (int64_t)w * 16;
+        const uint32_t miss = w0 & (w0 >> 1) & 0x55555555u;
+        const bool tail = HIST && w == a.nwords - 1 && (a.n_snps & 15);
+        uint32_t outw[8];
+        if (!has_anc && c0 == c1) {
+          // neither ancestors nor children: every score is 1.0 (:102)
+          if (tail) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1, zeros, nmiss); continue; }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) wa[k] = ldg_word(a.packed, a6[k], a.wpr, w);
-    } else {
+          for (int k = 0; k < 8; ++k) outw[k] = 0x3C003C00u;
+          if (HIST) {
+            if (miss) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) wa[k] = 0xFFFFFFFFu;
-    }
-    // observed-state masks of the focal animal, one bit per cell at even positions
-    const uint32_t lo = w0, hi = w0 >> 1;
-    const uint32_t o0 = ~(lo | hi) & 0x55555555u;        // code 0
-    const uint32_t o1 = (lo & ~hi) & 0x55555555u;        // code 1
-    const uint32_t o2 = (hi & ~lo) & 0x55555555u;        // code 2
-    // children: per cell m = sum over genotyped children of the float16 difference in units of 1/3
-    //   obs 0: 2 per child in state 2, 1 per child in state 0 ... (bayesnet/model.py:93-116 with the
-    //   other parent unknown, D7): child 0 -> [0,1,2][obs], child 1 -> 0, child 2 -> [2,1,0][obs]
-    uint32_t m16[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m16[k] = 0;
-    uint32_t anyv = 0, acc_lo = 0, acc_hi = 0;
-    int pend = 0;
-    const int c0 = a.child_off[row], c1 = a.child_off[row + 1];
-    for (int c = c0; c < c1; ++c) {
-      const uint32_t wc = __ldg(a.packed + (int64_t)a.child_row[c] * a.wpr + w);
-      const uint32_t cl = wc, ch = wc >> 1;
-      const uint32_t is0 = ~(cl | ch) & 0x55555555u;
-      const uint32_t is2 = (ch & ~cl) & 0x55555555u;
-      anyv |= ~(cl & ch) & 0x55555555u;
-      const uint32_t one = (is0 | is2) & o1;
-      const uint32_t two = (is2 & o0) | (is0 & o2);
-      const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
-      acc_lo += contrib & 0x33333333u;            // even cells, 4-bit lanes
-      acc_hi += (contrib >> 2) & 0x33333333u;     // odd cells
-      if (++pend == 7) {                          // 7 * 2 = 14 < 16: flush nibble lanes
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          m16[k] += ((acc_lo >> (4 * k)) & 0xFu) | (((acc_hi >> (4 * k)) & 0xFu) << 16);
-        acc_lo = acc_hi = 0;
-        pend = 0;
-      }
-    }
-    if (pend) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        m16[k] += ((acc_lo >> (4 * k)) & 0xFu) | (((acc_hi >> (4 * k)) & 0xFu) << 16);
-    }
-    uint32_t outw[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      uint32_t pair = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = 2 * k + h;
-        const uint32_t obs = (w0 >> (2 * i)) & 3u;
-        uint16_t r = 0x3C00;  // 1.0: unobserved, or neither ancestors nor usable children (:102)
-        if (obs != 3u) {
-          const bool kids = (anyv >> (2 * i)) & 1u;
-          const uint32_t m = (m16[k] >> (16 * h)) & 0xFFFFu;
-          if (has_anc) {
-            const uint32_t idx = ((wa[0] >> (2 * i)) & 3u) | (((wa[1] >> (2 * i)) & 3u) << 2) |
-                                 (((wa[2] >> (2 * i)) & 3u) << 4) | (((wa[3] >> (2 * i)) & 3u) << 6) |
-                                 (((wa[4] >> (2 * i)) & 3u) << 8) | (((wa[5] >> (2 * i)) & 3u) << 10);
-            const uint2 e = s_lut[idx];
-            const uint16_t sc = obs == 0 ? (uint16_t)(e.x & 0xFFFFu) : (obs == 1 ? (uint16_t)(e.x >> 16) : (uint16_t)(e.y & 0xFFFFu));
-            r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
-          } else if (kids) {
-            r = gfx_child_score(m);
+              for (int k = 0; k < 8; ++k) {
+                if ((miss >> (4 * k)) & 1u) outw[k] |= 0x0000FFFFu;
+                if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
+              }
+            }
+            const uint32_t nm = __popc(miss);
+            nmiss += nm;
+            ones += 16u - nm;
+          }
+          r2_store(dst, outw);
+          continue;
+        }
+        bool slow = tail;
+        if (has_anc) {
+          if (!parents_ok) slow = true;
+          else if (((wS & (wS >> 1)) | (wD & (wD >> 1))) & 0x55555555u) {
+            if (loopy) continue;   // k_mendel_rank_generic owns this word
+            slow = true;
           }
         }
-        pair |= (uint32_t)r << (16 * h);
+        uint32_t m16[8], anyv = 0;
+        bool big = false;
+        if (!slow && c1 > c0) {
+          r2_children(a, c0, c1, w, w0, m16, anyv);
+          uint32_t any = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) any |= m16[k];
+          big = any & 0xFFE0FFE0u;                                                          // (class, m) counters hold m < 32
+          if (any & 0xFC00FC00u) slow = true;                                               // packed-half path: m < 1024
+          if (!has_anc && (miss || anyv != 0x55555555u)) slow = true;                        // 1.0 cells among child scores
+        }
+        if (slow) { r2_slow_word<HIST>(a, smem, row, w, w0, has_anc, c0, c1, zeros, nmiss); continue; }
+        if (has_anc) {
+          // 4-row transposition of 2-bit fields: one byte obs | sire << 2 | dam << 4 per cell
+          const uint32_t M2 = 0x33333333u, M4 = 0x0F0F0F0Fu;
+          const uint32_t A = (w0 & M2) | ((wS << 2) & ~M2);          // nibble n: cell 2n
+          const uint32_t B = ((w0 >> 2) & M2) | (wS & ~M2);          // nibble n: cell 2n + 1
+          const uint32_t Cc = wD & M2, Dd = (wD >> 2) & M2;
+          const uint32_t X = (A & M4) | ((Cc << 4) & ~M4);           // byte t: cell 4t
+          const uint32_t Y = ((A >> 4) & M4) | (Cc & ~M4);           // byte t: cell 4t + 2
+          const uint32_t Z = (B & M4) | ((Dd << 4) & ~M4);           // byte t: cell 4t + 1
+          const uint32_t W = ((B >> 4) & M4) | (Dd & ~M4);           // byte t: cell 4t + 3
+          if (c1 == c0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t offa = __byte_perm((k & 1) ? Y : X, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
+              const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
+              const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
+              const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
+              if (HIST) {
+                atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offa), 1u);
+                atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offb), 1u);
+              }
+              outw[k] = __byte_perm(ea, eb, 0x5410u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t offa = __byte_perm((k & 1) ? Y : X, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
+              const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
+              const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
+              const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
+              if (HIST && !big) {
+                atomicAdd(reinterpret_cast<uint32_t*>(smem + (ea >> 16) + ((m16[k] & 0xFFFFu) << 7)), 1u);
+                atomicAdd(reinterpret_cast<uint32_t*>(smem + (eb >> 16) + ((m16[k] >> 16) << 7)), 1u);
+              }
+              const __half2 cs = __hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3);
+              outw[k] = r2_u(__hadd2(cs, r2_h2(__byte_perm(ea, eb, 0x5410u))));
+            }
+            if (HIST && miss) {   // NaN + 0 lost the marker
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if ((miss >> (4 * k)) & 1u) outw[k] |= 0x0000FFFFu;
+                if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
+              }
+            }
+            if (HIST && big) r2_hist_patterns(a.hist, s_bins, outw, miss, 16, zeros, nmiss);
+          }
+        } else {
+          // founder with children, nothing missing: the score is the children term alone (class 0 = score 0)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (HIST && !big) {
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_CM_OFF + lane4 + ((m16[k] & 0xFFFFu) << 7)), 1u);
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_CM_OFF + lane4 + ((m16[k] >> 16) << 7)), 1u);
+            }
+            outw[k] = r2_u(__hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3));
+          }
+          if (HIST && big) r2_hist_patterns(a.hist, s_bins, outw, 0u, 16, zeros, nmiss);
+        }
+        r2_store(dst, outw);
       }
-      outw[k] = pair;
     }
-    uint4* dst = reinterpret_cast<uint4*>(a.raw + row * a.ld_raw + w * 16);
-    dst[0] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
-    dst[1] = make_uint4(outw[4], outw[5], outw[6], outw[7]);
+    task = __shfl_sync(0xffffffffu, next, 0);
+  }
+  if (!HIST) return;
+  // ---- retire: counters -> float16 patterns -> global histogram ------------------------------------
+  for (int o = 16; o > 0; o >>= 1) {
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+  }
+  if (lane == 0) {
+    if (zeros) atomicAdd(&s_bins[R2_BIN_N - 1], zeros);          // 0x4FFF (31.98) cannot be a score: scratch slots
+    if (ones) atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], ones);
+    if (nmiss) atomicAdd(&s_bins[R2_BIN_N - 2], nmiss);
+  }
+  __syncthreads();
+  {
+    const uint32_t* s_fast = reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF);
+    const uint32_t* s_cm = reinterpret_cast<const uint32_t*>(smem + R2_CM_OFF);
+    const int t = threadIdx.x;
+    if (t < 64) {
+      unsigned long long sum = 0;
+      for (int l = 0; l < 32; ++l) sum += s_fast[t * 64 + 32 + ((l + t) & 31)];
+      const uint32_t sc = a.lut6[t] & 0xFFFFu;
+      if (sum) atomicAdd(&a.hist[sc == 0xFFFFu ? 65536u : sc], sum);
+    } else if (t < 64 + 256) {
+      const int cm = t - 64, cls = cm >> 5, m = cm & 31;
+      unsigned long long sum = 0;
+      for (int l = 0; l < 32; ++l) sum += s_cm[cm * 32 + ((l + t) & 31)];
+      const uint16_t sc = a.class_sc[cls];
+      // the marker class only ever has m = 0 (an unobserved cell receives no children units)
+      const uint32_t pat = sc == 0xFFFFu ? 65536u : (uint32_t)gfx_half_add(gfx_child_score((uint32_t)m), sc);
+      if (sum) atomicAdd(&a.hist[pat], sum);
+    }
+    for (int i = t; i < (int)R2_BIN_N; i += blockDim.x) {
+      const uint32_t v = s_bins[i];
+      if (!v) continue;
+      const uint32_t bin = i == (int)R2_BIN_N - 1 ? 0u : (i == (int)R2_BIN_N - 2 ? 65536u : R2_BIN_LO + i);
+      atomicAdd(&a.hist[bin], (unsigned long long)v);
+    }
   }
 }
 
@@ -836,74 +1159,121 @@ struct GenericRankArgs {
   const int32_t* rank_blanket;
   const int32_t* child_off;
   const int32_t* child_row;
+  const int32_t* anc6;
   BlanketDev bl;
   const uint64_t* bl_kid;
   int* status;
+  unsigned long long* hist;   // nullptr: plain scores (missing cells 1.0), else histogram + 0xFFFF marker
 };
 
-// Rows whose blanket is not the plain tree: one thread per cell, full inference.
+// Rows whose blanket is not the plain tree: one thread per cell, full inference.  Words in which both parents
+// are observed in all 16 cells are d-separated from the loop and belong to k_mendel_rank (same test there).
 __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) {
   const int64_t padded = ((a.n_snps + 15) / 16) * 16;
   const int64_t total = (int64_t)a.n_rows_sel * padded;
   double tab[GFX_TAB];
   uint8_t code[GFX_MAXN];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int sel = (int)(i / padded);
-    const int64_t j = i - (int64_t)sel * padded;
-    const int row = a.rows[sel];
-    uint16_t r = 0x3C00;
-    const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
-    if (obs != 3) {
-      const int bid = a.rank_blanket[row];
-      const int off = a.bl.off[bid];
-      CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
-      LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
-      double anc[3], tot;
-      if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot)) atomicExch(a.status, 1);
-      const uint16_t sc = gfx_anc_score(anc, obs);
-      uint32_t m = 0;
-      bool kids = false;
-      for (int c = a.child_off[row]; c < a.child_off[row + 1]; ++c) {
-        const int k = cell_code(a.packed, a.wpr, a.child_row[c], j);
-        if (k != 3) kids = true;
-        if (k == 0) m += obs;            // [0,1,2][obs]
-        else if (k == 2) m += 2 - obs;   // [2,1,0][obs]
+  const int64_t span = (((total + 31) >> 5) << 5);   // whole warps stay in the loop (warp-aggregated histogram)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (int64_t)gridDim.x * blockDim.x) {
+    bool mine = i < total;
+    uint32_t r = 0x3C00u;
+    bool count = false;
+    if (mine) {
+      const int sel = (int)(i / padded);
+      const int64_t j = i - (int64_t)sel * padded;
+      const int row = a.rows[sel];
+      const int rS = a.anc6[(int64_t)row * 6], rD = a.anc6[(int64_t)row * 6 + 1];
+      if (rS >= 0 && rD >= 0) {
+        const uint32_t wS = __ldg(a.packed + (int64_t)rS * a.wpr + (j >> 4)), wD = __ldg(a.packed + (int64_t)rD * a.wpr + (j >> 4));
+        if ((((wS & (wS >> 1)) | (wD & (wD >> 1))) & 0x55555555u) == 0u) mine = false;
       }
-      r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+      if (mine) {
+        const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
+        if (obs != 3) {
+          const int bid = a.rank_blanket[row];
+          const int off = a.bl.off[bid];
+          CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
+          LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
+          double anc[3], tot;
+          if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot)) atomicExch(a.status, 1);
+          const uint16_t sc = gfx_anc_score(anc, obs);
+          uint32_t m = 0;
+          bool kids = false;
+          for (int c = a.child_off[row]; c < a.child_off[row + 1]; ++c) {
+            const int k = cell_code(a.packed, a.wpr, a.child_row[c], j);
+            if (k != 3) kids = true;
+            if (k == 0) m += obs;            // [0,1,2][obs]
+            else if (k == 2) m += 2 - obs;   // [2,1,0][obs]
+          }
+          r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+        } else if (a.hist) {
+          r = 0xFFFFu;
+        }
+        a.raw[(int64_t)row * a.ld_raw + j] = (uint16_t)r;
+        count = j < a.n_snps;
+      }
     }
-    a.raw[(int64_t)row * a.ld_raw + j] = r;
+    if (a.hist) {
+      // one atomic per distinct pattern of the warp
+      const uint32_t act = __ballot_sync(0xffffffffu, count);
+      if (count) {
+        const uint32_t peers = __match_any_sync(act, r);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
+          atomicAdd(&a.hist[r == 0xFFFFu ? 65536u : r], (unsigned long long)__popc(peers));
+      }
+    }
   }
 }
 
-extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr,
-                               uint16_t* raw, int64_t ld_raw, void* stream) {
+static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, uint16_t* raw,
+                              int64_t ld_raw, uint64_t* hist, cudaStream_t stream) {
   if (!s || !packed || !raw) return fail(GFX_E_INVALID, "null argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
   const int64_t nwords = (n_snps + 15) / 16;
   if (n_snps <= 0 || wpr < nwords || ld_raw < nwords * 16 || (ld_raw % 8) != 0 || (((uintptr_t)raw) % 16) != 0)
     return fail(GFX_E_INVALID, "gfx_mendel_rank: need wpr >= ceil(s/16), ld_raw >= 16*ceil(s/16), ld_raw % 8 == 0, raw 16-byte aligned");
-  RankArgs a{packed, wpr, nwords, raw, ld_raw, s->h.n_rows, s->anc6, s->rank_flags, s->child_off, s->child_row, s->rank_lut};
+  const int64_t chunks = (nwords + R2_CHUNK_WORDS - 1) / R2_CHUNK_WORDS;
+  if ((int64_t)s->h.n_rows * chunks >= (int64_t)0xFFFF0000ll || nwords > 0x7FFFFF00ll)
+    return fail(GFX_E_INVALID, "gfx_mendel_rank: matrix too large for one call (rows * ceil(words/128) must stay below 2^32)");
+  RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, s->rank_rows, s->child_row,
+             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist, s->rank_ctr, (uint32_t)chunks};
   static bool attr_set = false;
   if (!attr_set) {
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
     attr_set = true;
   }
-  const int64_t tasks = (int64_t)s->h.n_rows * ((nwords + 31) / 32);
-  int blocks = (int)((tasks + 7) / 8);
-  const int cap = s->num_sms * 6;
-  if (blocks > cap) blocks = cap;
+  GFX_CUDA(cudaMemsetAsync(s->rank_ctr, 0, sizeof(unsigned int), stream));
+  if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
+  const int64_t tasks = (int64_t)s->h.n_rows * chunks;
+  int blocks = (int)std::min<int64_t>((tasks + 31) / 32, s->num_sms);
   if (blocks < 1) blocks = 1;
-  k_mendel_rank<<<blocks, 256, 32768, (cudaStream_t)stream>>>(a);
+  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_SMEM, stream>>>(a);
+  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_SMEM, stream>>>(a);
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
+                      s->anc6,
                       BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr},
-                      s->bl_kid, s->status};
+                      s->bl_kid, s->status, (unsigned long long*)hist};
     const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
-    k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, (cudaStream_t)stream>>>(g);
+    k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, stream>>>(g);
     GFX_LAUNCHED();
   }
   return GFX_OK;
+}
+
+extern "C" int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr,
+                               uint16_t* raw, int64_t ld_raw, void* stream) {
+  return launch_mendel_rank(s, packed, n_snps, wpr, raw, ld_raw, nullptr, (cudaStream_t)stream);
+}
+
+// Fused variant: scores + their 65 537-bin histogram in one pass; missing cells carry the marker 0xFFFF
+// (what gfx_mendel_rank followed by gfx_rank_hist produces).
+extern "C" int gfx_mendel_rank_hist(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr,
+                                    uint16_t* raw, int64_t ld_raw, uint64_t* hist, void* stream) {
+  if (!hist) return fail(GFX_E_INVALID, "gfx_mendel_rank_hist: null histogram");
+  return launch_mendel_rank(s, packed, n_snps, wpr, raw, ld_raw, hist, (cudaStream_t)stream);
 }
 
 // ---- histogram of raw scores ----------------------------------------------------------------------

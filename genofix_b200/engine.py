@@ -261,13 +261,23 @@ class Engine(object):
         self.thresholds_device(init_filter_p)
         self.correct_device(threshold_pair, threshold_single, tiethreshold, err_thresh)
 
-    def mendel_rank_device(self):
-        _lib.check(self.L.gfx_mendel_rank(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
-                                          self.raw.data_ptr(), self.ld_raw, self._stream()))
+    def mendel_rank_device(self, fused=True):
+        """Scores of every cell.  fused (the pipeline's form): one pass that also builds the histogram and
+        puts the 0xFFFF marker on missing cells; otherwise the plain scores (thresholds_device then runs
+        gfx_rank_hist as a second pass)."""
+        if fused:
+            _lib.check(self.L.gfx_mendel_rank_hist(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
+                                                   self.raw.data_ptr(), self.ld_raw, self.hist.data_ptr(), self._stream()))
+        else:
+            _lib.check(self.L.gfx_mendel_rank(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
+                                              self.raw.data_ptr(), self.ld_raw, self._stream()))
+        self._hist_ready = bool(fused)
 
     def thresholds_device(self, init_filter_p):
-        _lib.check(self.L.gfx_rank_hist(self.raw.data_ptr(), self.ld_raw, self.packed_orig.data_ptr(), self.wpr, self.n,
-                                        self.s, self.hist.data_ptr(), self._stream()))
+        if not getattr(self, "_hist_ready", False):
+            _lib.check(self.L.gfx_rank_hist(self.raw.data_ptr(), self.ld_raw, self.packed_orig.data_ptr(), self.wpr, self.n,
+                                            self.s, self.hist.data_ptr(), self._stream()))
+        self._hist_ready = False
         self.host_hist.copy_(self.hist, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
         elut, test_p, n_nan = rank_transform_table(self.host_hist.numpy().view(np.uint64), init_filter_p)

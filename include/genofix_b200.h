@@ -114,6 +114,12 @@ int gfx_unpack2(const uint32_t* packed_dev, int64_t n, int64_t s, int64_t wpr,
 int gfx_mendel_rank(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
                     uint16_t* raw_dev, int64_t ld_raw, void* stream);
 
+/* Fused form used by the pipeline: gfx_mendel_rank + gfx_rank_hist in ONE pass over the matrix (the scores are
+ * written once and never re-read): raw_dev receives the scores with the 0xFFFF marker on missing cells, hist_dev
+ * (65537 uint64, zeroed here) the histogram described below.  Rows of packed_dev must be padded with code 3. */
+int gfx_mendel_rank_hist(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
+                         uint16_t* raw_dev, int64_t ld_raw, uint64_t* hist_dev, void* stream);
+
 /* Histogram of the raw float16 bit patterns over non-missing cells (65536 x uint64) plus the
  * number of missing cells in hist_dev[65536]: everything the rank transform and both quantiles need
  * (correct_genotypes3.py:593-606,666-667).  hist_dev must hold 65537 uint64 and is zeroed here.

@@ -276,3 +276,59 @@ def test_config3_scale_permutation_property():
     assert np.array_equal(inc[kid_rows[sel]], bad.sum(axis=1))
     assert np.all(raw_a[kid_rows[sel]][bad].astype(np.float32) > 0)
     assert 0 < int((a != obs).sum()) < obs.size // 10
+
+
+def _two_pass_and_fused(eng, obs):
+    """(raw, hist) of gfx_mendel_rank + gfx_rank_hist and of the fused gfx_mendel_rank_hist on the same matrix"""
+    import torch
+    eng._alloc(obs.shape[1])
+    hin = eng.host_in.numpy()
+    hin[:, :eng.s] = obs
+    hin[:, eng.s:] = 9
+    eng.codes.copy_(eng.host_in)
+    eng.load_codes_device(eng.codes)
+    res = []
+    for fused in (False, True):
+        eng.raw.fill_(0x1234)
+        eng.mendel_rank_device(fused=fused)
+        if not fused:
+            plain = eng.raw[:, :eng.s].cpu().numpy().view(np.uint16).copy()
+            eng.thresholds_device(0.9)
+        torch.cuda.synchronize()
+        eng.check_status()
+        res.append((eng.raw[:, :eng.s].cpu().numpy().view(np.uint16).copy(), eng.hist.cpu().numpy().view(np.uint64).copy()))
+    return plain, res[0], res[1]
+
+
+@pytest.mark.parametrize("case", ["c2_clean", "missing", "loopy", "big_litters", "ragged"])
+def test_fused_rank_histogram_equals_two_passes(case):
+    """The fused kernel (lane-private table fast path, packed-half children term, (class, m) counters) against
+    the per-cell definition: every score pattern, every 0xFFFF marker and every one of the 65 537 bins."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    if case == "c2_clean":
+        rows = synth.make_pedigree(3000, 6, seed=1234)
+        obs = synth.inject_errors(synth.gene_drop(rows, 2048, seed=3), 0.01, seed=3)
+        ids = rows[:, 0]
+    elif case == "missing":
+        rows, ids, obs = _random_case(21, n=900, gens=6, s=700, miss=0.04, drop=0.1)
+    elif case == "loopy":
+        rows = synth.make_pedigree(1500, 15, sire_frac=0.06, dam_frac=0.3, seed=44, related_mating_p=0.25,
+                                   unknown_parents_frac=0.1)
+        obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 530, seed=44), 0.01, seed=44), 0.02, seed=45)
+        ids = rows[:, 0]
+    elif case == "big_litters":   # 2 sires per generation: m far above 32 on the sires' rows
+        rows = synth.make_pedigree(1200, 4, sire_frac=0.004, dam_frac=0.2, seed=9)
+        obs = synth.inject_errors(synth.gene_drop(rows, 512, seed=9), 0.02, seed=9)
+        ids = rows[:, 0]
+    else:
+        rows, ids, obs = _random_case(33, n=300, gens=5, s=2049, miss=0.01, drop=0.0)
+    eng = Engine(PedigreeDAG.from_table(rows), ids, 2)
+    plain, (raw2, hist2), (raw1, hist1) = _two_pass_and_fused(eng, obs)
+    assert np.array_equal(raw1, raw2), "%d score patterns differ" % int((raw1 != raw2).sum())
+    assert np.array_equal(hist1, hist2), np.nonzero(hist1 != hist2)[0][:10]
+    assert int(hist1.sum()) == obs.size
+    assert np.array_equal(raw1 == 0xFFFF, obs > 2)
+    # plain (unfused, unmarked) scores: 1.0 where the marker goes
+    assert np.array_equal(np.where(raw1 == 0xFFFF, 0x3C00, raw1), plain)

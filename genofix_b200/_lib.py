@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenofix_b200.so")
+LIB_PATH = os.environ.get("GFX_LIB_PATH") or os.path.join(_HERE, "libgenofix_b200.so")   # override: kernel experiments only
 
 GFX_OK = 0
 GFX_E_INVALID = -1

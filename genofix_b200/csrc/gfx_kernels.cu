@@ -17,6 +17,7 @@
 #include "gfx_schedule.h"
 
 #define GFX_BIG_SLOTS 64
+#define R2_QUEUES_HOST 32   // task queues of k_mendel_rank (R2_QUEUES)
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -199,7 +200,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   std::vector<uint32_t> lut6;
   std::vector<uint16_t> class_sc;
   if (!build_rank_fast(lut, lut6, class_sc, err)) { delete s; return fail(GFX_E_INVALID, err); }
-  std::vector<unsigned int> rank_ctr(4, 0u);
+  std::vector<unsigned int> rank_ctr(R2_QUEUES_HOST, 0u);
   std::vector<RankRow> rank_rows(h.n_rows);
   {
     std::vector<int32_t> order(h.n_rows);
@@ -428,11 +429,23 @@ struct RankArgs {
   const uint16_t* class_sc;
   unsigned long long* hist;   // 65537 bins or nullptr (HIST = false)
   unsigned int* task_ctr;
-  uint32_t chunks;            // R2_CHUNK_WORDS-word chunks per row
+  uint32_t chunks;            // chunks per row
+  int chunk_words;            // words per chunk (multiple of 32)
 };
 
+#ifndef R2_THREADS
 #define R2_THREADS 1024
-#define R2_CHUNK_WORDS 64
+#endif
+#ifndef R2_CHUNK_WORDS
+#define R2_CHUNK_WORDS 128
+#endif
+#ifndef R2_KIDS4
+#define R2_KIDS4 1
+#endif
+#ifndef R2_SCHED
+#define R2_SCHED 2
+#endif
+#define R2_QUEUES 32   // = warp size: one lane per queue when looking for work
 #define R2_CM_OFF 0u          // u32 [8 classes][32 m][32 lanes]
 #define R2_FAST_OFF 32768u    // u32 [64 idx6][64]: lanes 0..31 table entries, 32..63 counters
 #define R2_BINS_OFF 49152u    // u32 [8192] patterns 0x3000..0x4FFF
@@ -463,10 +476,51 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
   const uint32_t o2 = (hi & ~lo) & 0x55555555u;
 #pragma unroll
   for (int k = 0; k < 8; ++k) m16[k] = 0;
-  uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1
   uint32_t bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;   // byte t: cells 4t, 4t + 2, 4t + 1, 4t + 3
-  int pend = 0, pend8 = 0;
+  int pend8 = 0;
   anyv = 0;
+#if R2_KIDS4
+  for (int c = c0; c < c1; c += 8) {
+    // eight children per round, all loads issued before the first use (absent ones read as all-missing): the loop
+    // is bound by the latency of these loads, not by the arithmetic
+    uint32_t wc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = c + u < c1 ? __ldg(a.child_row + c + u) : -1;
+      wc[u] = r >= 0 ? __ldg(a.packed + (int64_t)r * a.wpr + w) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1 && c + 4 >= c1) break;
+      uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1 (4 children * 2 units = 8 < 16)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t cl = wc[4 * half + u], ch = wc[4 * half + u] >> 1;
+        const uint32_t is0 = ~(cl | ch) & 0x55555555u;
+        const uint32_t is2 = (ch & ~cl) & 0x55555555u;
+        anyv |= ~(cl & ch);
+        const uint32_t one = (is0 | is2) & o1;
+        const uint32_t two = (is2 & o0) | (is0 & o2);
+        const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
+        acc_lo += contrib & 0x33333333u;
+        acc_hi += (contrib >> 2) & 0x33333333u;
+      }
+      bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
+      bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+    }
+    if (++pend8 == 15) {                        // 15 * 16 = 240 < 256
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+        m16[2 * t + 1] += __byte_perm(bl1, bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+      }
+      bl0 = bl1 = bh0 = bh1 = 0;
+      pend8 = 0;
+    }
+  }
+#else
+  uint32_t acc_lo = 0, acc_hi = 0;
+  int pend = 0;
   for (int c = c0; c < c1; ++c) {
     const uint32_t wc = __ldg(a.packed + (int64_t)__ldg(a.child_row + c) * a.wpr + w);
     const uint32_t cl = wc, ch = wc >> 1;
@@ -475,15 +529,15 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
     anyv |= ~(cl & ch);
     const uint32_t one = (is0 | is2) & o1;
     const uint32_t two = (is2 & o0) | (is0 & o2);
-    const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
+    const uint32_t contrib = one | (two << 1);
     acc_lo += contrib & 0x33333333u;
     acc_hi += (contrib >> 2) & 0x33333333u;
-    if (++pend == 7) {                          // 7 * 2 = 14 < 16
+    if (++pend == 7) {
       bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
       bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
       acc_lo = acc_hi = 0;
       pend = 0;
-      if (++pend8 == 17) {                      // 17 * 14 = 238 < 256
+      if (++pend8 == 17) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
@@ -496,6 +550,7 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
   }
   bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
   bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+#endif
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     // halves: low = byte t of bl, high = byte t of bh
@@ -569,8 +624,9 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
   r2_store(a.raw + row * a.ld_raw + w * 16, outw);
 }
 
+#define R2_CTAS (R2_THREADS <= 512 ? 2 : 1)
 template <bool HIST>
-__global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
+__global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a) {
   extern __shared__ __align__(16) char smem[];
   {
     uint2* s_lut = reinterpret_cast<uint2*>(smem + R2_LUT_OFF);
@@ -591,6 +647,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
     for (int i = threadIdx.x; i < (int)(R2_FAST_OFF / 4); i += blockDim.x) s_z[i] = 0;                 // (class, m) counters
     uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF);
     for (int i = threadIdx.x; i < (int)R2_BIN_N; i += blockDim.x) s_bins[i] = 0;
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t*>(smem + R2_SMEM) = 0u;   // block-local ticket counter
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -600,18 +657,69 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
   const __half2 K3 = r2_h2(0xDD55DD55u);    // -1024 * float16(1/3) = -341.25
   uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF);
   uint32_t zeros = 0, ones = 0, nmiss = 0;
-  uint32_t task = 0;
-  if (lane == 0) task = atomicAdd(a.task_ctr, 1u);
-  task = __shfl_sync(0xffffffffu, task, 0);
+  // Task = (row record, R2_CHUNK_WORDS-word chunk); records are sorted heaviest first.  Tasks are dealt round-robin
+  // to the blocks (static, balanced because the order is by cost); inside a block the warps draw tickets from a
+  // shared-memory counter (dynamic, no global same-address atomics).  Two tickets are kept in flight so that the
+  // next task's row record is loaded while the current task is processed.
+#if R2_SCHED == 2
+  uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + R2_SMEM);
+#define R2_TASK_OF(k) ((k) * gridDim.x + blockIdx.x)
+  uint32_t tk = 0;
+  if (lane == 0) tk = atomicAdd(s_ticket, 2u);
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  uint32_t task = R2_TASK_OF(tk), ntask = R2_TASK_OF(tk + 1u);
+  int4 q0 = make_int4(0, 0, 0, 0), q1 = q0;
+  if (task < tasks) {
+    q0 = __ldg(reinterpret_cast<const int4*>(a.rows + task / a.chunks));
+    q1 = __ldg(reinterpret_cast<const int4*>(a.rows + task / a.chunks) + 1);
+  }
   while (task < tasks) {
+    int4 nq0 = make_int4(0, 0, 0, 0), nq1 = nq0;
+    if (ntask < tasks) {
+      nq0 = __ldg(reinterpret_cast<const int4*>(a.rows + ntask / a.chunks));
+      nq1 = __ldg(reinterpret_cast<const int4*>(a.rows + ntask / a.chunks) + 1);
+    }
     uint32_t next = 0;
-    if (lane == 0) next = atomicAdd(a.task_ctr, 1u);   // in flight while this task is processed
+    if (lane == 0) next = atomicAdd(s_ticket, 1u);
+    const int wbeg = (int)(task % a.chunks) * a.chunk_words;
+    const int wend = min(wbeg + a.chunk_words, a.nwords);
+#else
+#if R2_SCHED
+  uint32_t q = blockIdx.x % R2_QUEUES;
+  uint32_t ticket = 0;
+  if (lane == 0) ticket = atomicAdd(a.task_ctr + q, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  for (;;) {
+    const uint32_t task = ticket * R2_QUEUES + q;
+    if (task >= tasks) {
+      // this queue is dry: every lane looks at one queue, the warp moves to the next live one
+      const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(a.task_ctr + lane);
+      const uint32_t live = __ballot_sync(0xffffffffu, (uint64_t)seen * R2_QUEUES + lane < tasks);
+      if (!live) break;
+      q = (q + __ffs(__funnelshift_r(live, live, q + 1))) & (R2_QUEUES - 1);
+      if (lane == 0) ticket = atomicAdd(a.task_ctr + q, 1u);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      continue;
+    }
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(a.task_ctr + q, 1u);   // in flight while this task is processed
+#else
+  uint32_t ticket = 0;
+  if (lane == 0) ticket = atomicAdd(a.task_ctr, 1u);
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  for (;;) {
+    const uint32_t task = ticket;
+    if (task >= tasks) break;
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(a.task_ctr, 1u);
+#endif
     // task order: chunk-major inside a row record, records heaviest first
     const uint32_t rec = task / a.chunks;
-    const int wbeg = (int)(task - rec * a.chunks) * R2_CHUNK_WORDS;
-    const int wend = min(wbeg + R2_CHUNK_WORDS, a.nwords);
+    const int wbeg = (int)(task % a.chunks) * a.chunk_words;
+    const int wend = min(wbeg + a.chunk_words, a.nwords);
     const int4 q0 = __ldg(reinterpret_cast<const int4*>(a.rows + rec));
     const int4 q1 = __ldg(reinterpret_cast<const int4*>(a.rows + rec) + 1);
+#endif
     const int row = q0.x, c0 = q0.y, c1 = q0.y + q0.z;
     const bool has_anc = q0.w & 1, loopy = q0.w & 2;
     const int rS = q1.x, rD = q1.y;
@@ -620,12 +728,20 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
       const uint32_t* prow0 = a.packed + (int64_t)row * a.wpr;
       const uint32_t* prowS = a.packed + (int64_t)(parents_ok ? rS : row) * a.wpr;
       const uint32_t* prowD = a.packed + (int64_t)(parents_ok ? rD : row) * a.wpr;
-      int w = wbeg + lane;
+      // the 32-word steps of a chunk are walked from a per-task rotated start: otherwise every warp of the
+      // GPU sits at the same offset of its row at the same time (rows are a fixed stride apart: channel camping)
+      const int n_iter = (wend - wbeg + 31) >> 5;
+      int pos = n_iter > 0 ? (int)__umulhi(task * 2654435761u, (uint32_t)n_iter) : 0;
+      int wn = wbeg + pos * 32 + lane;
       uint32_t n0 = 0, nS = 0, nD = 0;
-      if (w < wend) { n0 = __ldg(prow0 + w); nS = __ldg(prowS + w); nD = __ldg(prowD + w); }
-      for (; w < wend; w += 32) {
+      if (n_iter > 0 && wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
+      for (int it = 0; it < n_iter; ++it) {
+        const int w = wn;
         const uint32_t w0 = n0, wS = nS, wD = nD;
-        if (w + 32 < wend) { n0 = __ldg(prow0 + w + 32); nS = __ldg(prowS + w + 32); nD = __ldg(prowD + w + 32); }
+        pos = pos + 1 == n_iter ? 0 : pos + 1;
+        wn = wbeg + pos * 32 + lane;
+        if (it + 1 < n_iter && wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
+        if (w >= wend) continue;
         uint16_t* dst = a.raw + (int64_t)row * a.ld_raw + (int64_t)w * 16;
         const uint32_t miss = w0 & (w0 >> 1) & 0x55555555u;
         const bool tail = HIST && w == a.nwords - 1 && (a.n_snps & 15);
@@ -714,7 +830,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
                 if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
               }
             }
-            if (HIST && big) r2_hist_patterns(a.hist, s_bins, outw, miss, 16, zeros, nmiss);
+            if (HIST && big) {
+              uint32_t tmp[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
+              r2_hist_patterns(a.hist, s_bins, tmp, miss, 16, zeros, nmiss);
+            }
           }
         } else {
           // founder with children, nothing missing: the score is the children term alone (class 0 = score 0)
@@ -726,12 +847,23 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_mendel_rank(RankArgs a) {
             }
             outw[k] = r2_u(__hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3));
           }
-          if (HIST && big) r2_hist_patterns(a.hist, s_bins, outw, 0u, 16, zeros, nmiss);
+          if (HIST && big) {
+            uint32_t tmp[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
+            r2_hist_patterns(a.hist, s_bins, tmp, 0u, 16, zeros, nmiss);
+          }
         }
         r2_store(dst, outw);
       }
     }
-    task = __shfl_sync(0xffffffffu, next, 0);
+#if R2_SCHED == 2
+    task = ntask; q0 = nq0; q1 = nq1;
+    next = __shfl_sync(0xffffffffu, next, 0);
+    ntask = R2_TASK_OF(next);
+#else
+    ticket = __shfl_sync(0xffffffffu, next, 0);
+#endif
   }
   if (!HIST) return;
   // ---- retire: counters -> float16 patterns -> global histogram ------------------------------------
@@ -1166,27 +1298,39 @@ struct GenericRankArgs {
   unsigned long long* hist;   // nullptr: plain scores (missing cells 1.0), else histogram + 0xFFFF marker
 };
 
-// Rows whose blanket is not the plain tree: one thread per cell, full inference.  Words in which both parents
-// are observed in all 16 cells are d-separated from the loop and belong to k_mendel_rank (same test there).
+// Rows whose blanket is not the plain tree.  A warp scans 32 words of such a row: words in which both parents
+// are observed in all 16 cells are d-separated from the loop and belong to k_mendel_rank (same test there);
+// the others are processed two at a time, one cell per lane, with the full inference.
 __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) {
-  const int64_t padded = ((a.n_snps + 15) / 16) * 16;
-  const int64_t total = (int64_t)a.n_rows_sel * padded;
+  const int nwords = (int)((a.n_snps + 15) / 16);
+  const int chunks = (nwords + 31) / 32;
   double tab[GFX_TAB];
   uint8_t code[GFX_MAXN];
-  const int64_t span = (((total + 31) >> 5) << 5);   // whole warps stay in the loop (warp-aggregated histogram)
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < span; i += (int64_t)gridDim.x * blockDim.x) {
-    bool mine = i < total;
-    uint32_t r = 0x3C00u;
-    bool count = false;
-    if (mine) {
-      const int sel = (int)(i / padded);
-      const int64_t j = i - (int64_t)sel * padded;
-      const int row = a.rows[sel];
-      const int rS = a.anc6[(int64_t)row * 6], rD = a.anc6[(int64_t)row * 6 + 1];
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < (int64_t)a.n_rows_sel * chunks; t += nwarps) {
+    const int sel = (int)(t / chunks);
+    const int wbase = (int)(t - (int64_t)sel * chunks) * 32;
+    const int row = a.rows[sel];
+    const int rS = a.anc6[(int64_t)row * 6], rD = a.anc6[(int64_t)row * 6 + 1];
+    bool flag = false;
+    if (wbase + lane < nwords) {
+      flag = true;
       if (rS >= 0 && rD >= 0) {
-        const uint32_t wS = __ldg(a.packed + (int64_t)rS * a.wpr + (j >> 4)), wD = __ldg(a.packed + (int64_t)rD * a.wpr + (j >> 4));
-        if ((((wS & (wS >> 1)) | (wD & (wD >> 1))) & 0x55555555u) == 0u) mine = false;
+        const uint32_t wS = __ldg(a.packed + (int64_t)rS * a.wpr + wbase + lane), wD = __ldg(a.packed + (int64_t)rD * a.wpr + wbase + lane);
+        flag = (((wS & (wS >> 1)) | (wD & (wD >> 1))) & 0x55555555u) != 0u;
       }
+    }
+    uint32_t fm = __ballot_sync(0xffffffffu, flag);
+    while (fm) {
+      const int wa = __ffs(fm) - 1;
+      fm &= fm - 1;
+      int wb = -1;
+      if (fm) { wb = __ffs(fm) - 1; fm &= fm - 1; }
+      const int wsel = lane < 16 ? wa : wb;
+      const bool mine = wsel >= 0;
+      const int64_t j = (int64_t)(wbase + (mine ? wsel : 0)) * 16 + (lane & 15);
+      uint32_t r = 0x3C00u;
       if (mine) {
         const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
         if (obs != 3) {
@@ -1210,16 +1354,15 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
           r = 0xFFFFu;
         }
         a.raw[(int64_t)row * a.ld_raw + j] = (uint16_t)r;
-        count = j < a.n_snps;
       }
-    }
-    if (a.hist) {
-      // one atomic per distinct pattern of the warp
-      const uint32_t act = __ballot_sync(0xffffffffu, count);
-      if (count) {
-        const uint32_t peers = __match_any_sync(act, r);
-        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1)
-          atomicAdd(&a.hist[r == 0xFFFFu ? 65536u : r], (unsigned long long)__popc(peers));
+      if (a.hist) {
+        // one atomic per distinct pattern of the warp
+        const bool count = mine && j < a.n_snps;
+        const uint32_t act = __ballot_sync(0xffffffffu, count);
+        if (count) {
+          const uint32_t peers = __match_any_sync(act, r);
+          if (lane == __ffs(peers) - 1) atomicAdd(&a.hist[r == 0xFFFFu ? 65536u : r], (unsigned long long)__popc(peers));
+        }
       }
     }
   }
@@ -1232,31 +1375,36 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   const int64_t nwords = (n_snps + 15) / 16;
   if (n_snps <= 0 || wpr < nwords || ld_raw < nwords * 16 || (ld_raw % 8) != 0 || (((uintptr_t)raw) % 16) != 0)
     return fail(GFX_E_INVALID, "gfx_mendel_rank: need wpr >= ceil(s/16), ld_raw >= 16*ceil(s/16), ld_raw % 8 == 0, raw 16-byte aligned");
-  const int64_t chunks = (nwords + R2_CHUNK_WORDS - 1) / R2_CHUNK_WORDS;
+  // measured: 64..128-word chunks run fastest (short tasks interleave the latency-bound rows with children and the
+  // store-bound rows without); 128 when that still leaves >= 32 tasks per warp
+  const int64_t warps = (int64_t)s->num_sms * R2_CTAS * (R2_THREADS / 32);
+  int chunk_words = 128;
+  if ((int64_t)s->h.n_rows * ((nwords + 127) / 128) < 32 * warps) chunk_words = 64;
+  const int64_t chunks = (nwords + chunk_words - 1) / chunk_words;
   if ((int64_t)s->h.n_rows * chunks >= (int64_t)0xFFFF0000ll || nwords > 0x7FFFFF00ll)
     return fail(GFX_E_INVALID, "gfx_mendel_rank: matrix too large for one call (rows * ceil(words/128) must stay below 2^32)");
   RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, s->rank_rows, s->child_row,
-             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist, s->rank_ctr, (uint32_t)chunks};
+             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist, s->rank_ctr, (uint32_t)chunks, chunk_words};
   static bool attr_set = false;
   if (!attr_set) {
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
     attr_set = true;
   }
-  GFX_CUDA(cudaMemsetAsync(s->rank_ctr, 0, sizeof(unsigned int), stream));
+  GFX_CUDA(cudaMemsetAsync(s->rank_ctr, 0, sizeof(unsigned int) * R2_QUEUES_HOST, stream));
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
   const int64_t tasks = (int64_t)s->h.n_rows * chunks;
-  int blocks = (int)std::min<int64_t>((tasks + 31) / 32, s->num_sms);
+  int blocks = (int)std::min<int64_t>((tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
   if (blocks < 1) blocks = 1;
-  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_SMEM, stream>>>(a);
-  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_SMEM, stream>>>(a);
+  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);
+  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
                       s->anc6,
                       BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr},
                       s->bl_kid, s->status, (unsigned long long*)hist};
-    const int64_t total = (int64_t)s->n_loopy_rows * nwords * 16;
+    const int64_t total = (int64_t)s->n_loopy_rows * ((nwords + 31) / 32) * 32;   // one warp per 32 words
     k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, stream>>>(g);
     GFX_LAUNCHED();
   }

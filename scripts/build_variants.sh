@@ -1,0 +1,16 @@
+#!/bin/bash
+# kernel experiments: builds variants of the library with different -D settings into genofix_b200/variants/
+cd "$(dirname "$0")/.."
+build() { # name flags...
+  name=$1; shift
+  nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared "$@" \
+    -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
+}
+build base
+build c64 -DR2_CHUNK_WORDS=64
+build c256 -DR2_CHUNK_WORDS=256
+build t512 -DR2_THREADS=512
+build t512c64 -DR2_THREADS=512 -DR2_CHUNK_WORDS=64
+build sched0 -DR2_SCHED=0
+wait
+ls -la genofix_b200/variants

@@ -185,19 +185,21 @@ def run_cuda(args):
             eng.correct_device(PARAMS["threshold_pair"], PARAMS["threshold_single"], PARAMS["tiethreshold"], PARAMS["err_thresh"])
             if record:
                 ev[2].record()
-                phase_events.append(("hist_thresholds", ev[0], ev[1]))
+                phase_events.append(("thresholds_host_roundtrip", ev[0], ev[1]))
                 phase_events.append(("correct_pairs_singles", ev[1], ev[2]))
             tall.add_(eng.tallies[:eng.n])
         if world > 1:
             dist.all_reduce(tall)   # the one collective: per-animal error tallies
 
+    host_outs = [np.empty_like(c) for c in host_chunks]   # caller-owned result matrices (genofix.py writes into `corrected`)
+
     def step_e2e():
+        # the public multi-chunk call (genofix.py's chunk loop): host uint8 in, host uint8 out, every step
         total = 0
-        for ci, (a, b) in enumerate(bounds):
-            out = eng.correct(host_chunks[ci], PARAMS["threshold_pair"], PARAMS["threshold_single"],
-                              init_filter_p=PARAMS["init_filter_p"], tiethreshold=PARAMS["tiethreshold"],
-                              err_thresh=PARAMS["err_thresh"])
-            total += int(eng.stats["corrected_per_animal"].sum())
+        for out, stats in eng.correct_chunks(iter(host_chunks), PARAMS["threshold_pair"], PARAMS["threshold_single"],
+                                             init_filter_p=PARAMS["init_filter_p"], tiethreshold=PARAMS["tiethreshold"],
+                                             err_thresh=PARAMS["err_thresh"], outs=host_outs):
+            total += int(stats["corrected_per_animal"].sum())
         return total
 
     def barrier():
@@ -262,12 +264,12 @@ def run_cuda(args):
     phases["mendel_rank"] = sum(rk_ms)
     phase_share = {k: v / ms for k, v in phases.items()}
     roofline = dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
-                    kernel="k_mendel_rank (+ k_mendel_rank_generic for loopy blankets): the HBM-bound peeling kernel "
-                           "BASELINE.json's north_star names",
+                    kernel="k_mendel_rank<HIST> (Mendel rank fused with the score histogram; + k_mendel_rank_generic for loopy "
+                           "blankets): the HBM-bound peeling kernel BASELINE.json's north_star names",
                     algorithmic_bytes_per_cell=RANK_BYTES_PER_CELL,
                     peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
                     share_of_step=sum(rk_ms) / ms,
-                    note="the step is dominated by the correction kernels (k_correct, k_correct_general), which are "
+                    note="the step is dominated by the correction kernels (k_correct, k_correct_jobs), which are "
                          "instruction/latency bound: phase shares in phase_share, launch list in profiles/",
                     correct_kernels=dict(share_of_step=phase_share.get("correct_pairs_singles"),
                                          algorithmic_bytes_per_cell=2.5,

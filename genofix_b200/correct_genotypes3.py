@@ -66,6 +66,28 @@ class CorrectGenotypes(object):
         print("predicted errors %s of %s" % (errors_all, G.size - errors_all))
         return pd.DataFrame(out, index=genotypes.index, columns=genotypes.columns)
 
+    def correctChunks(self, genotypes, column_chunks, pedigree, empC, threshold_pair, threshold_single, back=2,
+                      init_filter_p=0.9, filter_e=0.7, tiethreshold=0.05, threads=1, err_thresh=1,
+                      weight_empirical=3, outputerrors=False, DEBUGDIR=None, debugreal=None):
+        """The chunk loop of genofix.py:207-237 as one call: yields (columns, corrected DataFrame) for every
+        list of columns in `column_chunks`, each chunk corrected exactly like correctMatrix(genotypes[columns], ...)
+        would, with the host<->device copies of neighbouring chunks overlapped with the kernels."""
+        import pandas as pd
+        if empC is not None:
+            raise NotImplementedError("pass empC=None (see correctMatrix)")
+        eng = engine_for(pedigree, np.asarray(genotypes.index, dtype=np.int64), back)
+        column_chunks = [list(c) for c in column_chunks]
+        self.last_stats = []
+
+        def arrays():
+            for cols in column_chunks:
+                yield np.ascontiguousarray(genotypes.loc[:, cols].to_numpy(dtype=np.uint8, copy=False))
+        for cols, (out, stats) in zip(column_chunks, eng.correct_chunks(arrays(), threshold_pair, threshold_single,
+                                                                        init_filter_p=init_filter_p, tiethreshold=tiethreshold,
+                                                                        err_thresh=err_thresh)):
+            self.last_stats.append(stats)
+            yield cols, pd.DataFrame(out, index=genotypes.index, columns=cols)
+
     # ------------------------------------------------------------------------------------------
     # static workers of the reference; they operate on the matrix bound by initializer()
     # ------------------------------------------------------------------------------------------

@@ -1570,6 +1570,9 @@ struct FocalArgs {
   uint8_t* sbits;         // per deferred cell: decision bits of every job (0xFF = to be computed), row stride maxj
   uint2* items;           // deferred jobs: (cell slot, job index within the animal)
   unsigned long long wl_cap, item_cap;
+  uint2* items_sorted;    // the same items grouped by job entry (same blanket, same side): convergent warps
+  uint32_t *key_count, *key_off, *key_cur;   // per job entry of the generation: items, first position, cursor
+  int n_keys, e_base;     // keys = entry index - e_base
   int maxj;
 };
 
@@ -1817,7 +1820,10 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv
     if (ok) { a.sbits[slot * a.maxj + (e - e0)] = (uint8_t)bits; continue; }
     a.sbits[slot * a.maxj + (e - e0)] = 0xFF;
     const unsigned long long it = atomicAdd(a.item_count, 1ull);
-    if (it < a.item_cap) a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0));
+    if (it < a.item_cap) {
+      a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0));
+      atomicAdd(a.key_count + (e - a.e_base), 1u);
+    }
     else first |= 0x8000;   // no room for the job item: the cell is redone by the fallback kernel
   }
   if (!parked) { write_cell(a, row, j, obs0, S); return true; }
@@ -2008,6 +2014,45 @@ __global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
   }
 }
 
+// Deferred jobs are grouped by job entry before they run: the threads of a warp then walk the same blanket from
+// the same query and differ only in the evidence of their SNP (measured before: 3 of 32 lanes active).
+__global__ void __launch_bounds__(1024) k_jobs_scan(FocalArgs a) {
+  __shared__ uint32_t s_part[1024];
+  const int t = threadIdx.x;
+  const int per = (a.n_keys + 1023) / 1024;
+  uint32_t sum = 0;
+  for (int i = t * per; i < min((t + 1) * per, a.n_keys); ++i) sum += a.key_count[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t v = t >= o ? s_part[t - o] : 0u;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_part[t] - sum;
+  for (int i = t * per; i < min((t + 1) * per, a.n_keys); ++i) {
+    a.key_off[i] = run;
+    a.key_cur[i] = 0u;
+    run += a.key_count[i];
+  }
+}
+__global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
+  unsigned long long n = *a.item_count;
+  if (n > a.item_cap) n = a.item_cap;
+  unsigned long long ncell = *a.wl_count;
+  if (ncell > a.wl_cap) ncell = a.wl_cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint2 it = a.items[i];
+    // items of cells that found no slot were never counted; they keep their cell on the fallback path
+    if (it.x >= ncell) continue;
+    const int key = a.focal_off[a.wl[it.x].x] + (int)it.y - a.e_base;
+    const uint32_t pos = a.key_off[key] + atomicAdd(a.key_cur + key, 1u);
+    a.items_sorted[pos] = it;
+  }
+}
+
 // Deferred jobs, one thread each: tree message passing, then the general elimination.
 __global__ void __launch_bounds__(128) k_correct_jobs(FocalArgs a) {
   unsigned long long n = *a.item_count;
@@ -2016,7 +2061,7 @@ __global__ void __launch_bounds__(128) k_correct_jobs(FocalArgs a) {
   if (ncell > a.wl_cap) ncell = a.wl_cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint2 it = a.items[i];
+    const uint2 it = a.items_sorted[i];
     if (it.x >= ncell) continue;
     const uint2 c = a.wl[it.x];
     const int f = (int)c.x;
@@ -2094,7 +2139,8 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
                        const int32_t* job_bl, int n_focal, const int32_t* focal_row, const int32_t* focal_off,
                        const int32_t* focal_order, const int32_t* entry, uint32_t* live, int64_t n_snps, int64_t wpr,
                        const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_correct_params* p,
-                       uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, int maxj, cudaStream_t stream) {
+                       uint32_t* snapshot, int64_t scratch_words, double* post, int32_t* tallies, int maxj, int e_base, int n_keys,
+                       cudaStream_t stream) {
   if (n_jobs <= 0 || n_focal <= 0) return GFX_OK;
   const int64_t dwords = ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK) * (GFX_CORRECT_CHUNK / 32);
   const int64_t fixed = (int64_t)s->h.n_rows * wpr + (int64_t)s->h.n_rows * dwords + 4;
@@ -2123,20 +2169,26 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.wl_count = (unsigned long long*)tail;
   a.item_count = a.wl_count + 2;
   const int maxj_p = ((maxj + 7) / 8) * 8;
-  char* base = (char*)(tail + 8);
+  a.n_keys = n_keys; a.e_base = e_base;
+  const int64_t nk4 = ((int64_t)n_keys + 3) / 4 * 4;
+  a.key_count = tail + 8;             // zeroed with the counters
+  a.key_off = a.key_count + nk4;
+  a.key_cur = a.key_off + nk4;
+  char* base = (char*)(a.key_cur + nk4);
   const int64_t avail = (char*)(snapshot + scratch_words) - base;
-  const int64_t per_slot = 32 + 8 + 8 + 16 + maxj_p;
+  const int64_t per_slot = 32 + 8 + 8 + 16 + 16 + maxj_p;
   const int64_t scap = avail > 0 ? avail / per_slot : 0;
   if (scap < 1024) return fail(GFX_E_INVALID, "scratch too small for the deferred-cell lists");
   a.skids = (double*)base;                       base += scap * 32;
   a.wl = (uint2*)base;                           base += scap * 8;
   a.st = (uint2*)base;                           base += scap * 8;
   a.items = (uint2*)base;                        base += scap * 16;
+  a.items_sorted = (uint2*)base;                 base += scap * 16;
   a.sbits = (uint8_t*)base;
   a.wl_cap = (unsigned long long)scap;
   a.item_cap = (unsigned long long)scap * 2;
   a.maxj = maxj_p;
-  GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(tail + 8)) - (char*)a.deferred, stream));  // bitmap + counters
+  GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(a.key_count + nk4)) - (char*)a.deferred, stream));  // bitmap + counters + key counts
   a.task_count = a.wl_count + 1;
   a.focal_order = focal_order;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
@@ -2147,6 +2199,10 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   int64_t lblocks = (wtasks + 3) / 4;
   if (lblocks > (int64_t)s->num_sms * 6) lblocks = (int64_t)s->num_sms * 6;
   k_correct<<<(int)lblocks, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_jobs_scan<<<1, 1024, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_jobs_scatter<<<s->num_sms * 4, 256, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_jobs<<<s->num_sms * 8, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
@@ -2172,7 +2228,7 @@ extern "C" int gfx_correct_pairs(const gfx_schedule* s, int32_t generation, uint
   // focal_off holds global offsets into app_entry: pass the un-shifted entry array
   return run_correct(s, 2, nj, s->job_row0 + j0, s->job_row1 + j0, s->job_bl + j0, nfoc, s->app_focal_row + f0,
                      s->app_focal_off + f0, s->app_order + f0, s->app_entry, live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words,
-                     post, tallies, maxj, (cudaStream_t)stream);
+                     post, tallies, maxj, s->h.app_focal_off[f0], s->h.app_focal_off[f0 + nfoc] - s->h.app_focal_off[f0], (cudaStream_t)stream);
 }
 
 extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_t n_snps, int64_t wpr,
@@ -2183,7 +2239,7 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
   const int n = (int)s->h.single_row.size();
   return run_correct(s, 1, n, s->single_row, nullptr, s->single_bl, n, s->single_row, s->single_off, s->single_order,
                      s->single_entry,
-                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, 1, (cudaStream_t)stream);
+                     live, n_snps, wpr, raw, ld_raw, elut, p, snapshot, scratch_words, post, tallies, 1, 0, n, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

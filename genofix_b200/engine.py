@@ -6,6 +6,7 @@ kernel of libgenofix_b200.so; the one host-side numeric step is the rank transfo
 bit-identical to the reference's own numpy calls (correct_genotypes3.py:600-603).
 """
 import ctypes as C
+import os
 import warnings
 
 import numpy as np
@@ -31,11 +32,13 @@ def _ptr(a):
 _POOL = None
 
 
-def _parallel_copy(dst, src, threads=8):
+def _parallel_copy(dst, src, threads=None):
     """dst[...] = src for large 2-D arrays, row blocks on a few threads (numpy releases the GIL while copying):
     staging a 100 MB chunk through pinned memory is otherwise the longest step of the end-to-end call."""
     global _POOL
     n = dst.shape[0]
+    if threads is None:
+        threads = max(1, min(16, os.cpu_count() or 1))
     if dst.size < (1 << 22) or n < threads:
         dst[...] = src
         return
@@ -227,7 +230,7 @@ class Engine(object):
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
         # snapshot + fallback bitmap + lists of parked cells / deferred jobs (~76 bytes per parked cell)
-        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 16 + max(1 << 18, n * self.s // 4),
+        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 64 + 4 * n + max(1 << 18, n * self.s // 4),
                                 dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
@@ -380,6 +383,115 @@ class Engine(object):
         out = np.empty((self.n, self.s), dtype=np.uint8)
         _parallel_copy(out, self.host_out.numpy()[:, :self.s])
         return out
+
+    # ---- end-to-end on a sequence of chunks (host buffers), copies overlapped with compute -----------------
+    def _alloc_pipe(self):
+        if getattr(self, "_pipe_shape", None) == self._shape:
+            return
+        t = self.torch
+        dev = self.codes.device
+        n = self.n
+        self.p_in = [t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True) for _ in range(2)]
+        self.p_out = [t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True) for _ in range(2)]
+        self.p_codes_in = [t.empty((n, self.ldc), dtype=t.uint8, device=dev) for _ in range(2)]
+        self.p_codes_out = [t.empty((n, self.ldc), dtype=t.uint8, device=dev) for _ in range(2)]
+        self.p_packed = [t.empty((n, self.wpr), dtype=t.int32, device=dev) for _ in range(2)]
+        self.p_tall_dev = [t.empty(2 * n, dtype=t.int32, device=dev) for _ in range(2)]
+        self.p_tall = [t.empty(2 * n, dtype=t.int32, pin_memory=True) for _ in range(2)]
+        if not hasattr(self, "s_in"):
+            self.s_in, self.s_c, self.s_out = t.cuda.Stream(), t.cuda.Stream(), t.cuda.Stream()
+        self._pipe_shape = self._shape
+
+    def correct_chunks(self, chunks, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
+                       outs=None):
+        """Generator over (corrected uint8 [n, s_i], stats) for an iterable of uint8 [n, s_i] chunks -- the chunk loop of
+        genofix.py:207-237 with every chunk an independent correctMatrix call.  Same results as calling correct()
+        chunk by chunk; here three streams and two buffer sets overlap a chunk's kernels with the host staging +
+        H2D copy of the next chunk and the D2H copy + un-staging of the previous one.  `outs`: optional list of
+        caller-owned uint8 [n, s_i] arrays to receive the results (saves allocating and first-touching them)."""
+        t = self.torch
+        it = iter(chunks)
+        state = {"ev_comp": [None, None], "ev_out": [None, None], "k": 0}
+
+        def stage(G, slot):
+            G = np.asarray(G)
+            if G.ndim != 2 or G.shape[0] != self.n:
+                raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+            if self._shape != G.shape[1]:
+                t.cuda.synchronize()          # chunk width changed (last, ragged chunk): drain, then re-allocate
+                self._alloc(G.shape[1])
+                state["ev_comp"] = [None, None]
+                state["ev_out"] = [None, None]
+            self._alloc_pipe()
+            hin = self.p_in[slot].numpy()
+            _parallel_copy(hin[:, :self.s], G)
+            if self.ldc > self.s:
+                hin[:, self.s:] = 9
+            with t.cuda.stream(self.s_in):
+                if state["ev_comp"][slot] is not None:
+                    self.s_in.wait_event(state["ev_comp"][slot])     # the kernels that read p_packed[slot] are done
+                self.p_codes_in[slot].copy_(self.p_in[slot], non_blocking=True)
+                _lib.check(self.L.gfx_pack2(self.p_codes_in[slot].data_ptr(), self.n, self.s, self.p_codes_in[slot].stride(0),
+                                            self.p_packed[slot].data_ptr(), self.wpr, self._stream()))
+                ev = t.cuda.Event()
+                ev.record(self.s_in)
+            return ev
+
+        def finish(slot, s, test_p, n_nan):
+            state["ev_out"][slot].synchronize()
+            _lib.check(self.L.gfx_check_device_status(self.schedule.handle, C.c_void_p(self.s_out.cuda_stream)))
+            tall = self.p_tall[slot].numpy()
+            stats = dict(test_p=test_p, n_nan=n_nan, corrected_per_animal=tall[:self.n].copy(),
+                         excluded_per_animal=tall[self.n:].copy(), posteriors=None)
+            out = outs[state["k"]] if outs is not None else np.empty((self.n, s), dtype=np.uint8)
+            state["k"] += 1
+            if out.shape != (self.n, s) or out.dtype != np.uint8:
+                raise ValueError("outs[%d] must be uint8 [%d, %d]" % (state["k"] - 1, self.n, s))
+            _parallel_copy(out, self.p_out[slot].numpy()[:, :s])
+            return out, stats
+
+        cur = next(it, None)
+        if cur is None:
+            return
+        slot = 0
+        ev_in = stage(cur, slot)
+        prev = None
+        while cur is not None:
+            with t.cuda.stream(self.s_c):
+                self.s_c.wait_event(ev_in)
+                self.packed_orig = self.p_packed[slot]
+                self.mendel_rank_device()
+                self.thresholds_device(init_filter_p)           # host round trip: synchronises s_c
+                self.correct_device(threshold_pair, threshold_single, tiethreshold, err_thresh)
+                if state["ev_out"][slot] is not None:
+                    self.s_c.wait_event(state["ev_out"][slot])   # the D2H that read p_codes_out[slot] is done
+                self.unpack_device(self.p_codes_out[slot])
+                self.p_tall_dev[slot].copy_(self.tallies, non_blocking=True)
+                state["ev_comp"][slot] = t.cuda.Event()
+                state["ev_comp"][slot].record(self.s_c)
+            with t.cuda.stream(self.s_out):
+                self.s_out.wait_event(state["ev_comp"][slot])
+                self.p_out[slot].copy_(self.p_codes_out[slot], non_blocking=True)
+                self.p_tall[slot].copy_(self.p_tall_dev[slot], non_blocking=True)
+                state["ev_out"][slot] = t.cuda.Event()
+                state["ev_out"][slot].record(self.s_out)
+            mine = (slot, self.s, self.test_p, self.n_nan)
+            # the GPU is busy with this chunk's correction: stage the next chunk, hand back the previous one
+            nxt = next(it, None)
+            if nxt is not None and np.asarray(nxt).shape[1] != self.s and prev is not None:
+                yield finish(*prev)       # a re-allocation is coming: nothing may stay in the old buffers
+                prev = None
+            if nxt is not None and np.asarray(nxt).shape[1] != self.s:
+                yield finish(*mine)
+                mine = None
+            ev_in = stage(nxt, 1 - slot) if nxt is not None else None
+            if prev is not None:
+                yield finish(*prev)
+            prev = mine
+            cur = nxt
+            slot = 1 - slot
+        if prev is not None:
+            yield finish(*prev)
 
     # ---- config 5: trio scan ---------------------------------------------------------------------------
     def trio_scan(self, G=None):

@@ -87,14 +87,14 @@ def main(argv=None):
     mine = chunks_for_rank(len(jobs), rank, world)
     results = {}
     for ji in mine:
-        chromosome, cols = jobs[ji]
-        print("[rank %d] chromosome %s: correcting chunk of %d snps" % (rank, chromosome, len(cols)))
-        res = c.correctMatrix(corrected.loc[:, cols], pedigree, None, args.threshold_pairs, args.threshold_singles,
-                              back=args.lookback, tiethreshold=args.tiethreshold,
-                              init_filter_p=args.initquantilefilter, filter_e=args.filter_e,
-                              weight_empirical=args.weight_empirical, threads=args.threads, DEBUGDIR=out_dir)
-        results[ji] = res
-        tall += c.last_stats["corrected_per_animal"]
+        print("[rank %d] chromosome %s: chunk of %d snps" % (rank, jobs[ji][0], len(jobs[ji][1])))
+    for k, (cols, res) in enumerate(c.correctChunks(corrected, [jobs[ji][1] for ji in mine], pedigree, None,
+                                                    args.threshold_pairs, args.threshold_singles, back=args.lookback,
+                                                    tiethreshold=args.tiethreshold, init_filter_p=args.initquantilefilter,
+                                                    filter_e=args.filter_e, weight_empirical=args.weight_empirical,
+                                                    threads=args.threads, DEBUGDIR=out_dir)):
+        results[mine[k]] = res
+        tall += c.last_stats[k]["corrected_per_animal"]
     if world > 1:
         import torch
         import torch.distributed as dist

@@ -332,3 +332,28 @@ def test_fused_rank_histogram_equals_two_passes(case):
     assert np.array_equal(raw1 == 0xFFFF, obs > 2)
     # plain (unfused, unmarked) scores: 1.0 where the marker goes
     assert np.array_equal(np.where(raw1 == 0xFFFF, 0x3C00, raw1), plain)
+
+
+def test_pipelined_chunks_equal_chunk_by_chunk_calls():
+    """Engine.correct_chunks (three streams, two buffer sets) against Engine.correct on every chunk, including a
+    ragged last chunk that forces a re-allocation in the middle of the pipeline."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(2000, 6, seed=5)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 1700, seed=5), 0.01, seed=5), 0.01, seed=6)
+    bounds = [(0, 512), (512, 1024), (1024, 1536), (1536, 1700)]
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    ref = []
+    for a, b in bounds:
+        out = eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+        ref.append((out, eng.stats["test_p"], eng.stats["corrected_per_animal"].copy(), eng.stats["excluded_per_animal"].copy()))
+    eng2 = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    got = list(eng2.correct_chunks((np.ascontiguousarray(obs[:, a:b]) for a, b in bounds), 0.5, 0.64,
+                                   init_filter_p=0.95, tiethreshold=0.4))
+    assert len(got) == len(ref)
+    for (out, st), (rout, rtp, rc, rx) in zip(got, ref):
+        assert np.array_equal(out, rout)
+        assert st["test_p"] == rtp
+        assert np.array_equal(st["corrected_per_animal"], rc) and np.array_equal(st["excluded_per_animal"], rx)
+    assert sum(int((o != obs[:, a:b]).sum()) for (o, _), (a, b) in zip(got, bounds)) > 0

@@ -1679,7 +1679,8 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 // evaluated in any order / by different threads; only the apply walk below is sequential.
 // GENERAL = false: slot peeling only, returns false when the job needs tree message passing or the general
 // elimination.
-template <bool GENERAL>
+// MODE 0: slot peeling only; 1: + tree message passing; 2: + general elimination.  false = needs a higher mode.
+template <int MODE>
 __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, int64_t j, int obs0, uint32_t rxf,
                                          bool has_kids, const double* kids, uint32_t* bits_out) {
   const uint32_t tp = a.c.tp_raw;
@@ -1716,8 +1717,9 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     double tot_me = 1.0, tot_ot = 1.0;
     const int sme = a.nf == 2 ? side : 0;
     if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
-      if constexpr (!GENERAL) return false;
+      if constexpr (MODE == 0) return false;
       else if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
+      else if constexpr (MODE == 1) return false;
       else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
     } else {
       GFX_COUNT(a.bl, 1, 1);
@@ -1727,9 +1729,11 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
       // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
       double tmp[3];
       if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
-        if constexpr (!GENERAL) return false;
-        else if (!xpeel_query(LB, qot, qme, tmp, &tot_ot) && query_general(LB, a.bl, qot, qme, tmp, &tot_ot))
-          atomicExch(a.status, 1);
+        if constexpr (MODE == 0) return false;
+        else if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
+          if constexpr (MODE == 1) return false;
+          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
+        }
       }
     }
     if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
@@ -1808,7 +1812,7 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv
   int first = 0;
   for (int e = e0; e < e1; ++e) {
     uint32_t bits;
-    const bool ok = job_bits<false>(a, row, a.entry[e], j, obs0, rxf, has_kids, kids, &bits);
+    const bool ok = job_bits<0>(a, row, a.entry[e], j, obs0, rxf, has_kids, kids, &bits);
     if (ok && !parked) { apply_bits(a, row, j, rxf, bits, S); continue; }
     if (!parked) {
       if (e1 - e0 > a.maxj) return false;
@@ -1955,7 +1959,10 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
 // SNPs of the chunk with ballots and then runs one cell per lane.  Cells that need the general path
 // go to the work list (or, if that is full, the overflow bitmap) untouched.
 #define GFX_LEAN_CHUNK 128
-__global__ void __launch_bounds__(128, 6) k_correct(FocalArgs a) {
+#ifndef KC_BLOCKS
+#define KC_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
   __shared__ uint8_t s_list[4][GFX_LEAN_CHUNK];
   __shared__ double s_kv[108];
   __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
@@ -2053,28 +2060,65 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
   }
 }
 
-// Deferred jobs, one thread each: tree message passing, then the general elimination.
-__global__ void __launch_bounds__(128) k_correct_jobs(FocalArgs a) {
-  unsigned long long n = *a.item_count;
-  if (n > a.item_cap) n = a.item_cap;
+// Deferred jobs, one thread each, in two rounds so that a warp never mixes the cheap and the expensive kind:
+// round A = tree message passing; what it cannot answer is handed to round B = general elimination.
+// Warps draw 32 items at a time from a global counter (the general eliminations have a long tail).
+template <int MODE>
+__device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list, unsigned long long n, unsigned long long* ticket) {
   unsigned long long ncell = *a.wl_count;
   if (ncell > a.wl_cap) ncell = a.wl_cap;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint2 it = a.items_sorted[i];
-    if (it.x >= ncell) continue;
-    const uint2 c = a.wl[it.x];
-    const int f = (int)c.x;
-    const int64_t j = (int64_t)c.y;
-    const int row = a.focal_row[f];
-    const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);
-    const uint32_t rxf = cell_rx(a.c, row, j);
-    const double* kd = a.skids + (unsigned long long)it.x * 4;
-    const double kids[3] = {kd[0], kd[1], kd[2]};
-    uint32_t bits;
-    job_bits<true>(a, row, a.entry[a.focal_off[f] + (int)it.y], j, obs0, rxf, kd[3] != 0.0, kids, &bits);
-    a.sbits[(unsigned long long)it.x * a.maxj + it.y] = (uint8_t)bits;
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1ull);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t * 32ull >= n) break;
+    const unsigned long long i = t * 32ull + lane;
+    bool again = false;
+    uint2 it = make_uint2(0u, 0u);
+    if (i < n) {
+      it = list[i];
+      if (it.x < ncell) {
+        const uint2 c = a.wl[it.x];
+        const int f = (int)c.x;
+        const int64_t j = (int64_t)c.y;
+        const int row = a.focal_row[f];
+        const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);
+        const uint32_t rxf = cell_rx(a.c, row, j);
+        const double* kd = a.skids + (unsigned long long)it.x * 4;
+        const double kids[3] = {kd[0], kd[1], kd[2]};
+        uint32_t bits;
+        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + (int)it.y], j, obs0, rxf, kd[3] != 0.0, kids, &bits))
+          a.sbits[(unsigned long long)it.x * a.maxj + it.y] = (uint8_t)bits;
+        else
+          again = true;
+      }
+    }
+    if (MODE == 1) {
+      // hand over to round B (a.items is free again: the scatter pass has copied it)
+      const uint32_t m = __ballot_sync(0xffffffffu, again);
+      if (m) {
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(a.wl_count + 5, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (again) a.items[base + __popc(m & ((1u << lane) - 1u))] = it;
+      }
+    }
   }
+}
+#ifndef KJ_BLOCKS
+#define KJ_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, KJ_BLOCKS) k_correct_jobs(FocalArgs a) {
+  unsigned long long n = *a.item_count;
+  if (n > a.item_cap) n = a.item_cap;
+  jobs_round<1>(a, a.items_sorted, n, a.wl_count + 4);
+}
+#ifndef KG_BLOCKS
+#define KG_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, KG_BLOCKS) k_correct_jobs_general(FocalArgs a) {
+  jobs_round<2>(a, a.items, a.wl_count[5], a.wl_count + 6);
 }
 
 // Finishes the serial walk of every parked cell once all its jobs have bits.
@@ -2171,7 +2215,7 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   const int maxj_p = ((maxj + 7) / 8) * 8;
   a.n_keys = n_keys; a.e_base = e_base;
   const int64_t nk4 = ((int64_t)n_keys + 3) / 4 * 4;
-  a.key_count = tail + 8;             // zeroed with the counters
+  a.key_count = tail + 16;            // zeroed with the 8 counters
   a.key_off = a.key_count + nk4;
   a.key_cur = a.key_off + nk4;
   char* base = (char*)(a.key_cur + nk4);
@@ -2197,7 +2241,7 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   if (blocks > cap) blocks = cap;
   const int64_t wtasks = (int64_t)n_focal * ((n_snps + GFX_LEAN_CHUNK - 1) / GFX_LEAN_CHUNK);
   int64_t lblocks = (wtasks + 3) / 4;
-  if (lblocks > (int64_t)s->num_sms * 6) lblocks = (int64_t)s->num_sms * 6;
+  if (lblocks > (int64_t)s->num_sms * KC_BLOCKS) lblocks = (int64_t)s->num_sms * KC_BLOCKS;
   k_correct<<<(int)lblocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_jobs_scan<<<1, 1024, 0, stream>>>(a);
@@ -2205,6 +2249,8 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   k_jobs_scatter<<<s->num_sms * 4, 256, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_jobs<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  GFX_LAUNCHED();
+  k_correct_jobs_general<<<s->num_sms * 8, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_apply<<<s->num_sms * 4, 128, 0, stream>>>(a);
   GFX_LAUNCHED();

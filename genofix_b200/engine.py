@@ -170,6 +170,19 @@ def weighted_quantile_linear(values, counts, q):
     return np.float64(_lerp(a, b, gamma))
 
 
+_E_ALL = None
+
+
+def _e_all():
+    """log(log(x + 1) + 1) of every float16 value (constant; numpy's log so that it matches the reference)."""
+    global _E_ALL
+    if _E_ALL is None:
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _E_ALL = np.log(np.log(_ALL_HALF + 1) + 1)
+    return _E_ALL
+
+
 def rank_transform_table(hist, init_filter_p):
     """hist: uint64[65537] from gfx_rank_hist.  Returns (elut float64[65536], test_p, n_nan_cells).
 
@@ -180,7 +193,7 @@ def rank_transform_table(hist, init_filter_p):
     n_missing = int(hist[65536])
     with np.errstate(all="ignore"), warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        e_all = np.log(np.log(_ALL_HALF + 1) + 1)
+        e_all = _e_all()
         present = counts > 0
         if n_missing > 0:
             present = present.copy()
@@ -202,10 +215,10 @@ class Engine(object):
     """One schedule + device buffers; `correct()` is the host-buffer (end-to-end) call,
     the `*_device` methods work on resident data."""
 
-    def __init__(self, pedigree, ids, back=2):
+    def __init__(self, pedigree, ids, back=2, schedule=None):
         self.torch = _torch()
         self.L = _lib.lib()
-        self.schedule = Schedule(pedigree, ids, back)
+        self.schedule = schedule if schedule is not None else Schedule(pedigree, ids, back)
         self.n = self.schedule.n_rows
         self.back = int(back)
         self._shape = None
@@ -510,6 +523,77 @@ class Engine(object):
         _lib.check(self.L.gfx_trio_scan(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
                                         inc.data_ptr(), tst.data_ptr(), self._stream()))
         return inc.cpu().numpy(), tst.cpu().numpy()
+
+
+class MultiLane(object):
+    """L engines on one schedule, one host thread and one set of streams each: independent chunks are corrected
+    concurrently, so that the latency-bound correction kernels of one chunk share the GPU with those of another and
+    the host round trip of the thresholds is hidden.  Results do not depend on L (chunks are independent)."""
+
+    def __init__(self, pedigree, ids, back=2, lanes=2):
+        first = Engine(pedigree, ids, back)
+        self.engines = [first] + [Engine(pedigree, ids, back, schedule=first.schedule) for _ in range(lanes - 1)]
+        self.schedule = first.schedule
+        self.n = first.n
+        self.device = first.torch.cuda.current_device()
+
+    def _run_lanes(self, fn):
+        """fn(lane index, engine) in one thread per lane; re-raises the first exception."""
+        import threading
+        errs = []
+
+        def wrap(l):
+            try:
+                self.engines[0].torch.cuda.set_device(self.device)
+                fn(l, self.engines[l])
+            except BaseException as e:  # noqa: B902 -- re-raised in the caller's thread
+                errs.append(e)
+        th = [threading.Thread(target=wrap, args=(l,)) for l in range(len(self.engines))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+
+    def correct_chunks(self, chunks, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
+                       outs=None):
+        """Same contract as Engine.correct_chunks (results in input order); chunk k runs on lane k mod L."""
+        import queue
+        import threading
+        L = len(self.engines)
+        chunks = list(chunks)
+        results = [None] * len(chunks)
+        done = [threading.Event() for _ in chunks]
+        errs = []
+
+        def lane(l, eng):
+            mine = list(range(l, len(chunks), L))
+            try:
+                gen = eng.correct_chunks((chunks[k] for k in mine), threshold_pair, threshold_single, init_filter_p=init_filter_p,
+                                         tiethreshold=tiethreshold, err_thresh=err_thresh,
+                                         outs=[outs[k] for k in mine] if outs is not None else None)
+                for k, r in zip(mine, gen):
+                    results[k] = r
+                    done[k].set()
+            except BaseException as e:  # noqa: B902
+                errs.append(e)
+                for k in mine:
+                    done[k].set()
+        th = [threading.Thread(target=lambda l=l: (self.engines[0].torch.cuda.set_device(self.device), lane(l, self.engines[l])))
+              for l in range(L)]
+        for x in th:
+            x.start()
+        try:
+            for k in range(len(chunks)):
+                done[k].wait()
+                if errs:
+                    raise errs[0]
+                yield results[k]
+                results[k] = None
+        finally:
+            for x in th:
+                x.join()
 
 
 _ENGINES = {}

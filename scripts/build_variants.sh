@@ -7,10 +7,10 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build c64 -DR2_CHUNK_WORDS=64
-build c256 -DR2_CHUNK_WORDS=256
-build t512 -DR2_THREADS=512
-build t512c64 -DR2_THREADS=512 -DR2_CHUNK_WORDS=64
-build sched0 -DR2_SCHED=0
+build kc8 -DKC_BLOCKS=8
+build kc4 -DKC_BLOCKS=4
+build kj6 -DKJ_BLOCKS=6 -DKG_BLOCKS=6
+build kg8 -DKJ_BLOCKS=8 -DKG_BLOCKS=8
+build kg2 -DKG_BLOCKS=2
 wait
 ls -la genofix_b200/variants

@@ -357,3 +357,26 @@ def test_pipelined_chunks_equal_chunk_by_chunk_calls():
         assert st["test_p"] == rtp
         assert np.array_equal(st["corrected_per_animal"], rc) and np.array_equal(st["excluded_per_animal"], rx)
     assert sum(int((o != obs[:, a:b]).sum()) for (o, _), (a, b) in zip(got, bounds)) > 0
+
+
+def test_multilane_results_do_not_depend_on_lane_count():
+    """Two lanes (two host threads, two stream sets, one shared schedule) give the chunk-by-chunk results."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine, MultiLane
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(2000, 6, seed=15)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 1500, seed=15), 0.01, seed=15), 0.01, seed=16)
+    bounds = [(0, 300), (300, 600), (600, 900), (900, 1200), (1200, 1500)]
+    ped = PedigreeDAG.from_table(rows)
+    eng = Engine(ped, rows[:, 0], 2)
+    ref = []
+    for a, b in bounds:
+        out = eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+        ref.append((out, eng.stats["test_p"], eng.stats["corrected_per_animal"].copy()))
+    ml = MultiLane(ped, rows[:, 0], 2, lanes=2)
+    outs = [np.empty((len(rows), b - a), np.uint8) for a, b in bounds]
+    got = list(ml.correct_chunks([np.ascontiguousarray(obs[:, a:b]) for a, b in bounds], 0.5, 0.64, init_filter_p=0.95,
+                                 tiethreshold=0.4, outs=outs))
+    for k, ((out, st), (rout, rtp, rc)) in enumerate(zip(got, ref)):
+        assert out is outs[k]
+        assert np.array_equal(out, rout) and st["test_p"] == rtp and np.array_equal(st["corrected_per_animal"], rc)

@@ -39,15 +39,16 @@ def parse():
     ap.add_argument("--animals", type=int, default=N_ANIMALS)
     ap.add_argument("--snps", type=int, default=N_SNPS)
     ap.add_argument("--chunk", type=int, default=CHUNK)
-    ap.add_argument("--lanes", type=int, default=2, help="chunks corrected concurrently per GPU (streams + host threads)")
+    ap.add_argument("--generations", type=int, default=N_GENERATIONS)
+    ap.add_argument("--lanes", type=int, default=3, help="chunks corrected concurrently per GPU (streams + host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
 
 
-def make_inputs(n_animals, n_snps, seed):
+def make_inputs(n_animals, n_snps, seed, generations=N_GENERATIONS):
     from genofix_b200 import synth
-    rows = synth.make_pedigree(n_animals, N_GENERATIONS, sire_frac=0.05, dam_frac=0.5, seed=1234)
+    rows = synth.make_pedigree(n_animals, generations, sire_frac=0.05, dam_frac=0.5, seed=1234)
     truth = synth.gene_drop(rows, n_snps, seed=seed)
     obs = synth.inject_errors(truth, 0.01, seed=seed)
     return rows, obs
@@ -131,7 +132,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from genofix_b200 import _lib
-    from genofix_b200.engine import MultiLane
+    from genofix_b200.engine import MultiLane, pinned_array
     from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -140,7 +141,7 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
-    rows, obs = make_inputs(args.animals, args.snps, seed=1234 + rank)
+    rows, obs = make_inputs(args.animals, args.snps, seed=1234 + rank, generations=args.generations)
     ped = PedigreeDAG.from_table(rows)
     n_chunks = (args.snps + args.chunk - 1) // args.chunk
     bounds = [(c * args.chunk, min(args.snps, (c + 1) * args.chunk)) for c in range(n_chunks)]
@@ -154,7 +155,8 @@ def run_cuda(args):
     host_chunks = []
     for (a, b) in bounds:
         eng._alloc(b - a)
-        sub = np.ascontiguousarray(obs[:, a:b])
+        sub = pinned_array((obs.shape[0], b - a))       # e2e inputs: pinned host memory (bench contract)
+        sub[...] = obs[:, a:b]
         host_chunks.append(sub)
         hin = eng.host_in.numpy()
         hin[:, :eng.s] = sub
@@ -207,7 +209,7 @@ def run_cuda(args):
         if world > 1:
             dist.all_reduce(tall)   # the one collective: per-animal error tallies
 
-    host_outs = [np.empty_like(c) for c in host_chunks]   # caller-owned result matrices (genofix.py writes into `corrected`)
+    host_outs = [pinned_array(c.shape) for c in host_chunks]   # caller-owned, pinned result matrices
 
     def step_e2e():
         # the public multi-chunk call (genofix.py's chunk loop): host uint8 in, host uint8 out, every step
@@ -323,8 +325,10 @@ def run_cuda(args):
                     steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="u8/f16/f64 (2-bit codes, float16 scores, float64 posteriors)",
                     data="synthetic",
-                    config=dict(workload="10k-animal 6-generation synthetic pedigree x 50k SNPs, 1% errors (BASELINE configs[1]), "
-                                         "corrected in 10k-SNP chunks like genofix.py", animals=args.animals, snps=args.snps,
+                    config=dict(workload=("10k-animal 6-generation synthetic pedigree x 50k SNPs, 1% errors (BASELINE configs[1]), "
+                                          "corrected in 10k-SNP chunks like genofix.py") if (args.animals, args.snps, args.generations) ==
+                                (N_ANIMALS, N_SNPS, N_GENERATIONS) else "%d-animal %d-generation synthetic pedigree x %d SNPs, 1%% errors"
+                                % (args.animals, args.generations, args.snps), animals=args.animals, snps=args.snps,
                                 chunk_snps=args.chunk, back=BACK, lanes=lanes, per_gpu_matrix="%d x %d" % (args.animals, args.snps),
                                 l2="each step streams %.0f MB of packed codes + %.0f MB of float16 scores per chunk (> 126 MB L2)"
                                    % (args.animals * args.chunk / 4 / 1e6, args.animals * args.chunk * 2 / 1e6), **PARAMS),
@@ -340,6 +344,17 @@ def run_cuda(args):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: everything libraries write to fd 1 (NCCL prints its version there) goes to stderr
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _json_out = os.fdopen(_json_fd, "w")
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001 -- the JSON line is the only print of this module
+        kw.setdefault("file", _json_out)
+        _print(*args, **kw)
+        _json_out.flush()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

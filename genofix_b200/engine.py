@@ -38,7 +38,8 @@ def _parallel_copy(dst, src, threads=None):
     global _POOL
     n = dst.shape[0]
     if threads is None:
-        threads = max(1, min(16, os.cpu_count() or 1))
+        # one rank per GPU: share the host cores with the other ranks of the box
+        threads = max(2, min(16, (os.cpu_count() or 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
     if dst.size < (1 << 22) or n < threads:
         dst[...] = src
         return
@@ -406,7 +407,7 @@ class Engine(object):
         n = self.n
         self.p_in = [t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True) for _ in range(2)]
         self.p_out = [t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True) for _ in range(2)]
-        self.p_codes_in = [t.empty((n, self.ldc), dtype=t.uint8, device=dev) for _ in range(2)]
+        self.p_codes_in = [t.full((n, self.ldc), 9, dtype=t.uint8, device=dev) for _ in range(2)]   # pad columns stay 9
         self.p_codes_out = [t.empty((n, self.ldc), dtype=t.uint8, device=dev) for _ in range(2)]
         self.p_packed = [t.empty((n, self.wpr), dtype=t.int32, device=dev) for _ in range(2)]
         self.p_tall_dev = [t.empty(2 * n, dtype=t.int32, device=dev) for _ in range(2)]
@@ -421,10 +422,20 @@ class Engine(object):
         genofix.py:207-237 with every chunk an independent correctMatrix call.  Same results as calling correct()
         chunk by chunk; here three streams and two buffer sets overlap a chunk's kernels with the host staging +
         H2D copy of the next chunk and the D2H copy + un-staging of the previous one.  `outs`: optional list of
-        caller-owned uint8 [n, s_i] arrays to receive the results (saves allocating and first-touching them)."""
+        caller-owned uint8 [n, s_i] arrays to receive the results.  Chunks and outs that live in pinned host memory
+        (pinned_array()) are read / written by the copy engines directly; anything else is staged through pinned
+        buffers with a threaded host copy."""
         t = self.torch
         it = iter(chunks)
-        state = {"ev_comp": [None, None], "ev_out": [None, None], "k": 0}
+        state = {"ev_comp": [None, None], "ev_out": [None, None], "hold": [None, None]}
+
+        def pinned_view(arr, s):
+            """torch view of a caller array the copy engines can reach directly, else None (staged copy)"""
+            if not (isinstance(arr, np.ndarray) and arr.dtype == np.uint8 and arr.flags.c_contiguous and arr.flags.writeable
+                    and arr.shape == (self.n, s)):
+                return None
+            tv = t.from_numpy(arr)
+            return tv if tv.is_pinned() else None
 
         def stage(G, slot):
             G = np.asarray(G)
@@ -436,37 +447,38 @@ class Engine(object):
                 state["ev_comp"] = [None, None]
                 state["ev_out"] = [None, None]
             self._alloc_pipe()
-            hin = self.p_in[slot].numpy()
-            _parallel_copy(hin[:, :self.s], G)
-            if self.ldc > self.s:
-                hin[:, self.s:] = 9
+            src = pinned_view(G, self.s)
+            if src is None:
+                hin = self.p_in[slot].numpy()
+                _parallel_copy(hin[:, :self.s], G)
+            state["hold"][slot] = (G, src)    # keep the caller's memory alive until the copy has run
             with t.cuda.stream(self.s_in):
                 if state["ev_comp"][slot] is not None:
                     self.s_in.wait_event(state["ev_comp"][slot])     # the kernels that read p_packed[slot] are done
-                self.p_codes_in[slot].copy_(self.p_in[slot], non_blocking=True)
+                self.p_codes_in[slot][:, :self.s].copy_(src if src is not None else self.p_in[slot][:, :self.s], non_blocking=True)
                 _lib.check(self.L.gfx_pack2(self.p_codes_in[slot].data_ptr(), self.n, self.s, self.p_codes_in[slot].stride(0),
                                             self.p_packed[slot].data_ptr(), self.wpr, self._stream()))
                 ev = t.cuda.Event()
                 ev.record(self.s_in)
             return ev
 
-        def finish(slot, s, test_p, n_nan):
+        def finish(slot, s, test_p, n_nan, k, out, direct):
             state["ev_out"][slot].synchronize()
             _lib.check(self.L.gfx_check_device_status(self.schedule.handle, C.c_void_p(self.s_out.cuda_stream)))
             tall = self.p_tall[slot].numpy()
             stats = dict(test_p=test_p, n_nan=n_nan, corrected_per_animal=tall[:self.n].copy(),
                          excluded_per_animal=tall[self.n:].copy(), posteriors=None)
-            out = outs[state["k"]] if outs is not None else np.empty((self.n, s), dtype=np.uint8)
-            state["k"] += 1
-            if out.shape != (self.n, s) or out.dtype != np.uint8:
-                raise ValueError("outs[%d] must be uint8 [%d, %d]" % (state["k"] - 1, self.n, s))
-            _parallel_copy(out, self.p_out[slot].numpy()[:, :s])
+            if not direct:
+                if out is None:
+                    out = np.empty((self.n, s), dtype=np.uint8)
+                _parallel_copy(out, self.p_out[slot].numpy()[:, :s])
             return out, stats
 
         cur = next(it, None)
         if cur is None:
             return
         slot = 0
+        k = 0
         ev_in = stage(cur, slot)
         prev = None
         while cur is not None:
@@ -482,13 +494,18 @@ class Engine(object):
                 self.p_tall_dev[slot].copy_(self.tallies, non_blocking=True)
                 state["ev_comp"][slot] = t.cuda.Event()
                 state["ev_comp"][slot].record(self.s_c)
+            out = outs[k] if outs is not None else None
+            if out is not None and (out.shape != (self.n, self.s) or out.dtype != np.uint8):
+                raise ValueError("outs[%d] must be uint8 [%d, %d]" % (k, self.n, self.s))
+            dst = pinned_view(out, self.s) if out is not None else None
             with t.cuda.stream(self.s_out):
                 self.s_out.wait_event(state["ev_comp"][slot])
-                self.p_out[slot].copy_(self.p_codes_out[slot], non_blocking=True)
+                (dst if dst is not None else self.p_out[slot][:, :self.s]).copy_(self.p_codes_out[slot][:, :self.s], non_blocking=True)
                 self.p_tall[slot].copy_(self.p_tall_dev[slot], non_blocking=True)
                 state["ev_out"][slot] = t.cuda.Event()
                 state["ev_out"][slot].record(self.s_out)
-            mine = (slot, self.s, self.test_p, self.n_nan)
+            mine = (slot, self.s, self.test_p, self.n_nan, k, out, dst is not None)
+            k += 1
             # the GPU is busy with this chunk's correction: stage the next chunk, hand back the previous one
             nxt = next(it, None)
             if nxt is not None and np.asarray(nxt).shape[1] != self.s and prev is not None:
@@ -523,6 +540,14 @@ class Engine(object):
         _lib.check(self.L.gfx_trio_scan(self.schedule.handle, self.packed_orig.data_ptr(), self.s, self.wpr,
                                         inc.data_ptr(), tst.data_ptr(), self._stream()))
         return inc.cpu().numpy(), tst.cpu().numpy()
+
+
+def pinned_array(shape, dtype=np.uint8):
+    """numpy array in page-locked host memory: correct_chunks moves such arrays with the copy engines directly
+    (no staging copy).  The array keeps its backing tensor alive."""
+    t = _torch()
+    buf = t.empty(tuple(shape), dtype=getattr(t, np.dtype(dtype).name), pin_memory=True)
+    return buf.numpy()
 
 
 class MultiLane(object):

@@ -7,10 +7,9 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build kc8 -DKC_BLOCKS=8
-build kc4 -DKC_BLOCKS=4
-build kj6 -DKJ_BLOCKS=6 -DKG_BLOCKS=6
-build kg8 -DKJ_BLOCKS=8 -DKG_BLOCKS=8
-build kg2 -DKG_BLOCKS=2
+build m64 -DGFX_MULTI_CHUNK=64
+build m64w4 -DGFX_MULTI_CHUNK=64 -DGFX_MULTI_WARPS=4
+build m128w4 -DGFX_MULTI_CHUNK=128 -DGFX_MULTI_WARPS=4
+build m256 -DGFX_MULTI_CHUNK=256
 wait
 ls -la genofix_b200/variants

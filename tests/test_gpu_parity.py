@@ -374,9 +374,15 @@ def test_multilane_results_do_not_depend_on_lane_count():
         out = eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
         ref.append((out, eng.stats["test_p"], eng.stats["corrected_per_animal"].copy()))
     ml = MultiLane(ped, rows[:, 0], 2, lanes=2)
-    outs = [np.empty((len(rows), b - a), np.uint8) for a, b in bounds]
-    got = list(ml.correct_chunks([np.ascontiguousarray(obs[:, a:b]) for a, b in bounds], 0.5, 0.64, init_filter_p=0.95,
-                                 tiethreshold=0.4, outs=outs))
+    from genofix_b200.engine import pinned_array
+    # a mix of pinned (moved by the copy engines directly) and pageable (staged) inputs and outputs
+    outs = [pinned_array((len(rows), b - a)) if i % 2 else np.empty((len(rows), b - a), np.uint8) for i, (a, b) in enumerate(bounds)]
+    ins = []
+    for i, (a, b) in enumerate(bounds):
+        x = pinned_array((len(rows), b - a)) if i % 3 == 0 else np.empty((len(rows), b - a), np.uint8)
+        x[...] = obs[:, a:b]
+        ins.append(x)
+    got = list(ml.correct_chunks(ins, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4, outs=outs))
     for k, ((out, st), (rout, rtp, rc)) in enumerate(zip(got, ref)):
         assert out is outs[k]
         assert np.array_equal(out, rout) and st["test_p"] == rtp and np.array_equal(st["corrected_per_animal"], rc)

@@ -2063,7 +2063,7 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
 // Deferred jobs, one thread each, in two rounds so that a warp never mixes the cheap and the expensive kind:
 // round A = tree message passing; what it cannot answer is handed to round B = general elimination.
 // Warps draw 32 items at a time from a global counter (the general eliminations have a long tail).
-template <int MODE>
+template <int MODE, int PER>
 __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list, unsigned long long n, unsigned long long* ticket) {
   unsigned long long ncell = *a.wl_count;
   if (ncell > a.wl_cap) ncell = a.wl_cap;
@@ -2072,11 +2072,11 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(ticket, 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
-    if (t * 32ull >= n) break;
-    const unsigned long long i = t * 32ull + lane;
+    if (t * (unsigned long long)PER >= n) break;
+    const unsigned long long i = t * (unsigned long long)PER + lane;
     bool again = false;
     uint2 it = make_uint2(0u, 0u);
-    if (i < n) {
+    if (lane < PER && i < n) {
       it = list[i];
       if (it.x < ncell) {
         const uint2 c = a.wl[it.x];
@@ -2112,13 +2112,16 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
 __global__ void __launch_bounds__(128, KJ_BLOCKS) k_correct_jobs(FocalArgs a) {
   unsigned long long n = *a.item_count;
   if (n > a.item_cap) n = a.item_cap;
-  jobs_round<1>(a, a.items_sorted, n, a.wl_count + 4);
+  jobs_round<1, 32>(a, a.items_sorted, n, a.wl_count + 4);
 }
 #ifndef KG_BLOCKS
 #define KG_BLOCKS 4
 #endif
+#ifndef KG_ITEMS
+#define KG_ITEMS 16   // jobs per ticket of the general round (measured: 16 beats 32 and 8)
+#endif
 __global__ void __launch_bounds__(128, KG_BLOCKS) k_correct_jobs_general(FocalArgs a) {
-  jobs_round<2>(a, a.items, a.wl_count[5], a.wl_count + 6);
+  jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6);
 }
 
 // Finishes the serial walk of every parked cell once all its jobs have bits.

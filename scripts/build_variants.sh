@@ -7,9 +7,9 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build m64 -DGFX_MULTI_CHUNK=64
-build m64w4 -DGFX_MULTI_CHUNK=64 -DGFX_MULTI_WARPS=4
-build m128w4 -DGFX_MULTI_CHUNK=128 -DGFX_MULTI_WARPS=4
-build m256 -DGFX_MULTI_CHUNK=256
+build g8i16 -DKG_BLOCKS=8 -DKG_ITEMS=16
+build g6i16 -DKG_BLOCKS=6 -DKG_ITEMS=16
+build g8i8 -DKG_BLOCKS=8 -DKG_ITEMS=8
+build g4i16 -DKG_ITEMS=16
 wait
 ls -la genofix_b200/variants

@@ -937,7 +937,13 @@ struct BlanketDev {
 };
 // diagnostic counters: 0 queries, 1 answered from the two parents, 2 eliminations, 3 big-table reruns,
 // 4 nodes touched, 5 suspect cells, 6 job evaluations, 7 children visited
+#ifdef GFX_DEBUG_COUNTERS
+#define GFX_COUNT_PTR(p, k) do { if (p) atomicAdd((p) + (k), 1ull); } while (0)
 #define GFX_COUNT(bl, k, v) do { if ((bl).counters) atomicAdd((bl).counters + (k), (unsigned long long)(v)); } while (0)
+#else
+#define GFX_COUNT_PTR(p, k) do { } while (0)
+#define GFX_COUNT(bl, k, v) do { } while (0)   // each site costs ~40 SASS instructions of warp-aggregated atomic: debug builds only
+#endif
 
 // Evidence is gathered lazily, walking outwards from the query only through unobserved nodes: the
 // usual case (both parents observed and not suspect) touches two rows instead of the whole blanket.
@@ -1090,7 +1096,7 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
     if (stage == 0) {
       const int st = (t == q || t == qother) ? 3 : L.status(t);
       if (st != 3) { r0 = st == 0 ? 1.0 : 0.0; r1 = st == 1 ? 1.0 : 0.0; r2 = st == 2 ? 1.0 : 0.0; --sp; continue; }
-      if ((visited >> t) & 1) { if (L.dbg) atomicAdd(L.dbg + 9, 1ull); return false; }
+      if ((visited >> t) & 1) { GFX_COUNT_PTR(L.dbg, 9); return false; }
       visited |= 1ull << t;
       const int a1 = L.p1[t];
       if (a1 < 0) {
@@ -1117,7 +1123,7 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
       f_flag[sp] = 0;
       f_stage[sp] = 3;
     } else if (stage == 7) {
-      if ((visited >> t) & 1) { if (L.dbg) atomicAdd(L.dbg + 9, 1ull); return false; }
+      if ((visited >> t) & 1) { GFX_COUNT_PTR(L.dbg, 9); return false; }
       visited |= 1ull << t;
       f_b[sp][0] = 1.0; f_b[sp][1] = 1.0; f_b[sp][2] = 1.0;
       f_m[sp] = L.kid[t];
@@ -1187,7 +1193,7 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
 }
 // out = normalised marginal, *total = unnormalised sum (0 => the reference's joint is 0/0)
 __device__ __noinline__ bool xpeel_query(const LazyBlanket& L, int q, int qother, double out[3], double* total) {
-  if (L.kid[q] != 0 || L.p1[q] < 0) { if (L.dbg) atomicAdd(L.dbg + 11, 1ull); return false; }
+  if (L.kid[q] != 0 || L.p1[q] < 0) { GFX_COUNT_PTR(L.dbg, 11); return false; }
   uint64_t visited = 1ull << q;
   double s[3], d[3];
   if (!belief_up(L, q, qother, visited, L.p1[q], q, s)) return false;

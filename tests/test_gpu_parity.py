@@ -386,3 +386,29 @@ def test_multilane_results_do_not_depend_on_lane_count():
     for k, ((out, st), (rout, rtp, rc)) in enumerate(zip(got, ref)):
         assert out is outs[k]
         assert np.array_equal(out, rout) and st["test_p"] == rtp and np.array_equal(st["corrected_per_animal"], rc)
+
+
+def test_huge_litter_paths_match_oracle():
+    """One sire with 2 300 genotyped children: the children units exceed the packed-half range of the rank kernel
+    (m >= 1024 -> per-cell path) and the litter exceeds the in-register children term of the correction kernel
+    (fallback kernel); both must still be bit-exact."""
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from genofix_b200 import synth
+    from oracle.genofix_oracle import Oracle
+    rs = np.random.default_rng(77)
+    rows = [[1, 0, 0, 1]] + [[i, 0, 0, 2] for i in range(2, 42)]          # 1 sire, 40 dams (founders)
+    kid = 42
+    for k in range(2300):
+        rows.append([kid, 1, int(rs.integers(2, 42)), 1 + k % 2])
+        kid += 1
+    rows = np.array(rows, dtype=np.int64)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 8, seed=5), 0.02, seed=5), 0.01, seed=6)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    out = eng.correct(obs, 0.5, 0.64, init_filter_p=0.9, tiethreshold=0.4)
+    o = Oracle(rows, rows[:, 0]).correct_matrix(obs, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4)
+    assert _same_f16(eng.raw_host(), o["raw"])
+    assert float(eng.raw_host()[0].astype(np.float32).max()) > 341.0      # m >= 1024 really happened on the sire's row
+    assert eng.stats["test_p"] == o["test_p"]
+    assert np.array_equal(out, o["corrected"])
+    assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])

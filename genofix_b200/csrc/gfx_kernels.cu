@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -17,7 +18,6 @@
 #include "gfx_schedule.h"
 
 #define GFX_BIG_SLOTS 64
-#define R2_QUEUES_HOST 32   // task queues of k_mendel_rank (R2_QUEUES)
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -79,8 +79,10 @@ struct gfx_schedule {
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
   uint32_t* rank_lut6 = nullptr;     // 64 entries (obs | sire << 2 | dam << 4): score | class << 16
   uint16_t* rank_class_sc = nullptr; // score of each of the <= 8 classes
-  unsigned int* rank_ctr = nullptr;  // task counter of k_mendel_rank
-  RankRow* rank_rows = nullptr;  // per-row records, heaviest first
+  std::vector<RankRow> rank_rows_h;     // per-row records of the rank kernel, heaviest first
+  struct RankTasks { int64_t nwords; RankRow* dev; uint32_t n; };
+  std::vector<RankTasks> rank_tasks;    // task tables, one per matrix width seen so far
+  std::mutex rank_mutex;
   double* kv = nullptr;        // 108 doubles, children-heuristic element table
   int* status = nullptr;
   unsigned long long* counters = nullptr;  // 16 diagnostic counters (gfx_debug_counters)
@@ -165,9 +167,11 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc, s->rank_ctr, s->rank_rows};
+                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& t : s->rank_tasks)
+    if (t.dev) cudaFree(t.dev);
   delete s;
 }
 
@@ -200,8 +204,8 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   std::vector<uint32_t> lut6;
   std::vector<uint16_t> class_sc;
   if (!build_rank_fast(lut, lut6, class_sc, err)) { delete s; return fail(GFX_E_INVALID, err); }
-  std::vector<unsigned int> rank_ctr(R2_QUEUES_HOST, 0u);
-  std::vector<RankRow> rank_rows(h.n_rows);
+  std::vector<RankRow>& rank_rows = s->rank_rows_h;
+  rank_rows.resize(h.n_rows);
   {
     std::vector<int32_t> order(h.n_rows);
     for (int r = 0; r < h.n_rows; ++r) order[r] = r;
@@ -227,7 +231,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(single_row, h.single_row); UP(single_bl, h.single_blanket); UP(single_off, single_off);
   UP(single_entry, single_entry);
   UP(app_order, h.app_order); UP(single_order, h.single_order);
-  UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(rank_lut6, lut6); UP(rank_class_sc, class_sc); UP(rank_ctr, rank_ctr); UP(rank_rows, rank_rows); UP(kv, kv); UP(status, status);
+  UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(rank_lut6, lut6); UP(rank_class_sc, class_sc); UP(kv, kv); UP(status, status);
 #undef UP
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * GFX_BIG_SLOTS);
@@ -422,30 +426,31 @@ struct RankArgs {
   int64_t ld_raw;
   int n_rows;
   const int32_t* anc6;
-  const RankRow* rows;
+  const RankRow* tasks;       // one record per task (pad0 = first word, pad1 = end word)
+  uint32_t n_tasks;
   const int32_t* child_row;
   const uint2* lut;
   const uint32_t* lut6;
   const uint16_t* class_sc;
   unsigned long long* hist;   // 65537 bins or nullptr (HIST = false)
-  unsigned int* task_ctr;
-  uint32_t chunks;            // chunks per row
-  int chunk_words;            // words per chunk (multiple of 32)
 };
 
 #ifndef R2_THREADS
 #define R2_THREADS 1024
 #endif
-#ifndef R2_CHUNK_WORDS
-#define R2_CHUNK_WORDS 128
-#endif
 #ifndef R2_KIDS4
 #define R2_KIDS4 1
 #endif
-#ifndef R2_SCHED
-#define R2_SCHED 2
+// words per task by number of children of the row (measured at 10k x 10k and 100k x 4096)
+#ifndef R2_WORDS_HEAVY
+#define R2_WORDS_HEAVY 32    // >= 8 children
 #endif
-#define R2_QUEUES 32   // = warp size: one lane per queue when looking for work
+#ifndef R2_WORDS_MID
+#define R2_WORDS_MID 128     // 1..7 children
+#endif
+#ifndef R2_WORDS_LIGHT
+#define R2_WORDS_LIGHT 128   // childless
+#endif
 #define R2_CM_OFF 0u          // u32 [8 classes][32 m][32 lanes]
 #define R2_FAST_OFF 32768u    // u32 [64 idx6][64]: lanes 0..31 table entries, 32..63 counters
 #define R2_BINS_OFF 49152u    // u32 [8192] patterns 0x3000..0x4FFF
@@ -561,22 +566,28 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
 }
 
 // histogram of one word's final patterns (words whose cells do not fit the lane-private counters)
+// zeros and missing cells are tallied in two scratch bins (patterns that cannot be scores) and mapped when the block retires
+#define R2_SLOT_ZERO (R2_BIN_N - 1u)   // 0x4FFF
+#define R2_SLOT_MISS (R2_BIN_N - 2u)   // 0x4FFE
 __device__ __noinline__ void r2_hist_patterns(unsigned long long* hist, uint32_t* s_bins, const uint32_t outw[8], uint32_t miss,
-                                              int lim, uint32_t& zeros, uint32_t& nmiss) {
+                                              int lim) {
+  uint32_t zeros = 0, nmiss = 0;
 #pragma unroll 1
   for (int i = 0; i < lim; ++i) {
     const uint32_t r = (outw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
     if ((miss >> (2 * i)) & 1u) ++nmiss;
     else if (r == 0u) ++zeros;
-    else if (r - R2_BIN_LO < R2_BIN_N) atomicAdd(&s_bins[r - R2_BIN_LO], 1u);
+    else if (r - R2_BIN_LO < R2_BIN_N - 2u) atomicAdd(&s_bins[r - R2_BIN_LO], 1u);
     else atomicAdd(&hist[r], 1ull);
   }
+  if (zeros) atomicAdd(&s_bins[R2_SLOT_ZERO], zeros);
+  if (nmiss) atomicAdd(&s_bins[R2_SLOT_MISS], nmiss);
 }
 
 // Per-cell path with the full table; handles every case (and is the definition the fast path is tested against).
 template <bool HIST>
 __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t row, int64_t w, uint32_t w0, bool has_anc,
-                                          int c0, int c1, uint32_t& zeros, uint32_t& nmiss) {
+                                          int c0, int c1) {
   const uint2* s_lut = reinterpret_cast<const uint2*>(smem + R2_LUT_OFF);
   uint32_t wa[6];
   if (has_anc) {
@@ -620,7 +631,7 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
     outw[k] = pair;
   }
   if (HIST)
-    r2_hist_patterns(a.hist, reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF), outw, w0 & (w0 >> 1) & 0x55555555u, lim, zeros, nmiss);
+    r2_hist_patterns(a.hist, reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF), outw, w0 & (w0 >> 1) & 0x55555555u, lim);
   r2_store(a.raw + row * a.ld_raw + w * 16, outw);
 }
 
@@ -652,74 +663,36 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t lane4 = (uint32_t)lane * 4u;
-  const uint32_t tasks = (uint32_t)a.n_rows * a.chunks;
   const __half2 C3 = r2_h2(0x35553555u);    // float16(1/3) = 1365 / 4096
   const __half2 K3 = r2_h2(0xDD55DD55u);    // -1024 * float16(1/3) = -341.25
   uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF);
-  uint32_t zeros = 0, ones = 0, nmiss = 0;
-  // Task = (row record, R2_CHUNK_WORDS-word chunk); records are sorted heaviest first.  Tasks are dealt round-robin
-  // to the blocks (static, balanced because the order is by cost); inside a block the warps draw tickets from a
-  // shared-memory counter (dynamic, no global same-address atomics).  Two tickets are kept in flight so that the
-  // next task's row record is loaded while the current task is processed.
-#if R2_SCHED == 2
+  // Task = 32-byte record (row, children range, flags, parent rows, first word, end word), built on the host per
+  // matrix width: rows sorted heaviest first and cut into chunks -- short ones for rows with many children (their
+  // children loop is latency bound and would otherwise be the tail), long ones for childless rows (per-task set-up).
+  // Tasks are dealt round-robin to the blocks (static, balanced because the order is by cost); inside a block the
+  // warps draw tickets from a shared-memory counter (dynamic, no global same-address atomics).  Two tickets are kept
+  // in flight so that the next task's record is loaded while the current task is processed.
   uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + R2_SMEM);
 #define R2_TASK_OF(k) ((k) * gridDim.x + blockIdx.x)
+  const uint32_t tasks = a.n_tasks;
   uint32_t tk = 0;
   if (lane == 0) tk = atomicAdd(s_ticket, 2u);
   tk = __shfl_sync(0xffffffffu, tk, 0);
   uint32_t task = R2_TASK_OF(tk), ntask = R2_TASK_OF(tk + 1u);
   int4 q0 = make_int4(0, 0, 0, 0), q1 = q0;
   if (task < tasks) {
-    q0 = __ldg(reinterpret_cast<const int4*>(a.rows + task / a.chunks));
-    q1 = __ldg(reinterpret_cast<const int4*>(a.rows + task / a.chunks) + 1);
+    q0 = __ldg(reinterpret_cast<const int4*>(a.tasks + task));
+    q1 = __ldg(reinterpret_cast<const int4*>(a.tasks + task) + 1);
   }
   while (task < tasks) {
     int4 nq0 = make_int4(0, 0, 0, 0), nq1 = nq0;
     if (ntask < tasks) {
-      nq0 = __ldg(reinterpret_cast<const int4*>(a.rows + ntask / a.chunks));
-      nq1 = __ldg(reinterpret_cast<const int4*>(a.rows + ntask / a.chunks) + 1);
+      nq0 = __ldg(reinterpret_cast<const int4*>(a.tasks + ntask));
+      nq1 = __ldg(reinterpret_cast<const int4*>(a.tasks + ntask) + 1);
     }
     uint32_t next = 0;
     if (lane == 0) next = atomicAdd(s_ticket, 1u);
-    const int wbeg = (int)(task % a.chunks) * a.chunk_words;
-    const int wend = min(wbeg + a.chunk_words, a.nwords);
-#else
-#if R2_SCHED
-  uint32_t q = blockIdx.x % R2_QUEUES;
-  uint32_t ticket = 0;
-  if (lane == 0) ticket = atomicAdd(a.task_ctr + q, 1u);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  for (;;) {
-    const uint32_t task = ticket * R2_QUEUES + q;
-    if (task >= tasks) {
-      // this queue is dry: every lane looks at one queue, the warp moves to the next live one
-      const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(a.task_ctr + lane);
-      const uint32_t live = __ballot_sync(0xffffffffu, (uint64_t)seen * R2_QUEUES + lane < tasks);
-      if (!live) break;
-      q = (q + __ffs(__funnelshift_r(live, live, q + 1))) & (R2_QUEUES - 1);
-      if (lane == 0) ticket = atomicAdd(a.task_ctr + q, 1u);
-      ticket = __shfl_sync(0xffffffffu, ticket, 0);
-      continue;
-    }
-    uint32_t next = 0;
-    if (lane == 0) next = atomicAdd(a.task_ctr + q, 1u);   // in flight while this task is processed
-#else
-  uint32_t ticket = 0;
-  if (lane == 0) ticket = atomicAdd(a.task_ctr, 1u);
-  ticket = __shfl_sync(0xffffffffu, ticket, 0);
-  for (;;) {
-    const uint32_t task = ticket;
-    if (task >= tasks) break;
-    uint32_t next = 0;
-    if (lane == 0) next = atomicAdd(a.task_ctr, 1u);
-#endif
-    // task order: chunk-major inside a row record, records heaviest first
-    const uint32_t rec = task / a.chunks;
-    const int wbeg = (int)(task % a.chunks) * a.chunk_words;
-    const int wend = min(wbeg + a.chunk_words, a.nwords);
-    const int4 q0 = __ldg(reinterpret_cast<const int4*>(a.rows + rec));
-    const int4 q1 = __ldg(reinterpret_cast<const int4*>(a.rows + rec) + 1);
-#endif
+    const int wbeg = q1.z, wend = q1.w;
     const int row = q0.x, c0 = q0.y, c1 = q0.y + q0.z;
     const bool has_anc = q0.w & 1, loopy = q0.w & 2;
     const int rS = q1.x, rD = q1.y;
@@ -748,7 +721,7 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
         uint32_t outw[8];
         if (!has_anc && c0 == c1) {
           // neither ancestors nor children: every score is 1.0 (:102)
-          if (tail) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1, zeros, nmiss); continue; }
+          if (tail) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1); continue; }
 #pragma unroll
           for (int k = 0; k < 8; ++k) outw[k] = 0x3C003C00u;
           if (HIST) {
@@ -759,9 +732,13 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
                 if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
               }
             }
-            const uint32_t nm = __popc(miss);
-            nmiss += nm;
-            ones += 16u - nm;
+            // one shared-memory update per warp step (redux.sync over the lanes still in the loop)
+            const uint32_t am = __activemask();
+            const uint32_t nm = __reduce_add_sync(am, __popc(miss));
+            if (lane == __ffs(am) - 1) {
+              atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], 16u * __popc(am) - nm);
+              if (nm) atomicAdd(&s_bins[R2_SLOT_MISS], nm);
+            }
           }
           r2_store(dst, outw);
           continue;
@@ -785,7 +762,7 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
           if (any & 0xFC00FC00u) slow = true;                                               // packed-half path: m < 1024
           if (!has_anc && (miss || anyv != 0x55555555u)) slow = true;                        // 1.0 cells among child scores
         }
-        if (slow) { r2_slow_word<HIST>(a, smem, row, w, w0, has_anc, c0, c1, zeros, nmiss); continue; }
+        if (slow) { r2_slow_word<HIST>(a, smem, row, w, w0, has_anc, c0, c1); continue; }
         if (has_anc) {
           // 4-row transposition of 2-bit fields: one byte obs | sire << 2 | dam << 4 per cell
           const uint32_t M2 = 0x33333333u, M4 = 0x0F0F0F0Fu;
@@ -803,10 +780,12 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
               const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
               const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
               const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
+#ifndef R2_X_NO_FAST_ATOMS
               if (HIST) {
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offa), 1u);
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offb), 1u);
               }
+#endif
               outw[k] = __byte_perm(ea, eb, 0x5410u);
             }
           } else {
@@ -816,10 +795,12 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
               const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
               const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
               const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
+#ifndef R2_X_NO_KIDS_ATOMS
               if (HIST && !big) {
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + (ea >> 16) + ((m16[k] & 0xFFFFu) << 7)), 1u);
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + (eb >> 16) + ((m16[k] >> 16) << 7)), 1u);
               }
+#endif
               const __half2 cs = __hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3);
               outw[k] = r2_u(__hadd2(cs, r2_h2(__byte_perm(ea, eb, 0x5410u))));
             }
@@ -830,12 +811,14 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
                 if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
               }
             }
+#ifndef R2_X_NO_BIG
             if (HIST && big) {
               uint32_t tmp[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
-              r2_hist_patterns(a.hist, s_bins, tmp, miss, 16, zeros, nmiss);
+              r2_hist_patterns(a.hist, s_bins, tmp, miss, 16);
             }
+#endif
           }
         } else {
           // founder with children, nothing missing: the score is the children term alone (class 0 = score 0)
@@ -851,32 +834,21 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
             uint32_t tmp[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
-            r2_hist_patterns(a.hist, s_bins, tmp, 0u, 16, zeros, nmiss);
+            r2_hist_patterns(a.hist, s_bins, tmp, 0u, 16);
           }
         }
         r2_store(dst, outw);
       }
     }
-#if R2_SCHED == 2
     task = ntask; q0 = nq0; q1 = nq1;
     next = __shfl_sync(0xffffffffu, next, 0);
     ntask = R2_TASK_OF(next);
-#else
-    ticket = __shfl_sync(0xffffffffu, next, 0);
-#endif
   }
+#ifdef R2_X_NO_EPILOGUE
+  return;
+#endif
   if (!HIST) return;
   // ---- retire: counters -> float16 patterns -> global histogram ------------------------------------
-  for (int o = 16; o > 0; o >>= 1) {
-    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
-    ones += __shfl_xor_sync(0xffffffffu, ones, o);
-    nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
-  }
-  if (lane == 0) {
-    if (zeros) atomicAdd(&s_bins[R2_BIN_N - 1], zeros);          // 0x4FFF (31.98) cannot be a score: scratch slots
-    if (ones) atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], ones);
-    if (nmiss) atomicAdd(&s_bins[R2_BIN_N - 2], nmiss);
-  }
   __syncthreads();
   {
     const uint32_t* s_fast = reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF);
@@ -899,7 +871,7 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
     for (int i = t; i < (int)R2_BIN_N; i += blockDim.x) {
       const uint32_t v = s_bins[i];
       if (!v) continue;
-      const uint32_t bin = i == (int)R2_BIN_N - 1 ? 0u : (i == (int)R2_BIN_N - 2 ? 65536u : R2_BIN_LO + i);
+      const uint32_t bin = i == (int)R2_SLOT_ZERO ? 0u : (i == (int)R2_SLOT_MISS ? 65536u : R2_BIN_LO + i);
       atomicAdd(&a.hist[bin], (unsigned long long)v);
     }
   }
@@ -1381,26 +1353,48 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   const int64_t nwords = (n_snps + 15) / 16;
   if (n_snps <= 0 || wpr < nwords || ld_raw < nwords * 16 || (ld_raw % 8) != 0 || (((uintptr_t)raw) % 16) != 0)
     return fail(GFX_E_INVALID, "gfx_mendel_rank: need wpr >= ceil(s/16), ld_raw >= 16*ceil(s/16), ld_raw % 8 == 0, raw 16-byte aligned");
-  // measured: 64..128-word chunks run fastest (short tasks interleave the latency-bound rows with children and the
-  // store-bound rows without); 128 when that still leaves >= 32 tasks per warp
-  const int64_t warps = (int64_t)s->num_sms * R2_CTAS * (R2_THREADS / 32);
-  int chunk_words = 128;
-  if ((int64_t)s->h.n_rows * ((nwords + 127) / 128) < 32 * warps) chunk_words = 64;
-  const int64_t chunks = (nwords + chunk_words - 1) / chunk_words;
-  if ((int64_t)s->h.n_rows * chunks >= (int64_t)0xFFFF0000ll || nwords > 0x7FFFFF00ll)
-    return fail(GFX_E_INVALID, "gfx_mendel_rank: matrix too large for one call (rows * ceil(words/128) must stay below 2^32)");
-  RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, s->rank_rows, s->child_row,
-             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist, s->rank_ctr, (uint32_t)chunks, chunk_words};
+  // task table for this matrix width (built once, cached in the schedule)
+  const RankRow* tasks_dev = nullptr;
+  uint32_t n_tasks = 0;
+  {
+    std::lock_guard<std::mutex> lock(const_cast<gfx_schedule*>(s)->rank_mutex);
+    gfx_schedule* ms = const_cast<gfx_schedule*>(s);
+    for (auto& t : ms->rank_tasks)
+      if (t.nwords == nwords) { tasks_dev = t.dev; n_tasks = t.n; }
+    if (!tasks_dev) {
+      std::vector<RankRow> tasks;
+      tasks.reserve((size_t)s->h.n_rows * ((nwords + 127) / 128 + 1));
+      for (const RankRow& r : s->rank_rows_h) {
+        const int64_t cw = r.nk >= 8 ? R2_WORDS_HEAVY : (r.nk >= 1 ? R2_WORDS_MID : R2_WORDS_LIGHT);
+        for (int64_t w = 0; w < nwords; w += cw) {
+          RankRow t = r;
+          t.pad0 = (int32_t)w;
+          t.pad1 = (int32_t)std::min<int64_t>(w + cw, nwords);
+          tasks.push_back(t);
+        }
+      }
+      if (tasks.size() >= 0xFFFF0000ull || nwords > 0x7FFFFF00ll)
+        return fail(GFX_E_INVALID, "gfx_mendel_rank: matrix too large for one call (more than 2^32 tasks)");
+      RankRow* dev = nullptr;
+      GFX_CUDA(cudaMalloc((void**)&dev, tasks.size() * sizeof(RankRow)));
+      cudaError_t e = cudaMemcpy(dev, tasks.data(), tasks.size() * sizeof(RankRow), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { cudaFree(dev); return fail(GFX_E_CUDA, std::string("task table upload: ") + cudaGetErrorString(e)); }
+      if (ms->rank_tasks.size() >= 8) { cudaDeviceSynchronize(); cudaFree(ms->rank_tasks.front().dev); ms->rank_tasks.erase(ms->rank_tasks.begin()); }
+      ms->rank_tasks.push_back({nwords, dev, (uint32_t)tasks.size()});
+      tasks_dev = dev;
+      n_tasks = (uint32_t)tasks.size();
+    }
+  }
+  RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, tasks_dev, n_tasks, s->child_row,
+             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist};
   static bool attr_set = false;
   if (!attr_set) {
     GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
     GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
     attr_set = true;
   }
-  GFX_CUDA(cudaMemsetAsync(s->rank_ctr, 0, sizeof(unsigned int) * R2_QUEUES_HOST, stream));
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
-  const int64_t tasks = (int64_t)s->h.n_rows * chunks;
-  int blocks = (int)std::min<int64_t>((tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
+  int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
   if (blocks < 1) blocks = 1;
   if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);
   else k_mendel_rank<false><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);

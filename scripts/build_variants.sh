@@ -7,9 +7,10 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build g8i16 -DKG_BLOCKS=8 -DKG_ITEMS=16
-build g6i16 -DKG_BLOCKS=6 -DKG_ITEMS=16
-build g8i8 -DKG_BLOCKS=8 -DKG_ITEMS=8
-build g4i16 -DKG_ITEMS=16
+build xfast -DR2_X_NO_FAST_ATOMS
+build xkids -DR2_X_NO_KIDS_ATOMS
+build xbig -DR2_X_NO_BIG
+build xepi -DR2_X_NO_EPILOGUE
+build xall -DR2_X_NO_FAST_ATOMS -DR2_X_NO_KIDS_ATOMS -DR2_X_NO_BIG -DR2_X_NO_EPILOGUE
 wait
 ls -la genofix_b200/variants

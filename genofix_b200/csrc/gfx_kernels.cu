@@ -701,8 +701,8 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
       const uint32_t* prow0 = a.packed + (int64_t)row * a.wpr;
       const uint32_t* prowS = a.packed + (int64_t)(parents_ok ? rS : row) * a.wpr;
       const uint32_t* prowD = a.packed + (int64_t)(parents_ok ? rD : row) * a.wpr;
-      // the 32-word steps of a chunk are walked from a per-task rotated start: otherwise every warp of the
-      // GPU sits at the same offset of its row at the same time (rows are a fixed stride apart: channel camping)
+      // the 32-word steps of a chunk are walked from a per-task rotated start, so that the warps of the GPU do not
+      // all sit at the same offset of their rows at the same time (rows are a fixed stride apart); measured neutral
       const int n_iter = (wend - wbeg + 31) >> 5;
       int pos = n_iter > 0 ? (int)__umulhi(task * 2654435761u, (uint32_t)n_iter) : 0;
       int wn = wbeg + pos * 32 + lane;
@@ -721,29 +721,20 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
         uint32_t outw[8];
         if (!has_anc && c0 == c1) {
           // neither ancestors nor children: every score is 1.0 (:102)
-          if (tail) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1); continue; }
+          // (words with a missing cell take the per-cell path: patching the marker in here costs 32 predicated
+          // instructions on every word, missing or not)
+          if (tail || (HIST && miss)) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1); continue; }
 #pragma unroll
           for (int k = 0; k < 8; ++k) outw[k] = 0x3C003C00u;
           if (HIST) {
-            if (miss) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if ((miss >> (4 * k)) & 1u) outw[k] |= 0x0000FFFFu;
-                if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
-              }
-            }
-            // one shared-memory update per warp step (redux.sync over the lanes still in the loop)
+            // one shared-memory update per warp step
             const uint32_t am = __activemask();
-            const uint32_t nm = __reduce_add_sync(am, __popc(miss));
-            if (lane == __ffs(am) - 1) {
-              atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], 16u * __popc(am) - nm);
-              if (nm) atomicAdd(&s_bins[R2_SLOT_MISS], nm);
-            }
+            if (lane == __ffs(am) - 1) atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], 16u * __popc(am));
           }
           r2_store(dst, outw);
           continue;
         }
-        bool slow = tail;
+        bool slow = tail || (HIST && miss && c1 > c0);   // NaN marker + children term: per-cell path
         if (has_anc) {
           if (!parents_ok) slow = true;
           else if (((wS & (wS >> 1)) | (wD & (wD >> 1))) & 0x55555555u) {
@@ -780,12 +771,10 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
               const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
               const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
               const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
-#ifndef R2_X_NO_FAST_ATOMS
               if (HIST) {
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offa), 1u);
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF + 128u + offb), 1u);
               }
-#endif
               outw[k] = __byte_perm(ea, eb, 0x5410u);
             }
           } else {
@@ -795,30 +784,19 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
               const uint32_t offb = __byte_perm((k & 1) ? W : Z, lane4, 0x5504u | ((uint32_t)(k >> 1) << 4));
               const uint32_t ea = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offa);
               const uint32_t eb = *reinterpret_cast<const uint32_t*>(smem + R2_FAST_OFF + offb);
-#ifndef R2_X_NO_KIDS_ATOMS
               if (HIST && !big) {
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + (ea >> 16) + ((m16[k] & 0xFFFFu) << 7)), 1u);
                 atomicAdd(reinterpret_cast<uint32_t*>(smem + (eb >> 16) + ((m16[k] >> 16) << 7)), 1u);
               }
-#endif
               const __half2 cs = __hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3);
               outw[k] = r2_u(__hadd2(cs, r2_h2(__byte_perm(ea, eb, 0x5410u))));
             }
-            if (HIST && miss) {   // NaN + 0 lost the marker
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if ((miss >> (4 * k)) & 1u) outw[k] |= 0x0000FFFFu;
-                if ((miss >> (4 * k)) & 4u) outw[k] |= 0xFFFF0000u;
-              }
-            }
-#ifndef R2_X_NO_BIG
             if (HIST && big) {
               uint32_t tmp[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
-              r2_hist_patterns(a.hist, s_bins, tmp, miss, 16);
+              r2_hist_patterns(a.hist, s_bins, tmp, 0u, 16);
             }
-#endif
           }
         } else {
           // founder with children, nothing missing: the score is the children term alone (class 0 = score 0)
@@ -844,9 +822,6 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
     next = __shfl_sync(0xffffffffu, next, 0);
     ntask = R2_TASK_OF(next);
   }
-#ifdef R2_X_NO_EPILOGUE
-  return;
-#endif
   if (!HIST) return;
   // ---- retire: counters -> float16 patterns -> global histogram ------------------------------------
   __syncthreads();

@@ -220,6 +220,24 @@ def run_cuda(args):
             total += int(stats["corrected_per_animal"].sum())
         return total
 
+    # the same step fed with 2-bit packed blocks (what gfutils.packedgens.PackedGens streams from disk): extra key
+    from genofix_b200.gfutils.packedgens import pack_codes
+    packed_chunks, packed_outs = [], []
+    for c in host_chunks:
+        pc = pack_codes(c)
+        pin = pinned_array(pc.shape, np.uint32)
+        pin[...] = pc
+        packed_chunks.append((pin, c.shape[1]))
+        packed_outs.append(pinned_array(pc.shape, np.uint32))
+
+    def step_e2e_packed():
+        total = 0
+        for out, stats in ml.correct_chunks(iter(packed_chunks), PARAMS["threshold_pair"], PARAMS["threshold_single"],
+                                            init_filter_p=PARAMS["init_filter_p"], tiethreshold=PARAMS["tiethreshold"],
+                                            err_thresh=PARAMS["err_thresh"], outs=packed_outs, packed_io=True):
+            total += int(stats["corrected_per_animal"].sum())
+        return total
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -254,10 +272,17 @@ def run_cuda(args):
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - w0
-    tm = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    step_e2e_packed()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_packed()
+    barrier()
+    e2e_packed_s = time.perf_counter() - w0
+    tm = torch.tensor([ms, e2e_s * 1e3, e2e_packed_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(tm[0]), float(tm[1])
+    ms, e2e_ms, e2e_packed_ms = float(tm[0]), float(tm[1]), float(tm[2])
     cells_step = args.animals * args.snps * world
     value = cells_step * args.steps / (ms / 1e3)
     e2e_value = cells_step * args.steps / (e2e_ms / 1e3)
@@ -334,6 +359,11 @@ def run_cuda(args):
                                    % (args.animals * args.chunk / 4 / 1e6, args.animals * args.chunk * 2 / 1e6), **PARAMS),
                     e2e=dict(value=e2e_value, unit="cells/s", h2d_bytes_per_step=int(args.animals * args.snps),
                              d2h_bytes_per_step=int(args.animals * args.snps), ms_per_step=e2e_ms / args.steps),
+                    e2e_packed_io=dict(value=cells_step * args.steps / (e2e_packed_ms / 1e3), unit="cells/s",
+                                       ms_per_step=e2e_packed_ms / args.steps,
+                                       h2d_bytes_per_step=int(sum(p.nbytes for p, _ in packed_chunks)),
+                                       d2h_bytes_per_step=int(sum(p.nbytes for p in packed_outs)),
+                                       note="same call with packed_io=True: 2-bit blocks as stored by gfutils.packedgens (GFX2BIT1)"),
                     gpu_launches=launches, roofline=roofline, phase_share=phase_share, clocks=clocks,
                     corrected_cells_per_step=corrected_total)
         if cb is not None:

@@ -24,6 +24,8 @@
 #define GFX_TAB 729           // 3^GFX_WMAX
 #define GFX_WMAX_BIG 9        // rare wide blankets rerun on a pooled global-memory table
 #define GFX_TAB_BIG 19683     // 3^GFX_WMAX_BIG
+#define GFX_WMAX_HUGE 13      // last resort: a few 12.75 MB tables (suspect filters can open most of a pair blanket)
+#define GFX_TAB_HUGE 1594323  // 3^GFX_WMAX_HUGE
 #define GFX_MAXN 64           // max nodes in one blanket (bit masks are uint64)
 #define GFX_HD __host__ __device__ __forceinline__
 
@@ -108,7 +110,7 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
     }
   }
   need &= inc;  // observed parents were marked too; their own factors count only if connected
-  int8_t open[GFX_WMAX_BIG];
+  int8_t open[GFX_WMAX_HUGE];
   int w = 0, size = 1;
   uint64_t folded = 0;
   double fv[GFX_MAXN * 3];  // belief vectors of folded nodes (only touched entries are used)

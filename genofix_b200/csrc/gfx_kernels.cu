@@ -18,6 +18,7 @@
 #include "gfx_schedule.h"
 
 #define GFX_BIG_SLOTS 64
+#define GFX_HUGE_SLOTS 4
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -87,7 +88,8 @@ struct gfx_schedule {
   int* status = nullptr;
   unsigned long long* counters = nullptr;  // 16 diagnostic counters (gfx_debug_counters)
   double* big_pool = nullptr;  // GFX_BIG_SLOTS tables of GFX_TAB_BIG doubles for rare wide blankets
-  int* big_flags = nullptr;
+  int* big_flags = nullptr;    // GFX_BIG_SLOTS flags, then GFX_HUGE_SLOTS flags
+  double* huge_pool = nullptr; // GFX_HUGE_SLOTS tables of GFX_TAB_HUGE doubles
 };
 
 template <class T>
@@ -167,7 +169,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc};
+                  s->big_pool, s->big_flags, s->huge_pool, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : s->rank_tasks)
@@ -234,8 +236,9 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(rank_lut6, lut6); UP(rank_class_sc, class_sc); UP(kv, kv); UP(status, status);
 #undef UP
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * GFX_BIG_SLOTS);
-  if (e == cudaSuccess) e = cudaMemset(s->big_flags, 0, sizeof(int) * GFX_BIG_SLOTS);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * (GFX_BIG_SLOTS + GFX_HUGE_SLOTS));
+  if (e == cudaSuccess) e = cudaMemset(s->big_flags, 0, sizeof(int) * (GFX_BIG_SLOTS + GFX_HUGE_SLOTS));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->huge_pool, sizeof(double) * (size_t)GFX_TAB_HUGE * GFX_HUGE_SLOTS);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(unsigned long long) * 16);
   if (e == cudaSuccess) e = cudaMemset(s->counters, 0, sizeof(unsigned long long) * 16);
   if (e != cudaSuccess) {
@@ -303,7 +306,7 @@ extern "C" int gfx_check_device_status(const gfx_schedule* s, void* stream) {
   if (st != 0) {
     int zero = 0;
     GFX_CUDA(cudaMemcpy(s->status, &zero, sizeof(int), cudaMemcpyHostToDevice));
-    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX_BIG (9) simultaneously unobserved variables");
+    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX_HUGE (13) simultaneously unobserved variables");
   }
   return GFX_OK;
 }
@@ -880,6 +883,7 @@ struct BlanketDev {
   const int8_t *p1, *p2, *last, *q0, *q1;
   double* big_pool;
   int* big_flags;
+  double* huge_pool;
   unsigned long long* counters;
 };
 // diagnostic counters: 0 queries, 1 answered from the two parents, 2 eliminations, 3 big-table reruns,
@@ -1228,6 +1232,20 @@ __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& b
     *total = big[3];
     __threadfence();
     atomicExch(bl.big_flags + slot, 0);
+    if (bad) {
+      // still too wide: one of the few huge tables (milliseconds per query, but a result instead of an error)
+      int hs = (int)((blockIdx.x * blockDim.x + threadIdx.x) % GFX_HUGE_SLOTS);
+      for (;;) {
+        if (atomicCAS(bl.big_flags + GFX_BIG_SLOTS + hs, 0, 1) == 0) break;
+        hs = (hs + 1) % GFX_HUGE_SLOTS;
+        __nanosleep(1000);
+      }
+      double* huge = bl.huge_pool + (size_t)hs * GFX_TAB_HUGE;
+      bad = gfx_eliminate(b, q, code, obs, comp, cand, huge, out, GFX_WMAX_HUGE);
+      *total = huge[3];
+      __threadfence();
+      atomicExch(bl.big_flags + GFX_BIG_SLOTS + hs, 0);
+    }
     return bad;
   }
   *total = tab[3];
@@ -1377,7 +1395,7 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
                       s->anc6,
-                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr},
+                      BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->huge_pool, s->debug ? s->counters : nullptr},
                       s->bl_kid, s->status, (unsigned long long*)hist};
     const int64_t total = (int64_t)s->n_loopy_rows * ((nwords + 31) / 32) * 32;   // one warp per 32 words
     k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, stream>>>(g);
@@ -2175,7 +2193,7 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.n_snps = n_snps; a.nf = nf; a.n_focal = n_focal;
   a.focal_row = focal_row; a.focal_off = focal_off; a.entry = entry;
   a.job_row0 = job_row0; a.job_row1 = job_row1; a.job_bl = job_bl;
-  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->debug ? s->counters : nullptr};
+  a.bl = BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->huge_pool, s->debug ? s->counters : nullptr};
   a.bl_kid = s->bl_kid;
   a.bl_tree = s->bl_tree;
   a.bl_slotrow = s->bl_slotrow;

@@ -410,6 +410,8 @@ class Engine(object):
         self.p_codes_in = [t.full((n, self.ldc), 9, dtype=t.uint8, device=dev) for _ in range(2)]   # pad columns stay 9
         self.p_codes_out = [t.empty((n, self.ldc), dtype=t.uint8, device=dev) for _ in range(2)]
         self.p_packed = [t.empty((n, self.wpr), dtype=t.int32, device=dev) for _ in range(2)]
+        self.p_packed_out = [t.empty((n, self.wpr), dtype=t.int32, device=dev) for _ in range(2)]
+        self.p_pin_packed_in = self.p_pin_packed_out = None     # pinned staging for packed I/O, allocated on first use
         self.p_tall_dev = [t.empty(2 * n, dtype=t.int32, device=dev) for _ in range(2)]
         self.p_tall = [t.empty(2 * n, dtype=t.int32, pin_memory=True) for _ in range(2)]
         if not hasattr(self, "s_in"):
@@ -417,47 +419,66 @@ class Engine(object):
         self._pipe_shape = self._shape
 
     def correct_chunks(self, chunks, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
-                       outs=None):
+                       outs=None, packed_io=False):
         """Generator over (corrected uint8 [n, s_i], stats) for an iterable of uint8 [n, s_i] chunks -- the chunk loop of
         genofix.py:207-237 with every chunk an independent correctMatrix call.  Same results as calling correct()
         chunk by chunk; here three streams and two buffer sets overlap a chunk's kernels with the host staging +
         H2D copy of the next chunk and the D2H copy + un-staging of the previous one.  `outs`: optional list of
         caller-owned uint8 [n, s_i] arrays to receive the results.  Chunks and outs that live in pinned host memory
         (pinned_array()) are read / written by the copy engines directly; anything else is staged through pinned
-        buffers with a threaded host copy."""
+        buffers with a threaded host copy.
+
+        packed_io=True: every chunk is a pair (P, n_snps) with P the 2-bit packed block uint32 [n, wpr] in the kernels'
+        own layout (gfutils.packedgens.PackedGens.packed_columns / pack_codes) and the results are packed blocks of
+        the same shape: a quarter of the bytes cross PCIe and the pack / unpack kernels are skipped."""
         t = self.torch
         it = iter(chunks)
+        dt_io = np.uint32 if packed_io else np.uint8
+
+        def width(item):
+            return int(item[1]) if packed_io else np.asarray(item).shape[1]
+
+        def io_shape(s_):
+            return (self.n, ((((s_ + 15) // 16) + 3) // 4) * 4) if packed_io else (self.n, s_)
         state = {"ev_comp": [None, None], "ev_out": [None, None], "hold": [None, None]}
 
         def pinned_view(arr, s):
             """torch view of a caller array the copy engines can reach directly, else None (staged copy)"""
-            if not (isinstance(arr, np.ndarray) and arr.dtype == np.uint8 and arr.flags.c_contiguous and arr.flags.writeable
-                    and arr.shape == (self.n, s)):
+            if not (isinstance(arr, np.ndarray) and arr.dtype == dt_io and arr.flags.c_contiguous and arr.flags.writeable
+                    and arr.shape == io_shape(s)):
                 return None
-            tv = t.from_numpy(arr)
+            tv = t.from_numpy(arr.view(np.int32) if packed_io else arr)
             return tv if tv.is_pinned() else None
 
-        def stage(G, slot):
-            G = np.asarray(G)
-            if G.ndim != 2 or G.shape[0] != self.n:
-                raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
-            if self._shape != G.shape[1]:
+        def stage(item, slot):
+            s_new = width(item)
+            G = np.asarray(item[0] if packed_io else item)
+            if G.ndim != 2 or G.shape[0] != self.n or (packed_io and (G.dtype != np.uint32 or G.shape != io_shape(s_new))):
+                raise ValueError("chunk must be %s %s" % ("uint32" if packed_io else "uint8", (io_shape(s_new),)))
+            if self._shape != s_new:
                 t.cuda.synchronize()          # chunk width changed (last, ragged chunk): drain, then re-allocate
-                self._alloc(G.shape[1])
+                self._alloc(s_new)
                 state["ev_comp"] = [None, None]
                 state["ev_out"] = [None, None]
             self._alloc_pipe()
             src = pinned_view(G, self.s)
             if src is None:
-                hin = self.p_in[slot].numpy()
-                _parallel_copy(hin[:, :self.s], G)
+                if packed_io:
+                    if self.p_pin_packed_in is None:
+                        self.p_pin_packed_in = [t.empty((self.n, self.wpr), dtype=t.int32, pin_memory=True) for _ in range(2)]
+                    _parallel_copy(self.p_pin_packed_in[slot].numpy().view(np.uint32), G)
+                else:
+                    _parallel_copy(self.p_in[slot].numpy()[:, :self.s], G)
             state["hold"][slot] = (G, src)    # keep the caller's memory alive until the copy has run
             with t.cuda.stream(self.s_in):
                 if state["ev_comp"][slot] is not None:
                     self.s_in.wait_event(state["ev_comp"][slot])     # the kernels that read p_packed[slot] are done
-                self.p_codes_in[slot][:, :self.s].copy_(src if src is not None else self.p_in[slot][:, :self.s], non_blocking=True)
-                _lib.check(self.L.gfx_pack2(self.p_codes_in[slot].data_ptr(), self.n, self.s, self.p_codes_in[slot].stride(0),
-                                            self.p_packed[slot].data_ptr(), self.wpr, self._stream()))
+                if packed_io:
+                    self.p_packed[slot].copy_(src if src is not None else self.p_pin_packed_in[slot], non_blocking=True)
+                else:
+                    self.p_codes_in[slot][:, :self.s].copy_(src if src is not None else self.p_in[slot][:, :self.s], non_blocking=True)
+                    _lib.check(self.L.gfx_pack2(self.p_codes_in[slot].data_ptr(), self.n, self.s, self.p_codes_in[slot].stride(0),
+                                                self.p_packed[slot].data_ptr(), self.wpr, self._stream()))
                 ev = t.cuda.Event()
                 ev.record(self.s_in)
             return ev
@@ -470,8 +491,11 @@ class Engine(object):
                          excluded_per_animal=tall[self.n:].copy(), posteriors=None)
             if not direct:
                 if out is None:
-                    out = np.empty((self.n, s), dtype=np.uint8)
-                _parallel_copy(out, self.p_out[slot].numpy()[:, :s])
+                    out = np.empty(io_shape(s), dtype=dt_io)
+                if packed_io:
+                    _parallel_copy(out, self.p_pin_packed_out[slot].numpy().view(np.uint32))
+                else:
+                    _parallel_copy(out, self.p_out[slot].numpy()[:, :s])
             return out, stats
 
         cur = next(it, None)
@@ -490,17 +514,25 @@ class Engine(object):
                 self.correct_device(threshold_pair, threshold_single, tiethreshold, err_thresh)
                 if state["ev_out"][slot] is not None:
                     self.s_c.wait_event(state["ev_out"][slot])   # the D2H that read p_codes_out[slot] is done
-                self.unpack_device(self.p_codes_out[slot])
+                if packed_io:
+                    self.p_packed_out[slot].copy_(self.packed_live, non_blocking=True)
+                else:
+                    self.unpack_device(self.p_codes_out[slot])
                 self.p_tall_dev[slot].copy_(self.tallies, non_blocking=True)
                 state["ev_comp"][slot] = t.cuda.Event()
                 state["ev_comp"][slot].record(self.s_c)
             out = outs[k] if outs is not None else None
-            if out is not None and (out.shape != (self.n, self.s) or out.dtype != np.uint8):
-                raise ValueError("outs[%d] must be uint8 [%d, %d]" % (k, self.n, self.s))
+            if out is not None and (out.shape != io_shape(self.s) or out.dtype != dt_io):
+                raise ValueError("outs[%d] must be %s %s" % (k, np.dtype(dt_io).name, (io_shape(self.s),)))
             dst = pinned_view(out, self.s) if out is not None else None
+            if packed_io and dst is None and self.p_pin_packed_out is None:
+                self.p_pin_packed_out = [t.empty((self.n, self.wpr), dtype=t.int32, pin_memory=True) for _ in range(2)]
             with t.cuda.stream(self.s_out):
                 self.s_out.wait_event(state["ev_comp"][slot])
-                (dst if dst is not None else self.p_out[slot][:, :self.s]).copy_(self.p_codes_out[slot][:, :self.s], non_blocking=True)
+                if packed_io:
+                    (dst if dst is not None else self.p_pin_packed_out[slot]).copy_(self.p_packed_out[slot], non_blocking=True)
+                else:
+                    (dst if dst is not None else self.p_out[slot][:, :self.s]).copy_(self.p_codes_out[slot][:, :self.s], non_blocking=True)
                 self.p_tall[slot].copy_(self.p_tall_dev[slot], non_blocking=True)
                 state["ev_out"][slot] = t.cuda.Event()
                 state["ev_out"][slot].record(self.s_out)
@@ -508,10 +540,10 @@ class Engine(object):
             k += 1
             # the GPU is busy with this chunk's correction: stage the next chunk, hand back the previous one
             nxt = next(it, None)
-            if nxt is not None and np.asarray(nxt).shape[1] != self.s and prev is not None:
+            if nxt is not None and width(nxt) != self.s and prev is not None:
                 yield finish(*prev)       # a re-allocation is coming: nothing may stay in the old buffers
                 prev = None
-            if nxt is not None and np.asarray(nxt).shape[1] != self.s:
+            if nxt is not None and width(nxt) != self.s:
                 yield finish(*mine)
                 mine = None
             ev_in = stage(nxt, 1 - slot) if nxt is not None else None
@@ -546,8 +578,10 @@ def pinned_array(shape, dtype=np.uint8):
     """numpy array in page-locked host memory: correct_chunks moves such arrays with the copy engines directly
     (no staging copy).  The array keeps its backing tensor alive."""
     t = _torch()
-    buf = t.empty(tuple(shape), dtype=getattr(t, np.dtype(dtype).name), pin_memory=True)
-    return buf.numpy()
+    dtype = np.dtype(dtype)
+    if dtype == np.uint32:     # torch's unsigned types are limited: allocate int32, hand out a uint32 view
+        return t.empty(tuple(shape), dtype=t.int32, pin_memory=True).numpy().view(np.uint32)
+    return t.empty(tuple(shape), dtype=getattr(t, dtype.name), pin_memory=True).numpy()
 
 
 class MultiLane(object):
@@ -582,7 +616,7 @@ class MultiLane(object):
             raise errs[0]
 
     def correct_chunks(self, chunks, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
-                       outs=None):
+                       outs=None, packed_io=False):
         """Same contract as Engine.correct_chunks (results in input order); chunk k runs on lane k mod L."""
         import queue
         import threading
@@ -597,7 +631,7 @@ class MultiLane(object):
             try:
                 gen = eng.correct_chunks((chunks[k] for k in mine), threshold_pair, threshold_single, init_filter_p=init_filter_p,
                                          tiethreshold=tiethreshold, err_thresh=err_thresh,
-                                         outs=[outs[k] for k in mine] if outs is not None else None)
+                                         outs=[outs[k] for k in mine] if outs is not None else None, packed_io=packed_io)
                 for k, r in zip(mine, gen):
                     results[k] = r
                     done[k].set()

@@ -61,7 +61,12 @@ def main(argv=None):
     if args.empC is not None and rank == 0:
         print("WARNING: -P/--empC is ignored; the empirical blend is not executable in the reference at HEAD")
     print("building cache index from %s" % args.genotypes_input_file)
-    g_cache = GensCache(args.genotypes_input_file, header=True)
+    if args.genotypes_input_file.endswith(".g2b"):
+        # 2-bit packed container (genofix_b200.gfutils.packedgens): no text parsing, same GensCache surface
+        from genofix_b200.gfutils.packedgens import PackedGens
+        g_cache = PackedGens(args.genotypes_input_file)
+    else:
+        g_cache = GensCache(args.genotypes_input_file, header=True)
     print("Detected %s individuals and %s snps in input file" % (len(g_cache.all_ids), len(g_cache.snps)))
     snps = [str(x) for x in genomein["snpid"]]
     chromosome2snp = defaultdict(list)

@@ -412,3 +412,49 @@ def test_huge_litter_paths_match_oracle():
     assert eng.stats["test_p"] == o["test_p"]
     assert np.array_equal(out, o["corrected"])
     assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
+
+
+def test_packed_io_equals_uint8_io(tmp_path):
+    """correct_chunks(packed_io=True) fed from a GFX2BIT1 container (word-aligned SNP blocks, ragged last block, pinned and
+    pageable buffers) returns the packed form of what the uint8 path returns."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine, MultiLane, pinned_array
+    from genofix_b200.gfutils.packedgens import PackedGens, pack_codes, unpack_codes
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(2000, 6, seed=15)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 1100, seed=15), 0.01, seed=15), 0.01, seed=16)
+    path = str(tmp_path / "m.g2b")
+    PackedGens.write(path, rows[:, 0], ["snp%d" % i for i in range(obs.shape[1])], obs)
+    g = PackedGens(path)
+    bounds = [(0, 400), (400, 800), (800, 1100)]
+    ped = PedigreeDAG.from_table(rows)
+    eng = Engine(ped, rows[:, 0], 2)
+    ref = [eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4) for a, b in bounds]
+    chunks = []
+    for i, (a, b) in enumerate(bounds):
+        blk = g.packed_columns(a, b, out=pinned_array((len(rows), ((b - a + 15) // 16 + 3) // 4 * 4), np.uint32) if i % 2 == 0 else None)
+        chunks.append((blk, b - a))
+    ml = MultiLane(ped, rows[:, 0], 2, lanes=2)
+    got = list(ml.correct_chunks(chunks, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4, packed_io=True))
+    for (P, st), r, (a, b) in zip(got, ref, bounds):
+        assert P.dtype == np.uint32 and np.array_equal(unpack_codes(P, b - a), r)
+        assert np.array_equal(P, pack_codes(r))
+
+
+def test_very_wide_eliminations_get_a_result():
+    """A small, inbred population (6 sires per generation) with 1 % missing calls: suspect filtering opens more than nine
+    variables of a pair blanket at once.  That used to end in GFX_E_TOO_WIDE; the third-level table pool answers it."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle.genofix_oracle import Oracle
+    rows = synth.make_pedigree(1500, 6, seed=25)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 1100, seed=25), 0.01, seed=25), 0.01, seed=26)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    for a, b in [(0, 400), (400, 800), (800, 1100)]:
+        out = eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)   # must not raise
+        assert out.shape == (len(rows), b - a)
+    sub = np.ascontiguousarray(obs[:, :32])
+    out = eng.correct(sub, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    o = Oracle(rows, rows[:, 0]).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
+    assert _same_f16(eng.raw_host(), o["raw"]) and np.array_equal(out, o["corrected"])

@@ -252,3 +252,37 @@ def test_chunking_known_answers():
     assert spans(2500, 1000, 4) == [(0, 1008, 1009), (1000, 2008, 1009), (2000, 2499, 500)]
     assert spans(25, 10, 1) == [(0, 12, 13), (10, 24, 15), (20, 24, 5)]
     assert spans(23, 10, 3) == [(0, 22, 23), (10, 22, 13)]
+
+
+def test_packed_container_roundtrip(tmp_path):
+    """GFX2BIT1 container: pack/unpack, GensCache surface, SNP-block reads at word boundaries and ragged ends, write-back."""
+    from genofix_b200.gfutils.packedgens import PackedGens, pack_codes, unpack_codes, words_per_row
+    rs = np.random.default_rng(0)
+    G = rs.choice([0, 1, 2, 9], size=(37, 1003), p=[.3, .4, .28, .02]).astype(np.uint8)
+    P = pack_codes(G)
+    assert P.shape == (37, words_per_row(1003)) and P.dtype == np.uint32
+    assert np.array_equal(unpack_codes(P, 1003), G)
+    assert np.all(unpack_codes(P, P.shape[1] * 16)[:, 1003:] == 9)          # padding cells are "missing"
+    path = str(tmp_path / "x.g2b")
+    PackedGens.write(path, np.arange(100, 137), ["s%d" % i for i in range(1003)], G)
+    g = PackedGens(path)
+    assert g.all_ids == list(range(100, 137)) and g.snps[5] == "s5" and g.n_snps == 1003
+    assert np.array_equal(g.getMatrix([105, 100, 999]), G[[5, 0]])           # unknown ids are skipped like the reference
+    for a, b in [(0, 1003), (16, 516), (992, 1003), (160, 176)]:
+        blk = g.packed_columns(a, b)
+        assert np.array_equal(blk, pack_codes(G[:, a:b])), (a, b)
+    with pytest.raises(ValueError):
+        g.packed_columns(5, 100)
+    g2 = PackedGens(path, mode="r+")
+    g2.store_columns(16, 516, pack_codes((G[:, 16:516] + 1) % 3))
+    g2.packed.flush()
+    M = PackedGens(path).getMatrix(range(100, 137))
+    assert np.array_equal(M[:, 16:516], (G[:, 16:516] + 1) % 3) and np.array_equal(M[:, :16], G[:, :16]) and np.array_equal(M[:, 516:], G[:, 516:])
+    # text -> container
+    txt = tmp_path / "g.ssv"
+    with open(txt, "w") as f:
+        f.write("id " + " ".join("s%d" % i for i in range(20)) + "\n")
+        for i in range(5):
+            f.write("%d %s\n" % (i + 1, " ".join(str(x) for x in G[i, :20])))
+    g3 = PackedGens.from_text(str(txt), str(tmp_path / "g.g2b"))
+    assert np.array_equal(g3.getMatrix([1, 2, 3, 4, 5]), G[:5, :20]) and g3.snps == ["s%d" % i for i in range(20)]

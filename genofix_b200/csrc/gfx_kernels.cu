@@ -457,8 +457,7 @@ struct RankArgs {
 #define R2_CM_OFF 0u          // u32 [8 classes][32 m][32 lanes]
 #define R2_FAST_OFF 32768u    // u32 [64 idx6][64]: lanes 0..31 table entries, 32..63 counters
 #define R2_BINS_OFF 49152u    // u32 [8192] patterns 0x3000..0x4FFF
-#define R2_LUT_OFF 81920u     // uint2 [4096] full table (slow path)
-#define R2_SMEM (81920u + 32768u)
+#define R2_SMEM 81920u
 #define R2_BIN_LO 0x3000u
 #define R2_BIN_N 0x2000u
 
@@ -488,35 +487,41 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
   int pend8 = 0;
   anyv = 0;
 #if R2_KIDS4
-  for (int c = c0; c < c1; c += 8) {
-    // eight children per round, all loads issued before the first use (absent ones read as all-missing): the loop
-    // is bound by the latency of these loads, not by the arithmetic
-    uint32_t wc[8];
+  // four children per round; the next round's rows are loaded while the current round is counted (absent children
+  // read as all-missing).  The loop is bound by the latency of these loads, not by the arithmetic.
+  uint32_t nx[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int r = c + u < c1 ? __ldg(a.child_row + c + u) : -1;
-      wc[u] = r >= 0 ? __ldg(a.packed + (int64_t)r * a.wpr + w) : 0xFFFFFFFFu;
-    }
+  for (int u = 0; u < 4; ++u) {
+    const int r = c0 + u < c1 ? __ldg(a.child_row + c0 + u) : -1;
+    nx[u] = r >= 0 ? __ldg(a.packed + (int64_t)r * a.wpr + w) : 0xFFFFFFFFu;
+  }
+  for (int c = c0; c < c1; c += 4) {
+    uint32_t wc[4];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (half == 1 && c + 4 >= c1) break;
-      uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1 (4 children * 2 units = 8 < 16)
+    for (int u = 0; u < 4; ++u) wc[u] = nx[u];
+    if (c + 4 < c1) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t cl = wc[4 * half + u], ch = wc[4 * half + u] >> 1;
-        const uint32_t is0 = ~(cl | ch) & 0x55555555u;
-        const uint32_t is2 = (ch & ~cl) & 0x55555555u;
-        anyv |= ~(cl & ch);
-        const uint32_t one = (is0 | is2) & o1;
-        const uint32_t two = (is2 & o0) | (is0 & o2);
-        const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
-        acc_lo += contrib & 0x33333333u;
-        acc_hi += (contrib >> 2) & 0x33333333u;
+        const int r = c + 4 + u < c1 ? __ldg(a.child_row + c + 4 + u) : -1;
+        nx[u] = r >= 0 ? __ldg(a.packed + (int64_t)r * a.wpr + w) : 0xFFFFFFFFu;
       }
-      bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
-      bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
     }
-    if (++pend8 == 15) {                        // 15 * 16 = 240 < 256
+    uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1 (4 children * 2 units = 8 < 16)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t cl = wc[u], ch = wc[u] >> 1;
+      const uint32_t is0 = ~(cl | ch) & 0x55555555u;
+      const uint32_t is2 = (ch & ~cl) & 0x55555555u;
+      anyv |= ~(cl & ch);
+      const uint32_t one = (is0 | is2) & o1;
+      const uint32_t two = (is2 & o0) | (is0 & o2);
+      const uint32_t contrib = one | (two << 1);  // 2-bit lanes holding 0,1,2
+      acc_lo += contrib & 0x33333333u;
+      acc_hi += (contrib >> 2) & 0x33333333u;
+    }
+    bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
+    bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+    if (++pend8 == 31) {                        // 31 * 8 = 248 < 256
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
@@ -591,7 +596,6 @@ __device__ __noinline__ void r2_hist_patterns(unsigned long long* hist, uint32_t
 template <bool HIST>
 __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t row, int64_t w, uint32_t w0, bool has_anc,
                                           int c0, int c1) {
-  const uint2* s_lut = reinterpret_cast<const uint2*>(smem + R2_LUT_OFF);
   uint32_t wa[6];
   if (has_anc) {
     const int32_t* a6 = a.anc6 + row * 6;
@@ -620,7 +624,7 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
           const uint32_t idx = ((wa[0] >> (2 * i)) & 3u) | (((wa[1] >> (2 * i)) & 3u) << 2) |
                                (((wa[2] >> (2 * i)) & 3u) << 4) | (((wa[3] >> (2 * i)) & 3u) << 6) |
                                (((wa[4] >> (2 * i)) & 3u) << 8) | (((wa[5] >> (2 * i)) & 3u) << 10);
-          const uint2 e = s_lut[idx];
+          const uint2 e = __ldg(a.lut + idx);   // 32 KB table, L1 resident; only this path needs it
           const uint16_t sc = obs == 0 ? (uint16_t)(e.x & 0xFFFFu) : (obs == 1 ? (uint16_t)(e.x >> 16) : (uint16_t)(e.y & 0xFFFFu));
           r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
         } else if (kids) {
@@ -643,8 +647,6 @@ template <bool HIST>
 __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a) {
   extern __shared__ __align__(16) char smem[];
   {
-    uint2* s_lut = reinterpret_cast<uint2*>(smem + R2_LUT_OFF);
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_lut[i] = a.lut[i];
     uint32_t* s_fast = reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF);
     for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
       const int idx = i >> 6, l = i & 63;
@@ -704,19 +706,14 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
       const uint32_t* prow0 = a.packed + (int64_t)row * a.wpr;
       const uint32_t* prowS = a.packed + (int64_t)(parents_ok ? rS : row) * a.wpr;
       const uint32_t* prowD = a.packed + (int64_t)(parents_ok ? rD : row) * a.wpr;
-      // the 32-word steps of a chunk are walked from a per-task rotated start, so that the warps of the GPU do not
-      // all sit at the same offset of their rows at the same time (rows are a fixed stride apart); measured neutral
-      const int n_iter = (wend - wbeg + 31) >> 5;
-      int pos = n_iter > 0 ? (int)__umulhi(task * 2654435761u, (uint32_t)n_iter) : 0;
-      int wn = wbeg + pos * 32 + lane;
+      int wn = wbeg + lane;
       uint32_t n0 = 0, nS = 0, nD = 0;
-      if (n_iter > 0 && wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
-      for (int it = 0; it < n_iter; ++it) {
+      if (wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
+      for (; wn - lane < wend; ) {
         const int w = wn;
         const uint32_t w0 = n0, wS = nS, wD = nD;
-        pos = pos + 1 == n_iter ? 0 : pos + 1;
-        wn = wbeg + pos * 32 + lane;
-        if (it + 1 < n_iter && wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
+        wn += 32;
+        if (wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
         if (w >= wend) continue;
         uint16_t* dst = a.raw + (int64_t)row * a.ld_raw + (int64_t)w * 16;
         const uint32_t miss = w0 & (w0 >> 1) & 0x55555555u;

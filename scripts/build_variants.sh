@@ -7,10 +7,7 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build xfast -DR2_X_NO_FAST_ATOMS
-build xkids -DR2_X_NO_KIDS_ATOMS
-build xbig -DR2_X_NO_BIG
-build xepi -DR2_X_NO_EPILOGUE
-build xall -DR2_X_NO_FAST_ATOMS -DR2_X_NO_KIDS_ATOMS -DR2_X_NO_BIG -DR2_X_NO_EPILOGUE
+build t512 -DR2_THREADS=512
+build t768 -DR2_THREADS=768
 wait
 ls -la genofix_b200/variants

@@ -357,12 +357,12 @@ def run_cuda(args):
                                 chunk_snps=args.chunk, back=BACK, lanes=lanes, per_gpu_matrix="%d x %d" % (args.animals, args.snps),
                                 l2="each step streams %.0f MB of packed codes + %.0f MB of float16 scores per chunk (> 126 MB L2)"
                                    % (args.animals * args.chunk / 4 / 1e6, args.animals * args.chunk * 2 / 1e6), **PARAMS),
-                    e2e=dict(value=e2e_value, unit="cells/s", h2d_bytes_per_step=int(args.animals * args.snps),
-                             d2h_bytes_per_step=int(args.animals * args.snps), ms_per_step=e2e_ms / args.steps),
+                    e2e=dict(value=e2e_value, unit="cells/s", h2d_bytes_per_step=int(args.animals * args.snps) * world,
+                             d2h_bytes_per_step=int(args.animals * args.snps) * world, ms_per_step=e2e_ms / args.steps),
                     e2e_packed_io=dict(value=cells_step * args.steps / (e2e_packed_ms / 1e3), unit="cells/s",
                                        ms_per_step=e2e_packed_ms / args.steps,
-                                       h2d_bytes_per_step=int(sum(p.nbytes for p, _ in packed_chunks)),
-                                       d2h_bytes_per_step=int(sum(p.nbytes for p in packed_outs)),
+                                       h2d_bytes_per_step=int(sum(p.nbytes for p, _ in packed_chunks)) * world,
+                                       d2h_bytes_per_step=int(sum(p.nbytes for p in packed_outs)) * world,
                                        note="same call with packed_io=True: 2-bit blocks as stored by gfutils.packedgens (GFX2BIT1)"),
                     gpu_launches=launches, roofline=roofline, phase_share=phase_share, clocks=clocks,
                     corrected_cells_per_step=corrected_total)

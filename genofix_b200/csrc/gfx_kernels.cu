@@ -2413,6 +2413,171 @@ extern "C" int gfx_build_cut_table(const double* elut, double test_p, double sus
   return GFX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Simulator pieces on the device: gene drop, error injection, evaluation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t gfx_mix64(uint64_t x) {   // splitmix64 finaliser: counter-based, no state
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ uint64_t gfx_rand(uint64_t seed, uint64_t a, uint64_t b) {
+  return gfx_mix64(gfx_mix64(seed ^ (a * 0xD6E8FEB86659FD93ull)) ^ b);
+}
+
+// One level of the pedigree (parents are in earlier levels).  hap word: bit 2i = paternal, bit 2i+1 = maternal allele
+// of SNP i.  Every SNP segregates independently (free recombination): the transmitted allele of a parent is one
+// of its two alleles with probability 1/2 each (simulate.py:187-230 with quickgsim's meiosis reduced to independent
+// loci); founders draw both alleles with frequency 1/2 (simulate.py:206-207).
+__global__ void __launch_bounds__(256) k_gene_drop(const int32_t* __restrict__ order, int n_level, const int32_t* __restrict__ sire_row,
+                                                   const int32_t* __restrict__ dam_row, int64_t nwords, int64_t wpr, uint64_t seed,
+                                                   uint32_t* __restrict__ hap) {
+  const int64_t total = (int64_t)n_level * nwords;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / nwords, w = i - k * nwords;
+    const int r = order[k];
+    const int rs = sire_row[r], rd = dam_row[r];
+    const uint64_t rnd = gfx_rand(seed, (uint64_t)r, (uint64_t)w);
+    const uint32_t pick_s = (uint32_t)rnd & 0x55555555u, pick_d = (uint32_t)(rnd >> 32) & 0x55555555u;
+    uint32_t pat, mat;   // alleles at the even bit positions
+    if (rs >= 0) {
+      const uint32_t h = hap[(int64_t)rs * wpr + w];
+      pat = ((h & ~pick_s) | ((h >> 1) & pick_s)) & 0x55555555u;
+    } else {
+      pat = (uint32_t)(gfx_mix64(rnd) & 0x55555555u);
+    }
+    if (rd >= 0) {
+      const uint32_t h = hap[(int64_t)rd * wpr + w];
+      mat = ((h & ~pick_d) | ((h >> 1) & pick_d)) & 0x55555555u;
+    } else {
+      mat = (uint32_t)((gfx_mix64(rnd) >> 32) & 0x55555555u);
+    }
+    hap[(int64_t)r * wpr + w] = pat | (mat << 1);
+  }
+}
+
+extern "C" int gfx_gene_drop(int32_t n, const int32_t* sire_row_dev, const int32_t* dam_row_dev, const int32_t* order_dev,
+                             const int32_t* level_off_host, int32_t n_levels, int64_t n_snps, int64_t wpr, uint64_t seed,
+                             uint32_t* hap_dev, void* stream) {
+  if (n <= 0 || !sire_row_dev || !dam_row_dev || !order_dev || !level_off_host || n_levels <= 0 || !hap_dev || n_snps <= 0)
+    return fail(GFX_E_INVALID, "gfx_gene_drop: bad argument");
+  const int64_t nwords = (n_snps + 15) / 16;
+  if (wpr < nwords) return fail(GFX_E_INVALID, "gfx_gene_drop: wpr < ceil(n_snps / 16)");
+  for (int l = 0; l < n_levels; ++l) {
+    const int cnt = level_off_host[l + 1] - level_off_host[l];
+    if (cnt <= 0) continue;
+    k_gene_drop<<<grid_for((int64_t)cnt * nwords, 256, device_sms(), 8), 256, 0, (cudaStream_t)stream>>>(
+        order_dev + level_off_host[l], cnt, sire_row_dev, dam_row_dev, nwords, wpr, seed, hap_dev);
+    GFX_LAUNCHED();
+  }
+  return GFX_OK;
+}
+
+// genotype code = number of 1-alleles; cells beyond n_snps (and the padding words) become 3 = missing
+__global__ void __launch_bounds__(256) k_haps_to_codes(const uint32_t* __restrict__ hap, int64_t n, int64_t n_snps, int64_t wpr,
+                                                       uint32_t* __restrict__ packed) {
+  const int64_t total = n * wpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t w = i % wpr;
+    const uint32_t h = hap[i];
+    const uint32_t p = h & 0x55555555u, m = (h >> 1) & 0x55555555u;
+    uint32_t code = (p ^ m) | ((p & m) << 1);
+    const int64_t rem = n_snps - w * 16;
+    if (rem <= 0) code = 0xFFFFFFFFu;
+    else if (rem < 16) code |= 0xFFFFFFFFu << (2 * rem);
+    packed[i] = code;
+  }
+}
+extern "C" int gfx_haps_to_codes(const uint32_t* hap_dev, int64_t n, int64_t n_snps, int64_t wpr, uint32_t* packed_dev, void* stream) {
+  if (!hap_dev || !packed_dev || n <= 0 || n_snps <= 0 || wpr < (n_snps + 15) / 16) return fail(GFX_E_INVALID, "gfx_haps_to_codes: bad argument");
+  k_haps_to_codes<<<grid_for(n * wpr, 256, device_sms(), 8), 256, 0, (cudaStream_t)stream>>>(hap_dev, n, n_snps, wpr, packed_dev);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// Every observed cell is hit with probability `rate` and then shows one of the two OTHER genotypes with equal
+// probability (simulate.py:318-331 draws ceil(N S rate) cells with replacement; here the count is binomial).
+__global__ void __launch_bounds__(256) k_inject_errors(uint32_t* __restrict__ packed, int64_t n, int64_t n_snps, int64_t wpr,
+                                                       uint32_t thresh, uint64_t seed) {
+  const int64_t nwords = (n_snps + 15) / 16;
+  const int64_t total = n * nwords;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nwords, w = i - r * nwords;
+    uint32_t v = packed[r * wpr + w];
+    bool dirty = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t rnd = gfx_rand(seed, (uint64_t)i, (uint64_t)k);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t u = (uint32_t)(rnd >> (32 * h));
+        const int c = 2 * k + h;
+        const uint32_t code = (v >> (2 * c)) & 3u;
+        if ((u >> 1) < thresh && code != 3u) {
+          const uint32_t other = (code + 1u + (u & 1u)) % 3u;
+          v = (v & ~(3u << (2 * c))) | (other << (2 * c));
+          dirty = true;
+        }
+      }
+    }
+    if (dirty) packed[r * wpr + w] = v;
+  }
+}
+extern "C" int gfx_inject_errors(uint32_t* packed_dev, int64_t n, int64_t n_snps, int64_t wpr, double rate, uint64_t seed, void* stream) {
+  if (!packed_dev || n <= 0 || n_snps <= 0 || wpr < (n_snps + 15) / 16 || !(rate >= 0.0 && rate <= 1.0))
+    return fail(GFX_E_INVALID, "gfx_inject_errors: bad argument");
+  const uint32_t thresh = (uint32_t)(rate * 2147483648.0);   // 31-bit uniform
+  k_inject_errors<<<grid_for(n * ((n_snps + 15) / 16), 256, device_sms(), 8), 256, 0, (cudaStream_t)stream>>>(packed_dev, n, n_snps, wpr,
+                                                                                                            thresh, seed);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// Evaluation of a correction run (simulate.py:426-515): bit-parallel comparison of truth / observed / corrected.
+// out[0] errors (observed != truth)  [1] fixed (error, corrected == truth)  [2] blanked (error, corrected missing)
+// out[3] wrong fix (error, changed, neither)  [4] new errors (no error, changed)  [5] missed (error, unchanged)  [6] cells
+__global__ void __launch_bounds__(256) k_confusion(const uint32_t* __restrict__ truth, const uint32_t* __restrict__ obs,
+                                                   const uint32_t* __restrict__ fixed, int64_t n, int64_t n_snps, int64_t wpr,
+                                                   unsigned long long* __restrict__ out) {
+  const int64_t nwords = (n_snps + 15) / 16;
+  const int64_t total = n * nwords;
+  unsigned int c[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nwords, w = i - r * nwords;
+    const uint32_t t = truth[r * wpr + w], o = obs[r * wpr + w], k = fixed[r * wpr + w];
+    uint32_t valid = 0x55555555u;
+    const int64_t rem = n_snps - w * 16;
+    if (rem < 16) valid = ((1u << (2 * rem)) - 1u) & 0x55555555u;
+    // per-cell "differs" masks at the even bit positions
+    const uint32_t d_to = ((t ^ o) | ((t ^ o) >> 1)) & valid, d_ok = ((o ^ k) | ((o ^ k) >> 1)) & valid;
+    const uint32_t d_tk = ((t ^ k) | ((t ^ k) >> 1)) & valid, kmiss = k & (k >> 1) & valid;
+    c[0] += __popc(d_to);
+    c[1] += __popc(d_to & ~d_tk);
+    c[2] += __popc(d_to & d_ok & kmiss);
+    c[3] += __popc(d_to & d_ok & d_tk & ~kmiss);
+    c[4] += __popc(~d_to & valid & d_ok);
+    c[5] += __popc(d_to & ~d_ok);
+    c[6] += __popc(valid);
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    unsigned int v = c[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + q, (unsigned long long)v);
+  }
+}
+extern "C" int gfx_confusion(const uint32_t* truth_dev, const uint32_t* obs_dev, const uint32_t* fixed_dev, int64_t n, int64_t n_snps,
+                             int64_t wpr, uint64_t* out8_dev, void* stream) {
+  if (!truth_dev || !obs_dev || !fixed_dev || !out8_dev || n <= 0 || n_snps <= 0 || wpr < (n_snps + 15) / 16)
+    return fail(GFX_E_INVALID, "gfx_confusion: bad argument");
+  GFX_CUDA(cudaMemsetAsync(out8_dev, 0, 8 * sizeof(uint64_t), (cudaStream_t)stream));
+  k_confusion<<<grid_for(n * ((n_snps + 15) / 16), 256, device_sms(), 4), 256, 0, (cudaStream_t)stream>>>(
+      truth_dev, obs_dev, fixed_dev, n, n_snps, wpr, (unsigned long long*)out8_dev);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
 extern "C" int gfx_founders(const gfx_pedigree_desc* ped, const uint8_t* restrict_host, int32_t* out_idx, int32_t* out_n) {
   if (!ped || !out_idx || !out_n) return fail(GFX_E_INVALID, "null argument");
   int n = 0;

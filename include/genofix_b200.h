@@ -229,6 +229,24 @@ int gfx_infer_pair_host(int32_t n, const int8_t* p1, const int8_t* p2, const uin
  * par 0..2 or anything else = unknown. */
 int gfx_kids_term_host(int32_t n, const uint8_t* kid, const uint8_t* par, double* out3);
 
+/* ---------------------------------------------------------------------------------------------
+ * Simulator pieces on the device (simulate.py:187-340 gene drop + error injection, :426-515 evaluation;
+ * quickgsim/genome.py:86-115 meiosis reduced to independent loci, i.e. free recombination).
+ *   gfx_gene_drop      hap_dev uint32 [n, wpr]: bit 2i = paternal, bit 2i+1 = maternal allele of SNP i.  Rows are processed
+ *                      level by level: order_dev lists the rows, level_off_host[l..l+1] delimits level l, the parents of a
+ *                      level are in earlier levels; sire_row / dam_row = -1 for founders (alleles with frequency 1/2).
+ *   gfx_haps_to_codes  2-bit genotype codes (padding = 3) from the haplotypes.
+ *   gfx_inject_errors  every observed cell with probability `rate` shows one of the two other genotypes.
+ *   gfx_confusion      out8_dev: errors, fixed, blanked, wrong fix, new errors, missed, cells, 0.
+ * ------------------------------------------------------------------------------------------- */
+int gfx_gene_drop(int32_t n, const int32_t* sire_row_dev, const int32_t* dam_row_dev, const int32_t* order_dev,
+                  const int32_t* level_off_host, int32_t n_levels, int64_t n_snps, int64_t wpr, uint64_t seed,
+                  uint32_t* hap_dev, void* stream);
+int gfx_haps_to_codes(const uint32_t* hap_dev, int64_t n, int64_t n_snps, int64_t wpr, uint32_t* packed_dev, void* stream);
+int gfx_inject_errors(uint32_t* packed_dev, int64_t n, int64_t n_snps, int64_t wpr, double rate, uint64_t seed, void* stream);
+int gfx_confusion(const uint32_t* truth_dev, const uint32_t* obs_dev, const uint32_t* fixed_dev, int64_t n, int64_t n_snps,
+                  int64_t wpr, uint64_t* out8_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

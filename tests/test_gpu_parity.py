@@ -458,3 +458,45 @@ def test_very_wide_eliminations_get_a_result():
     out = eng.correct(sub, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
     o = Oracle(rows, rows[:, 0]).correct_matrix(sub, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
     assert _same_f16(eng.raw_host(), o["raw"]) and np.array_equal(out, o["corrected"])
+
+
+def test_device_simulator_properties_and_evaluation():
+    """Device gene drop / error injection / evaluation: Mendelian consistency of the drop (trio scan finds nothing),
+    allele frequency 1/2, error rate and 'never the same genotype', evaluation counts equal to numpy on the unpacked
+    matrices, and the whole simulate loop (drop -> errors -> correct -> score) on packed device data."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.gfutils.packedgens import unpack_codes
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from genofix_b200.simulate_device import DeviceSimulator
+    rows = synth.make_pedigree(3000, 6, seed=8)
+    s = 1000
+    sim = DeviceSimulator(rows, s, seed=99)
+    truth = sim.gene_drop()
+    T = unpack_codes(truth.cpu().numpy().view(np.uint32), s)
+    assert set(np.unique(T)) <= {0, 1, 2} and abs(T.mean() - 1.0) < 0.02
+    assert np.all(truth.cpu().numpy().view(np.uint32)[:, (s + 15) // 16:] == 0xFFFFFFFF)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    inc, tested = eng.trio_scan(T)
+    assert inc.sum() == 0 and tested.sum() > 0                       # a clean drop is Mendel consistent
+    assert np.array_equal(unpack_codes(sim.gene_drop().cpu().numpy().view(np.uint32), s), T)   # deterministic in the seed
+    obs = sim.inject_errors(truth, 0.01)
+    O = unpack_codes(obs.cpu().numpy().view(np.uint32), s)
+    rate = (O != T).mean()
+    assert 0.008 < rate < 0.012 and set(np.unique(O)) <= {0, 1, 2}
+    inc2, _ = eng.trio_scan(O)
+    assert inc2.sum() > 0
+    # correct the packed matrix in place on the device and score it there
+    eng.use_packed(obs, s)
+    eng.correct_resident(0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    K = unpack_codes(eng.packed_live.cpu().numpy().view(np.uint32), s)
+    ev = sim.confusion(truth, obs, eng.packed_live)
+    was_err, changed = T != O, K != O
+    assert ev["errors"] == int(was_err.sum()) and ev["cells"] == T.size
+    assert ev["fixed"] == int((was_err & (K == T)).sum())
+    assert ev["blanked"] == int((was_err & changed & (K == 9)).sum())
+    assert ev["wrong_fix"] == int((was_err & changed & (K != T) & (K != 9)).sum())
+    assert ev["new_errors"] == int((~was_err & changed).sum())
+    assert ev["missed"] == int((was_err & ~changed).sum())
+    assert ev["fixed"] > 0.1 * ev["errors"] and ev["new_errors"] < ev["fixed"]      # the correction does net good
+    print(ev)

@@ -17,6 +17,18 @@ print(r.stdout[-900:]); print(r.stderr[-600:])
 r = subprocess.run([sys.executable, "src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/gfout",
                     "-i", tmp + "/simout/simulatedgenome_with_1errors.ssv.gz", "-C", "600"], capture_output=True, text=True, cwd=ROOT)
 print(r.stdout[-700:]); print(r.stderr[-600:])
+r = subprocess.run([sys.executable, "src/simulate/simulate.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/simdev",
+                    "-c", "500", "-t", "0.4", "-l", "0.64", "--device_sim"], capture_output=True, text=True, cwd=ROOT)
+print("device_sim:", r.stdout[-600:]); print(r.stderr[-600:])
+# the same matrix through the 2-bit container
+from genofix_b200.gfutils.packedgens import PackedGens
+PackedGens.from_text(tmp + "/simout/simulatedgenome_with_1errors.ssv.gz", tmp + "/errors.g2b")
+r = subprocess.run([sys.executable, "src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/gfout2",
+                    "-i", tmp + "/errors.g2b", "-C", "600"], capture_output=True, text=True, cwd=ROOT)
+print("g2b:", r.stdout[-300:]); print(r.stderr[-600:])
+import filecmp
+print("g2b output identical to text-input output:", filecmp.cmp(tmp + "/gfout/simulatedgenome_corrected_errors_threshold.ssv",
+                                                                tmp + "/gfout2/simulatedgenome_corrected_errors_threshold.ssv", shallow=False))
 r = subprocess.run([sys.executable, "src/gfutils/extract_founders.py", "-p", tmp + "/ped.fam"], capture_output=True, text=True, cwd=ROOT)
 print("founders:", len(r.stdout.split()), r.stderr[-300:])
 shutil.rmtree(tmp, ignore_errors=True)

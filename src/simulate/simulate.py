@@ -54,6 +54,9 @@ def build_parser():
                    choices=["weightedminfill", "minneighbors", "minweight", "minfill"])
     p.add_argument("-T", "--threads", dest="threads", type=int, default=multiprocessing.cpu_count())
     p.add_argument("--microarray_errors", dest="microarray_errors", action="store_true", default=False)
+    p.add_argument("--device_sim", dest="device_sim", action="store_true", default=False,
+                   help="gene drop, error injection, correction and scoring on the GPU (2-bit packed, nothing but the "
+                        "statistics comes back); the chunk size is rounded to a multiple of 16 SNPs")
     return p
 
 
@@ -84,6 +87,40 @@ def drop_rows(pedigree):
     return rows
 
 
+def run_on_device(args, pedigree, snps, out_dir):
+    """The whole loop on the device: simulate.py:187-340 (drop + errors), the correction, :426-515 (scoring)."""
+    import torch
+    from genofix_b200.engine import Engine
+    from genofix_b200.simulate_device import DeviceSimulator
+    rows = drop_rows(pedigree)
+    n, s = len(rows), len(snps)
+    sim = DeviceSimulator(rows, s, seed=1234)
+    truth = sim.gene_drop()
+    obs = sim.inject_errors(truth, args.error_rate / 100)
+    fixed = obs.clone()
+    eng = Engine(pedigree, rows[:, 0], args.lookback)
+    step = max(16, (args.chunk // 16) * 16)
+    tic = time.time()
+    for a in range(0, s, step):
+        b = min(s, a + step)
+        eng._alloc(b - a)
+        nw = (b - a + 15) // 16
+        blk = torch.full((n, eng.wpr), -1, dtype=torch.int32, device=obs.device)
+        blk[:, :nw] = obs[:, a // 16:a // 16 + nw]
+        eng.use_packed(blk, b - a)
+        eng.correct_resident(args.threshold_pairs, args.threshold_singles, init_filter_p=args.initquantilefilter,
+                             tiethreshold=args.tiethreshold, err_thresh=args.err_thresh)
+        fixed[:, a // 16:a // 16 + nw] = eng.packed_live[:, :nw]
+    eng.check_status()
+    secs = time.time() - tic
+    stats = sim.confusion(truth, obs, fixed)
+    stats.update(animals=n, snps=s, seconds=secs, threshold_singles=args.threshold_singles, threshold_pairs=args.threshold_pairs,
+                 tiethreshold=args.tiethreshold, lookback=args.lookback, initquantilefilter=args.initquantilefilter)
+    pd.DataFrame([stats]).to_csv("%s/statistics.tsv" % out_dir, sep="\t", index=False)
+    print(stats)
+    return 0
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     out_dir = args.outdir
@@ -93,6 +130,8 @@ def main(argv=None):
     snps = [str(x) for x in genomein["snpid"]]
     if args.first_n_snps is not None:
         snps = snps[:args.first_n_snps]
+    if args.device_sim:
+        return run_on_device(args, pedigree, snps, out_dir)
     if args.founders_haplo_file or args.founders_geno_file:
         raise NotImplementedError("founder genotype import is part of the simulator, outside this path")
     if args.prior_pop_genome is None:

@@ -21,7 +21,8 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(HERE, f) for f in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + os.environ.get("NVCC_FLAGS", "").split() + \
+          [os.path.join(HERE, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -441,9 +441,6 @@ struct RankArgs {
 #ifndef R2_THREADS
 #define R2_THREADS 1024
 #endif
-#ifndef R2_KIDS4
-#define R2_KIDS4 1
-#endif
 // words per task by number of children of the row (measured at 10k x 10k and 100k x 4096)
 #ifndef R2_WORDS_HEAVY
 #define R2_WORDS_HEAVY 32    // >= 8 children
@@ -486,7 +483,6 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
   uint32_t bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;   // byte t: cells 4t, 4t + 2, 4t + 1, 4t + 3
   int pend8 = 0;
   anyv = 0;
-#if R2_KIDS4
   // four children per round; the next round's rows are loaded while the current round is counted (absent children
   // read as all-missing).  The loop is bound by the latency of these loads, not by the arithmetic.
   uint32_t nx[4];
@@ -531,39 +527,6 @@ __device__ __forceinline__ void r2_children(const RankArgs& a, int c0, int c1, i
       pend8 = 0;
     }
   }
-#else
-  uint32_t acc_lo = 0, acc_hi = 0;
-  int pend = 0;
-  for (int c = c0; c < c1; ++c) {
-    const uint32_t wc = __ldg(a.packed + (int64_t)__ldg(a.child_row + c) * a.wpr + w);
-    const uint32_t cl = wc, ch = wc >> 1;
-    const uint32_t is0 = ~(cl | ch) & 0x55555555u;
-    const uint32_t is2 = (ch & ~cl) & 0x55555555u;
-    anyv |= ~(cl & ch);
-    const uint32_t one = (is0 | is2) & o1;
-    const uint32_t two = (is2 & o0) | (is0 & o2);
-    const uint32_t contrib = one | (two << 1);
-    acc_lo += contrib & 0x33333333u;
-    acc_hi += (contrib >> 2) & 0x33333333u;
-    if (++pend == 7) {
-      bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
-      bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
-      acc_lo = acc_hi = 0;
-      pend = 0;
-      if (++pend8 == 17) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          m16[2 * t] += __byte_perm(bl0, bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
-          m16[2 * t + 1] += __byte_perm(bl1, bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
-        }
-        bl0 = bl1 = bh0 = bh1 = 0;
-        pend8 = 0;
-      }
-    }
-  }
-  bl0 += acc_lo & 0x0F0F0F0Fu; bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
-  bh0 += acc_hi & 0x0F0F0F0Fu; bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
-#endif
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     // halves: low = byte t of bl, high = byte t of bh

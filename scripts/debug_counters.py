@@ -1,3 +1,5 @@
+"""Diagnostic counters of the correction kernels.  They are compiled out of the default build: rebuild with
+`NVCC_FLAGS=-DGFX_DEBUG_COUNTERS` (genofix_b200/build.py) to get non-zero numbers."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes as C

@@ -72,5 +72,5 @@ print(json.dumps(dict(workload="config 5: trio consistency scan %d animals x %d 
                       ms_per_scan=ms, cells_per_s=cells / (ms / 1e3), trios=trios, sample_check_ok=bool(ok),
                       roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                                     algorithmic_bytes_per_cell=0.25,
-                                    note="kid rows are read once; sire/dam rows are re-read per trio (L2 hits when families are adjacent)"),
+                                    note="one warp per (sire, dam) family: kid rows are read once, the parents once per group of 4 kids"),
                       schedule_build_s=t_sched, inconsistent_total=int(inc.sum()), tested_total=int(tst.sum()))))

@@ -7,7 +7,8 @@ build() { # name flags...
     -o genofix_b200/variants/lib_$name.so genofix_b200/csrc/gfx_kernels.cu genofix_b200/csrc/gfx_schedule.cpp &
 }
 build base
-build t512 -DR2_THREADS=512
-build t768 -DR2_THREADS=768
+build f4b4 -DGFX_FAM_BLOCKS=4
+build f3b4 -DGFX_FAM_KIDS=3 -DGFX_FAM_BLOCKS=4
+build f4b5 -DGFX_FAM_BLOCKS=5
 wait
 ls -la genofix_b200/variants

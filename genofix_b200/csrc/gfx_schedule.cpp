@@ -150,13 +150,17 @@ struct Builder {
       uint8_t tr = 0;
       for (int fi = 0; fi < nf; ++fi) {
         const int qf = local[focal[fi]];
+        // the OTHER focal animal is never evidence (correct_genotypes3.py:230-238 drops both) and has no child in the
+        // blanket: as somebody's child it is barren (its factor sums to 1) and does not couple anything
+        const int qo_t = nf > 1 ? local[focal[1 - fi]] : -1;
+        const uint64_t drop_t = (qo_t >= 0 && bs.kidmask[base + qo_t] == 0) ? (1ull << qo_t) : 0ull;
         bool ok = bs.kidmask[base + qf] == 0 && bs.p1[base + qf] >= 0;
         std::vector<int> stk;
         if (ok) { stk.push_back(bs.p1[base + qf]); stk.push_back(bs.p2[base + qf]); }
         while (ok && !stk.empty()) {
           const int u = stk.back();
           stk.pop_back();
-          if (__builtin_popcountll(bs.kidmask[base + u]) != 1) { ok = false; break; }
+          if (__builtin_popcountll(bs.kidmask[base + u] & ~drop_t) != 1) { ok = false; break; }
           if (bs.p1[base + u] >= 0) { stk.push_back(bs.p1[base + u]); stk.push_back(bs.p2[base + u]); }
         }
         if (ok) tr |= (uint8_t)(1u << fi);
@@ -180,7 +184,9 @@ struct Builder {
             const int u = snode[sl];
             if (u < 0) continue;
             srow[sl] = u == qo ? -2 : (bs.row[base + u] >= 0 ? bs.row[base + u] : -1);
-            if (__builtin_popcountll(bs.kidmask[base + u]) != 1) bad |= (uint16_t)(1u << sl);
+            // (the other focal animal as a child is barren: see the tree flags above)
+            const uint64_t drop = (qo >= 0 && bs.kidmask[base + qo] == 0) ? (1ull << qo) : 0ull;
+            if (__builtin_popcountll(bs.kidmask[base + u] & ~drop) != 1) bad |= (uint16_t)(1u << sl);
             if (bs.p1[base + u] >= 0) {
               if (sl < 6) { snode[2 * sl + 2] = bs.p1[base + u]; snode[2 * sl + 3] = bs.p2[base + u]; }
               else bad |= (uint16_t)(1u << sl);   // parents beyond the slot tree

@@ -869,6 +869,9 @@ struct LazyBlanket {
   uint32_t cut;           // raw pattern from which a node is "suspect" and dropped from the evidence
   bool filter;
   unsigned long long* dbg = nullptr;            // false: plain evidence (rank), true: drop suspect nodes (correct)
+#ifdef GFX_DEBUG_COUNTERS
+  uint32_t* xflags = nullptr;   // events of one xpeel query: 1 observed extra child, 2 its other parent unobserved, 4 DOWN frame, 8 depth > 3
+#endif
   __device__ __forceinline__ int status(int t) const {
     const int r = __ldg(rows + t);
     if (r < 0) return 3;
@@ -1007,6 +1010,10 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
     if (stage == 0) {
       const int st = (t == q || t == qother) ? 3 : L.status(t);
       if (st != 3) { r0 = st == 0 ? 1.0 : 0.0; r1 = st == 1 ? 1.0 : 0.0; r2 = st == 2 ? 1.0 : 0.0; --sp; continue; }
+#ifdef GFX_DEBUG_COUNTERS
+      if (L.xflags && sp > 0 && (f_stage[sp - 1] == 4 || f_stage[sp - 1] == 6)) *L.xflags |= 2u;
+      if (L.xflags && sp > 3) *L.xflags |= 8u;
+#endif
       if ((visited >> t) & 1) { GFX_COUNT_PTR(L.dbg, 9); return false; }
       visited |= 1ull << t;
       const int a1 = L.p1[t];
@@ -1034,6 +1041,9 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
       f_flag[sp] = 0;
       f_stage[sp] = 3;
     } else if (stage == 7) {
+#ifdef GFX_DEBUG_COUNTERS
+      if (L.xflags) *L.xflags |= 4u;
+#endif
       if ((visited >> t) & 1) { GFX_COUNT_PTR(L.dbg, 9); return false; }
       visited |= 1ull << t;
       f_b[sp][0] = 1.0; f_b[sp][1] = 1.0; f_b[sp][2] = 1.0;
@@ -1080,6 +1090,9 @@ __device__ __noinline__ bool belief_up(const LazyBlanket& L, int q, int qother, 
         f_m[sp] = m;
         f_kid[sp] = (int8_t)k;
         if (sk != 3) {
+#ifdef GFX_DEBUG_COUNTERS
+          if (L.xflags) *L.xflags |= 1u;
+#endif
           f_sk[sp] = (int8_t)sk;
           f_flag[sp] = 1;
           f_stage[sp] = 4;
@@ -1107,8 +1120,25 @@ __device__ __noinline__ bool xpeel_query(const LazyBlanket& L, int q, int qother
   if (L.kid[q] != 0 || L.p1[q] < 0) { GFX_COUNT_PTR(L.dbg, 11); return false; }
   uint64_t visited = 1ull << q;
   double s[3], d[3];
+#ifdef GFX_DEBUG_COUNTERS
+  uint32_t xf = 0;
+  LazyBlanket& LM = const_cast<LazyBlanket&>(L);
+  LM.xflags = &xf;
+  const bool ok_s = belief_up(L, q, qother, visited, L.p1[q], q, s);
+  const bool ok_d = ok_s && belief_up(L, q, qother, visited, L.p2[q], q, d);
+  LM.xflags = nullptr;
+  if (L.dbg) {
+    // 12: pure tree walk (slot peeling gave up for depth / barren children)  13: observed extra children with observed other parents
+    // 14: needs recursion (other parent unobserved or DOWN frames)           15: the same classes among the FAILED walks (<< 2 bits)
+    const int cls = (xf & 6u) ? 14 : ((xf & 1u) ? 13 : 12);
+    if (ok_d) atomicAdd(L.dbg + cls, 1ull);
+    else atomicAdd(L.dbg + 15, 1ull << (20 * (cls - 12)));
+  }
+  if (!ok_d) return false;
+#else
   if (!belief_up(L, q, qother, visited, L.p1[q], q, s)) return false;
   if (!belief_up(L, q, qother, visited, L.p2[q], q, d)) return false;
+#endif
   const double sa = s[0] + 0.5 * s[1], sb = 0.5 * s[1] + s[2], da = d[0] + 0.5 * d[1], db = 0.5 * d[1] + d[2];
   const double u0 = sa * da, u2 = sb * db, u1 = sa * db + sb * da;
   const double t = (u0 + u1) + u2;

@@ -286,3 +286,19 @@ def test_packed_container_roundtrip(tmp_path):
             f.write("%d %s\n" % (i + 1, " ".join(str(x) for x in G[i, :20])))
     g3 = PackedGens.from_text(str(txt), str(tmp_path / "g.g2b"))
     assert np.array_equal(g3.getMatrix([1, 2, 3, 4, 5]), G[:5, :20]) and g3.snps == ["s%d" % i for i in range(20)]
+
+
+def test_levels_from_parents_orders_parents_first():
+    from genofix_b200.simulate_device import levels_from_parents
+    #        0   1   2   3   4   5
+    sire = [-1, -1, 0, 0, 2, -1]
+    dam = [-1, -1, 1, 1, 3, 4]
+    order, off = levels_from_parents(sire, dam)
+    pos = {int(r): i for i, r in enumerate(order)}
+    for k in range(6):
+        for p in (sire[k], dam[k]):
+            if p >= 0:
+                assert pos[p] < pos[k]
+    assert list(off) == [0, 2, 4, 5, 6]                 # founders {0,1}, then {2,3}, {4}, {5}
+    with pytest.raises(ValueError):
+        levels_from_parents([1, 0], [-1, -1])           # a cycle

@@ -2278,16 +2278,64 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
 // trio consistency scan: bit-parallel over 16 SNPs per word
 // ------------------------------------------------------------------------------------------------
 // One warp per FAMILY (trios with the same sire and dam are adjacent in trio_row, fam_off delimits them): per
-// 16-byte quad the lane loads the sire's and the dam's codes once and then the codes of up to 8 kids, whose tallies
+// 16-byte quad the lane loads the sire's and the dam's codes once and then the codes of up to 4 kids, whose tallies
 // live in registers, so the parents cross the L2 -> SM link once per family instead of once per kid (the per-trio
 // form moved 3 rows per kid and was bound by that link: 7 TB/s of L2 reads for 2.6 TB/s of algorithmic bytes).
-// Families with more than 8 kids are walked in groups of 8.  No atomics: a kid belongs to one family.
-#ifndef GFX_FAM_KIDS
-#define GFX_FAM_KIDS 4
-#endif
+// Families are walked in groups of 4 kids (more per group costs occupancy).  No atomics: a kid belongs to one family.
 #ifndef GFX_FAM_BLOCKS
 #define GFX_FAM_BLOCKS 4
 #endif
+// NK kids of one family (compile-time count: no predicated work for absent kids)
+template <int NK>
+__device__ __forceinline__ void trio_family_group(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nquads, int64_t n_snps,
+                                                  const uint4* ps, const uint4* pd, const int32_t* __restrict__ rows, int lane,
+                                                  long long* __restrict__ inc, long long* __restrict__ tested) {
+  const uint4* pk[NK];
+  int n_inc[NK], n_tst[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    pk[k] = reinterpret_cast<const uint4*>(packed + (int64_t)rows[k] * wpr);
+    n_inc[k] = 0; n_tst[k] = 0;
+  }
+  for (int64_t q = lane; q < nquads; q += 32) {
+    const uint4 sq = __ldg(ps + q), dq = __ldg(pd + q);
+    uint4 kq[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) kq[k] = __ldg(pk[k] + q);
+    const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t s = sw[i], d = dw[i];
+      uint32_t valid = 0x55555555u;
+      const int64_t rem = n_snps - (q * 4 + i) * 16;
+      if (rem < 16) valid = rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & 0x55555555u);
+      const uint32_t s0 = ~(s | (s >> 1)), s2 = (s >> 1) & ~s;
+      const uint32_t d0 = ~(d | (d >> 1)), d2 = (d >> 1) & ~d;
+      const uint32_t par_ok = ~(s & (s >> 1)) & ~(d & (d >> 1)) & valid;
+      const uint32_t no0 = s2 | d2, no2 = s0 | d0, no1 = (s0 & d0) | (s2 & d2);   // kid states the parents exclude
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
+        const uint32_t k0 = ~(kk | (kk >> 1)), k1 = kk & ~(kk >> 1), k2 = (kk >> 1) & ~kk;
+        const uint32_t present = ~(kk & (kk >> 1)) & par_ok;
+        // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
+        const uint32_t bad = (k0 & no0) | (k2 & no2) | (k1 & no1);
+        n_tst[k] += __popc(present);
+        n_inc[k] += __popc(bad & present);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    int a = n_inc[k], b = n_tst[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { inc[rows[k]] = a; tested[rows[k]] = b; }
+  }
+}
+
 __global__ void __launch_bounds__(256, GFX_FAM_BLOCKS) k_trio_scan(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nwords,
                                                    int64_t n_snps, const int32_t* __restrict__ trio_row,
                                                    const int32_t* __restrict__ fam_off, int n_fam,
@@ -2301,57 +2349,13 @@ __global__ void __launch_bounds__(256, GFX_FAM_BLOCKS) k_trio_scan(const uint32_
     const int r0 = trio_row[t0];
     const uint4* ps = reinterpret_cast<const uint4*>(packed + (int64_t)prow[2 * r0] * wpr);
     const uint4* pd = reinterpret_cast<const uint4*>(packed + (int64_t)prow[2 * r0 + 1] * wpr);
-    for (int g0 = t0; g0 < t1; g0 += GFX_FAM_KIDS) {
-      const int nk = min(GFX_FAM_KIDS, t1 - g0);
-      const uint4* pk[GFX_FAM_KIDS];
-      int n_inc[GFX_FAM_KIDS], n_tst[GFX_FAM_KIDS];
-#pragma unroll
-      for (int k = 0; k < GFX_FAM_KIDS; ++k) {
-        pk[k] = reinterpret_cast<const uint4*>(packed + (int64_t)trio_row[g0 + (k < nk ? k : 0)] * wpr);
-        n_inc[k] = 0; n_tst[k] = 0;
-      }
-      for (int64_t q = lane; q < nquads; q += 32) {
-        const uint4 sq = __ldg(ps + q), dq = __ldg(pd + q);
-        uint4 kq[GFX_FAM_KIDS];
-#pragma unroll
-        for (int k = 0; k < GFX_FAM_KIDS; ++k)
-          if (k < nk) kq[k] = __ldg(pk[k] + q);
-        const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t s = sw[i], d = dw[i];
-          uint32_t valid = 0x55555555u;
-          const int64_t rem = n_snps - (q * 4 + i) * 16;
-          if (rem < 16) valid = rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & 0x55555555u);
-          const uint32_t s0 = ~(s | (s >> 1)), s2 = (s >> 1) & ~s;
-          const uint32_t d0 = ~(d | (d >> 1)), d2 = (d >> 1) & ~d;
-          const uint32_t par_ok = ~(s & (s >> 1)) & ~(d & (d >> 1)) & valid;
-          const uint32_t no0 = s2 | d2, no2 = s0 | d0, no1 = (s0 & d0) | (s2 & d2);   // kid states the parents exclude
-#pragma unroll
-          for (int k = 0; k < GFX_FAM_KIDS; ++k) {
-            if (k < nk) {
-              const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
-              const uint32_t k0 = ~(kk | (kk >> 1)), k1 = kk & ~(kk >> 1), k2 = (kk >> 1) & ~kk;
-              const uint32_t present = ~(kk & (kk >> 1)) & par_ok;
-              // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
-              const uint32_t bad = (k0 & no0) | (k2 & no2) | (k1 & no1);
-              n_tst[k] += __popc(present);
-              n_inc[k] += __popc(bad & present);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < GFX_FAM_KIDS; ++k) {
-        if (k < nk) {
-          int a = n_inc[k], b = n_tst[k];
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          if (lane == 0) { const int r = trio_row[g0 + k]; inc[r] = a; tested[r] = b; }
-        }
-      }
+    for (int g0 = t0; g0 < t1; g0 += 4) {
+      const int nk = min(4, t1 - g0);
+      const int32_t* rows = trio_row + g0;
+      if (nk == 4) trio_family_group<4>(packed, wpr, nquads, n_snps, ps, pd, rows, lane, inc, tested);
+      else if (nk == 3) trio_family_group<3>(packed, wpr, nquads, n_snps, ps, pd, rows, lane, inc, tested);
+      else if (nk == 2) trio_family_group<2>(packed, wpr, nquads, n_snps, ps, pd, rows, lane, inc, tested);
+      else trio_family_group<1>(packed, wpr, nquads, n_snps, ps, pd, rows, lane, inc, tested);
     }
   }
 }

@@ -1937,11 +1937,15 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
   return true;
 }
 
-// Lean kernel.  A warp takes (focal animal, 256-SNP chunk) tasks from a global counter -- animals are
+// Lean kernel.  A warp takes (focal animal, GFX_LEAN_CHUNK-SNP chunk) tasks from a global counter -- animals are
 // ordered heaviest first, so the many-mate sires do not end up as the tail --, compacts the suspect
 // SNPs of the chunk with ballots and then runs one cell per lane.  Cells that need the general path
 // go to the work list (or, if that is full, the overflow bitmap) untouched.
-#define GFX_LEAN_CHUNK 128
+// SNPs per warp task (measured on config 2: 256 -> 16.8 ms, 128 -> 16.3, 64 -> 15.1, 32 -> 14.8 ms per chunk: short tasks
+// balance better and the suspect cells are dense enough that one ballot round fills the warp)
+#ifndef GFX_LEAN_CHUNK
+#define GFX_LEAN_CHUNK 32
+#endif
 #ifndef KC_BLOCKS
 #define KC_BLOCKS 6
 #endif

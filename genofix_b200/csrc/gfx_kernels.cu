@@ -2096,10 +2096,13 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
 #ifndef KJ_BLOCKS
 #define KJ_BLOCKS 4
 #endif
+#ifndef KJ_ITEMS
+#define KJ_ITEMS 32   // jobs per ticket of the tree-message-passing round
+#endif
 __global__ void __launch_bounds__(128, KJ_BLOCKS) k_correct_jobs(FocalArgs a) {
   unsigned long long n = *a.item_count;
   if (n > a.item_cap) n = a.item_cap;
-  jobs_round<1, 32>(a, a.items_sorted, n, a.wl_count + 4);
+  jobs_round<1, KJ_ITEMS>(a, a.items_sorted, n, a.wl_count + 4);
 }
 #ifndef KG_BLOCKS
 #define KG_BLOCKS 4

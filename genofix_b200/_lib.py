@@ -18,7 +18,7 @@ GFX_E_NOMEM = -5
 EXPORTS = [
     "gfx_last_error", "gfx_version", "gfx_launch_count", "gfx_schedule_create", "gfx_schedule_create_host",
     "gfx_schedule_destroy", "gfx_schedule_info", "gfx_schedule_copy", "gfx_pack2", "gfx_unpack2",
-    "gfx_mendel_rank", "gfx_mendel_rank_hist", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
+    "gfx_mendel_rank", "gfx_mendel_rank_hist", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_rank_rowsum_f16", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
     "gfx_check_device_status", "gfx_debug_counters", "gfx_trio_scan", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
     "gfx_kids_term_host", "gfx_gene_drop", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
 ]
@@ -76,6 +76,7 @@ def lib():
     L.gfx_mendel_rank_hist.argtypes = [vp, vp, i64, i64, vp, i64, vp, vp]
     L.gfx_rank_hist.argtypes = [vp, i64, vp, i64, i64, i64, vp, vp]
     L.gfx_rank_rowsum.argtypes = [vp, i64, vp, i64, i64, i64, vp, C.c_double, vp, vp]
+    L.gfx_rank_rowsum_f16.argtypes = [vp, i64, i64, i64, vp, vp, i32, vp, vp]
     L.gfx_correct_pairs.argtypes = [vp, i32, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
     L.gfx_correct_singles.argtypes = [vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
     L.gfx_gene_drop.argtypes = [i32, vp, vp, vp, vp, i32, i64, i64, C.c_uint64, vp, vp]

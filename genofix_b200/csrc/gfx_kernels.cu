@@ -1506,6 +1506,64 @@ extern "C" int gfx_rank_rowsum(const uint16_t* raw, int64_t ld_raw, const uint32
   return GFX_OK;
 }
 
+// ---- per-animal tally exactly as pandas computes it in the reference ------------------------------------
+// error_checker.py:193-204 / preindex.py:259-266 keep the transformed rank matrix in FLOAT16 and sum it with
+// DataFrame.sum(axis=1): a float16 accumulator per animal that takes the SNP columns one after the other, every
+// addition carried out in float32 and rounded to float16 (numpy's half add).  That chain is order dependent, so it
+// is reproduced literally: one thread per selected animal walks its row in column order; the next 64 bytes of
+// scores are in flight while the current 32 cells are added.  e16[raw pattern] is the float16 E of every score
+// pattern (built on the host with numpy); e16[0xFFFF] is the value of cells that were missing in the input.
+__global__ void __launch_bounds__(128) k_rank_rowsum_f16(const uint16_t* __restrict__ raw, int64_t ld_raw, int64_t n_snps,
+                                                         const uint16_t* __restrict__ e16, const int32_t* __restrict__ rows,
+                                                         int n_sel, uint16_t* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_sel) return;
+  const int64_t r = rows ? __ldg(rows + t) : t;
+  const uint16_t* src = raw + r * ld_raw;          // ld_raw is a multiple of 64: rows are 128-byte aligned
+  const int64_t nblk = n_snps >> 5;                 // blocks of 32 cells = 4 x uint4
+  float acc = 0.0f;                                 // always holds a float16 value
+  uint4 nx[4];
+  if (nblk > 0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nx[u] = __ldg(reinterpret_cast<const uint4*>(src) + u);
+  }
+  for (int64_t b = 0; b < nblk; ++b) {
+    uint4 cur[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nx[u];
+    if (b + 1 < nblk) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nx[u] = __ldg(reinterpret_cast<const uint4*>(src + (b + 1) * 32) + u);
+    }
+    float x[32];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t wv[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[u * 8 + 2 * k] = __half2float(__ushort_as_half(__ldg(e16 + (wv[k] & 0xFFFFu))));
+        x[u * 8 + 2 * k + 1] = __half2float(__ushort_as_half(__ldg(e16 + (wv[k] >> 16))));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc = __half2float(__float2half_rn(acc + x[i]));
+  }
+  for (int64_t j = nblk << 5; j < n_snps; ++j)
+    acc = __half2float(__float2half_rn(acc + __half2float(__ushort_as_half(__ldg(e16 + __ldg(src + j))))));
+  out[t] = __half_as_ushort(__float2half_rn(acc));
+}
+
+extern "C" int gfx_rank_rowsum_f16(const uint16_t* raw, int64_t ld_raw, int64_t n, int64_t n_snps, const uint16_t* e16,
+                                   const int32_t* rows, int32_t n_sel, uint16_t* out, void* stream) {
+  if (!raw || !e16 || !out || n <= 0 || n_snps <= 0 || n_sel < 0 || ld_raw < n_snps || (ld_raw & 63))
+    return fail(GFX_E_INVALID, "gfx_rank_rowsum_f16: bad argument");
+  if (!rows && n_sel != n) return fail(GFX_E_INVALID, "gfx_rank_rowsum_f16: n_sel must equal n without a row list");
+  if (n_sel == 0) return GFX_OK;
+  k_rank_rowsum_f16<<<(n_sel + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw, ld_raw, n_snps, e16, rows, n_sel, out);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
 // ---- correctPair / correctSingle + apply, fused per focal animal -----------------------------------
 //
 // One warp owns 32 consecutive SNPs of one focal animal of the generation and walks that animal's

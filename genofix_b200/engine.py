@@ -574,6 +574,79 @@ class Engine(object):
         return inc.cpu().numpy(), tst.cpu().numpy()
 
 
+    # ---- per-animal Mendel tally (error_checker.py:193-204, preindex.py:259-266) -----------------------------
+    def mendel_tally(self, G, rows=None, missing_value=-1.0, want_matrix=True):
+        """Transformed ranks and their per-animal sums in the reference's float16 arithmetic.
+
+        G: uint8 [n, s] (0,1,2,9) or None to use the matrix already on the device; rows: row indices to tally
+        (error_checker.py: the animals with both parents genotyped) or None for all.  Returns
+        (E16 float16 [len(rows), s] or None, sums float16 [len(rows)], max16) -- the sums are NOT yet divided by their
+        nanmax (the caller does, error_checker.py:202): sharded callers need the raw sums."""
+        t = self.torch
+        if G is not None:
+            G = np.asarray(G)
+            if G.ndim != 2 or G.shape[0] != self.n:
+                raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+            self._alloc(G.shape[1])
+            hin = self.host_in.numpy()
+            _parallel_copy(hin[:, :self.s], G)
+            if self.ldc > self.s:
+                hin[:, self.s:] = 9
+            self.codes.copy_(self.host_in, non_blocking=True)
+            self.load_codes_device(self.codes)
+        self.mendel_rank_device(fused=True)      # scores + histogram, 0xFFFF marker on missing cells
+        self._hist_ready = False
+        self.host_hist.copy_(self.hist, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        e16, m16 = half_transform_table(self.host_hist.numpy().view(np.uint64), missing_value)
+        dev = self.raw.device
+        e16_dev = t.from_numpy(e16.view(np.int16)).to(dev)
+        if rows is None:
+            rows_np = np.arange(self.n, dtype=np.int32)
+            rows_dev = None
+        else:
+            rows_np = np.ascontiguousarray(rows, dtype=np.int32)
+            if rows_np.ndim != 1 or (len(rows_np) and (rows_np.min() < 0 or rows_np.max() >= self.n)):
+                raise ValueError("rows out of range")
+            rows_dev = t.from_numpy(rows_np).to(dev)
+        out = t.empty(max(len(rows_np), 1), dtype=t.int16, device=dev)
+        _lib.check(self.L.gfx_rank_rowsum_f16(self.raw.data_ptr(), self.ld_raw, self.n, self.s, e16_dev.data_ptr(),
+                                              rows_dev.data_ptr() if rows_dev is not None else None, len(rows_np),
+                                              out.data_ptr(), self._stream()))
+        sums = out[:len(rows_np)].cpu().numpy().view(np.float16)
+        E16 = None
+        if want_matrix:
+            src = self.raw if rows_dev is None else self.raw.index_select(0, rows_dev.long())
+            E16 = e16[src[:, :self.s].cpu().numpy().view(np.uint16)]
+        return E16, sums, m16
+
+
+_ALL_HALF_E16 = None
+
+
+def half_transform_table(hist, missing_value):
+    """float16 E of every score pattern, as error_checker.py:193-197 / preindex.py:259-263 compute it on their
+    float16 frame: log(log(x + 1) + 1) / nanmax(.), every step a float16 ufunc.  hist: uint64[65537] of the score
+    patterns present (bin 65536 = missing cells, whose score is 1.0 until it is overwritten).  Entry 0xFFFF of the
+    table is the value of a missing cell.  Returns (table float16[65536], max float16)."""
+    global _ALL_HALF_E16
+    hist = np.asarray(hist, dtype=np.uint64)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if _ALL_HALF_E16 is None:
+            all16 = np.arange(65536, dtype=np.uint16).view(np.float16)
+            _ALL_HALF_E16 = np.log(np.log(all16 + 1) + 1)
+            assert _ALL_HALF_E16.dtype == np.float16
+        present = hist[:65536] > 0
+        if hist[65536] > 0:
+            present = present.copy()
+            present[0x3C00] = True
+        m = np.nanmax(_ALL_HALF_E16[present]) if present.any() else np.float16(np.nan)
+        table = _ALL_HALF_E16 / m
+    table[0xFFFF] = np.float16(missing_value)
+    return table, np.float16(m)
+
+
 def pinned_array(shape, dtype=np.uint8):
     """numpy array in page-locked host memory: correct_chunks moves such arrays with the copy engines directly
     (no staging copy).  The array keeps its backing tensor alive."""

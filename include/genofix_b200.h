@@ -134,6 +134,16 @@ int gfx_rank_rowsum(const uint16_t* raw_dev, int64_t ld_raw, const uint32_t* pac
                     int64_t n, int64_t n_snps, const double* elut_dev, double missing_value,
                     double* rowsum_dev, void* stream);
 
+/* The same tally in the reference's own arithmetic (error_checker.py:193-204, preindex.py:259-266): the transformed
+ * ranks are FLOAT16 there and DataFrame.sum(axis=1) adds the SNP columns one after the other into a float16
+ * accumulator (every addition in float32, rounded to float16).  raw_dev: scores with the 0xFFFF marker on missing
+ * cells (after gfx_mendel_rank_hist / gfx_rank_hist); e16_dev: 65536 float16 bit patterns, E of every score
+ * pattern, entry 0xFFFF = value of a missing cell (-1 in error_checker.py:196-197, 1 in preindex.py:262-263);
+ * rows_dev: n_sel row indices (the animals with both parents genotyped, error_checker.py:138-153) or NULL for all
+ * n rows; rowsum16_dev: n_sel float16 bit patterns.  ld_raw must be a multiple of 64. */
+int gfx_rank_rowsum_f16(const uint16_t* raw_dev, int64_t ld_raw, int64_t n, int64_t n_snps, const uint16_t* e16_dev,
+                        const int32_t* rows_dev, int32_t n_sel, uint16_t* rowsum16_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Correction: correctPair + pair apply per generation (correct_genotypes3.py:169-327,684-848) and
  * correctSingle + single apply (:330-430,851-944).

@@ -671,3 +671,67 @@ def founders(ped, restrict_ids=None):
         has_s = set(k for k, s in ped.sire.items() if k in rs and s in rs)
         has_d = set(k for k, d in ped.dam.items() if k in rs and d in rs)
     return sorted(x for x in animals if x not in has_s or x not in has_d)
+
+
+# --------------------------------------------------------------------------------------------
+# pedigree/error_checker.py:138-204 and empirical/preindex.py:166-170,259-266: per-animal Mendel tally
+# --------------------------------------------------------------------------------------------
+def trio_candidates(ped, all_ids, kids):
+    """error_checker.py:138-153: `animalswithparents` = kids of the list (in genotype-file order) whose sire AND dam
+    are genotyped; `candidates` = those kids and their parents (the reference builds a set; here: sorted ids)."""
+    genotyped = set(int(x) for x in all_ids)
+    wanted = set(int(x) for x in kids)
+    with_parents = []
+    for k in (int(x) for x in all_ids):
+        if k in wanted:
+            s, d = ped.parents(k)
+            if s in genotyped and d in genotyped:
+                with_parents.append(k)
+    cand = set()
+    for k in with_parents:
+        cand.add(k)
+        cand.update(ped.parents(k))
+    return with_parents, sorted(cand)
+
+
+def half_transform(raw16, G, missing_value):
+    """error_checker.py:193-197 / preindex.py:259-263 on a FLOAT16 matrix: every step of
+    log(log(x + 1) + 1) / nanmax(.) is a float16 ufunc (computed in float32, rounded to float16)."""
+    raw16 = np.asarray(raw16, dtype=np.float16)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E = np.log(np.log(raw16 + 1) + 1)
+        assert E.dtype == np.float16
+        E = E / np.nanmax(E)
+        E[np.asarray(G) == 9] = missing_value
+    return E
+
+
+def half_rowsum(E16):
+    """DataFrame.sum(axis=1) of a float16 frame (error_checker.py:201, preindex.py:265): pandas reduces the
+    [SNP, animal] block along its first axis with dtype float16, i.e. one float16 accumulator per animal that
+    takes the SNP columns in order (checked against the reference's own output in tests/golden/errchk_*.npz)."""
+    E16 = np.asarray(E16, dtype=np.float16)
+    acc = np.zeros(E16.shape[0], dtype=np.float16)
+    for j in range(E16.shape[1]):
+        acc = acc + E16[:, j]
+    return acc
+
+
+def error_checker(ped_rows, all_ids, G, kids, missing_value=-1.0, back=2):
+    """error_checker.py main (:138-204) without the file handling.  Returns (animalswithparents, candidates,
+    probs_errors float16 [len(animalswithparents), S], individualSumProbs float16).  The Mendel ranks see ONLY the
+    candidate animals as genotyped (the reference restricts the matrix to them, :155-157)."""
+    ped = ped_rows if isinstance(ped_rows, OraclePedigree) else OraclePedigree(ped_rows)
+    with_parents, cand = trio_candidates(ped, all_ids, kids)
+    row_all = {int(k): i for i, k in enumerate(all_ids)}
+    Gc = np.asarray(G)[[row_all[k] for k in cand]]
+    raw = Oracle(ped, cand).mendel_rank(Gc, back)            # :164-187 (correct_genotypes2's twin of mendelProbsSingle)
+    E = half_transform(raw, Gc, missing_value)
+    pos = {k: i for i, k in enumerate(cand)}
+    Ew = E[[pos[k] for k in with_parents]]
+    sums = half_rowsum(Ew)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sums = sums / np.nanmax(sums) if len(sums) else sums  # :202
+    return with_parents, cand, Ew, sums

@@ -106,6 +106,34 @@ def topo_sort(rows):
     return np.array(out, dtype=np.int64)
 
 
+
+# pedigree/error_checker.py main(): per-animal Mendel tallies in the reference's float16 arithmetic
+ERRCHK_CASES = {
+    "errchk_a": dict(ped=dict(n_animals=60, n_generations=5, sire_frac=0.3, dam_frac=0.6, seed=7),
+                     n_snps=30, err=0.03, miss=0.03, drop=0.0, kids="all"),
+    "errchk_b": dict(ped=dict(n_animals=96, n_generations=6, sire_frac=0.25, dam_frac=0.5, seed=11,
+                              related_mating_p=0.6, unknown_parents_frac=0.1),
+                     n_snps=32, err=0.02, miss=0.05, drop=0.12, kids="odd"),
+    # long rows: the float16 accumulator passes 256 and loses low bits, so the summation order is visible
+    "errchk_long": dict(ped=dict(n_animals=48, n_generations=4, sire_frac=0.3, dam_frac=0.6, seed=5),
+                        n_snps=1500, err=0.3, miss=0.02, drop=0.0, kids="all"),
+}
+
+
+def make_errchk(name):
+    case = ERRCHK_CASES[name]
+    ped_rows, ids, truth, obs = build_inputs(case)
+    kids = [int(x) for x in ids] if case["kids"] == "all" else [int(x) for x in ids if int(x) % 2 == 1]
+    t0 = time.time()
+    r = rh.run_error_checker(ped_rows, ids, obs, kids)
+    dt = time.time() - t0
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ped_rows=ped_rows, ids=ids, obs=obs.astype(np.uint8),
+                        kids=np.array(kids, dtype=np.int64), with_parents=r["with_parents"],
+                        probs_errors=r["probs_errors"].view(np.uint16), sums=r["sums"].view(np.uint16),
+                        reference_seconds=dt)
+    print("%s: %d animals x %d SNPs, %d trio kids, reference %.1f s" % (name, len(ids), obs.shape[1],
+                                                                       len(r["with_parents"]), dt))
+
 def make_case(name):
     case = CASES[name]
     ped_rows, ids, truth, obs = build_inputs(case)
@@ -226,9 +254,11 @@ def make_kats():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    names = sys.argv[1:] or ["kats"] + list(CASES)
+    names = sys.argv[1:] or ["kats"] + list(CASES) + list(ERRCHK_CASES)
     for n in names:
         if n == "kats":
             make_kats()
+        elif n in ERRCHK_CASES:
+            make_errchk(n)
         else:
             make_case(n)

@@ -200,3 +200,60 @@ def run_mendel_probs(genotypes_df, ped_rows, back=2):
             raw[i] = np.squeeze(e)
             probs[i] = p
     return raw, probs
+
+
+def run_error_checker(ped_rows, ids, obs, kids, chrom="chrA", quiet=True):
+    """Run the reference's pedigree/error_checker.py main() (:57-204) on files written from the arrays.
+
+    File conventions the reference needs: the header's last name keeps its newline (gensrandaccess.py:27), so a
+    padding SNP on another chromosome closes the header; chromosome names must not parse as integers (:119 vs :109).
+    Returns dict(with_parents=ids of probs_errors.csv rows, probs_errors=float16 [K, S], sums=float16 [K])."""
+    load()
+    import pandas as pd
+    import pedigree.error_checker as ec
+    S = obs.shape[1]
+    snps = ["SNP%d" % i for i in range(S)]
+    buf = io.StringIO()
+    with tempfile.TemporaryDirectory() as d:
+        with open(d + "/gens.txt", "w") as f:
+            f.write("id " + " ".join(snps) + " pad\n")
+            for k, row in zip(ids, obs):
+                f.write(str(int(k)) + " " + " ".join(str(int(x)) for x in row) + " 0\n")
+        with open(d + "/ped.txt", "w") as f:
+            for r in ped_rows:
+                f.write(" ".join(str(int(x)) for x in r[:4]) + "\n")
+        with open(d + "/kids.txt", "w") as f:
+            f.write("kid\n")
+            for k in kids:
+                f.write("%d\n" % int(k))
+        with open(d + "/map.csv", "w") as f:
+            f.write("snpid,chrom,pos,topAllele,B\n")
+            for i, s in enumerate(snps):
+                f.write("%s,%s,%d,A,B\n" % (s, chrom, 100 * i + 1))
+            f.write("pad,chrB,1,A,B\n")
+        argv0 = sys.argv
+        main_mod = sys.modules["__main__"]
+        doc0 = getattr(main_mod, "__doc__", None)
+        if not doc0:
+            main_mod.__doc__ = "harness\nerror_checker driver\n"   # :69 reads __main__.__doc__
+        sys.argv = ["error_checker.py", "-g", d + "/gens.txt", "-p", d + "/ped.txt", "-k", d + "/kids.txt",
+                    "-s", d + "/map.csv", "-T", "1", "-c", chrom, "-o", d + "/out"]
+        try:
+            import warnings
+            ctx = contextlib.redirect_stdout(buf) if quiet else contextlib.nullcontext()
+            with deterministic_pools(), ctx, contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"), \
+                    warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ec.main()
+        finally:
+            sys.argv = argv0
+            main_mod.__doc__ = doc0
+        pe = pd.read_csv(d + "/out/probs_errors.csv", index_col=0)
+        sums = np.loadtxt(d + "/out/individual_sum_probs_errors.csv", delimiter=",", ndmin=1)
+    # to_csv prints the shortest repr of each float16, which identifies the float16 value uniquely
+    pe16 = pe.to_numpy().astype(np.float16)
+    assert np.allclose(pe16.astype(np.float64), pe.to_numpy(), rtol=2e-3, atol=1e-7, equal_nan=True)
+    s16 = sums.astype(np.float16)
+    assert np.array_equal(s16.astype(np.float64), sums, equal_nan=True)
+    return dict(with_parents=np.array([int(x) for x in pe.index], dtype=np.int64), probs_errors=pe16, sums=s16,
+                stdout=buf.getvalue())

@@ -500,3 +500,101 @@ def test_device_simulator_properties_and_evaluation():
     assert ev["missed"] == int((was_err & ~changed).sum())
     assert ev["fixed"] > 0.1 * ev["errors"] and ev["new_errors"] < ev["fixed"]      # the correction does net good
     print(ev)
+
+
+# ---- pedigree/error_checker.py: per-animal Mendel tallies in the reference's float16 arithmetic -------------------
+def _errchk_frame(g):
+    import pandas as pd
+    return pd.DataFrame(g["obs"], index=[int(x) for x in g["ids"]], columns=["SNP%d" % i for i in range(g["obs"].shape[1])])
+
+
+@pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long"])
+def test_error_checker_matches_reference_golden(name):
+    """probs_errors.csv and individual_sum_probs_errors.csv of the UNMODIFIED reference (error_checker.py:199-204),
+    bit for bit: k_mendel_rank<HIST> -> float16 table -> k_rank_rowsum_f16."""
+    from genofix_b200.pedigree.error_checker import mendel_error_tally
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    g = load_golden(name)
+    pe, sums = mendel_error_tally(_errchk_frame(g), PedigreeDAG.from_table(g["ped_rows"]), g["kids"])
+    assert [int(x) for x in pe.index] == [int(x) for x in g["with_parents"]]
+    assert pe.to_numpy().dtype == np.float16
+    assert np.array_equal(pe.to_numpy().view(np.uint16), g["probs_errors"])
+    assert sums.dtype == np.float16 and np.array_equal(sums.view(np.uint16), g["sums"])
+
+
+@pytest.mark.parametrize("missing_value", [-1.0, 1.0])
+def test_error_checker_matches_oracle_seeded(missing_value):
+    """Seeded pedigree with ungenotyped animals, missing calls and a kids list that is a subset; missing_value = 1 is
+    preindex.py:262-263."""
+    import pandas as pd
+    from genofix_b200 import synth
+    from genofix_b200.pedigree.error_checker import mendel_error_tally
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    rows = synth.make_pedigree(260, 6, sire_frac=0.2, dam_frac=0.5, seed=41, related_mating_p=0.3)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 150, seed=5), 0.05, seed=6), 0.04, seed=7)
+    rs = np.random.Generator(np.random.PCG64(8))
+    keep = rs.random(len(rows)) >= 0.15
+    ids, obs = rows[keep, 0], obs[keep]
+    kids = [int(x) for x in ids if rs.random() < 0.7]
+    df = pd.DataFrame(obs, index=[int(x) for x in ids], columns=["S%d" % i for i in range(obs.shape[1])])
+    pe, sums = mendel_error_tally(df, PedigreeDAG.from_table(rows), kids, missing_value=missing_value)
+    wp, _cand, E, osums = go.error_checker(rows, ids, obs, kids, missing_value=missing_value)
+    assert len(wp) > 50 and [int(x) for x in pe.index] == wp
+    assert np.array_equal(pe.to_numpy().view(np.uint16), E.view(np.uint16))
+    assert np.array_equal(sums.view(np.uint16), osums.view(np.uint16))
+
+
+def test_mendel_tally_is_the_float16_chain_at_scale():
+    """3 000 animals x 4 099 SNPs (ragged width, accumulators far beyond 2048 where float16 steps are 2): the kernel's
+    sums equal the column-by-column float16 chain over the very matrix it summed, for all rows and for a row subset."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    rows = synth.make_pedigree(3000, 6, sire_frac=0.1, dam_frac=0.5, seed=17)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 4099, seed=2), 0.2, seed=3), 0.03, seed=4)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    E, sums, m16 = eng.mendel_tally(obs, None, 1.0)
+    assert E.shape == obs.shape and E.dtype == np.float16
+    assert np.all(E[obs == 9] == np.float16(1.0)) and np.nanmax(E[obs != 9]) == np.float16(1.0)
+    assert np.array_equal(sums.view(np.uint16), go.half_rowsum(E).view(np.uint16))
+    assert float(np.nanmax(sums)) > 600
+    sel = np.random.Generator(np.random.PCG64(1)).permutation(3000)[:777].astype(np.int32)
+    E2, sums2, _ = eng.mendel_tally(None, sel, -1.0)
+    assert np.array_equal(E2 == np.float16(-1.0), obs[sel] == 9)
+    assert np.array_equal(sums2.view(np.uint16), go.half_rowsum(E2).view(np.uint16))
+
+
+def test_error_checker_cli_writes_the_reference_files(tmp_path):
+    """src/pedigree/error_checker.py with the reference's command line on files laid out as the reference needs them
+    (oracle/ref_harness.run_error_checker); the two csv files parse back to the golden float16 values."""
+    import subprocess
+    import sys
+    import pandas as pd
+    from conftest import ROOT
+    g = load_golden("errchk_a")
+    d = str(tmp_path)
+    S = g["obs"].shape[1]
+    snps = ["SNP%d" % i for i in range(S)]
+    with open(d + "/gens.txt", "w") as f:
+        f.write("id " + " ".join(snps) + " pad\n")
+        for k, row in zip(g["ids"], g["obs"]):
+            f.write(str(int(k)) + " " + " ".join(str(int(x)) for x in row) + " 0\n")
+    with open(d + "/ped.txt", "w") as f:
+        for r in g["ped_rows"]:
+            f.write(" ".join(str(int(x)) for x in r[:4]) + "\n")
+    with open(d + "/kids.txt", "w") as f:
+        f.write("kid\n" + "".join("%d\n" % int(k) for k in g["kids"]))
+    with open(d + "/map.csv", "w") as f:
+        f.write("snpid,chrom,pos,topAllele,B\n")
+        for i, s in enumerate(snps):
+            f.write("%s,chrA,%d,A,B\n" % (s, 100 * i + 1))
+        f.write("pad,chrB,1,A,B\n")
+    subprocess.run([sys.executable, ROOT + "/src/pedigree/error_checker.py", "-g", d + "/gens.txt", "-p", d + "/ped.txt",
+                    "-k", d + "/kids.txt", "-s", d + "/map.csv", "-c", "chrA", "-o", d + "/out"], check=True)
+    pe = pd.read_csv(d + "/out/probs_errors.csv", index_col=0)
+    assert [int(x) for x in pe.index] == [int(x) for x in g["with_parents"]]
+    assert np.array_equal(pe.to_numpy().astype(np.float16).view(np.uint16), g["probs_errors"])
+    sums = np.loadtxt(d + "/out/individual_sum_probs_errors.csv", delimiter=",", ndmin=1)
+    assert np.array_equal(sums.astype(np.float16).view(np.uint16), g["sums"])

@@ -302,3 +302,31 @@ def test_levels_from_parents_orders_parents_first():
     assert list(off) == [0, 2, 4, 5, 6]                 # founders {0,1}, then {2,3}, {4}, {5}
     with pytest.raises(ValueError):
         levels_from_parents([1, 0], [-1, -1])           # a cycle
+
+
+@pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long"])
+def test_error_checker_host_side_matches_oracle(name):
+    """Trio selection (error_checker.py:138-153) and the float16 transform table (:193-197) of the product's host
+    side against the oracle and the reference's own output; no GPU involved."""
+    from genofix_b200.engine import half_transform_table
+    from genofix_b200.pedigree.error_checker import trio_candidates
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    g = load_golden(name)
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    wp, cand = trio_candidates(ped, g["ids"], g["kids"])
+    owp, ocand = go.trio_candidates(go.OraclePedigree(g["ped_rows"]), g["ids"], g["kids"])
+    assert wp == owp and cand == ocand
+    assert np.array_equal(np.array(wp), g["with_parents"])
+    # table from the histogram of the oracle's scores == transform of the matrix itself
+    row = {int(k): i for i, k in enumerate(g["ids"])}
+    Gc = g["obs"][[row[k] for k in cand]]
+    raw = go.Oracle(g["ped_rows"], cand).mendel_rank(Gc, 2)
+    pat = raw.view(np.uint16).astype(np.int64)
+    hist = np.zeros(65537, dtype=np.uint64)
+    np.add.at(hist, np.where(Gc == 9, 65536, pat).ravel(), 1)
+    table, _m = half_transform_table(hist, -1.0)
+    E = table[np.where(Gc == 9, 0xFFFF, pat)]
+    assert np.array_equal(E.view(np.uint16), go.half_transform(raw, Gc, -1.0).view(np.uint16))
+    pos = {k: i for i, k in enumerate(cand)}
+    assert np.array_equal(E[[pos[k] for k in wp]].view(np.uint16), g["probs_errors"])

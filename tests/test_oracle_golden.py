@@ -76,3 +76,34 @@ def test_kats_empirical_counts_and_windows():
         assert np.array_equal(vals, g["cj_val_%d" % w])
     for n, sur, i, a, b in g["windows"]:
         assert go.ld_window(int(n), int(i), int(sur)) == (int(a), int(b))
+
+
+ERRCHK = ["errchk_a", "errchk_b", "errchk_long"]
+
+
+@pytest.mark.parametrize("name", ERRCHK)
+def test_oracle_error_checker_matches_reference(name):
+    """pedigree/error_checker.py main() run unmodified (oracle/ref_harness.run_error_checker): the selected kids, the
+    float16 probs_errors.csv matrix and individual_sum_probs_errors.csv, bit for bit."""
+    from oracle import genofix_oracle as go
+    g = load_golden(name)
+    wp, _cand, E, sums = go.error_checker(g["ped_rows"], g["ids"], g["obs"], g["kids"])
+    assert np.array_equal(np.array(wp, dtype=np.int64), g["with_parents"])
+    assert np.array_equal(E.view(np.uint16), g["probs_errors"])
+    assert np.array_equal(sums.view(np.uint16), g["sums"])
+
+
+def test_error_checker_golden_pins_the_float16_accumulator():
+    """errchk_long is long enough that the float16 accumulator loses low bits: a float64 sum rounded at the end does
+    not reproduce the reference's file (35 of 36 animals differ), the column-by-column float16 chain does."""
+    from oracle import genofix_oracle as go
+    g = load_golden("errchk_long")
+    E = g["probs_errors"].view(np.float16)
+    ref = g["sums"]
+    wide = E.astype(np.float64).sum(axis=1).astype(np.float16)
+    chain = go.half_rowsum(E)
+    with np.errstate(all="ignore"):
+        wide = wide / np.nanmax(wide)
+        chain = chain / np.nanmax(chain)
+    assert (wide.view(np.uint16) != ref).sum() > 30
+    assert np.array_equal(chain.view(np.uint16), ref)

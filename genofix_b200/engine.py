@@ -171,6 +171,40 @@ def weighted_quantile_linear(values, counts, q):
     return np.float64(_lerp(a, b, gamma))
 
 
+def weighted_nanquantile(values, counts, qs, alpha=0.0, beta=1.0):
+    """np.nanquantile(x, qs, method=...) for x = values repeated counts times, for the continuous methods numpy
+    defines through _compute_virtual_index: (alpha, beta) = (0, 1) is 'interpolated_inverted_cdf'
+    (empirical/preindex.py:270,301); 'linear' uses another index formula, see weighted_quantile_linear.  values keep
+    their dtype: for float16 data numpy subtracts the two neighbouring order statistics in float16 and interpolates in
+    float64 (numpy.lib._function_base_impl._lerp), which is reproduced here.  Returns float64 [len(qs)]."""
+    values = np.asarray(values)
+    counts = np.asarray(counts, dtype=np.int64)
+    keep = (counts > 0) & ~np.isnan(values.astype(np.float64))
+    v, c = values[keep], counts[keep]
+    qs = np.asarray(qs, dtype=np.float64)
+    if len(v) == 0:
+        return np.full(qs.shape, np.nan)
+    order = np.argsort(v.astype(np.float64), kind="stable")
+    v = v[order]
+    cum = np.cumsum(c[order])
+    n = int(cum[-1])
+    vi = n * qs + (alpha + qs * (1 - alpha - beta)) - 1            # _compute_virtual_index
+    lo = np.floor(vi)
+    hi = lo + 1
+    above, below = vi >= n - 1, vi < 0                              # _get_indexes
+    lo[above], hi[above] = n - 1, n - 1
+    lo[below], hi[below] = 0, 0
+    gamma = vi - np.floor(vi)
+    a = v[np.searchsorted(cum, lo.astype(np.int64), side="right")]
+    b = v[np.searchsorted(cum, hi.astype(np.int64), side="right")]
+    with np.errstate(all="ignore"):
+        d = np.subtract(b, a)                                       # in the data dtype
+        r = np.asanyarray(np.add(a, d * gamma), dtype=np.float64)
+        alt = np.subtract(b, d * (1 - gamma))
+        r = np.where(gamma >= 0.5, alt, r)
+    return np.asarray(r, dtype=np.float64)
+
+
 _E_ALL = None
 
 
@@ -574,6 +608,16 @@ class Engine(object):
         return inc.cpu().numpy(), tst.cpu().numpy()
 
 
+    def rank_rowsum_device(self, missing_value=1.0):
+        """float64 sum over the SNPs of this matrix of E (the table of thresholds_device; missing cells count
+        `missing_value`), per animal, on the device: the partial sums a SNP-sharded run all-reduces
+        (`parallel.allreduce_tallies`).  Fixed summation order: repeatable bit for bit."""
+        t = self.torch
+        out = t.empty(self.n, dtype=t.float64, device=self.raw.device)
+        _lib.check(self.L.gfx_rank_rowsum(self.raw.data_ptr(), self.ld_raw, self.packed_orig.data_ptr(), self.wpr, self.n,
+                                          self.s, self.elut.data_ptr(), float(missing_value), out.data_ptr(), self._stream()))
+        return out
+
     # ---- per-animal Mendel tally (error_checker.py:193-204, preindex.py:259-266) -----------------------------
     def mendel_tally(self, G, rows=None, missing_value=-1.0, want_matrix=True):
         """Transformed ranks and their per-animal sums in the reference's float16 arithmetic.
@@ -598,7 +642,9 @@ class Engine(object):
         self._hist_ready = False
         self.host_hist.copy_(self.hist, non_blocking=True)
         t.cuda.current_stream().synchronize()
-        e16, m16 = half_transform_table(self.host_hist.numpy().view(np.uint64), missing_value)
+        self.tally_hist = self.host_hist.numpy().view(np.uint64).copy()      # score patterns present (65536 = missing)
+        e16, m16 = half_transform_table(self.tally_hist, missing_value)
+        self.tally_table = e16
         dev = self.raw.device
         e16_dev = t.from_numpy(e16.view(np.int16)).to(dev)
         if rows is None:

@@ -735,3 +735,68 @@ def error_checker(ped_rows, all_ids, G, kids, missing_value=-1.0, back=2):
         warnings.simplefilter("ignore")
         sums = sums / np.nanmax(sums) if len(sums) else sums  # :202
     return with_parents, cand, Ew, sums
+
+
+# --------------------------------------------------------------------------------------------
+# empirical/preindex.py:166-346: Mendel-filtered LD index per kid-seed chunk and chromosome
+# --------------------------------------------------------------------------------------------
+PREINDEX_SKIP = ("", "0", "-999", "-9")   # preindex.py:198
+
+
+def preindex_chunks(ped, all_ids, seedskidschunk):
+    """preindex.py:166-189: kids with both parents genotyped, in genotype-file order, cut into seed chunks; per chunk
+    the kids plus their genotyped parents (`candidate_kids`)."""
+    genotyped = set(int(x) for x in all_ids)
+    with_parents = [k for k in (int(x) for x in all_ids) if all(p in genotyped for p in ped.parents(k))]
+    n = max(1, seedskidschunk)
+    chunks = [with_parents[i:i + n] for i in range(0, len(with_parents), n)]   # chunk(l, n, 0, 0), :160-163
+    out = []
+    for kid_ids in (c for c in chunks if len(c) > 0):
+        cand = set(kid_ids)
+        for k in kid_ids:
+            cand.update(ped.parents(k))
+        out.append((kid_ids, sorted(cand)))
+    return out
+
+
+def preindex_chunk(ped_rows, all_ids, G, cand, chrom_cols, surround, init_filter_p, pseudocount=1e-4, back=2):
+    """One seed chunk of preindex.py (:191-346).  chrom_cols: {chromosome name: column indices in map order}.
+    The animals evaluated are the candidates whose sire and dam are candidates too (:216-223) and the Mendel ranks see
+    ONLY those animals as genotyped (:224).  The rank quantiles are taken on the first chromosome of the chunk and
+    reused for the others (:301-302).  Returns {chromosome: dict(eval_ids, quantQ, n_unmasked, sums, freq)} with
+    freq[i] = float64 [3^w_i] of SNP i's window in state-product order (empty windows: zero-length)."""
+    ped = ped_rows if isinstance(ped_rows, OraclePedigree) else OraclePedigree(ped_rows)
+    row_all = {int(k): i for i, k in enumerate(all_ids)}
+    cset = set(cand)
+    eval_ids = sorted(k for k in cand if all(p in cset for p in ped.parents(k)))
+    G = np.asarray(G)
+    quants = None
+    out = {}
+    for chrom in sorted(chrom_cols):
+        cols = list(chrom_cols[chrom])
+        if chrom in PREINDEX_SKIP or len(cols) < 2:
+            continue
+        Ge = G[[row_all[k] for k in eval_ids]][:, cols]
+        raw = Oracle(ped, eval_ids).mendel_rank(Ge, back)                        # :230-253
+        E = half_transform(raw, Ge, 1.0)                                         # :259-263
+        sums = half_rowsum(E)                                                    # :265-266
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sums = sums / np.nanmax(sums)
+            if quants is None:
+                quants = np.nanquantile(E.flatten(), [0.95, 0.99, init_filter_p], method="interpolated_inverted_cdf")
+        quantQ = quants[2]
+        mask = np.array(E <= quantQ, dtype=bool)                                 # :331
+        S = len(cols)
+        freq = []
+        for i in range(S):                                                       # jalleledist3.py:143-174
+            a, b = ld_window(S, i, surround)
+            w = max(b - a, 0)
+            if w == 0:
+                freq.append(np.zeros(0))
+                continue
+            res = count_joint_frq(Ge[:, a:b], mask[:, a:b], w, pseudocount)
+            freq.append(np.array([res[v] for v in itertools.product([0, 1, 2], repeat=w)]))
+        out[chrom] = dict(eval_ids=eval_ids, quantQ=quantQ, quants=quants, n_unmasked=int(np.count_nonzero(mask)),
+                          sums=sums, freq=freq)
+    return out

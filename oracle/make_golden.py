@@ -134,6 +134,41 @@ def make_errchk(name):
     print("%s: %d animals x %d SNPs, %d trio kids, reference %.1f s" % (name, len(ids), obs.shape[1],
                                                                        len(r["with_parents"]), dt))
 
+
+# empirical/preindex.py main(): Mendel-filtered LD index (quantile cut, mask, window frequencies)
+PREIDX_CASES = {
+    "preidx_a": dict(ped=dict(n_animals=60, n_generations=5, sire_frac=0.3, dam_frac=0.6, seed=7),
+                     n_snps=30, err=0.03, miss=0.03, drop=0.0, surround=1, q=0.9, seed_chunk=10000, split=15),
+    "preidx_b": dict(ped=dict(n_animals=96, n_generations=6, sire_frac=0.25, dam_frac=0.5, seed=11,
+                              related_mating_p=0.6, unknown_parents_frac=0.1),
+                     n_snps=40, err=0.05, miss=0.05, drop=0.12, surround=2, q=0.8, seed_chunk=10000, split=22),
+}
+
+
+def make_preidx(name):
+    case = PREIDX_CASES[name]
+    ped_rows, ids, truth, obs = build_inputs(case)
+    chrom = ["chrA" if i < case["split"] else "chrB" for i in range(case["n_snps"])]
+    t0 = time.time()
+    res, stdout = rh.run_preindex(ped_rows, ids, obs, chrom, surround=case["surround"], init_filter_p=case["q"],
+                                  seedskidschunk=case["seed_chunk"])
+    dt = time.time() - t0
+    cut = [float(x) for x in re.findall(r"cuttoff [0-9.]+-quantile = (\S+)", stdout)]
+    kept = [(int(a), int(b)) for a, b in re.findall(r"calc empirical ld on genotype with (\d+) of (\d+)", stdout)]
+    arrays = {}
+    for ci, c in enumerate(sorted(res)):
+        w = max(len(f) for f in res[c]["freq"])
+        tab = np.full((len(res[c]["freq"]), w), np.nan)
+        for i, f in enumerate(res[c]["freq"]):
+            tab[i, :len(f)] = f
+        arrays["freq_" + c] = tab
+        arrays["wlen_" + c] = np.array([len(x) for x in res[c]["windows"]])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ped_rows=ped_rows, ids=ids, obs=obs.astype(np.uint8),
+                        chrom=np.array(chrom), surround=case["surround"], q=case["q"], seed_chunk=case["seed_chunk"],
+                        quantQ=np.array(cut), kept=np.array(kept), chroms=np.array(sorted(res)),
+                        reference_seconds=dt, **arrays)
+    print("%s: %d animals x %d SNPs, cut %s, kept %s, reference %.1f s" % (name, len(ids), obs.shape[1], cut, kept, dt))
+
 def make_case(name):
     case = CASES[name]
     ped_rows, ids, truth, obs = build_inputs(case)
@@ -254,11 +289,13 @@ def make_kats():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    names = sys.argv[1:] or ["kats"] + list(CASES) + list(ERRCHK_CASES)
+    names = sys.argv[1:] or ["kats"] + list(CASES) + list(ERRCHK_CASES) + list(PREIDX_CASES)
     for n in names:
         if n == "kats":
             make_kats()
         elif n in ERRCHK_CASES:
             make_errchk(n)
+        elif n in PREIDX_CASES:
+            make_preidx(n)
         else:
             make_case(n)

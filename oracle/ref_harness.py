@@ -257,3 +257,63 @@ def run_error_checker(ped_rows, ids, obs, kids, chrom="chrA", quiet=True):
     assert np.array_equal(s16.astype(np.float64), sums, equal_nan=True)
     return dict(with_parents=np.array([int(x) for x in pe.index], dtype=np.int64), probs_errors=pe16, sums=s16,
                 stdout=buf.getvalue())
+
+
+def run_preindex(ped_rows, ids, obs, chrom_of_snp, surround=1, init_filter_p=0.9, seedskidschunk=10000, quiet=True):
+    """Run the reference's empirical/preindex.py main() (:59-346) on files written from the arrays (same file
+    conventions as run_error_checker; the map file has no header and columns chrom,snpid,cM,pos, :141).
+    Returns {chromosome: dict(snps, windows, freq=list of float64 arrays in state-product order)} read back from the
+    pickled indexes, plus the stdout (quantiles and mask counts are only printed)."""
+    load()
+    import gzip
+    import itertools
+    import cloudpickle
+    import empirical.preindex as pi
+    S = obs.shape[1]
+    snps = ["SNP%d" % i for i in range(S)]
+    buf = io.StringIO()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        with open(d + "/gens.txt", "w") as f:
+            f.write("id " + " ".join(snps) + " pad\n")
+            for k, row in zip(ids, obs):
+                f.write(str(int(k)) + " " + " ".join(str(int(x)) for x in row) + " 0\n")
+        with open(d + "/ped.txt", "w") as f:
+            for r in ped_rows:
+                f.write(" ".join(str(int(x)) for x in r[:4]) + "\n")
+        with open(d + "/map.csv", "w") as f:
+            for i, s in enumerate(snps):
+                f.write("%s,%s,0,%d\n" % (chrom_of_snp[i], s, 100 * i + 1))
+            f.write("0,pad,0,1\n")          # chromosome "0" is skipped (:198)
+        argv0 = sys.argv
+        main_mod = sys.modules["__main__"]
+        doc0 = getattr(main_mod, "__doc__", None)
+        if not doc0:
+            main_mod.__doc__ = "harness\npreindex driver\n"
+        sys.argv = ["preindex.py", "-g", d + "/gens.txt", "-p", d + "/ped.txt", "-s", d + "/map.csv", "-w", str(surround),
+                    "-T", "1", "-q", str(init_filter_p), "-c", str(seedskidschunk), "-o", d + "/out"]
+        try:
+            import warnings
+            ctx = contextlib.redirect_stdout(buf) if quiet else contextlib.nullcontext()
+            with deterministic_pools(), ctx, contextlib.redirect_stderr(io.StringIO()), np.errstate(all="ignore"), \
+                    warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                pi.main()
+        finally:
+            sys.argv = argv0
+            main_mod.__doc__ = doc0
+        for chrom in sorted(set(chrom_of_snp)):
+            path = d + "/out/%s/empiricalIndex.idx.gz" % chrom
+            if not os.path.exists(path):
+                continue
+            with gzip.open(path, "rb") as f:
+                e = cloudpickle.load(f)
+            names = list(e.snp_ordered)
+            freq = []
+            for s in names:
+                win = e.windows[s]
+                tab = e.snp2frequency[s]
+                freq.append(np.array([tab[tuple(zip(win, v))] for v in itertools.product([0, 1, 2], repeat=len(win))]
+                                     if len(win) else [], dtype=np.float64))
+            out[chrom] = dict(snps=names, windows=[list(e.windows[s]) for s in names], freq=freq)
+    return out, buf.getvalue()

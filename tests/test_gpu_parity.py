@@ -598,3 +598,138 @@ def test_error_checker_cli_writes_the_reference_files(tmp_path):
     assert np.array_equal(pe.to_numpy().astype(np.float16).view(np.uint16), g["probs_errors"])
     sums = np.loadtxt(d + "/out/individual_sum_probs_errors.csv", delimiter=",", ndmin=1)
     assert np.array_equal(sums.astype(np.float16).view(np.uint16), g["sums"])
+
+
+def test_rank_rowsum_float64_partial_sums():
+    """gfx_rank_rowsum: per-animal float64 sums of E (the quantity SNP-sharded ranks all-reduce) against
+    numpy on the same E matrix to 1e-12 relative and repeatable bit for bit."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    rows = synth.make_pedigree(1200, 6, sire_frac=0.1, dam_frac=0.5, seed=9)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 1003, seed=2), 0.02, seed=3), 0.03, seed=4)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    for mv in (1.0, -1.0):
+        a = eng.rank_rowsum_device(mv).cpu().numpy()
+        b = eng.rank_rowsum_device(mv).cpu().numpy()
+        assert np.array_equal(a, b, equal_nan=True)
+        E = eng.E_host()
+        E[obs == 9] = mv
+        ref = E.sum(axis=1)
+        nan = np.isnan(ref)           # half-sib matings give loopy blankets: contradictory evidence there is a NaN rank (D16)
+        assert np.array_equal(np.isnan(a), nan)
+        assert np.all(np.abs(a[~nan] - ref[~nan]) <= 1e-12 * np.maximum(1.0, np.abs(ref[~nan])))
+    assert (~nan).sum() > 600 and float(np.nanmax(a)) > 0
+
+
+# ---- empirical/preindex.py: Mendel-filtered LD index ----------------------------------------------------------------
+def _preidx_inputs(g, cand):
+    import pandas as pd
+    row = {int(k): i for i, k in enumerate(g["ids"])}
+    names = ["SNP%d" % i for i in range(g["obs"].shape[1])]
+    df = pd.DataFrame(g["obs"][[row[k] for k in cand]], index=cand, columns=names)
+    c2s = {"0": ["pad"]}
+    for n, c in zip(names, g["chrom"]):
+        c2s.setdefault(str(c), []).append(n)
+    return df, c2s
+
+
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+def test_preindex_matches_reference_golden(name):
+    """The indexes the UNMODIFIED reference pickled (preindex.py:339-346): rank cut, cells under the cut and every
+    window frequency, bit for bit: k_mendel_rank<HIST> -> histogram quantile -> mask -> k_window_counts."""
+    from genofix_b200.empirical.preindex import index_chunk, seed_chunks
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    g = load_golden(name)
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    chunks = seed_chunks(ped, g["ids"], int(g["seed_chunk"]))
+    assert len(chunks) == 1
+    df, c2s = _preidx_inputs(g, chunks[0][1])
+    res = index_chunk(df, ped, c2s, int(g["surround"]), float(g["q"]))
+    assert sorted(res) == [str(c) for c in g["chroms"]]
+    for ci, c in enumerate(sorted(res)):
+        empC, info = res[c]
+        assert info["quantQ"] == g["quantQ"][ci]
+        assert (info["n_unmasked"], len(info["eval_ids"]) * len(c2s[c])) == tuple(g["kept"][ci])
+        for i, s in enumerate(empC.snp_ordered):
+            w = int(g["wlen_" + c][i])
+            assert len(empC.windows[s]) == w
+            if w:
+                assert np.array_equal(empC._freq[s], g["freq_" + c][i][:3 ** w])
+
+
+def test_preindex_matches_oracle_on_several_seed_chunks():
+    """Seeded pedigree cut into seed chunks of 60 kids, three chromosomes of different length (one below the
+    2-SNP minimum), surround 3 (7-SNP windows): every chunk's index against the oracle."""
+    from genofix_b200 import synth
+    from genofix_b200.empirical.preindex import index_chunk, seed_chunks
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    import pandas as pd
+    rows = synth.make_pedigree(240, 6, sire_frac=0.2, dam_frac=0.5, seed=77, related_mating_p=0.2)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 41, seed=8), 0.05, seed=9), 0.03, seed=10)
+    ids = rows[:, 0]
+    names = ["S%d" % i for i in range(41)]
+    chrom = ["2"] * 24 + ["10"] * 16 + ["7"]
+    cc, c2s = {}, {}
+    for i, c in enumerate(chrom):
+        cc.setdefault(c, []).append(i)
+        c2s.setdefault(c, []).append(names[i])
+    ped = PedigreeDAG.from_table(rows)
+    oped = go.OraclePedigree(rows)
+    chunks = seed_chunks(ped, ids, 60)
+    assert len(chunks) >= 3 and chunks == go.preindex_chunks(oped, ids, 60)
+    row = {int(k): i for i, k in enumerate(ids)}
+    for kid_ids, cand in chunks[:3]:
+        df = pd.DataFrame(obs[[row[k] for k in cand]], index=cand, columns=names)
+        res = index_chunk(df, ped, c2s, 3, 0.85)
+        ref = go.preindex_chunk(oped, ids, obs, cand, cc, 3, 0.85)
+        assert sorted(res) == sorted(ref) == ["10", "2"]
+        for c in res:
+            empC, info = res[c]
+            assert info["eval_ids"] == ref[c]["eval_ids"]
+            assert info["quantQ"] == ref[c]["quantQ"] and info["n_unmasked"] == ref[c]["n_unmasked"]
+            assert np.array_equal(info["individualSumProbs"].view(np.uint16), ref[c]["sums"].view(np.uint16))
+            for i, s in enumerate(empC.snp_ordered):
+                f = ref[c]["freq"][i]
+                assert len(empC.windows[s]) == (0 if len(f) == 0 else round(np.log(len(f)) / np.log(3)))
+                if len(f):
+                    assert np.array_equal(empC._freq[s], f)
+
+
+def test_preindex_cli_writes_the_reference_indexes(tmp_path):
+    """src/empirical/preindex.py with the reference's command line; the pickled indexes hold the golden frequencies."""
+    import gzip
+    import pickle
+    import subprocess
+    import sys
+    from conftest import ROOT
+    g = load_golden("preidx_a")
+    d = str(tmp_path)
+    S = g["obs"].shape[1]
+    snps = ["SNP%d" % i for i in range(S)]
+    with open(d + "/gens.txt", "w") as f:
+        f.write("id " + " ".join(snps) + " pad\n")
+        for k, r in zip(g["ids"], g["obs"]):
+            f.write(str(int(k)) + " " + " ".join(str(int(x)) for x in r) + " 0\n")
+    with open(d + "/ped.txt", "w") as f:
+        for r in g["ped_rows"]:
+            f.write(" ".join(str(int(x)) for x in r[:4]) + "\n")
+    with open(d + "/map.csv", "w") as f:
+        for i, s in enumerate(snps):
+            f.write("%s,%s,0,%d\n" % (g["chrom"][i], s, 100 * i + 1))
+        f.write("0,pad,0,1\n")
+    subprocess.run([sys.executable, ROOT + "/src/empirical/preindex.py", "-g", d + "/gens.txt", "-p", d + "/ped.txt",
+                    "-s", d + "/map.csv", "-w", str(int(g["surround"])), "-q", str(float(g["q"])), "-o", d + "/out"], check=True)
+    for c in (str(x) for x in g["chroms"]):
+        with gzip.open(d + "/out/%s/empiricalIndex.idx.gz" % c, "rb") as f:
+            empC = pickle.load(f)
+        for i, s in enumerate(empC.snp_ordered):
+            w = int(g["wlen_" + c][i])
+            assert len(empC.windows[s]) == w
+            if w:
+                tab = empC.snp2frequency[s]
+                import itertools
+                vals = np.array([tab[tuple(zip(empC.windows[s], v))] for v in itertools.product([0, 1, 2], repeat=w)])
+                assert np.array_equal(vals, g["freq_" + c][i][:3 ** w])

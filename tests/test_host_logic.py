@@ -330,3 +330,32 @@ def test_error_checker_host_side_matches_oracle(name):
     assert np.array_equal(E.view(np.uint16), go.half_transform(raw, Gc, -1.0).view(np.uint16))
     pos = {k: i for i, k in enumerate(cand)}
     assert np.array_equal(E[[pos[k] for k in wp]].view(np.uint16), g["probs_errors"])
+
+
+def test_weighted_nanquantile_is_numpy_nanquantile_on_float16():
+    """preindex.py:270,301: np.nanquantile(float16 data, q, method='interpolated_inverted_cdf') from a histogram of the
+    values, bit for bit (numpy subtracts the neighbours in float16 and interpolates in float64)."""
+    import warnings
+    from genofix_b200.engine import weighted_nanquantile
+    rs = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rs.integers(1, 400))
+        x = rs.choice(rs.random(int(rs.integers(1, 12))).astype(np.float16), size=n)
+        if trial % 5 == 0:
+            x[rs.integers(0, n)] = np.nan
+        qs = [0.95, 0.99, float(rs.random())]
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = np.nanquantile(x, qs, method="interpolated_inverted_cdf")
+        vals, cnt = np.unique(x.view(np.uint16), return_counts=True)
+        got = weighted_nanquantile(vals.view(np.float16), cnt, qs, 0.0, 1.0)
+        assert np.array_equal(ref, got, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+def test_preindex_seed_chunks_match_oracle(name):
+    from genofix_b200.empirical.preindex import seed_chunks
+    g = load_golden(name)
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    for size in (10000, 7, 1):
+        assert seed_chunks(ped, g["ids"], size) == go.preindex_chunks(go.OraclePedigree(g["ped_rows"]), g["ids"], size)

@@ -107,3 +107,32 @@ def test_error_checker_golden_pins_the_float16_accumulator():
         chain = chain / np.nanmax(chain)
     assert (wide.view(np.uint16) != ref).sum() > 30
     assert np.array_equal(chain.view(np.uint16), ref)
+
+
+def _chrom_cols(g):
+    cc = {}
+    for i, c in enumerate(g["chrom"]):
+        cc.setdefault(str(c), []).append(i)
+    return cc
+
+
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+def test_oracle_preindex_matches_reference(name):
+    """empirical/preindex.py main() run unmodified (oracle/ref_harness.run_preindex): the rank cut it printed, the
+    number of cells under the cut and every window frequency of the pickled indexes, bit for bit."""
+    from oracle import genofix_oracle as go
+    g = load_golden(name)
+    ped = go.OraclePedigree(g["ped_rows"])
+    chunks = go.preindex_chunks(ped, g["ids"], int(g["seed_chunk"]))
+    assert len(chunks) == 1
+    res = go.preindex_chunk(ped, g["ids"], g["obs"], chunks[0][1], _chrom_cols(g), int(g["surround"]), float(g["q"]))
+    assert sorted(res) == [str(c) for c in g["chroms"]]
+    for ci, c in enumerate(sorted(res)):
+        r = res[c]
+        assert r["quantQ"] == g["quantQ"][ci]
+        assert r["n_unmasked"] == g["kept"][ci][0]
+        assert len(r["eval_ids"]) * len(_chrom_cols(g)[c]) == g["kept"][ci][1]
+        for i, f in enumerate(r["freq"]):
+            w = int(g["wlen_" + c][i])
+            assert len(f) == (3 ** w if w else 0)
+            assert np.array_equal(f, g["freq_" + c][i][:len(f)])

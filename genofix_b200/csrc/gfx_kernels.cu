@@ -438,8 +438,11 @@ struct RankArgs {
   unsigned long long* hist;   // 65537 bins or nullptr (HIST = false)
 };
 
+// 896 threads per SM: ptxas gets 72 registers instead of 64, which ends the spilling of the prefetched words and the
+// per-step re-derivation of the row pointers (1024 threads: 100.3 us per 10k x 10k chunk, 896: 93.1 us; 768: 94.0 us;
+// 640 / 512: 99.8 / 103.5 us -- profiles/r1_rank_variants_{a,b}.jsonl)
 #ifndef R2_THREADS
-#define R2_THREADS 1024
+#define R2_THREADS 896
 #endif
 // words per task by number of children of the row (measured at 10k x 10k and 100k x 4096)
 #ifndef R2_WORDS_HEAVY
@@ -605,7 +608,10 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
   r2_store(a.raw + row * a.ld_raw + w * 16, outw);
 }
 
+#ifndef R2_CTAS
 #define R2_CTAS (R2_THREADS <= 512 ? 2 : 1)
+#endif
+#define R2_DYN_SMEM (R2_SMEM + 16u)
 template <bool HIST>
 __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a) {
   extern __shared__ __align__(16) char smem[];
@@ -669,6 +675,8 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
       const uint32_t* prow0 = a.packed + (int64_t)row * a.wpr;
       const uint32_t* prowS = a.packed + (int64_t)(parents_ok ? rS : row) * a.wpr;
       const uint32_t* prowD = a.packed + (int64_t)(parents_ok ? rD : row) * a.wpr;
+      // keep the three row pointers live: without this ptxas re-derives them (six 64-bit products) every warp step
+      asm volatile("" : "+l"(prow0), "+l"(prowS), "+l"(prowD));
       int wn = wbeg + lane;
       uint32_t n0 = 0, nS = 0, nD = 0;
       if (wn < wend) { n0 = __ldg(prow0 + wn); nS = __ldg(prowS + wn); nD = __ldg(prowD + wn); }
@@ -1372,15 +1380,15 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
              s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist};
   static bool attr_set = false;
   if (!attr_set) {
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM + 16));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM));
+    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM));
     attr_set = true;
   }
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
   int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
   if (blocks < 1) blocks = 1;
-  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);
-  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_SMEM + 16, stream>>>(a);
+  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
+  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,

@@ -608,6 +608,19 @@ class Engine(object):
         return inc.cpu().numpy(), tst.cpu().numpy()
 
 
+    def load_host(self, G):
+        """Upload a uint8 [n, s] host matrix (0,1,2,9) and pack it (the first lines of `correct()`)."""
+        G = np.asarray(G)
+        if G.ndim != 2 or G.shape[0] != self.n:
+            raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+        self._alloc(G.shape[1])
+        hin = self.host_in.numpy()
+        _parallel_copy(hin[:, :self.s], G)
+        if self.ldc > self.s:
+            hin[:, self.s:] = 9
+        self.codes.copy_(self.host_in, non_blocking=True)
+        self.load_codes_device(self.codes)
+
     def rank_rowsum_device(self, missing_value=1.0):
         """float64 sum over the SNPs of this matrix of E (the table of thresholds_device; missing cells count
         `missing_value`), per animal, on the device: the partial sums a SNP-sharded run all-reduces

@@ -55,3 +55,29 @@ def correct_sharded(n_snps, chunk_snps, correct_chunk, n_animals, rank=0, world=
         tall += torch.as_tensor(np.asarray(t, dtype=np.int64), device=device)
     allreduce_tallies(tall)
     return out, tall
+
+
+def mendel_tally_sharded(n_chunks, hist_of_chunk, rowsum_of_chunk, table_from_hist, n_animals, rank=0, world=1, device="cpu"):
+    """Per-animal Mendel tally (error_checker.py:193-204) of a matrix whose SNP chunks are dealt round-robin to ranks.
+    Unlike the correction path, the rank transform here is normalised by the maximum over the WHOLE matrix, so the
+    chunk-local state is exchanged twice ("if chunks had to be split"):
+      1. all-reduce (sum) of the 65 537-bin histogram of score patterns -> every rank builds the same transform table
+         (`table_from_hist(hist)`, exact: the table depends on the set of patterns present only);
+      2. all-reduce (sum) of the float64 partial row sums (`rowsum_of_chunk(ci, table)` -> float64 [n_animals]).
+    The float16 accumulation chain of the single-GPU form (`gfx_rank_rowsum_f16`) is order dependent and cannot be
+    sharded; the sharded tally is the float64 sum, identical on every rank and independent of the number of ranks up to
+    the rounding of a sum of `world` partial sums (compare to 1e-12 relative).
+    Returns (global histogram int64 [65537] numpy, row sums float64 [n_animals] numpy)."""
+    import torch
+    mine = chunks_for_rank(n_chunks, rank, world)
+    hist = torch.zeros(65537, dtype=torch.int64, device=device)
+    for ci in mine:
+        hist += torch.as_tensor(np.asarray(hist_of_chunk(ci)).astype(np.int64), device=device)
+    allreduce_tallies(hist)
+    hist_np = hist.cpu().numpy()
+    table = table_from_hist(hist_np)
+    sums = torch.zeros(n_animals, dtype=torch.float64, device=device)
+    for ci in mine:
+        sums += torch.as_tensor(np.asarray(rowsum_of_chunk(ci, table), dtype=np.float64), device=device)
+    allreduce_tallies(sums)
+    return hist_np, sums.cpu().numpy()

@@ -84,3 +84,70 @@ def test_chunks_for_rank_partition():
             flat = sorted(x for o in owned for x in o)
             assert flat == list(range(n))
             assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+
+
+def _tally_inputs():
+    from genofix_b200 import synth
+    from oracle.genofix_oracle import Oracle
+    rows = synth.make_pedigree(90, 5, sire_frac=0.3, dam_frac=0.6, seed=12)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 44, seed=6), 0.05, seed=7), 0.04, seed=8)
+    raw = Oracle(rows, rows[:, 0]).mendel_rank(obs, 2)          # stands in for k_mendel_rank
+    chunks = [list(range(i, min(i + 8, 44))) for i in range(0, 44, 8)]
+    return obs, raw, chunks
+
+
+def _tally_callbacks(obs, raw, chunks):
+    from genofix_b200.engine import rank_transform_table
+
+    def hist_of_chunk(ci):
+        cols = chunks[ci]
+        pat = np.where(obs[:, cols] == 9, 65536, raw[:, cols].view(np.uint16).astype(np.int64))
+        return np.bincount(pat.ravel(), minlength=65537)
+
+    def table_from_hist(hist):
+        return rank_transform_table(hist.astype(np.uint64), 0.9)[0]     # float64 E of every score pattern
+
+    def rowsum_of_chunk(ci, table):
+        cols = chunks[ci]
+        E = table[raw[:, cols].view(np.uint16)]
+        E[obs[:, cols] == 9] = -1.0                                     # error_checker.py:196-197
+        return E.sum(axis=1)
+    return hist_of_chunk, rowsum_of_chunk, table_from_hist
+
+
+def _tally_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from genofix_b200 import parallel
+    r, w = parallel.init_from_env("gloo")
+    obs, raw, chunks = _tally_inputs()
+    h, rs, tf = _tally_callbacks(obs, raw, chunks)
+    hist, sums = parallel.mendel_tally_sharded(len(chunks), h, rs, tf, obs.shape[0], r, w)
+    np.savez(os.path.join(tmp, "tally%d.npz" % r), hist=hist, sums=sums)
+    import torch.distributed as dist
+    dist.destroy_process_group()
+
+
+def test_two_rank_mendel_tally_matches_single_process(tmp_path):
+    """The error_checker tally over SNP shards: histogram all-reduce -> one transform table, row-sum all-reduce."""
+    port = _free_port()
+    mp.spawn(_tally_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, ROOT)
+    from genofix_b200 import parallel
+    from oracle import genofix_oracle as go
+    obs, raw, chunks = _tally_inputs()
+    h, rs, tf = _tally_callbacks(obs, raw, chunks)
+    hist1, sums1 = parallel.mendel_tally_sharded(len(chunks), h, rs, tf, obs.shape[0], 0, 1)
+    z = [np.load(os.path.join(str(tmp_path), "tally%d.npz" % r)) for r in range(2)]
+    assert np.array_equal(z[0]["hist"], z[1]["hist"]) and np.array_equal(z[0]["hist"], hist1)
+    assert np.array_equal(z[0]["sums"], z[1]["sums"])                    # all-reduced: identical on every rank
+    assert np.allclose(z[0]["sums"], sums1, rtol=1e-12, atol=0)
+    # against the whole-matrix float64 transform (what error_checker.py computes, in float64 instead of float16)
+    with np.errstate(all="ignore"):
+        E = np.log(np.log(raw.astype(np.float64) + 1) + 1)
+        E = E / np.nanmax(E)
+    E[obs == 9] = -1.0
+    assert np.allclose(sums1, E.sum(axis=1), rtol=1e-12, atol=0)
+    # and it ranks the animals like the reference's float16 tally does, up to float16 resolution
+    half = go.half_rowsum(go.half_transform(raw, obs, -1.0)).astype(np.float64)
+    assert np.max(np.abs(half - sums1)) < 0.05 * max(1.0, np.max(np.abs(sums1)))

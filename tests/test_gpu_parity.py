@@ -786,3 +786,28 @@ def test_static_call_surface_matches_oracle():
             assert _log_close(got.prob[names[j]], p)
             checked += 1
     assert checked > 50
+
+
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a B200")
+def test_sharded_error_tally_single_rank_matches_float64_oracle():
+    """mendel_error_tally_sharded with world = 1 and 7-SNP chunks (histogram pass, table, row-sum pass) against the
+    float64 form of error_checker.py:193-204 computed from the oracle's scores."""
+    from genofix_b200.pedigree.error_checker import mendel_error_tally_sharded
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    g = load_golden("errchk_b")
+    wp, sums = mendel_error_tally_sharded(_errchk_frame(g), PedigreeDAG.from_table(g["ped_rows"]), g["kids"], chunk_snps=7)
+    assert [int(x) for x in wp] == [int(x) for x in g["with_parents"]]
+    oped = go.OraclePedigree(g["ped_rows"])
+    owp, cand = go.trio_candidates(oped, g["ids"], g["kids"])
+    row = {int(k): i for i, k in enumerate(g["ids"])}
+    Gc = g["obs"][[row[k] for k in cand]]
+    raw = go.Oracle(oped, cand).mendel_rank(Gc, 2)
+    with np.errstate(all="ignore"):
+        E = np.log(np.log(raw.astype(np.float64) + 1) + 1)
+        E = E / np.nanmax(E)
+    E[Gc == 9] = -1.0
+    pos = {k: i for i, k in enumerate(cand)}
+    ref = E[[pos[k] for k in owp]].sum(axis=1)
+    ref = ref / np.nanmax(ref)
+    assert np.allclose(sums, ref, rtol=1e-12, atol=1e-15)

@@ -255,7 +255,11 @@ class CorrectGenotypes(object):
         ids = list(cur.genotypes.index)
         r = ids.index(kid)
         if r not in posts:
-            raise KeyError("%s is part of a mating pair; use correctPair" % kid)
+            if r in set(int(x) for x in eng.schedule.array(0)):
+                raise KeyError("%s is part of a mating pair; use correctPair" % kid)
+            # neither ancestors nor genotyped children: the reference prints "illegal lone node" and returns None (:417-419)
+            print("WARN: %s is an illegal lone node in the pedigree graph" % kid)
+            return None
         p, valid = posts[r]
         sus = np.nonzero(valid)[0]
         if len(sus) == 0:

@@ -771,7 +771,7 @@ def test_static_call_surface_matches_oracle():
         assert (ref is None) == (got is None)
         if ref is None:
             continue
-        assert sorted(got.prob_sire.keys()) == [names[j] for j in sorted(ref)]
+        assert set(got.prob_sire.keys()) == set(names[j] for j in ref)
         for j, (ps, pd_, _ops, _opd) in ref.items():
             assert _log_close(got.prob_sire[names[j]], ps) and _log_close(got.prob_dam[names[j]], pd_)
             checked += 1
@@ -782,7 +782,7 @@ def test_static_call_surface_matches_oracle():
         assert (ref is None) == (got is None)
         if ref is None:
             continue
-        assert sorted(got.prob.keys()) == [names[j] for j in sorted(ref)]
+        assert set(got.prob.keys()) == set(names[j] for j in ref)
         for j, (p, _op) in ref.items():
             assert _log_close(got.prob[names[j]], p)
             checked += 1

@@ -1,0 +1,80 @@
+"""Host logic of the two callers around the path -- pedigree/error_checker.py (mendel_error_tally) and
+empirical/preindex.py (index_chunk) -- on CPU against the outputs of the UNMODIFIED reference (tests/golden/errchk_*.npz,
+preidx_*.npz).  The two device calls (Engine.mendel_tally, window_counts_device) are replaced by oracle-backed stand-ins,
+so what is checked is the product's Python: trio selection, candidate restriction, the float16 transform table, the
+histogram quantile, the mask and the window bookkeeping.  The same fixtures run against the real kernels in
+tests/test_gpu_parity.py."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden
+from genofix_b200.engine import half_transform_table
+from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+from oracle import genofix_oracle as go
+
+
+def _stand_in_engine(ped_rows):
+    class StandIn(object):
+        def __init__(self, ped, ids, back):
+            self.ids, self.back = [int(x) for x in ids], back
+
+        def mendel_tally(self, G, rows, missing_value, want_matrix=True):
+            raw = go.Oracle(ped_rows, self.ids).mendel_rank(G, self.back)          # stands in for k_mendel_rank<HIST>
+            pat = raw.view(np.uint16).astype(np.int64)
+            self.tally_hist = np.bincount(np.where(G == 9, 65536, pat).ravel(), minlength=65537).astype(np.uint64)
+            self.tally_table, m = half_transform_table(self.tally_hist, missing_value)
+            E = self.tally_table[np.where(G == 9, 0xFFFF, pat)]
+            E = E if rows is None else E[rows]
+            return E, go.half_rowsum(E), m                                       # stands in for k_rank_rowsum_f16
+    return StandIn
+
+
+def _stand_in_window_counts(G, mask, starts, lens):
+    out = np.zeros((len(starts), 3 ** max(lens)), np.int64)                       # stands in for k_window_counts
+    for i, (a, w) in enumerate(zip(starts, lens)):
+        sub = G[:, a:a + w]
+        ok = mask[:, a:a + w].all(axis=1) & (sub <= 2).all(axis=1)
+        idx = (sub[ok].astype(np.int64) * (3 ** np.arange(w - 1, -1, -1))).sum(axis=1)
+        np.add.at(out[i], idx, 1)
+    return out
+
+
+@pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long"])
+def test_error_checker_host_logic_reproduces_reference_files(name, monkeypatch):
+    import genofix_b200.pedigree.error_checker as ec
+    g = load_golden(name)
+    monkeypatch.setattr(ec, "Engine", _stand_in_engine(g["ped_rows"]))
+    df = pd.DataFrame(g["obs"], index=[int(x) for x in g["ids"]], columns=["SNP%d" % i for i in range(g["obs"].shape[1])])
+    pe, sums = ec.mendel_error_tally(df, PedigreeDAG.from_table(g["ped_rows"]), g["kids"])
+    assert [int(x) for x in pe.index] == [int(x) for x in g["with_parents"]]
+    assert np.array_equal(pe.to_numpy().view(np.uint16), g["probs_errors"])
+    assert np.array_equal(sums.view(np.uint16), g["sums"])
+
+
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+def test_preindex_host_logic_reproduces_reference_indexes(name, monkeypatch):
+    import genofix_b200.empirical.jalleledist3 as jd
+    import genofix_b200.empirical.preindex as pp
+    g = load_golden(name)
+    monkeypatch.setattr(pp, "Engine", _stand_in_engine(g["ped_rows"]))
+    monkeypatch.setattr(jd, "window_counts_device", _stand_in_window_counts)
+    ped = PedigreeDAG.from_table(g["ped_rows"])
+    (kid_ids, cand), = pp.seed_chunks(ped, g["ids"], int(g["seed_chunk"]))
+    row = {int(k): i for i, k in enumerate(g["ids"])}
+    names = ["SNP%d" % i for i in range(g["obs"].shape[1])]
+    df = pd.DataFrame(g["obs"][[row[k] for k in cand]], index=cand, columns=names)
+    c2s = {"0": ["pad"]}
+    for n, c in zip(names, g["chrom"]):
+        c2s.setdefault(str(c), []).append(n)
+    res = pp.index_chunk(df, ped, c2s, int(g["surround"]), float(g["q"]))
+    assert sorted(res) == [str(c) for c in g["chroms"]]
+    for ci, c in enumerate(sorted(res)):
+        empC, info = res[c]
+        assert info["quantQ"] == g["quantQ"][ci]
+        assert (info["n_unmasked"], len(info["eval_ids"]) * len(c2s[c])) == tuple(g["kept"][ci])
+        for i, s in enumerate(empC.snp_ordered):
+            w = int(g["wlen_" + c][i])
+            assert len(empC.windows[s]) == w
+            if w:
+                assert np.array_equal(empC._freq[s], g["freq_" + c][i][:3 ** w])

@@ -142,6 +142,9 @@ PREIDX_CASES = {
     "preidx_b": dict(ped=dict(n_animals=96, n_generations=6, sire_frac=0.25, dam_frac=0.5, seed=11,
                               related_mating_p=0.6, unknown_parents_frac=0.1),
                      n_snps=40, err=0.05, miss=0.05, drop=0.12, surround=2, q=0.8, seed_chunk=10000, split=22),
+    # four seed chunks: the printed cut / kept counts are per chunk, the pickled index is the LAST chunk's (:339-346)
+    "preidx_c": dict(ped=dict(n_animals=60, n_generations=5, sire_frac=0.3, dam_frac=0.6, seed=7),
+                     n_snps=30, err=0.03, miss=0.03, drop=0.0, surround=1, q=0.9, seed_chunk=15, split=15),
 }
 
 

@@ -52,7 +52,7 @@ def test_error_checker_host_logic_reproduces_reference_files(name, monkeypatch):
     assert np.array_equal(sums.view(np.uint16), g["sums"])
 
 
-@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b", "preidx_c"])
 def test_preindex_host_logic_reproduces_reference_indexes(name, monkeypatch):
     import genofix_b200.empirical.jalleledist3 as jd
     import genofix_b200.empirical.preindex as pp
@@ -60,21 +60,27 @@ def test_preindex_host_logic_reproduces_reference_indexes(name, monkeypatch):
     monkeypatch.setattr(pp, "Engine", _stand_in_engine(g["ped_rows"]))
     monkeypatch.setattr(jd, "window_counts_device", _stand_in_window_counts)
     ped = PedigreeDAG.from_table(g["ped_rows"])
-    (kid_ids, cand), = pp.seed_chunks(ped, g["ids"], int(g["seed_chunk"]))
+    chunks = pp.seed_chunks(ped, g["ids"], int(g["seed_chunk"]))
+    assert len(chunks) == (4 if name == "preidx_c" else 1)
     row = {int(k): i for i, k in enumerate(g["ids"])}
     names = ["SNP%d" % i for i in range(g["obs"].shape[1])]
-    df = pd.DataFrame(g["obs"][[row[k] for k in cand]], index=cand, columns=names)
     c2s = {"0": ["pad"]}
     for n, c in zip(names, g["chrom"]):
         c2s.setdefault(str(c), []).append(n)
-    res = pp.index_chunk(df, ped, c2s, int(g["surround"]), float(g["q"]))
-    assert sorted(res) == [str(c) for c in g["chroms"]]
-    for ci, c in enumerate(sorted(res)):
-        empC, info = res[c]
-        assert info["quantQ"] == g["quantQ"][ci]
-        assert (info["n_unmasked"], len(info["eval_ids"]) * len(c2s[c])) == tuple(g["kept"][ci])
-        for i, s in enumerate(empC.snp_ordered):
-            w = int(g["wlen_" + c][i])
-            assert len(empC.windows[s]) == w
-            if w:
-                assert np.array_equal(empC._freq[s], g["freq_" + c][i][:3 ** w])
+    k = 0
+    for ci, (_kid_ids, cand) in enumerate(chunks):
+        df = pd.DataFrame(g["obs"][[row[x] for x in cand]], index=cand, columns=names)
+        res = pp.index_chunk(df, ped, c2s, int(g["surround"]), float(g["q"]))
+        assert sorted(res) == [str(c) for c in g["chroms"]]
+        for c in sorted(res):
+            empC, info = res[c]
+            assert info["quantQ"] == g["quantQ"][k]              # printed per (seed chunk, chromosome)
+            assert (info["n_unmasked"], len(info["eval_ids"]) * len(c2s[c])) == tuple(g["kept"][k])
+            k += 1
+            if ci == len(chunks) - 1:                              # the pickled index is the last chunk's (:339-346)
+                for i, s_ in enumerate(empC.snp_ordered):
+                    w = int(g["wlen_" + c][i])
+                    assert len(empC.windows[s_]) == w
+                    if w:
+                        assert np.array_equal(empC._freq[s_], g["freq_" + c][i][:3 ** w])
+    assert k == len(g["quantQ"])

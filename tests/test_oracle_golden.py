@@ -116,23 +116,28 @@ def _chrom_cols(g):
     return cc
 
 
-@pytest.mark.parametrize("name", ["preidx_a", "preidx_b"])
+@pytest.mark.parametrize("name", ["preidx_a", "preidx_b", "preidx_c"])
 def test_oracle_preindex_matches_reference(name):
-    """empirical/preindex.py main() run unmodified (oracle/ref_harness.run_preindex): the rank cut it printed, the
-    number of cells under the cut and every window frequency of the pickled indexes, bit for bit."""
+    """empirical/preindex.py main() run unmodified (oracle/ref_harness.run_preindex): the rank cut it printed and the
+    number of cells under the cut for every (seed chunk, chromosome), and every window frequency of the pickled
+    indexes (the last chunk's: each chunk overwrites the file, preindex.py:339-346), bit for bit."""
     from oracle import genofix_oracle as go
     g = load_golden(name)
     ped = go.OraclePedigree(g["ped_rows"])
     chunks = go.preindex_chunks(ped, g["ids"], int(g["seed_chunk"]))
-    assert len(chunks) == 1
-    res = go.preindex_chunk(ped, g["ids"], g["obs"], chunks[0][1], _chrom_cols(g), int(g["surround"]), float(g["q"]))
-    assert sorted(res) == [str(c) for c in g["chroms"]]
-    for ci, c in enumerate(sorted(res)):
-        r = res[c]
-        assert r["quantQ"] == g["quantQ"][ci]
-        assert r["n_unmasked"] == g["kept"][ci][0]
-        assert len(r["eval_ids"]) * len(_chrom_cols(g)[c]) == g["kept"][ci][1]
-        for i, f in enumerate(r["freq"]):
-            w = int(g["wlen_" + c][i])
-            assert len(f) == (3 ** w if w else 0)
-            assert np.array_equal(f, g["freq_" + c][i][:len(f)])
+    assert len(chunks) == (4 if name == "preidx_c" else 1)
+    k = 0
+    for ci, (_kid_ids, cand) in enumerate(chunks):
+        res = go.preindex_chunk(ped, g["ids"], g["obs"], cand, _chrom_cols(g), int(g["surround"]), float(g["q"]))
+        assert sorted(res) == [str(c) for c in g["chroms"]]
+        for c in sorted(res):
+            r = res[c]
+            assert r["quantQ"] == g["quantQ"][k]
+            assert (r["n_unmasked"], len(r["eval_ids"]) * len(_chrom_cols(g)[c])) == tuple(g["kept"][k])
+            k += 1
+            if ci == len(chunks) - 1:
+                for i, f in enumerate(r["freq"]):
+                    w = int(g["wlen_" + c][i])
+                    assert len(f) == (3 ** w if w else 0)
+                    assert np.array_equal(f, g["freq_" + c][i][:len(f)])
+    assert k == len(g["quantQ"])

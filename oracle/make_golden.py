@@ -117,6 +117,8 @@ ERRCHK_CASES = {
     # long rows: the float16 accumulator passes 256 and loses low bits, so the summation order is visible
     "errchk_long": dict(ped=dict(n_animals=48, n_generations=4, sire_frac=0.3, dam_frac=0.6, seed=5),
                         n_snps=1500, err=0.3, miss=0.02, drop=0.0, kids="all"),
+    # the reference's own example pedigree: 4 560 animals, 4 235 kids with both parents genotyped (104 s of reference time)
+    "errchk_example": dict(ped="example.fam", n_snps=12, err=0.01, miss=0.0, drop=0.0, kids="all"),
 }
 
 

@@ -40,7 +40,7 @@ def _stand_in_window_counts(G, mask, starts, lens):
     return out
 
 
-@pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long"])
+@pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long", "errchk_example"])
 def test_error_checker_host_logic_reproduces_reference_files(name, monkeypatch):
     import genofix_b200.pedigree.error_checker as ec
     g = load_golden(name)

@@ -78,7 +78,7 @@ def test_kats_empirical_counts_and_windows():
         assert go.ld_window(int(n), int(i), int(sur)) == (int(a), int(b))
 
 
-ERRCHK = ["errchk_a", "errchk_b", "errchk_long"]
+ERRCHK = ["errchk_a", "errchk_b", "errchk_long", "errchk_example"]
 
 
 @pytest.mark.parametrize("name", ERRCHK)

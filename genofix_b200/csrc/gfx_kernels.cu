@@ -2451,6 +2451,12 @@ extern "C" int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed, int6
 // ------------------------------------------------------------------------------------------------
 // LD-window joint counts
 // ------------------------------------------------------------------------------------------------
+// Layout of one window's counters: [3^len full window][3^(len-2) inner window 1][3^(len-4) inner window 2]...,
+// inner windows 1 .. int((len - 2) / 2) - 1 -- the nested terms of jalleledist3.py:133-138 (the i = 0 pass of
+// that loop is the empty slice, D12, and needs no counter).  A row is in the reference's `subset` when ALL cells of
+// the window pass the mask; the inner window i then counts the rows whose INNER cells match, whatever the outer
+// cells hold (missing calls included), so it is not a marginal of the full histogram.
+__host__ __device__ __forceinline__ int gfx_window_levels(int len) { const int k = (len - 2) / 2; return k < 1 ? 1 : k; }
 __global__ void __launch_bounds__(256) k_window_counts(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ mask,
                                                        int64_t n, int64_t wpr, int64_t mwpr, const int32_t* __restrict__ win_start,
                                                        const int32_t* __restrict__ win_len, int n_windows, int stride,
@@ -2458,23 +2464,34 @@ __global__ void __launch_bounds__(256) k_window_counts(const uint32_t* __restric
   extern __shared__ uint32_t s_cnt[];
   for (int wi = blockIdx.x; wi < n_windows; wi += gridDim.x) {
     const int start = win_start[wi], len = win_len[wi];
-    const int nstates = gfx_pow3(len);
-    for (int i = threadIdx.x; i < nstates; i += blockDim.x) s_cnt[i] = 0;
+    const int nlev = gfx_window_levels(len);
+    int total = 0;
+    for (int l = 0; l < nlev; ++l) total += gfx_pow3(len - 2 * l);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) s_cnt[i] = 0;
     __syncthreads();
     for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
-      int idx = 0;
+      uint32_t code[16];
       bool ok = len > 0;
       for (int c = 0; c < len; ++c) {
         const int64_t j = start + c;
-        const uint32_t code = (__ldg(packed + r * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u;
-        if (code == 3u) { ok = false; break; }
+        code[c] = (__ldg(packed + r * wpr + (j >> 4)) >> (2 * (j & 15))) & 3u;
         if (mask && !((__ldg(mask + r * mwpr + (j >> 5)) >> (j & 31)) & 1u)) { ok = false; break; }
-        idx = idx * 3 + (int)code;
       }
-      if (ok) atomicAdd(&s_cnt[idx], 1u);
+      if (!ok) continue;
+      int off = 0;
+      for (int l = 0; l < nlev; ++l) {
+        int idx = 0;
+        bool present = true;
+        for (int c = l; c < len - l; ++c) {
+          if (code[c] == 3u) { present = false; break; }
+          idx = idx * 3 + (int)code[c];
+        }
+        if (present) atomicAdd(&s_cnt[off + idx], 1u);
+        off += gfx_pow3(len - 2 * l);
+      }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nstates; i += blockDim.x) counts[(int64_t)wi * stride + i] = s_cnt[i];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) counts[(int64_t)wi * stride + i] = s_cnt[i];
     __syncthreads();
   }
 }
@@ -2487,6 +2504,18 @@ extern "C" int gfx_window_counts(const uint32_t* packed, const uint32_t* mask, i
   (void)n_snps;
   const size_t smem = (size_t)stride * sizeof(uint32_t);
   if (smem > 200 * 1024) return fail(GFX_E_INVALID, "window too wide for shared memory (surround <= 4)");
+  {
+    // stride must hold the full histogram and the inner-window histograms of the widest window (<= 16 SNPs)
+    std::vector<int32_t> lens((size_t)n_windows);
+    GFX_CUDA(cudaMemcpyAsync(lens.data(), win_len, sizeof(int32_t) * (size_t)n_windows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GFX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int32_t len : lens) {
+      if (len < 0 || len > 16) return fail(GFX_E_INVALID, "gfx_window_counts: window length out of range");
+      int64_t total = 0;
+      for (int l = 0; l < gfx_window_levels(len); ++l) total += gfx_pow3(len - 2 * l);
+      if (total > stride) return fail(GFX_E_INVALID, "gfx_window_counts: stride smaller than the window's counters");
+    }
+  }
   GFX_CUDA(cudaFuncSetAttribute(k_window_counts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = n_windows < device_sms() * 4 ? n_windows : device_sms() * 4;
   k_window_counts<<<blocks, 256, smem, (cudaStream_t)stream>>>(packed, mask, n, wpr, mwpr, win_start, win_len, n_windows,

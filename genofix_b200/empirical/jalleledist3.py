@@ -2,9 +2,10 @@
 
 The counting (countJointFrq / countJointFrqAll, jalleledist3.py:120-174) is one CUDA kernel over all
 windows (gfx_window_counts): per window a 3^w-bin shared-memory histogram of the base-3 state index of
-every animal whose window cells all pass the mask.  The reference's nested "inner window" terms are
-marginals of that histogram, so the float recurrence of :133-138 (including its i = 0 quirk, SURVEY
-D12) is applied on the host in float64, in the reference's operation order.
+every animal whose window cells all pass the mask, plus one smaller histogram per nested "inner window"
+of :133-138 (a row with a missing call in an OUTER cell still counts there, as in the reference).  The
+float recurrence of :133-138 (including its i = 0 quirk) is applied on the host in float64,
+in the reference's operation order.
 """
 import ctypes as C
 import itertools
@@ -27,7 +28,8 @@ def window_bounds(n_snps, pos, surround):
 
 def window_counts_device(G, mask, starts, lens):
     """Integer joint counts for arbitrary windows.  G uint8 [n, s] (0,1,2, anything else = missing),
-    mask bool [n, s] or None.  Returns int64 [n_windows, 3^max_len]."""
+    mask bool [n, s] or None.  Returns int64 [n_windows, counters_per_window(max_len)]: per window the 3^len
+    full histogram followed by its inner-window histograms (include/genofix_b200.h)."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("genofix_b200 needs a CUDA device; there is no CPU fallback")
@@ -37,7 +39,7 @@ def window_counts_device(G, mask, starts, lens):
     starts = np.ascontiguousarray(starts, dtype=np.int32)
     lens = np.ascontiguousarray(lens, dtype=np.int32)
     nw = len(starts)
-    stride = int(3 ** max(int(lens.max()), 1))
+    stride = counters_per_window(max(int(lens.max()), 1))
     ld = ((s + 15) // 16) * 16
     host = np.full((n, ld), 9, np.uint8)
     host[:, :s] = G
@@ -62,18 +64,31 @@ def window_counts_device(G, mask, starts, lens):
     return counts.cpu().numpy().view(np.uint32).astype(np.int64)
 
 
+def inner_levels(w):
+    """Number of nested windows gfx_window_counts keeps per window: the full one + int((w-2)/2) - 1 inner ones."""
+    return max(1, int((w - 2) / 2))
+
+
+def counters_per_window(w):
+    return int(sum(3 ** (w - 2 * l) for l in range(inner_levels(w))))
+
+
 def frequencies_from_counts(counts, w, pseudocount, sum_inner_count=True):
-    """Apply jalleledist3.py:130-138 to the integer histogram of one window (3^w entries, first SNP =
-    most significant digit).  Returns float64 [3^w]."""
+    """Apply jalleledist3.py:130-138 to the counters of one window: 3^w entries of the full window (first SNP =
+    most significant digit) followed by the histograms of the inner windows 1, 2, ... (cells i .. w-1-i, counted
+    over the rows whose whole window passes the mask, whatever the outer cells hold).  Returns float64 [3^w]."""
     c = np.asarray(counts[:3 ** w], dtype=np.int64).reshape((3,) * w) if w > 0 else np.asarray(counts[:1])
     val = c.astype(np.float64) + pseudocount
     if sum_inner_count and w > 0:
+        off = 3 ** w
         for i in range(int((w - 2) / 2)):
             if i == 0:
                 obs = np.ones_like(val)          # np.count_nonzero(np.logical_and.reduce([])) == 1
             else:
-                axes = tuple(range(i)) + tuple(range(w - i, w))
-                obs = np.broadcast_to(c.sum(axis=axes, keepdims=True), c.shape).astype(np.float64)
+                wi = w - 2 * i
+                inner = np.asarray(counts[off:off + 3 ** wi], dtype=np.int64).reshape((1,) * i + (3,) * wi + (1,) * i)
+                off += 3 ** wi
+                obs = np.broadcast_to(inner, c.shape).astype(np.float64)
             obs = obs - val
             val = (obs / (i + 1)) + val
     return val.reshape(-1)

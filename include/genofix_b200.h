@@ -220,7 +220,10 @@ int gfx_founders(const gfx_pedigree_desc* ped, const uint8_t* restrict_host, int
  * whose window cells all pass the mask (mask bit = 1, 1 bit per SNP, `mwpr` uint32 words per row,
  * may be NULL = all pass) and are non-missing, the rows matching each of the 3^win_len state tuples
  * (first SNP of the window is the most significant base-3 digit, itertools.product order).
- * counts_dev: uint32 [n_windows * stride], stride >= 3^max_len.
+ * The nested inner windows of :133-138 (cells i .. len-1-i, i = 1 .. int((len-2)/2) - 1) are counted
+ * separately over the same rows -- a row with a missing call in an OUTER cell still counts there, as in the
+ * reference -- and follow the full histogram: [3^len][3^(len-2)][3^(len-4)]...
+ * counts_dev: uint32 [n_windows * stride], stride >= 3^max_len + 3^(max_len-2) + ... (the counters above).
  * ------------------------------------------------------------------------------------------- */
 int gfx_window_counts(const uint32_t* packed_dev, const uint32_t* mask_dev, int64_t n, int64_t n_snps,
                       int64_t wpr, int64_t mwpr, const int32_t* win_start_dev, const int32_t* win_len_dev,

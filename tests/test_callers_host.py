@@ -31,13 +31,37 @@ def _stand_in_engine(ped_rows):
 
 
 def _stand_in_window_counts(G, mask, starts, lens):
-    out = np.zeros((len(starts), 3 ** max(lens)), np.int64)                       # stands in for k_window_counts
+    """stands in for k_window_counts: per window the full histogram, then the histograms of the inner windows
+    (cells l .. w-1-l) over the rows whose whole window passes the mask (include/genofix_b200.h)"""
+    from genofix_b200.empirical.jalleledist3 import counters_per_window, inner_levels
+    out = np.zeros((len(starts), counters_per_window(max(lens))), np.int64)
     for i, (a, w) in enumerate(zip(starts, lens)):
-        sub = G[:, a:a + w]
-        ok = mask[:, a:a + w].all(axis=1) & (sub <= 2).all(axis=1)
-        idx = (sub[ok].astype(np.int64) * (3 ** np.arange(w - 1, -1, -1))).sum(axis=1)
-        np.add.at(out[i], idx, 1)
+        passes = mask[:, a:a + w].all(axis=1) if mask is not None else np.ones(len(G), bool)
+        off = 0
+        for l in range(inner_levels(w) if w > 0 else 0):
+            sub = G[:, a + l:a + w - l]
+            ok = passes & (sub <= 2).all(axis=1)
+            idx = (sub[ok].astype(np.int64) * (3 ** np.arange(w - 2 * l - 1, -1, -1))).sum(axis=1)
+            np.add.at(out[i], off + idx, 1)
+            off += 3 ** (w - 2 * l)
     return out
+
+
+def test_window_frequencies_with_missing_outer_cells_match_reference_semantics():
+    """a row with a missing call in an OUTER window cell still counts in the inner windows
+    (jalleledist3.py:133-138); checked against the oracle restatement of countJointFrq on every state."""
+    import itertools
+    from genofix_b200.empirical.jalleledist3 import frequencies_from_counts
+    rs = np.random.default_rng(11)
+    for w in (5, 6, 7, 8, 9):
+        n = 300
+        G = rs.choice([0, 1, 2, 9], size=(n, w), p=[.3, .3, .3, .1]).astype(np.uint8)
+        for mask in (np.ones((n, w), bool), rs.random((n, w)) < 0.97):
+            counts = _stand_in_window_counts(G, mask, [0], [w])[0]
+            vals = frequencies_from_counts(counts, w, 1e-4, True)
+            ref = go.count_joint_frq(G, mask, w, 1e-4, sum_inner_count=True)
+            want = np.array([ref[v] for v in itertools.product([0, 1, 2], repeat=w)])
+            assert np.array_equal(vals, want), w
 
 
 @pytest.mark.parametrize("name", ["errchk_a", "errchk_b", "errchk_long", "errchk_example"])

@@ -224,6 +224,29 @@ def test_window_counts_match_oracle():
             assert np.array_equal(counts[i, :3 ** w], vals.astype(np.int64)), (sur, i)
 
 
+@pytest.mark.parametrize("all_pass", [True, False])
+def test_window_frequencies_with_missing_calls_match_oracle(all_pass):
+    """The stored frequencies (pseudocount, inner-window recurrence, D12) on data WITH missing calls: rows with a 9
+    in an outer cell of the window count in the inner windows (jalleledist3.py:133-138)."""
+    import itertools
+    from genofix_b200.empirical.jalleledist3 import frequencies_from_counts, window_counts_device
+    from oracle import genofix_oracle as go
+    rs = np.random.default_rng(5)
+    n, s = 400, 24
+    G = rs.choice([0, 1, 2, 9], size=(n, s), p=[.3, .3, .3, .1]).astype(np.uint8)
+    mask = np.ones((n, s), bool) if all_pass else rs.random((n, s)) < 0.97
+    for sur in (2, 3, 4):
+        wins = [go.ld_window(s, i, sur) for i in range(s)]
+        counts = window_counts_device(G, None if all_pass else mask, [a for a, b in wins], [b - a for a, b in wins])
+        for i, (a, b) in enumerate(wins):
+            w = b - a
+            if w == 0 or (w == 9 and i % 4):   # 3^9 states in a Python loop: a quarter of the widest windows
+                continue
+            ref = go.count_joint_frq(G[:, a:b], mask[:, a:b], w, 1e-4, sum_inner_count=True)
+            want = np.array([ref[v] for v in itertools.product([0, 1, 2], repeat=w)])
+            assert np.array_equal(frequencies_from_counts(counts[i], w, 1e-4, True), want), (sur, i)
+
+
 def test_config4_deep_loopy_pedigree_matches_oracle():
     """BASELINE config 4 shape: 15 generations, few sires (inbreeding loops at depth 2/3), 10 % of the
     non-founders with both parents unknown, 5 % missing calls."""
@@ -737,7 +760,6 @@ def test_preindex_cli_writes_the_reference_indexes(tmp_path):
 
 # ---- the reference's static call surface (what its own worker pools call) -------------------------------------------
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a B200")
 def test_static_call_surface_matches_oracle():
     """initializer(matrix, pedigree, probs_errors) + CorrectGenotypes.mendelProbsSingle / correctPair(back + 1) /
     correctSingle(back), called the way correct_genotypes3.py:569-590,684-693,851-859 calls them, against the oracle on the
@@ -790,7 +812,6 @@ def test_static_call_surface_matches_oracle():
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a B200")
 def test_sharded_error_tally_single_rank_matches_float64_oracle():
     """mendel_error_tally_sharded with world = 1 and 7-SNP chunks (histogram pass, table, row-sum pass) against the
     float64 form of error_checker.py:193-204 computed from the oracle's scores."""

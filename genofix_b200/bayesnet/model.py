@@ -61,6 +61,9 @@ def generate_probs_differences_kids(kidstates, oneparentstates, observedstate):
         else:
             v = Cc if p == 0 else (A if p == 2 else B)
         out.append(np.float16(max(v)) - v[observedstate])
+    # the reference returns one entry per element of kidstates: the rows of the usable children first, then the
+    # untouched zero rows of its float16 table (model.py:100,113-115)
+    out.extend([np.float16(0)] * int((kid > 2).sum()))
     return out
 
 

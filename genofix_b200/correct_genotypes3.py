@@ -31,9 +31,12 @@ def initializer(corrected_genotype_c, pedigree_c, probs_errors, cacheIn=None):
         cur.probs_errors = probs_errors.copy()
     cur.cacheIn = cacheIn if cacheIn is not None else {}
     cur._gfx_cache = {}
+    cur._gfx_rowof = {k: i for i, k in enumerate(cur.genotypes.index)}      # id -> matrix row, once per binding
 
 
 def initializerEmp(empC):
+    """Bind an LD index to the current process (correct_genotypes3.py:34-40).  The reference copies `empC.frequency`
+    here, an attribute jalleledist3 objects do not have; the object itself is bound instead."""
     multiprocessing.current_process().indexemp = empC
 
 
@@ -92,6 +95,26 @@ class CorrectGenotypes(object):
     # static workers of the reference; they operate on the matrix bound by initializer()
     # ------------------------------------------------------------------------------------------
     @staticmethod
+    def getEmpProbs(snpWindowChunk, SNP_id):
+        """{(kid, observed state): normalised LD-window frequencies of the 3 states of SNP_id} for every animal of
+        the window chunk whose call at SNP_id is 0/1/2 and whose window has been seen (correct_genotypes3.py:69-82).
+        Uses the index bound by initializerEmp()."""
+        indexemp = multiprocessing.current_process().indexemp
+        cols = list(snpWindowChunk.columns)
+        G = snpWindowChunk.to_numpy()
+        tcol = cols.index(SNP_id)
+        kid2empiricalCount = dict()
+        for r, kid in enumerate(snpWindowChunk.index):
+            observed_state = G[r, tcol]
+            if observed_state in (0, 1, 2):
+                evidence = {snpid: G[r, c] for c, snpid in enumerate(cols)}
+                counts = indexemp.getCountTable(evidence, SNP_id)
+                total = np.nansum(counts)
+                if total > 0:
+                    kid2empiricalCount[(kid, observed_state)] = np.divide(counts, total)
+        return kid2empiricalCount
+
+    @staticmethod
     def _bound(back, need_ranks):
         cur = multiprocessing.current_process()
         if not hasattr(cur, "genotypes"):
@@ -121,7 +144,7 @@ class CorrectGenotypes(object):
         as zeros."""
         eng, raw = CorrectGenotypes._bound(back, False)
         cur = multiprocessing.current_process()
-        r = list(cur.genotypes.index).index(kid)
+        r = cur._gfx_rowof[kid]
         S = raw.shape[1]
         return np.zeros((S, 3), dtype=np.float16), raw[r].reshape(S, 1).copy(), {}
 
@@ -144,8 +167,10 @@ class CorrectGenotypes(object):
             E = cur.probs_errors.to_numpy(dtype=np.float64)
             # feed E through an identity table: raw := rank of the distinct values
             vals, inv = np.unique(E, return_inverse=True)
-            if len(vals) > 65536:
-                raise ValueError("too many distinct rank values")
+            if len(vals) > 0x7C01:
+                # gfx_build_cut_table orders the patterns 0 .. 0x7C00 only (0xFFFF marks a cell missing in the input)
+                raise ValueError("more than 31745 distinct rank values in probs_errors: the static workers index them "
+                                 "by float16-pattern order")
             elut = np.full(65536, np.nan)
             elut[:len(vals)] = vals
             eng.host_elut.numpy()[:] = elut
@@ -154,12 +179,10 @@ class CorrectGenotypes(object):
             saved_raw = eng.raw.clone()
             eng.raw[:, :eng.s] = rawidx
             eng.test_p = float(test_p)
-            # E for missing cells is whatever the caller put there: patch through packed_orig = no missing
             saved_orig = eng.packed_orig.clone()
-            nomiss = t.zeros_like(eng.packed_orig)
             try:
                 eng.packed_live.copy_(saved_orig)
-                posts = CorrectGenotypes._infer_only(eng, nomiss, kind, tiethreshold)
+                posts = CorrectGenotypes._infer_only(eng, kind, tiethreshold)
             finally:
                 eng.raw.copy_(saved_raw)
                 eng.packed_orig.copy_(saved_orig)
@@ -167,7 +190,7 @@ class CorrectGenotypes(object):
         return eng, cache[ckey]
 
     @staticmethod
-    def _infer_only(eng, orig_for_E, kind, tiethreshold):
+    def _infer_only(eng, kind, tiethreshold):
         """Run the inference kernels on the bound snapshot and return posteriors WITHOUT keeping the
         applied corrections (correctPair/correctSingle only compute results)."""
         from . import _lib
@@ -218,8 +241,8 @@ class CorrectGenotypes(object):
         """ResultPairInfer for one mating pair from the bound snapshot (correct_genotypes3.py:169-327)."""
         cur = multiprocessing.current_process()
         eng, posts = CorrectGenotypes._results_for("pair", None, back, tiethreshold, test_p, suspect_t)
-        ids = list(cur.genotypes.index)
-        key = (ids.index(sire), ids.index(dam))
+        rowof = cur._gfx_rowof
+        key = (rowof[sire], rowof[dam])
         if key not in posts:
             raise KeyError("(%s, %s) is not a mating pair of genotyped animals with a genotyped kid" % (sire, dam))
         ps, pd_, valid = posts[key]
@@ -252,8 +275,7 @@ class CorrectGenotypes(object):
         """ResultSingleInfer for one unpaired animal (correct_genotypes3.py:330-430)."""
         cur = multiprocessing.current_process()
         eng, posts = CorrectGenotypes._results_for("single", None, back, tiethreshold, test_p, suspect_t)
-        ids = list(cur.genotypes.index)
-        r = ids.index(kid)
+        r = cur._gfx_rowof[kid]
         if r not in posts:
             if r in set(int(x) for x in eng.schedule.array(0)):
                 raise KeyError("%s is part of a mating pair; use correctPair" % kid)

@@ -1615,7 +1615,7 @@ struct FocalArgs {
   const int32_t* focal_order;    // focal indices, heaviest first
   uint2* wl;              // per deferred cell: (focal, snp)
   uint2* st;              // per deferred cell: x = live state | first unresolved job << 8, y = applied | excluded << 16
-  double* skids;          // per deferred cell: children term (3) + flag
+  int4* skc;              // per deferred cell: class counts of the children term (K0, K1, K2, usable children)
   uint8_t* sbits;         // per deferred cell: decision bits of every job (0xFF = to be computed), row stride maxj
   uint2* items;           // deferred jobs: (cell slot, job index within the animal)
   unsigned long long wl_cap, item_cap;
@@ -1720,18 +1720,85 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 
 #define GFX_CORRECT_CHUNK 1024
 
-// All jobs of one suspect (focal animal, SNP) cell, in canonical order.  GENERAL = false is the lean
-// instantiation: ancestor terms by plain peeling only; it returns false (nothing written) as soon as a
-// job needs the general elimination, and the cell is redone by the GENERAL = true instantiation.
-// Posterior of ONE job of a cell, reduced to the decision bits of gfx_decision_bits (0 = the job is not
-// suspect at this SNP or yields no result).  Independent of the live state, so jobs of a cell can be
-// evaluated in any order / by different threads; only the apply walk below is sequential.
-// GENERAL = false: slot peeling only, returns false when the job needs tree message passing or the general
-// elimination.
-// MODE 0: slot peeling only; 1: + tree message passing; 2: + general elimination.  false = needs a higher mode.
+// ---- children term as class counts, decisions in exact arithmetic ------------------------------------------------
+// bayesnet/model.py:65-89 turns every usable child into one of four vectors: A = [2/3, 1/3, 0],
+// B = [1/3, 1/3, 1/3], C = [0, 1/3, 2/3] or Z = 0, selected by (child state, other parent's state); the children
+// term is their mean divided by its sum.  In exact arithmetic that is K / sum(K) with the INTEGERS
+// K = sum over the usable children of 3 * vector, so the posterior of a job is N / sum(N), N[x] = anc[x] * K[x]
+// (anc: exact dyadic rationals), and both decision tests of correct_genotypes3.py:741-744,809 / :932 compare
+// (max N - N[i]) / sum(N) with a constant.  The reference evaluates the same quantities in float64 with a relative
+// error below 1e-14, so the exact comparison gives the reference's answer whenever the margin exceeds
+// GFX_GUARD_EPS; inside that band (exact ties like 0.75 - 0.25 vs 0.5 are common) the job is replayed literally,
+// in numpy's summation order, by the deferred-job kernels.  Calls stay bit-exact, the fast path needs no float64
+// children sum at all.
+#define GFX_GUARD_EPS 1e-9
+#define GFX_BITS_GUARD 0xFFFFFFFFu
+struct KidCounts { int k0, k1, k2, ninc; };   // ninc: usable (genotyped, non-missing) children
+// s_ku[k * 4 + p]: x = K0 | K1 << 16, y = K2 | 1 << 16 of a child in state k whose other parent shows p (3 = unknown)
+__device__ __forceinline__ void kid_units_init(uint2* s_ku) {
+  if (threadIdx.x < 16) {
+    const int k = threadIdx.x >> 2, pp = threadIdx.x & 3;
+    int v = 3;                                   // 0 A, 1 B, 2 C, 3 Z / not usable
+    if (k == 0) v = pp == 2 ? 3 : 0;
+    else if (k == 1) v = pp == 0 ? 2 : (pp == 2 ? 0 : 1);
+    else if (k == 2) v = pp == 0 ? 3 : 2;
+    const uint32_t k0 = v == 0 ? 2u : (v == 1 ? 1u : 0u), k1 = v == 3 ? 0u : 1u, k2 = v == 2 ? 2u : (v == 1 ? 1u : 0u);
+    s_ku[threadIdx.x] = make_uint2(k0 | (k1 << 16), k2 | (k < 3 ? 1u << 16 : 0u));
+  }
+}
+#define GFX_KIDS_COUNT_MAX 30000   // 16-bit fields
+__device__ __forceinline__ KidCounts kids_counts(const CellCtx& c, const int32_t* __restrict__ child_row,
+                                                 const int32_t* __restrict__ child_other, int nk, int64_t wo, int sh,
+                                                 const uint2* s_ku) {
+  uint32_t a01 = 0, a2n = 0;
+  for (int i = 0; i < nk; ++i) {
+    const int r = __ldg(child_row + i), o = __ldg(child_other + i);
+    const uint32_t k = (__ldg(c.live + (int64_t)r * c.wpr + wo) >> sh) & 3u;
+    const uint32_t pp = o >= 0 ? ((__ldg(c.live + (int64_t)o * c.wpr + wo) >> sh) & 3u) : 3u;
+    const uint2 u = s_ku[k * 4u + pp];
+    a01 += u.x;
+    a2n += u.y;
+  }
+  return KidCounts{(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a2n & 0xFFFFu), (int)(a2n >> 16)};
+}
+// Decision bits (gfx_decision_bits layout) from unnormalised posterior numerators, or GFX_BITS_GUARD when a test
+// falls inside the guard band.  n >= 0, at least one > 0.
+__device__ __forceinline__ uint32_t guard_bits(double n0, double n1, double n2, int obs, double tie, double thr) {
+  const double z = (n0 + n1) + n2;
+  const double mx = fmax(n0, fmax(n1, n2));
+  const double eps = GFX_GUARD_EPS * z, bound = tie * z;
+  uint32_t r = 0x80u;
+  const double d0 = mx - n0, d1 = mx - n1, d2 = mx - n2;
+  bool guard = fabs(d0 - bound) <= eps || fabs(d1 - bound) <= eps || fabs(d2 - bound) <= eps;
+  if (d0 <= bound) r |= 1u;
+  if (d1 <= bound) r |= 2u;
+  if (d2 <= bound) r |= 4u;
+  if (obs <= 2) {
+    const double dd = obs == 0 ? d0 : (obs == 1 ? d1 : d2), bt = thr * z;
+    guard = guard || fabs(dd - bt) <= eps;
+    if (dd >= bt) r |= 8u;
+  }
+  return guard ? GFX_BITS_GUARD : r;
+}
+// The cases in which the children term is known without summing: no genotyped child (term absent), no usable child
+// ([1/3, 1/3, 1/3], model.py:89) or only vanished rows (zeros).  Returns true and the literal term then.
+__device__ __forceinline__ bool kids_literal_known(int nk, const KidCounts& K, bool* has_kids, double kids[3]) {
+  *has_kids = nk > 0;
+  if (nk <= 0) { kids[0] = kids[1] = kids[2] = 0.0; return true; }
+  if (K.ninc == 0) { kids[0] = kids[1] = kids[2] = 1.0 / 3.0; return true; }
+  if (K.k0 + K.k1 + K.k2 == 0) { kids[0] = kids[1] = kids[2] = 0.0; return true; }
+  return false;
+}
+
+// Posterior of ONE deferred job of a cell, reduced to the decision bits of gfx_decision_bits (0 = the job is not
+// suspect at this SNP or yields no result).  Independent of the live state, so jobs of a cell can be evaluated in
+// any order / by different threads; only the apply walk is sequential.
+// MODE 1: slot peeling + tree message passing; 2: + general elimination.  false = needs a higher mode.
+// The decision uses the class counts of the parked cell; the children term is summed literally (numpy's order) only
+// when a test falls inside the guard band, when the fast kernel already found that (`literal`), or for posteriors.
 template <int MODE>
 __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, int64_t j, int obs0, uint32_t rxf,
-                                         bool has_kids, const double* kids, uint32_t* bits_out) {
+                                         const KidCounts& K, bool literal, uint32_t* bits_out) {
   const uint32_t tp = a.c.tp_raw;
   const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
   const int job = a.nf == 2 ? (ent >> 1) : ent;
@@ -1766,8 +1833,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     double tot_me = 1.0, tot_ot = 1.0;
     const int sme = a.nf == 2 ? side : 0;
     if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
-      if constexpr (MODE == 0) return false;
-      else if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
+      if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
       else if constexpr (MODE == 1) return false;
       else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
     } else {
@@ -1778,8 +1844,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
       // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
       double tmp[3];
       if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
-        if constexpr (MODE == 0) return false;
-        else if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
+        if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (MODE == 1) return false;
           else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
         }
@@ -1787,7 +1852,26 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     }
     if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
   }
-  if (bid < 0 && !has_kids) return true;                    // lone node: no result (:287-288 / :417-419)
+  const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+  if (bid < 0 && nk <= 0) return true;                      // lone node: no result (:287-288 / :417-419)
+  bool has_kids;
+  double kids[3];
+  const bool known = kids_literal_known(nk, K, &has_kids, kids);
+  if (!known && !literal && !a.post) {
+    if (bid >= 0 && !(anc[0] == anc[0])) { *bits_out = 0x80u; return true; }   // NaN posterior: nothing passes a test
+    const double n0 = bid >= 0 ? anc[0] * (double)K.k0 : (double)K.k0, n1 = bid >= 0 ? anc[1] * (double)K.k1 : (double)K.k1,
+                 n2 = bid >= 0 ? anc[2] * (double)K.k2 : (double)K.k2;
+    if ((n0 + n1) + n2 > 0.0) {
+      const uint32_t b = guard_bits(n0, n1, n2, obs0, a.p.tiethreshold, a.p.threshold);
+      if (b != GFX_BITS_GUARD) { *bits_out = b; return true; }
+    } else {
+      // every product has an exact zero factor: the literal posterior is the unnormalised zero vector (:280-304)
+      const double z3[3] = {0.0, 0.0, 0.0};
+      *bits_out = gfx_decision_bits(z3, obs0, a.p.tiethreshold, a.p.threshold);
+      return true;
+    }
+  }
+  if (!known) kids_term_dev(a.c, a.child_row + k0, a.child_other + k0, nk, j, a.kv, kids);
   double p[3];
   gfx_combine(bid >= 0, anc, has_kids, kids, p);
   *bits_out = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
@@ -1836,32 +1920,140 @@ __device__ __forceinline__ void write_cell(const FocalArgs& a, int row, int64_t 
   if (S.excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, S.excluded);
 }
 
-// Lean per-cell walk.  Jobs are evaluated with slot peeling and applied in order; from the first job that
-// needs more, the cell gets a slot in the deferred list: its state is parked, the remaining easy jobs
-// still deposit their bits there, the hard jobs become items for k_correct_jobs, and k_correct_apply
-// finishes the walk.  Returns false if the whole cell must go to the fallback kernel (no slot left,
-// huge litter), in which case nothing has been written.
-__device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv, uint32_t* s_cls, int f, int row, int e0, int e1,
-                                          int64_t j) {
-  const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
-  const uint32_t rxf = cell_rx(a.c, row, j);
-  bool has_kids = false;
-  double kids[3] = {0, 0, 0};
-  GFX_COUNT(a.bl, 5, 1);
-  {
-    // children term: the same for every job of this animal, evaluated once with the warp converged
-    const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
-    if (nk > GFX_KIDS_FAST) return false;
-    if (nk > 0) { kids_term_fast(a.c, a.child_row + k0, a.child_other + k0, nk, j, s_kv, s_cls, kids); has_kids = true; }
-    GFX_COUNT(a.bl, 7, nk);
+// Plain peeling on the ancestor slots in integer arithmetic (the exact counterpart of slot_peel): al8 = 8 * P(node
+// passes allele 0) is 8 - 4 c for an observed state c, 4 for an unobserved founder of the blanket and the mean of
+// its parents' otherwise; anc64 = 64 * P(q) = [al_S al_D, al_S be_D + be_S al_D, be_S be_D].  The statuses of the
+// focal animal's own parents (slots 0 / 1 of every blanket of this animal) come from the per-cell cache (rows pS / pD,
+// codes, raw patterns): they differ between the jobs of a cell only through `cut`.
+struct ParentCache { int rS, rD; uint32_t cS, cD, xS, xD; };
+__device__ __forceinline__ int slot_status_cached(const CellCtx& c, int r, const ParentCache& P, int64_t wo, int sh, int64_t j,
+                                                  uint32_t cut) {
+  if (r >= 0 && r == P.rS) return (P.cS == 3u || P.xS >= cut) ? 3 : (int)P.cS;
+  if (r >= 0 && r == P.rD) return (P.cD == 3u || P.xD >= cut) ? 3 : (int)P.cD;
+  return slot_status(c, r, wo, sh, j, cut);
+}
+__device__ __forceinline__ bool fast_anc(const CellCtx& c, const int32_t* __restrict__ srow, uint32_t bad, const ParentCache& P,
+                                         int64_t wo, int sh, int64_t j, uint32_t cut, int anc64[3]) {
+  if (bad & 0x8000u) return false;
+  int st[2];
+  st[0] = slot_status_cached(c, __ldg(srow + 0), P, wo, sh, j, cut);
+  st[1] = slot_status_cached(c, __ldg(srow + 1), P, wo, sh, j, cut);
+  int al[2];
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    if (st[f] <= 2) { al[f] = 8 - 4 * st[f]; continue; }
+    if ((bad >> f) & 1u) return false;
+    int a2[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int s2 = 2 * f + 2 + g;
+      const int t2 = slot_status(c, __ldg(srow + s2), wo, sh, j, cut);
+      if (t2 <= 2) { a2[g] = 8 - 4 * t2; continue; }
+      if (t2 == 4) { a2[g] = -1; continue; }            // no parents: f is a founder of the blanket
+      if ((bad >> s2) & 1u) return false;
+      const int u0 = slot_status(c, __ldg(srow + 2 * s2 + 2), wo, sh, j, cut);
+      const int u1 = slot_status(c, __ldg(srow + 2 * s2 + 3), wo, sh, j, cut);
+      if (u0 == 4) { a2[g] = 4; continue; }             // unobserved founder
+      if ((u0 == 3 && ((bad >> (2 * s2 + 2)) & 1u)) || (u1 == 3 && ((bad >> (2 * s2 + 3)) & 1u))) return false;
+      const int x0 = u0 <= 2 ? 8 - 4 * u0 : 4, x1 = u1 <= 2 ? 8 - 4 * u1 : 4;
+      a2[g] = (x0 + x1) >> 1;                           // multiples of 2: exact
+    }
+    al[f] = a2[0] < 0 ? 4 : ((a2[0] + a2[1]) >> 1);     // both multiples of 2: exact
   }
+  const int be0 = 8 - al[0], be1 = 8 - al[1];
+  anc64[0] = al[0] * al[1];
+  anc64[2] = be0 * be1;
+  anc64[1] = al[0] * be1 + be0 * al[1];
+  return true;
+}
+
+// Fast per-cell walk.  Jobs are evaluated with integer slot peeling + class counts and applied in order; from the first
+// job that needs more (message passing, general elimination, or a literal replay inside the guard band), the cell
+// gets a slot in the deferred list: its state is parked, the remaining easy jobs still deposit their bits there, the
+// hard jobs become items for k_correct_jobs, and k_correct_apply finishes the walk.  Returns false if the whole cell
+// must go to the fallback kernel (no slot left, posteriors requested), in which case nothing has been written.
+#define GFX_ITEM_LITERAL 0x80000000u   // item flag: plain peeling answered the job, only the literal children sum is missing
+__device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku, int f, int row, int e0, int e1, int64_t j) {
+  const int64_t wo = j >> 4;
+  const int sh = 2 * (int)(j & 15);
+  const int obs0 = (int)((__ldg(a.c.live + (int64_t)row * a.c.wpr + wo) >> sh) & 3u);   // snapshot state of the focal animal
+  const uint32_t rxf = cell_rx(a.c, row, j);
+  const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
+  const uint32_t tp = a.c.tp_raw;
+  GFX_COUNT(a.bl, 5, 1);
+  // children term: the same for every job of this animal, counted once with the warp converged
+  const int k0 = a.child_off[row], nk = a.child_off[row + 1] - k0;
+  if (nk > GFX_KIDS_COUNT_MAX) return false;
+  const KidCounts K = kids_counts(a.c, a.child_row + k0, a.child_other + k0, nk, wo, sh, s_ku);
+  bool has_kids;
+  double kids_known[3];
+  const bool known = kids_literal_known(nk, K, &has_kids, kids_known);
+  ParentCache P;
+  P.rS = a.prow[2 * row]; P.rD = a.prow[2 * row + 1];
+  P.cS = P.cD = 3u; P.xS = P.xD = 0u;
+  if (P.rS >= 0) { P.cS = (__ldg(a.c.live + (int64_t)P.rS * a.c.wpr + wo) >> sh) & 3u; P.xS = cell_rx(a.c, P.rS, j); }
+  if (P.rD >= 0) { P.cD = (__ldg(a.c.live + (int64_t)P.rD * a.c.wpr + wo) >> sh) & 3u; P.xD = cell_rx(a.c, P.rD, j); }
+  const ParentCache none{-9, -9, 3u, 3u, 0u, 0u};
   ApplyState S{obs0, 0, 0, false, false};
   bool parked = false;
   unsigned long long slot = 0;
   int first = 0;
   for (int e = e0; e < e1; ++e) {
-    uint32_t bits;
-    const bool ok = job_bits<0>(a, row, a.entry[e], j, obs0, rxf, has_kids, kids, &bits);
+    const int ent = a.entry[e];
+    const int job = a.nf == 2 ? (ent >> 1) : ent;
+    const int side = a.nf == 2 ? (ent & 1) : 0;
+    bool sus = rxf >= tp;                                     // :181-185 / :342
+    uint32_t pidx;                                            // pattern of pmax (:220-228 / :374-376)
+    if (a.nf == 2) {
+      const int mrow = side == 0 ? a.job_row1[job] : a.job_row0[job];
+      const uint32_t rxm = cell_rx(a.c, mrow, j);
+      sus = sus || (rxm >= tp);
+      const uint32_t idxm = rxm == 0xFFFFu ? 65536u : rxm;
+      const int obs_m = (int)((__ldg(a.c.live + (int64_t)mrow * a.c.wpr + wo) >> sh) & 3u);
+      if (obs0 != 3 && obs_m != 3) pidx = idxf > idxm ? idxf : idxm;
+      else if (obs0 == 3 && obs_m == 3) pidx = 65536u;
+      else pidx = obs0 != 3 ? idxf : idxm;
+    } else {
+      pidx = obs0 != 3 ? idxf : 65536u;
+    }
+    uint32_t bits = 0, flag = 0;
+    bool ok = true;
+    const int bid = a.job_bl[job];
+    if (sus && !(bid < 0 && nk <= 0)) {                       // else: not suspect here, or a lone node without result
+      GFX_COUNT(a.bl, 6, 1);
+      int anc64[3] = {1, 1, 1};
+      if (bid >= 0) {
+        const uint32_t cut = __ldg(a.c.cutraw + pidx);
+        const int sme = a.nf == 2 ? side : 0;
+        ok = fast_anc(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], P, wo, sh, j, cut, anc64);
+        if (ok && a.nf == 2 && !((a.bl_tree[bid] >> (side ^ 1)) & 1u)) {
+          // the mate's component must have P(evidence) > 0 (:242-245 joint = False): certain when it peels plainly
+          int tmp[3];
+          ok = fast_anc(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], none, wo, sh, j,
+                        cut, tmp);
+        }
+      }
+      if (!ok) GFX_COUNT(a.bl, 8, 1);
+      if (ok) {
+        if (known) {
+          GFX_COUNT(a.bl, 10, 1);
+          // no children sum needed: the literal arithmetic of :280-304 on exact inputs
+          const double anc[3] = {anc64[0] * (1.0 / 64.0), anc64[1] * (1.0 / 64.0), anc64[2] * (1.0 / 64.0)};
+          double p[3];
+          gfx_combine(bid >= 0, anc, has_kids, kids_known, p);
+          bits = gfx_decision_bits(p, obs0, a.p.tiethreshold, a.p.threshold);
+        } else {
+          const int n0 = anc64[0] * K.k0, n1 = anc64[1] * K.k1, n2 = anc64[2] * K.k2;
+          if (n0 + n1 + n2 > 0) {
+            bits = guard_bits((double)n0, (double)n1, (double)n2, obs0, a.p.tiethreshold, a.p.threshold);
+            if (bits == GFX_BITS_GUARD) { ok = false; flag = GFX_ITEM_LITERAL; GFX_COUNT(a.bl, 9, 1); }
+          } else {
+            const double z3[3] = {0.0, 0.0, 0.0};   // exact zeros: the unnormalised zero vector (:280-304)
+            bits = gfx_decision_bits(z3, obs0, a.p.tiethreshold, a.p.threshold);
+          }
+        }
+      }
+    }
     if (ok && !parked) { apply_bits(a, row, j, rxf, bits, S); continue; }
     if (!parked) {
       if (e1 - e0 > a.maxj) return false;
@@ -1874,7 +2066,7 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv
     a.sbits[slot * a.maxj + (e - e0)] = 0xFF;
     const unsigned long long it = atomicAdd(a.item_count, 1ull);
     if (it < a.item_cap) {
-      a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0));
+      a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0) | flag);
       atomicAdd(a.key_count + (e - a.e_base), 1u);
     }
     else first |= 0x8000;   // no room for the job item: the cell is redone by the fallback kernel
@@ -1884,8 +2076,7 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const double* s_kv
   a.st[slot] = make_uint2((uint32_t)S.cur | ((uint32_t)(first & 0x7FFF) << 8) | ((first & 0x8000) ? 0x80000000u : 0u) |
                               (S.gate_done ? 0x40000000u : 0u) | (S.gate ? 0x20000000u : 0u),
                           (uint32_t)S.applied | ((uint32_t)S.excluded << 16));
-  double* kd = a.skids + slot * 4;
-  kd[0] = kids[0]; kd[1] = kids[1]; kd[2] = kids[2]; kd[3] = has_kids ? 1.0 : 0.0;
+  a.skc[slot] = make_int4(K.k0, K.k1, K.k2, K.ninc);
   return (first & 0x8000) == 0;
 }
 
@@ -2007,22 +2198,28 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
 // ordered heaviest first, so the many-mate sires do not end up as the tail --, compacts the suspect
 // SNPs of the chunk with ballots and then runs one cell per lane.  Cells that need the general path
 // go to the work list (or, if that is full, the overflow bitmap) untouched.
-// SNPs per warp task (measured on config 2: 256 -> 16.8 ms, 128 -> 16.3, 64 -> 15.1, 32 -> 14.8 ms per chunk: short tasks
-// balance better and the suspect cells are dense enough that one ballot round fills the warp)
+// SNPs per warp task of the pair generations (measured on config 2: 256 -> 16.8 ms, 128 -> 16.3, 64 -> 15.1, 32 -> 14.8 ms per
+// chunk: short tasks balance better and the suspect cells are dense enough that one ballot round fills the warp).
+// The singles are the opposite case: thousands of childless animals with ~1 % suspect cells, so a 32-SNP task finds
+// 0.4 cells and runs the cell walk with one lane (266 M warp instructions for 336 k job evaluations at 10 k x 4096);
+// their tasks cover 1024 SNPs and compact ~12 cells per walk.
 #ifndef GFX_LEAN_CHUNK
 #define GFX_LEAN_CHUNK 32
+#endif
+#ifndef GFX_LEAN_CHUNK_SINGLES
+#define GFX_LEAN_CHUNK_SINGLES 1024
 #endif
 #ifndef KC_BLOCKS
 #define KC_BLOCKS 6
 #endif
+template <int GFX_LEAN_CHUNK_T>
 __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
-  __shared__ uint8_t s_list[4][GFX_LEAN_CHUNK];
-  __shared__ double s_kv[108];
-  __shared__ uint32_t s_cls[GFX_KIDS_WORDS * 128];
-  for (int i = threadIdx.x; i < 108; i += blockDim.x) s_kv[i] = a.kv[i];
+  __shared__ uint16_t s_list[4][GFX_LEAN_CHUNK_T];
+  __shared__ uint2 s_ku[16];
+  kid_units_init(s_ku);
   __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t chunks = (a.n_snps + GFX_LEAN_CHUNK - 1) / GFX_LEAN_CHUNK;
+  const int64_t chunks = (a.n_snps + GFX_LEAN_CHUNK_T - 1) / GFX_LEAN_CHUNK_T;
   const int64_t tasks = (int64_t)a.n_focal * chunks;
   const uint32_t tp = a.c.tp_raw;
   for (;;) {
@@ -2033,13 +2230,14 @@ __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
     // animal-major task order, heaviest animals first: the long tasks of the many-mate sires start at once
     // (measured: chunk-major order is 40 % slower because the last chunk's heavy tasks start late)
     const int f = a.focal_order[task / chunks];
-    const int64_t j0 = (int64_t)(task % chunks) * GFX_LEAN_CHUNK;
+    const int64_t j0 = (int64_t)(task % chunks) * GFX_LEAN_CHUNK_T;
     const int row = a.focal_row[f];
     const int e0 = a.focal_off[f], e1 = a.focal_off[f + 1];
     // pass 1: SNPs where at least one job of this animal is suspect (:181-185 / :342); E >= test_p is a
     // comparison of raw patterns because E is monotone in the score
     int cnt = 0;
-    for (int t = 0; t < GFX_LEAN_CHUNK / 32; ++t) {
+    for (int t = 0; t < GFX_LEAN_CHUNK_T / 32; ++t) {
+      if (j0 + t * 32 >= a.n_snps) break;
       const int64_t j = j0 + t * 32 + lane;
       bool sus = false;
       if (j < a.n_snps) {
@@ -2052,7 +2250,7 @@ __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
           }
       }
       const uint32_t m = __ballot_sync(0xffffffffu, sus);
-      if (sus) s_list[wib][cnt + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(t * 32 + lane);
+      if (sus) s_list[wib][cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(t * 32 + lane);
       cnt += __popc(m);
     }
     __syncwarp();
@@ -2062,7 +2260,8 @@ __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
       bool defer = false;
       if (k < cnt) {
         j = j0 + s_list[wib][k];
-        defer = !lean_cell(a, s_kv, s_cls + threadIdx.x, f, row, e0, e1, j);
+        // posteriors requested: every cell takes the literal whole-cell kernel (the reference's own arithmetic)
+        defer = a.post != nullptr || !lean_cell(a, s_ku, f, row, e0, e1, j);
       }
       // (rare) whole cell to the fallback kernel through the bitmap
       if (defer) {
@@ -2107,7 +2306,7 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
     const uint2 it = a.items[i];
     // items of cells that found no slot were never counted; they keep their cell on the fallback path
     if (it.x >= ncell) continue;
-    const int key = a.focal_off[a.wl[it.x].x] + (int)it.y - a.e_base;
+    const int key = a.focal_off[a.wl[it.x].x] + (int)(it.y & ~GFX_ITEM_LITERAL) - a.e_base;
     const uint32_t pos = a.key_off[key] + atomicAdd(a.key_cur + key, 1u);
     a.items_sorted[pos] = it;
   }
@@ -2138,11 +2337,12 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
         const int row = a.focal_row[f];
         const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);
         const uint32_t rxf = cell_rx(a.c, row, j);
-        const double* kd = a.skids + (unsigned long long)it.x * 4;
-        const double kids[3] = {kd[0], kd[1], kd[2]};
+        const int4 kc = a.skc[it.x];
+        const KidCounts K{kc.x, kc.y, kc.z, kc.w};
+        const int ji = (int)(it.y & ~GFX_ITEM_LITERAL);
         uint32_t bits;
-        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + (int)it.y], j, obs0, rxf, kd[3] != 0.0, kids, &bits))
-          a.sbits[(unsigned long long)it.x * a.maxj + it.y] = (uint8_t)bits;
+        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, (it.y & GFX_ITEM_LITERAL) != 0u, &bits))
+          a.sbits[(unsigned long long)it.x * a.maxj + ji] = (uint8_t)bits;
         else
           again = true;
       }
@@ -2165,7 +2365,13 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
 #ifndef KJ_ITEMS
 #define KJ_ITEMS 32   // jobs per ticket of the tree-message-passing round
 #endif
-__global__ void __launch_bounds__(128, KJ_BLOCKS) k_correct_jobs(FocalArgs a) {
+// One warp per block in both deferred-job kernels: they end in a long tail of a few slow items, and a block keeps the
+// registers of all its warps until the last one retires -- with 4-warp blocks the tail pinned the register file of
+// every SM and the kernels of the other lanes (chunks) could not start next to it.
+#ifndef KJ_THREADS
+#define KJ_THREADS 32
+#endif
+__global__ void __launch_bounds__(KJ_THREADS, KJ_BLOCKS * 128 / KJ_THREADS) k_correct_jobs(FocalArgs a) {
   unsigned long long n = *a.item_count;
   if (n > a.item_cap) n = a.item_cap;
   jobs_round<1, KJ_ITEMS>(a, a.items_sorted, n, a.wl_count + 4);
@@ -2176,7 +2382,7 @@ __global__ void __launch_bounds__(128, KJ_BLOCKS) k_correct_jobs(FocalArgs a) {
 #ifndef KG_ITEMS
 #define KG_ITEMS 16   // jobs per ticket of the general round (measured: 16 beats 32 and 8)
 #endif
-__global__ void __launch_bounds__(128, KG_BLOCKS) k_correct_jobs_general(FocalArgs a) {
+__global__ void __launch_bounds__(KJ_THREADS, KG_BLOCKS * 128 / KJ_THREADS) k_correct_jobs_general(FocalArgs a) {
   jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6);
 }
 
@@ -2279,10 +2485,10 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.key_cur = a.key_off + nk4;
   char* base = (char*)(a.key_cur + nk4);
   const int64_t avail = (char*)(snapshot + scratch_words) - base;
-  const int64_t per_slot = 32 + 8 + 8 + 16 + 16 + maxj_p;
+  const int64_t per_slot = 16 + 8 + 8 + 16 + 16 + maxj_p;
   const int64_t scap = avail > 0 ? avail / per_slot : 0;
   if (scap < 1024) return fail(GFX_E_INVALID, "scratch too small for the deferred-cell lists");
-  a.skids = (double*)base;                       base += scap * 32;
+  a.skc = (int4*)base;                           base += scap * 16;
   a.wl = (uint2*)base;                           base += scap * 8;
   a.st = (uint2*)base;                           base += scap * 8;
   a.items = (uint2*)base;                        base += scap * 16;
@@ -2298,18 +2504,20 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   int64_t blocks = tasks;
   const int64_t cap = (int64_t)s->num_sms * 24;
   if (blocks > cap) blocks = cap;
-  const int64_t wtasks = (int64_t)n_focal * ((n_snps + GFX_LEAN_CHUNK - 1) / GFX_LEAN_CHUNK);
+  const int lean_chunk = nf == 2 ? GFX_LEAN_CHUNK : GFX_LEAN_CHUNK_SINGLES;
+  const int64_t wtasks = (int64_t)n_focal * ((n_snps + lean_chunk - 1) / lean_chunk);
   int64_t lblocks = (wtasks + 3) / 4;
   if (lblocks > (int64_t)s->num_sms * KC_BLOCKS) lblocks = (int64_t)s->num_sms * KC_BLOCKS;
-  k_correct<<<(int)lblocks, 128, 0, stream>>>(a);
+  if (nf == 2) k_correct<GFX_LEAN_CHUNK><<<(int)lblocks, 128, 0, stream>>>(a);
+  else k_correct<GFX_LEAN_CHUNK_SINGLES><<<(int)lblocks, 128, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_jobs_scan<<<1, 1024, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_jobs_scatter<<<s->num_sms * 4, 256, 0, stream>>>(a);
   GFX_LAUNCHED();
-  k_correct_jobs<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  k_correct_jobs<<<s->num_sms * 8 * (128 / KJ_THREADS), KJ_THREADS, 0, stream>>>(a);
   GFX_LAUNCHED();
-  k_correct_jobs_general<<<s->num_sms * 8, 128, 0, stream>>>(a);
+  k_correct_jobs_general<<<s->num_sms * 8 * (128 / KJ_THREADS), KJ_THREADS, 0, stream>>>(a);
   GFX_LAUNCHED();
   k_correct_apply<<<s->num_sms * 4, 128, 0, stream>>>(a);
   GFX_LAUNCHED();

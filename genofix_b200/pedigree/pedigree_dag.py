@@ -99,6 +99,7 @@ class PedigreeDAG(object):
         dag = PedigreeDAG()
         dag._set_arrays(ids, sire_idx, dam_idx, sex, rank)
         dag._both_sexes = is_male & is_female
+        dag._table = t      # kept so that `males` / `females` can be built in the reference's insertion order
         return dag
 
     @staticmethod
@@ -150,11 +151,23 @@ class PedigreeDAG(object):
 
     @property
     def males(self):
-        return self._get("males", lambda: set(int(x) for x in self.ids[self.sex == 1]))
+        def build():
+            t = getattr(self, "_table", None)
+            if t is None:
+                return set(int(x) for x in self.ids[self.sex == 1])
+            # the reference's own expression (pedigree_dag.py:190): same elements, same insertion order, so that
+            # iterating the set (split_pedigree, generationIndex) visits the animals in the reference's order
+            return set([int(r[1]) for r in t if int(r[1]) > 0] + [int(r[0]) for r in t if r[3] == 1 and int(r[0]) > 0])
+        return self._get("males", build)
 
     @property
     def females(self):
-        return self._get("females", lambda: set(int(x) for x in self.ids[(self.sex == 2) | self._both_sexes]))
+        def build():
+            t = getattr(self, "_table", None)
+            if t is None:
+                return set(int(x) for x in self.ids[(self.sex == 2) | self._both_sexes])
+            return set([int(r[2]) for r in t if int(r[2]) > 0] + [int(r[0]) for r in t if r[3] == 2 and int(r[0]) > 0])   # :191
+        return self._get("females", build)
 
     @property
     def kid2sire(self):
@@ -381,50 +394,92 @@ class PedigreeDAG(object):
         return lines
 
     def split_pedigree(self, min_cluster_size=100):
-        """Connected families of mating pairs (pedigree_dag.py:41-122): union-find over mates, kids
-        attached to a parent's cluster, then clusters smaller than min_cluster_size merged into a
-        cluster holding one of their parents or kids."""
-        n = len(self.ids)
-        root = np.arange(n)
+        """Clusters of animals around connected mating pairs (pedigree_dag.py:41-122).  The reference's procedure is
+        order dependent (first matching cluster wins, clusters are scanned by size, Python set iteration order decides
+        ties), so it is followed step by step on the same Python sets; only the membership tests use an index instead
+        of scanning.  Returns a list of sets of ids like the reference."""
+        allkids = self.males.union(self.females)
+        partner_pairs = list(set([(sire, dam) for sire, dam in [self.get_parents(kid) for kid in allkids]
+                                  if sire is not None and dam is not None]))                       # :42
+        clustered_pairs = []
+        member = defaultdict(list)      # animal -> positions of the clusters holding it (ascending; valid until the merges)
 
-        def find(x):
-            while root[x] != x:
-                root[x] = root[root[x]]
-                x = root[x]
-            return x
-        both = np.nonzero((self.sire_idx >= 0) & (self.dam_idx >= 0))[0]
-        for k in both:
-            a, b = find(self.sire_idx[k]), find(self.dam_idx[k])
-            if a != b:
-                root[b] = a
-        paired = np.zeros(n, bool)
-        paired[self.sire_idx[both]] = True
-        paired[self.dam_idx[both]] = True
-        for k in np.nonzero(~paired)[0]:
-            p = self.sire_idx[k] if self.sire_idx[k] >= 0 else self.dam_idx[k]
-            if p < 0:
-                raise Exception("%s illegal lone node in pedigree" % int(self.ids[k]))
-            root[find(k)] = find(p)
-        for _ in range(n):
-            comp = defaultdict(list)
-            for i in range(n):
-                comp[find(i)].append(i)
-            small = [c for c in comp.values() if len(c) < min_cluster_size]
-            merged = False
-            for c in sorted(small, key=len):
-                me = find(c[0])
-                for i in c:
-                    rel = [self.sire_idx[i], self.dam_idx[i]] + list(self._children_idx(i))
-                    tgt = [find(r) for r in rel if r >= 0 and find(r) != me]
-                    if tgt:
-                        root[me] = tgt[0]
-                        merged = True
+        def first_cluster(a, b):
+            """position of the first cluster that holds a or b, and which of the two it holds first (a wins a tie)"""
+            ia = member[a][0] if a is not None and member.get(a) else None
+            ib = member[b][0] if b is not None and member.get(b) else None
+            if ia is None and ib is None:
+                return None, None
+            if ib is None or (ia is not None and ia <= ib):
+                return ia, 0
+            return ib, 1
+        for sire, dam in partner_pairs:                                                               # :44-56
+            pos, which = first_cluster(sire, dam)
+            if pos is None:
+                clustered_pairs.append({sire, dam})
+                member[sire].append(len(clustered_pairs) - 1)
+                member[dam].append(len(clustered_pairs) - 1)
+            else:
+                new = dam if which == 0 else sire
+                if new not in clustered_pairs[pos]:
+                    clustered_pairs[pos].add(new)
+                    lst = member[new]
+                    lst.append(pos)
+                    lst.sort()
+        pairedkids = set([x[0] for x in partner_pairs] + [x[1] for x in partner_pairs])
+        singlekids = [x for x in allkids if x not in pairedkids]
+        for kid in singlekids:                                                                        # :61-74
+            sire, dam = self.get_parents(kid)
+            pos, _which = first_cluster(sire, dam)
+            if pos is None:
+                raise Exception("%s illegal lone node in pedigree" % kid)
+            if kid not in clustered_pairs[pos]:
+                clustered_pairs[pos].add(kid)
+                lst = member[kid]
+                lst.append(pos)
+                lst.sort()
+        # clusters that share an animal are merged, smallest first (:78-90); list positions change from here on
+        for _i in range(len(clustered_pairs)):
+            merged_any = False
+            for cluster in sorted(clustered_pairs, key=lambda x: len(x)):
+                for target in sorted([x for x in clustered_pairs if x != cluster], key=lambda x: len(x)):
+                    if not cluster.isdisjoint(target):
+                        target.update(cluster)
+                        clustered_pairs.remove(cluster)
+                        merged_any = True
                         break
-                if merged:
-                    break
-            if not merged:
-                break
-        comp = defaultdict(set)
-        for i in range(n):
-            comp[find(i)].add(int(self.ids[i]))
-        return list(comp.values())
+            if not merged_any:
+                break       # a pass without a merge leaves the list as it is: the remaining passes are no-ops
+        k2s, k2d, s2k, d2k = self.kid2sire, self.kid2dam, self.sire2kid, self.dam2kid
+        for size in range(min_cluster_size):                                                          # :94-121
+            for _i in range(len(clustered_pairs)):
+                found = False
+                for cluster in [x for x in clustered_pairs if len(x) == size]:
+                    sires = set([k2s[x] for x in cluster if x in k2s])
+                    dams = set([k2d[x] for x in cluster if x in k2d])
+                    parents = sires.union(dams)
+                    for target in sorted([x for x in clustered_pairs if x != cluster], key=lambda x: len(x)):
+                        if len(parents.intersection(target)) > 0:
+                            target.update(cluster)
+                            clustered_pairs.remove(cluster)
+                            found = True
+                            break
+                    if found:
+                        break
+                    kids = [list(s2k[x]) for x in cluster if x in s2k]
+                    if len(kids) > 0:
+                        kids = set(np.concatenate(kids))
+                    kids2 = [list(d2k[x]) for x in cluster if x in d2k]
+                    if len(kids2) > 0:
+                        kids = kids.union(set(np.concatenate(kids2)))      # AttributeError like the reference when `kids` is still a list
+                    for target in sorted([x for x in clustered_pairs if x != cluster], key=lambda x: len(x)):
+                        if len(kids.intersection(target)) > 0:
+                            target.update(cluster)
+                            clustered_pairs.remove(cluster)
+                            found = True
+                            break
+                    if found:
+                        break
+                if not found:
+                    break   # no cluster of this size can be merged any more: the remaining passes repeat the same scan
+        return clustered_pairs

@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
     python oracle/make_golden.py [name ...]
 The fixtures are committed; the GPU box only reads them.
 """
+import contextlib
+import io
 import os
 import re
 import sys
@@ -292,12 +294,100 @@ def make_kats():
     print("kats written")
 
 
+# --------------------------------------------------------------------------------------------
+# round 2: surfaces that had no pinned answers yet (split_pedigree, getCountTable, getEmpProbs)
+# --------------------------------------------------------------------------------------------
+def _no_lone_pedigree(n, gens, seed, **kw):
+    """synthetic pedigree without animals that are neither parents nor have parents (split_pedigree raises on those)"""
+    from genofix_b200 import synth
+    rows = synth.make_pedigree(n, gens, seed=seed, **kw)
+    parents = set(rows[:, 1]) | set(rows[:, 2])
+    keep = [(r[1] > 0 or r[2] > 0 or r[0] in parents) for r in rows]
+    return rows[np.array(keep)]
+
+
+def make_kats2():
+    """tests/golden/kats2.npz: PedigreeDAG.split_pedigree (pedigree/pedigree_dag.py:41-122) on example.fam and two synthetic
+    pedigrees, JointAllellicDistribution.getCountTable (empirical/jalleledist3.py:101-117) on indexes counted by the
+    reference's countJointFrqAll, and CorrectGenotypes.getEmpProbs (correct_genotypes3.py:69-82)."""
+    import itertools
+    import multiprocessing
+    import pandas as pd
+    from genofix_b200 import synth
+    ref = rh.load()
+    pdag, jad3, cg3 = ref["pdag"], ref["jad3"], ref["cg3"]
+    out = {}
+    # ---- split_pedigree: cluster number of every member, in the reference's list order ----
+    peds = {"example": (np.loadtxt(os.path.join(rh.REF_SRC, "..", "examples", "simulate", "example.fam"), dtype=np.int64,
+                                   usecols=(0, 1, 2, 3)), [100, 10]),
+            "syn_a": (_no_lone_pedigree(1500, 8, 5, sire_frac=0.1, dam_frac=0.5), [100, 30]),
+            "syn_b": (_no_lone_pedigree(800, 6, 9, sire_frac=0.3, dam_frac=0.6, related_mating_p=0.3), [50])}
+    for name, (rows, sizes) in peds.items():
+        out["split_rows_" + name] = rows
+        for mcs in sizes:
+            cl = pdag.PedigreeDAG.from_table(rows).split_pedigree(mcs)
+            flat = np.array([(i, int(a)) for i, c in enumerate(cl) for a in sorted(c)], dtype=np.int64)
+            out["split_%s_%d" % (name, mcs)] = flat
+            print("split", name, mcs, len(cl), "clusters")
+    lone = synth.make_pedigree(300, 4, seed=3)
+    out["split_rows_lone"] = lone
+    try:
+        pdag.PedigreeDAG.from_table(lone).split_pedigree(100)
+        out["split_lone_error"] = np.array("")
+    except Exception as e:  # noqa: B902 -- the message is the pinned behaviour
+        out["split_lone_error"] = np.array(str(e))
+    # ---- LD index counted by the reference, getCountTable / getEmpProbs on it ----
+    rs = np.random.Generator(np.random.PCG64(77))
+    n, s = 250, 14
+    names = ["SNP%d" % i for i in range(s)]
+    base = rs.integers(0, 3, size=(n, 1))
+    G = np.where(rs.random((n, s)) < 0.6, base, rs.integers(0, 3, size=(n, s))).astype(np.uint8)   # some LD
+    df = pd.DataFrame(G, index=np.arange(1, n + 1), columns=names)
+    out["emp_G"] = G
+    for sur in (1, 2, 3):
+        with contextlib.redirect_stdout(io.StringIO()), rh.deterministic_pools():
+            emp = jad3.JointAllellicDistribution("1", names, surround_size=sur)
+            emp.countJointFrqAll(df, threads=1)
+        freq = np.zeros((s, 3 ** (2 * sur + 1)))
+        wlen = np.zeros(s, dtype=np.int64)
+        for i, snp in enumerate(names):
+            win = emp.getWindow(snp)
+            wlen[i] = len(win)
+            for k, v in enumerate(itertools.product([0, 1, 2], repeat=len(win))):
+                freq[i, k] = emp.snp2frequency[snp][tuple(zip(win, v))]
+        out["emp_freq_%d" % sur] = freq
+        out["emp_wlen_%d" % sur] = wlen
+        # getCountTable for every (animal of the first 40, SNP): complete evidence (no 9: the reference raises there, D4)
+        ct = np.zeros((40, s, 3))
+        for a in range(40):
+            ev = {snp: int(G[a, j]) for j, snp in enumerate(names)}
+            for j, snp in enumerate(names):
+                ct[a, j] = emp.getCountTable(ev, snp)
+        out["emp_counttable_%d" % sur] = ct
+        # getEmpProbs on the window chunk of every SNP (D3: the worker state is installed directly, initializerEmp
+        # copies a `frequency` attribute jalleledist3 objects do not have)
+        multiprocessing.current_process().indexemp = emp
+        ep = np.full((s, n, 3), np.nan)
+        for j, snp in enumerate(names):
+            win = emp.getWindow(snp)
+            if snp not in win:
+                continue
+            res = cg3.CorrectGenotypes.getEmpProbs(df.loc[:, win].copy(deep=True), snp)
+            for (kid, _obs), v in res.items():
+                ep[j, kid - 1] = v
+        out["emp_probs_%d" % sur] = ep
+    np.savez_compressed(os.path.join(OUT, "kats2.npz"), **out)
+    print("kats2 written")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     names = sys.argv[1:] or ["kats"] + list(CASES) + list(ERRCHK_CASES) + list(PREIDX_CASES)
     for n in names:
         if n == "kats":
             make_kats()
+        elif n == "kats2":
+            make_kats2()
         elif n in ERRCHK_CASES:
             make_errchk(n)
         elif n in PREIDX_CASES:

@@ -14,7 +14,7 @@ out = eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
 print("test_p", eng.stats["test_p"], "info", eng.schedule.info)
 cnt = np.zeros(16, dtype=np.uint64)
 _lib.check(L.gfx_debug_counters(eng.schedule.handle, 1, cnt.ctypes.data_as(C.c_void_p)))
-names = ["queries", "parent-only", "eliminations", "big reruns", "nodes touched", "suspect cells", "job evals", "children visited", "xpeel", "x:visited-twice", "x:unobs-kid-with-kids", "x:q-has-kids", "x:ok tree-only", "x:ok obs-kids/obs-mates", "x:ok recursion", "x:failed (3 x 20 bits)"]
+names = ["queries", "parent-only", "eliminations", "big reruns", "nodes touched", "suspect cells", "job evals (fast + deferred)", "children visited", "fast: not plainly peelable (+ xpeel ok in deferred)", "fast: guard band (+ x:visited-twice)", "fast: children term known", "x:q-has-kids", "x:ok tree-only", "x:ok obs-kids/obs-mates", "x:ok recursion", "x:failed (3 x 20 bits)"]
 # per phase
 eng._alloc(obs.shape[1])
 eng.mendel_rank_device(); eng.thresholds_device(0.95)

@@ -191,6 +191,34 @@ def test_snp_permutation_property_at_scale():
     assert np.array_equal(c, o["corrected"])
 
 
+@pytest.mark.parametrize("params", [(0.5, 0.64, 0.95, 0.4), (0.25, 0.5, 0.9, 0.25), (0.75, 0.75, 0.9, 0.0),
+                                    (0.5, 0.5, 0.8, 0.5), (1.0 / 3.0, 2.0 / 3.0, 0.9, 1.0 / 3.0)])
+def test_exact_integer_decisions_equal_the_literal_replay(params):
+    """The product decides from class counts of the children term in exact arithmetic and replays numpy's float64
+    sums only inside a 1e-9 guard band; with posteriors requested every cell takes the literal whole-cell kernel.
+    Both must give the same calls and tallies -- on thresholds chosen to hit exact rational ties (1/2, 1/4, 3/4, 1/3,
+    tie threshold 0) and on a pedigree with loops, missing calls and ungenotyped animals."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    tp, ts, q, tie = params
+    for case in range(2):
+        if case == 0:
+            rows = synth.make_pedigree(3000, 6, seed=77)
+            ids = rows[:, 0]
+            obs = synth.inject_errors(synth.gene_drop(rows, 256, seed=77), 0.01, seed=77)
+        else:
+            rows, ids, obs = _random_case(78, n=900, gens=8, s=192, related=0.3, unknown=0.05, miss=0.04, drop=0.1)
+        eng = Engine(PedigreeDAG.from_table(rows), ids, 2)
+        fast = eng.correct(obs, tp, ts, init_filter_p=q, tiethreshold=tie)
+        st_fast = (eng.stats["corrected_per_animal"].copy(), eng.stats["excluded_per_animal"].copy())
+        lit = eng.correct(obs, tp, ts, init_filter_p=q, tiethreshold=tie, keep_posteriors=True)
+        assert np.array_equal(fast, lit), int((fast != lit).sum())
+        assert np.array_equal(st_fast[0], eng.stats["corrected_per_animal"])
+        assert np.array_equal(st_fast[1], eng.stats["excluded_per_animal"])
+        assert case == 1 or (fast != obs).any()
+
+
 def test_trio_scan_matches_oracle():
     from genofix_b200.engine import Engine
     from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
@@ -840,3 +868,26 @@ def test_error_checker_matches_reference_on_example_pedigree():
     """error_checker.py on the reference's own examples/simulate/example.fam (4 560 animals, 4 235 kids with both parents
     genotyped) x 12 SNPs: 104 s of reference time, every float16 rank and every per-animal sum bit for bit."""
     test_error_checker_matches_reference_golden("errchk_example")
+
+
+@pytest.mark.parametrize("sur", [1, 2, 3])
+def test_count_joint_frq_all_matches_reference_index(sur):
+    """countJointFrqAll on the GPU against the frequencies the reference's own countJointFrqAll stored for the same
+    table (kats2.npz; jalleledist3.py:143-174), then getCountTable on the device-built index."""
+    import pandas as pd
+    from genofix_b200.empirical.jalleledist3 import JointAllellicDistribution
+    g = load_golden("kats2")
+    G = g["emp_G"]
+    n, s = G.shape
+    names = ["SNP%d" % i for i in range(s)]
+    emp = JointAllellicDistribution("1", names, surround_size=sur)
+    emp.countJointFrqAll(pd.DataFrame(G, index=np.arange(1, n + 1), columns=names))
+    for i, snp in enumerate(names):
+        w = int(g["emp_wlen_%d" % sur][i])
+        if w:
+            assert np.array_equal(emp._freq[snp], g["emp_freq_%d" % sur][i][:3 ** w]), snp
+    ct = g["emp_counttable_%d" % sur]
+    for a in range(0, ct.shape[0], 7):
+        ev = {snp: int(G[a, j]) for j, snp in enumerate(names)}
+        for j, snp in enumerate(names):
+            assert np.array_equal(np.asarray(emp.getCountTable(ev, snp), dtype=float), ct[a, j])

@@ -359,3 +359,95 @@ def test_preindex_seed_chunks_match_oracle(name):
     ped = PedigreeDAG.from_table(g["ped_rows"])
     for size in (10000, 7, 1):
         assert seed_chunks(ped, g["ids"], size) == go.preindex_chunks(go.OraclePedigree(g["ped_rows"]), g["ids"], size)
+
+
+# ---- round 2: surfaces that had no pinned answers ----------------------------------------
+def test_product_model_functions_match_reference_kats():
+    """genofix_b200.bayesnet.model (the product functions, not the oracle's copies) against the answers of the
+    reference's bayesnet/model.py:65-133 stored in kats.npz."""
+    from genofix_b200.bayesnet import model
+    g = load_golden("kats")
+    for c in range(len(g["kid"])):
+        n = int((g["kid"][c] >= 0).sum())
+        ks = [int(k) for k in g["kid"][c, :n]]
+        ps = [None if p < 0 else int(p) for p in g["par"][c, :n]]
+        assert np.array_equal(np.asarray(model.generate_probs_kids(ks, ps), dtype=float), g["probs_kids"][c])
+        inc = [k in (0, 1, 2) for k in ks]
+        ks_i = [k for k, i in zip(ks, inc) if i]
+        ps_i = [p for p, i in zip(ps, inc) if i]
+        for o in range(3):
+            d = model.generate_probs_differences_kids(ks_i, ps_i, o) if ks_i else []
+            want = g["diff_kids"][c, o, :len(ks_i)]
+            assert len(d) == len(ks_i)
+            assert np.array_equal(np.array(d, dtype=np.float16).view(np.uint16), want.view(np.uint16))
+    # unusable children: one (zero) entry each, after the usable ones (model.py:100,113-115)
+    d = model.generate_probs_differences_kids([9, 0, 9, 2], [None, None, 1, None], 0)
+    assert len(d) == 4 and float(d[2]) == 0.0 and float(d[3]) == 0.0 and float(d[1]) > 0
+    assert model.generate_probs_differences_kids([9, 9], [None, 1], 1) == []
+    assert np.allclose(model.generate_probs_kids([1, 0, 1, 0, 1], [2, 2, 2, 2, 2]), [2 / 3, 1 / 3, 0])      # model.py:91
+    for args, want in (((2, 2, 1), 1.0), ((1, 1, 0), 0.25), ((2, 9, 0), 0.5), ((9, 2, 0), 0.5), ((9, 9, 1), 0)):   # :136-140
+        assert model.generate_probs_differences_parent(*args) == want
+    for i, p1 in enumerate([0, 1, 2, 9]):
+        for j, p2 in enumerate([0, 1, 2, 9]):
+            for o in range(3):
+                assert model.generate_probs_differences_parent(p1, p2, o) == g["diff_parent"][i, j, o]
+
+
+@pytest.mark.parametrize("name,mcs", [("example", 100), ("example", 10), ("syn_a", 100), ("syn_a", 30), ("syn_b", 50)])
+def test_split_pedigree_matches_reference(name, mcs):
+    """PedigreeDAG.split_pedigree against the clusters the reference's own method returned (pedigree_dag.py:41-122),
+    in the reference's list order."""
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    g = load_golden("kats2")
+    want = g["split_%s_%d" % (name, mcs)]
+    cl = PedigreeDAG.from_table(g["split_rows_" + name]).split_pedigree(mcs)
+    mine = np.array([(i, int(a)) for i, c in enumerate(cl) for a in sorted(c)], dtype=np.int64)
+    assert np.array_equal(mine, want)
+
+
+def test_split_pedigree_lone_node_raises_like_the_reference():
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    g = load_golden("kats2")
+    msg = str(g["split_lone_error"])
+    assert msg.endswith("illegal lone node in pedigree")
+    with pytest.raises(Exception) as e:
+        PedigreeDAG.from_table(g["split_rows_lone"]).split_pedigree(100)
+    assert str(e.value) == msg
+
+
+@pytest.mark.parametrize("sur", [1, 2, 3])
+def test_count_table_and_emp_probs_match_reference(sur):
+    """JointAllellicDistribution.getCountTable (jalleledist3.py:101-117) and CorrectGenotypes.getEmpProbs
+    (correct_genotypes3.py:69-82) on an index holding the frequencies the reference's countJointFrqAll stored
+    (complete evidence: with a missing call the reference raises)."""
+    import pandas as pd
+    from genofix_b200.correct_genotypes3 import CorrectGenotypes, initializerEmp
+    from genofix_b200.empirical.jalleledist3 import JointAllellicDistribution
+    g = load_golden("kats2")
+    G = g["emp_G"]
+    n, s = G.shape
+    names = ["SNP%d" % i for i in range(s)]
+    emp = JointAllellicDistribution("1", names, surround_size=sur)
+    for i, snp in enumerate(names):
+        w = int(g["emp_wlen_%d" % sur][i])
+        assert len(emp.getWindow(snp)) == w
+        emp._freq[snp] = g["emp_freq_%d" % sur][i][:3 ** w].copy()
+    ct = g["emp_counttable_%d" % sur]
+    for a in range(ct.shape[0]):
+        ev = {snp: int(G[a, j]) for j, snp in enumerate(names)}
+        for j, snp in enumerate(names):
+            assert np.array_equal(np.asarray(emp.getCountTable(ev, snp), dtype=float), ct[a, j]), (a, snp)
+    initializerEmp(emp)
+    df = pd.DataFrame(G, index=np.arange(1, n + 1), columns=names)
+    ep = g["emp_probs_%d" % sur]
+    for j, snp in enumerate(names):
+        win = emp.getWindow(snp)
+        if snp not in win:
+            assert np.isnan(ep[j]).all()          # D11: the last SNP's window does not contain it
+            continue
+        res = CorrectGenotypes.getEmpProbs(df.loc[:, win], snp)
+        got = np.full((n, 3), np.nan)
+        for (kid, obs), v in res.items():
+            assert obs == G[kid - 1, j]
+            got[kid - 1] = v
+        assert np.array_equal(got, ep[j], equal_nan=True), snp

@@ -1370,7 +1370,8 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
       GFX_CUDA(cudaMalloc((void**)&dev, tasks.size() * sizeof(RankRow)));
       cudaError_t e = cudaMemcpy(dev, tasks.data(), tasks.size() * sizeof(RankRow), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) { cudaFree(dev); return fail(GFX_E_CUDA, std::string("task table upload: ") + cudaGetErrorString(e)); }
-      if (ms->rank_tasks.size() >= 8) { cudaDeviceSynchronize(); cudaFree(ms->rank_tasks.front().dev); ms->rank_tasks.erase(ms->rank_tasks.begin()); }
+      // tables are never evicted: another lane (host thread on the same schedule) may be about to launch on one, and a
+      // table is 32 bytes per task -- a few MB per distinct matrix width
       ms->rank_tasks.push_back({nwords, dev, (uint32_t)tasks.size()});
       tasks_dev = dev;
       n_tasks = (uint32_t)tasks.size();
@@ -1378,11 +1379,16 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   }
   RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, tasks_dev, n_tasks, s->child_row,
              s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist};
-  static bool attr_set = false;
-  if (!attr_set) {
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM));
-    GFX_CUDA(cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM));
-    attr_set = true;
+  {
+    // once per process (one process per GPU); guarded: several lanes call this concurrently
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, []() {
+      attr_err = cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM);
+    });
+    GFX_CUDA(attr_err);
   }
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
   int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
@@ -2365,11 +2371,11 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
 #ifndef KJ_ITEMS
 #define KJ_ITEMS 32   // jobs per ticket of the tree-message-passing round
 #endif
-// One warp per block in both deferred-job kernels: they end in a long tail of a few slow items, and a block keeps the
-// registers of all its warps until the last one retires -- with 4-warp blocks the tail pinned the register file of
-// every SM and the kernels of the other lanes (chunks) could not start next to it.
+// Threads per block of the two deferred-job kernels.  One-warp blocks (so that the long tail of a few slow items
+// does not pin the registers of whole 4-warp blocks next to the other lanes' kernels) were measured: no gain in the
+// 3-lane bench step (47.7 vs 48.3 ms), slower alone -- profiles/r2_summary.md.
 #ifndef KJ_THREADS
-#define KJ_THREADS 32
+#define KJ_THREADS 128
 #endif
 __global__ void __launch_bounds__(KJ_THREADS, KJ_BLOCKS * 128 / KJ_THREADS) k_correct_jobs(FocalArgs a) {
   unsigned long long n = *a.item_count;

@@ -121,17 +121,28 @@ class PackedGens(object):
 
     def packed_columns(self, a, b, out=None):
         """Packed block of SNP columns [a, b) for all animals: uint32 [n, words_per_row(b - a)], ready for
-        Engine.correct_chunks(..., packed_io=True).  `a` must be a multiple of 16 (word boundary).
+        Engine.correct_chunks(..., packed_io=True).  Only the words of these columns are read from the file.  A start
+        that is not a multiple of 16 is handled by shifting across word boundaries.
         `out` may be a pinned array (genofix_b200.engine.pinned_array(shape, np.uint32))."""
-        if a % 16 or not (0 <= a < b <= self.n_snps):
-            raise ValueError("need 0 <= a < b <= n_snps and a % 16 == 0")
+        if not (0 <= a < b <= self.n_snps):
+            raise ValueError("need 0 <= a < b <= n_snps")
         s = b - a
         w0, nw, wpr = a // 16, (s + 15) // 16, words_per_row(s)
         if out is None:
             out = np.empty((self.n_animals, wpr), dtype=np.uint32)
         if out.shape != (self.n_animals, wpr) or out.dtype != np.uint32:
             raise ValueError("out must be uint32 [%d, %d]" % (self.n_animals, wpr))
-        out[:, :nw] = self.packed[:, w0:w0 + nw]
+        sh = 2 * (a % 16)
+        if sh == 0:
+            out[:, :nw] = self.packed[:, w0:w0 + nw]
+        else:
+            last = min(self.wpr, w0 + nw + 1)
+            src = np.asarray(self.packed[:, w0:last], dtype=np.uint32)
+            lo = src[:, :nw] >> np.uint32(sh)
+            hi = np.zeros_like(lo)
+            k = src.shape[1] - 1                     # words that have a successor inside the row
+            hi[:, :min(nw, k)] = src[:, 1:1 + min(nw, k)] << np.uint32(32 - sh)
+            out[:, :nw] = lo | hi
         out[:, nw:] = 0xFFFFFFFF
         if s % 16:   # cells of the last word beyond b belong to the next block: mark them missing (padding)
             out[:, nw - 1] |= np.uint32((0xFFFFFFFF << (2 * (s % 16))) & 0xFFFFFFFF)
@@ -139,11 +150,18 @@ class PackedGens(object):
 
     def store_columns(self, a, b, block):
         """Write a corrected packed block back (file opened with mode='r+'); padding cells are not stored."""
-        if a % 16 or not (0 <= a < b <= self.n_snps):
-            raise ValueError("need 0 <= a < b <= n_snps and a % 16 == 0")
+        if not (0 <= a < b <= self.n_snps):
+            raise ValueError("need 0 <= a < b <= n_snps")
         s = b - a
-        w0, nw = a // 16, (s + 15) // 16
         blk = np.asarray(block, dtype=np.uint32)
+        if a % 16:
+            # unaligned start: through the codes of the covering words (single writer only: neighbouring blocks share words)
+            w0, w1 = a // 16, (b + 15) // 16
+            codes = unpack_codes(np.asarray(self.packed[:, w0:w1]), (w1 - w0) * 16)
+            codes[:, a - 16 * w0:b - 16 * w0] = unpack_codes(blk, s)
+            self.packed[:, w0:w1] = pack_codes(codes)[:, :w1 - w0]
+            return
+        w0, nw = a // 16, (s + 15) // 16
         if s % 16 and b < self.n_snps:
             keep = np.uint32((1 << (2 * (s % 16))) - 1)
             self.packed[:, w0 + nw - 1] = (self.packed[:, w0 + nw - 1] & ~keep) | (blk[:, nw - 1] & keep)

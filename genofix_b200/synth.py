@@ -149,3 +149,34 @@ def inject_missing(G, rate=0.05, seed=4321):
     m = rs.random(G.shape) < rate
     out[m] = 9
     return out
+
+
+def complete_rows(rows):
+    """Pedigree rows with a founder row (sire = dam = 0) added for every animal that only appears as a parent,
+    ordered parents before offspring -- what gene_drop needs (the reference's example.fam lists kids only)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    known = set(int(x) for x in rows[:, 0])
+    extra = []
+    for col, sex in ((1, 1), (2, 2)):
+        for p in np.unique(rows[:, col]):
+            if p > 0 and int(p) not in known:
+                extra.append((int(p), 0, 0, sex))
+                known.add(int(p))
+    allrows = np.array(extra + [tuple(int(v) for v in r[:4]) for r in rows], dtype=np.int64)
+    by = {int(r[0]): r for r in allrows}
+    out, done = [], set()
+    for k in by:
+        stack = [k]
+        while stack:
+            x = stack[-1]
+            if x in done:
+                stack.pop()
+                continue
+            pend = [int(p) for p in by[x][1:3] if p > 0 and int(p) in by and int(p) not in done]
+            if pend:
+                stack.extend(pend)
+            else:
+                done.add(x)
+                out.append(by[x])
+                stack.pop()
+    return np.array(out, dtype=np.int64)

@@ -539,13 +539,18 @@ class Oracle(object):
 
     # ---- correct_genotypes3.py:531-950 -------------------------------------------------------
     def correct_matrix(self, G, threshold_pair, threshold_single, back=2, init_filter_p=0.9,
-                       tiethreshold=0.05, err_thresh=1, raw=None, keep_posteriors=False):
+                       tiethreshold=0.05, err_thresh=1, raw=None, keep_posteriors=False, transformed=None):
+        """transformed = (E, test_p): ranks already transformed and the threshold already taken over the WHOLE matrix
+        of which G is a block of columns (correct_matrix_parallel); the correction of a column needs nothing else."""
         ped = self.ped
         G0 = np.array(G, dtype=np.uint8)
         G = G0.copy()
-        if raw is None:
-            raw = self.mendel_rank(G0, back)
-        E, test_p = self.transform(raw, G0, init_filter_p)
+        if transformed is not None:
+            E, test_p = transformed
+        else:
+            if raw is None:
+                raw = self.mendel_rank(G0, back)
+            E, test_p = self.transform(raw, G0, init_filter_p)
         corrected_n = np.zeros(len(self.ids), dtype=np.int32)
         excluded_n = np.zeros(len(self.ids), dtype=np.int32)
         pairs = set()
@@ -598,6 +603,45 @@ class Oracle(object):
                     G[fr, j] = new
         return dict(corrected=G, raw=raw, E=E, test_p=test_p, corrected_per_animal=corrected_n,
                     excluded_per_animal=excluded_n, pair_posteriors=posts, single_posteriors=sposts)
+
+
+def _par_rank(args):
+    rows, ids, block, back = args
+    return Oracle(rows, ids).mendel_rank(block, back)
+
+
+def _par_correct(args):
+    rows, ids, block, E, test_p, kw = args
+    r = Oracle(rows, ids).correct_matrix(block, transformed=(E, test_p), **kw)
+    return r["corrected"], r["corrected_per_animal"], r["excluded_per_animal"]
+
+
+def correct_matrix_parallel(rows, ids, G, threshold_pair, threshold_single, back=2, init_filter_p=0.9, tiethreshold=0.05,
+                            err_thresh=1, procs=None):
+    """Oracle.correct_matrix of ONE matrix on several processes (same result, checked in tests/test_oracle_golden.py):
+    the Mendel rank of a column and its correction given the threshold are independent of the other columns; only the
+    normalisation by the maximum and the quantile (:600-606,666-667) look at the whole matrix, so those run once in
+    between.  For the parity tests at BASELINE sizes."""
+    import multiprocessing as mp
+    import os
+    procs = procs or os.cpu_count() or 1
+    G = np.asarray(G, dtype=np.uint8)
+    s = G.shape[1]
+    procs = max(1, min(procs, s))
+    cuts = [int(round(i * s / procs)) for i in range(procs + 1)]
+    blocks = [(cuts[i], cuts[i + 1]) for i in range(procs) if cuts[i + 1] > cuts[i]]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(blocks)) as pool:
+        raws = pool.map(_par_rank, [(rows, ids, np.ascontiguousarray(G[:, a:b]), back) for a, b in blocks])
+        raw = np.concatenate(raws, axis=1)
+        E, test_p = Oracle.transform(raw, G, init_filter_p)
+        kw = dict(threshold_pair=threshold_pair, threshold_single=threshold_single, back=back, init_filter_p=init_filter_p,
+                  tiethreshold=tiethreshold, err_thresh=err_thresh)
+        res = pool.map(_par_correct, [(rows, ids, np.ascontiguousarray(G[:, a:b]), np.ascontiguousarray(E[:, a:b]), test_p, kw)
+                                      for a, b in blocks])
+    corrected = np.concatenate([r[0] for r in res], axis=1)
+    return dict(corrected=corrected, raw=raw, E=E, test_p=test_p, corrected_per_animal=sum(r[1] for r in res),
+                excluded_per_animal=sum(r[2] for r in res))
 
 
 # --------------------------------------------------------------------------------------------

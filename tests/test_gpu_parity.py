@@ -410,8 +410,10 @@ def test_pipelined_chunks_equal_chunk_by_chunk_calls():
     assert sum(int((o != obs[:, a:b]).sum()) for (o, _), (a, b) in zip(got, bounds)) > 0
 
 
-def test_multilane_results_do_not_depend_on_lane_count():
-    """Two lanes (two host threads, two stream sets, one shared schedule) give the chunk-by-chunk results."""
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_multilane_results_do_not_depend_on_lane_count(lanes):
+    """Two / three lanes (one host thread and stream set each, one shared schedule; bench.py runs three) give the
+    chunk-by-chunk results."""
     from genofix_b200 import synth
     from genofix_b200.engine import Engine, MultiLane
     from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
@@ -424,7 +426,7 @@ def test_multilane_results_do_not_depend_on_lane_count():
     for a, b in bounds:
         out = eng.correct(np.ascontiguousarray(obs[:, a:b]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
         ref.append((out, eng.stats["test_p"], eng.stats["corrected_per_animal"].copy()))
-    ml = MultiLane(ped, rows[:, 0], 2, lanes=2)
+    ml = MultiLane(ped, rows[:, 0], 2, lanes=lanes)
     from genofix_b200.engine import pinned_array
     # a mix of pinned (moved by the copy engines directly) and pageable (staged) inputs and outputs
     outs = [pinned_array((len(rows), b - a)) if i % 2 else np.empty((len(rows), b - a), np.uint8) for i, (a, b) in enumerate(bounds)]
@@ -891,3 +893,251 @@ def test_count_joint_frq_all_matches_reference_index(sur):
         ev = {snp: int(G[a, j]) for j, snp in enumerate(names)}
         for j, snp in enumerate(names):
             assert np.array_equal(np.asarray(emp.getCountTable(ev, snp), dtype=float), ct[a, j])
+
+
+# ---- entry points end to end and the multi-GPU product path (item 1d / 5) -----------------------
+def _write_case(tmp, n=600, gens=6, s=1300, seed=3):
+    import os
+    from genofix_b200 import synth
+    from genofix_b200.gfutils.packedgens import PackedGens
+    rows = synth.make_pedigree(n, gens, sire_frac=0.1, dam_frac=0.5, seed=seed)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, s, seed=seed), 0.01, seed=seed), 0.01, seed=seed + 1)
+    np.savetxt(os.path.join(tmp, "ped.fam"), rows, fmt="%d")
+    names = ["SNP%d" % (i + 1) for i in range(s)]
+    with open(os.path.join(tmp, "snps.map"), "w") as f:
+        for i, nm in enumerate(names):
+            f.write("%d %s %.2f %d\n" % (1 if i < 700 else 2, nm, 0.01 * i, 1000 * i))      # chromosome 2 starts at column 700
+    with open(os.path.join(tmp, "geno.ssv"), "w") as f:
+        f.write(" ".join(["id"] + names) + "\n")
+        for k, r in zip(rows[:, 0], obs):
+            f.write(" ".join([str(int(k))] + [str(int(v)) for v in r]) + "\n")
+    PackedGens.write(os.path.join(tmp, "geno.g2b"), rows[:, 0], names, obs)
+    return rows, obs, names
+
+
+def _run(cmd, **kw):
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, cwd=ROOT, env=env, timeout=900, **kw)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    return r
+
+
+def _expected_by_chunks(rows, obs, chunk, bounds):
+    """Engine.correct on the chunks genofix.py forms: per chromosome [a, b), chunk() of `chunk` SNPs"""
+    from genofix_b200.chunking import chunk as chunk_fn
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    want = obs.copy()
+    tall = np.zeros(len(rows), dtype=np.int64)
+    for a, b in bounds:
+        for cols in chunk_fn(list(range(a, b)), chunk):
+            want[:, cols] = eng.correct(np.ascontiguousarray(obs[:, cols]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+            tall += eng.stats["corrected_per_animal"]
+    return want, tall
+
+
+@pytest.mark.timeout(900)
+def test_genofix_entry_point_text_and_container_inputs(tmp_path):
+    """src/genofix.py end to end on a text matrix and on the 2-bit container (chunks that start inside a word: chromosome 2
+    begins at column 700): both outputs equal Engine.correct chunk by chunk, the corrected container equals the text."""
+    import pandas as pd
+    from genofix_b200.gfutils.packedgens import PackedGens
+    tmp = str(tmp_path)
+    rows, obs, names = _write_case(tmp)
+    want, tall = _expected_by_chunks(rows, obs, 300, [(0, 700), (700, 1300)])
+    assert (want != obs).any()
+    for inp, out in (("geno.ssv", "out_text"), ("geno.g2b", "out_g2b")):
+        _run(["src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/" + out, "-i", tmp + "/" + inp, "-C", "300"])
+        got = pd.read_csv(tmp + "/" + out + "/simulatedgenome_corrected_errors_threshold.ssv", sep=" ", index_col=0)
+        assert list(got.columns) == names and [int(x) for x in got.index] == [int(x) for x in rows[:, 0]]
+        assert np.array_equal(got.to_numpy(dtype=np.uint8), want), inp
+        t = pd.read_csv(tmp + "/" + out + "/corrections_per_animal.tsv", sep="\t", header=None, index_col=0)
+        assert np.array_equal(t.iloc[:, 0].to_numpy(), tall)
+    g = PackedGens(tmp + "/out_g2b/simulatedgenome_corrected_errors_threshold.g2b")
+    assert np.array_equal(g.getMatrix(rows[:, 0]), want)
+
+
+@pytest.mark.timeout(900)
+def test_simulate_and_founder_entry_points(tmp_path):
+    """src/simulate/simulate.py (host and --device_sim) and src/gfutils/extract_founders.py run end to end."""
+    import os
+    tmp = str(tmp_path)
+    rows, _obs, _names = _write_case(tmp, n=500, s=600)
+    for extra, out in (([], "sim_host"), (["--device_sim"], "sim_dev")):
+        r = _run(["src/simulate/simulate.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/" + out, "-c", "300",
+                  "-t", "0.4", "-l", "0.64"] + extra)
+        assert os.path.exists(tmp + "/" + out + "/statistics.tsv"), r.stdout[-800:]
+    _run(["src/gfutils/extract_founders.py", "-p", tmp + "/ped.fam", "-o", tmp + "/founders.txt"])
+    founders = set(int(x) for x in open(tmp + "/founders.txt").read().split())
+    assert founders == set(int(k) for k, s, d, _ in rows if s == 0 or d == 0)
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.is_available() and torch.cuda.device_count() >= 2
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_genofix_equals_one_rank(tmp_path):
+    """torchrun --nproc-per-node 2 src/genofix.py on the container input: same files as the single-process run (needs 2 GPUs)."""
+    import filecmp
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    tmp = str(tmp_path)
+    _write_case(tmp)
+    _run(["src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/one", "-i", tmp + "/geno.g2b", "-C", "300"])
+    _run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29611",
+          "src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/two", "-i", tmp + "/geno.g2b", "-C", "300"])
+    for f in ("simulatedgenome_corrected_errors_threshold.ssv", "simulatedgenome_corrected_errors_threshold.g2b", "corrections_per_animal.tsv"):
+        assert filecmp.cmp(tmp + "/one/" + f, tmp + "/two/" + f, shallow=False), f
+
+
+_NCCL_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch
+from genofix_b200 import parallel, synth
+from genofix_b200.engine import Engine
+from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+rank, world = parallel.init_from_env("nccl")
+rows = synth.make_pedigree(700, 6, sire_frac=0.1, dam_frac=0.5, seed=21, related_mating_p=0.2)
+obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 900, seed=21), 0.01, seed=21), 0.02, seed=22)
+eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+def correct_chunk(cols):
+    out = eng.correct(np.ascontiguousarray(obs[:, cols]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    return out, eng.stats["corrected_per_animal"]
+shards, tall = parallel.correct_sharded(obs.shape[1], 128, correct_chunk, obs.shape[0], rank, world, device="cuda")
+np.savez(os.path.join(sys.argv[2], "rank%d.npz" % rank), tall=tall.cpu().numpy(),
+         **{"c%d" % ci: c for ci, (_, c) in shards.items()}, **{"i%d" % ci: np.array(cols) for ci, (cols, _) in shards.items()})
+torch.distributed.destroy_process_group()
+"""
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_nccl_sharding_with_the_cuda_engine(tmp_path):
+    """parallel.correct_sharded on 2 NCCL ranks with the CUDA engine: the union of the shards equals the single-rank
+    result, the all-reduced tallies are identical on both ranks (needs 2 GPUs)."""
+    import os
+    from conftest import ROOT
+    from genofix_b200 import parallel, synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    tmp = str(tmp_path)
+    script = os.path.join(tmp, "worker.py")
+    with open(script, "w") as f:
+        f.write(_NCCL_WORKER)
+    _run(["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29612",
+          script, ROOT, tmp])
+    rows = synth.make_pedigree(700, 6, sire_frac=0.1, dam_frac=0.5, seed=21, related_mating_p=0.2)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 900, seed=21), 0.01, seed=21), 0.02, seed=22)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+
+    def correct_chunk(cols):
+        out = eng.correct(np.ascontiguousarray(obs[:, cols]), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+        return out, eng.stats["corrected_per_animal"]
+    ref_shards, ref_tall = parallel.correct_sharded(obs.shape[1], 128, correct_chunk, obs.shape[0], 0, 1)
+    got = np.full_like(obs, 255)
+    talls, seen = [], set()
+    for r in range(2):
+        z = np.load(os.path.join(tmp, "rank%d.npz" % r))
+        talls.append(z["tall"])
+        for k in z.files:
+            if k.startswith("c"):
+                ci = int(k[1:])
+                assert ci % 2 == r and ci not in seen
+                seen.add(ci)
+                got[:, z["i%d" % ci]] = z[k]
+    ref = np.zeros_like(obs)
+    for ci, (cols, c) in ref_shards.items():
+        ref[:, cols] = c
+    assert seen == set(ref_shards) and np.array_equal(got, ref)
+    assert np.array_equal(talls[0], talls[1]) and np.array_equal(talls[0], ref_tall.numpy()) and talls[0].sum() > 0
+
+
+# ---- parity at the sizes BASELINE.json names (VERDICT r1 item 1) ------------------------------------------------------
+@pytest.mark.timeout(1500)
+def test_config1_example_pedigree_1000_snps_matches_oracle():
+    """BASELINE config 1 at its own size: the reference's example pedigree (4 560 animals) x 1 000 SNPs, 1 % errors, one
+    1 000-SNP chunk (simulate.py -c 1000), against the oracle port run on all host cores."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    g = load_golden("example_fam")
+    drop_rows = synth.complete_rows(g["ped_rows"])
+    ids = drop_rows[:, 0]
+    obs = synth.inject_errors(synth.gene_drop(drop_rows, 1000, seed=1234), 0.01, seed=1234)
+    eng = Engine(PedigreeDAG.from_table(g["ped_rows"]), ids, 2)
+    out = eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    o = go.correct_matrix_parallel(g["ped_rows"], ids, obs, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
+    assert _same_f16(eng.raw_host(), o["raw"])
+    assert eng.stats["test_p"] == o["test_p"]
+    assert np.array_equal(out, o["corrected"]), int((out != o["corrected"]).sum())
+    assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
+    assert np.array_equal(eng.stats["excluded_per_animal"], o["excluded_per_animal"])
+    assert (out != obs).sum() > 1000
+
+
+@pytest.mark.timeout(1500)
+def test_config4_named_size_matches_oracle():
+    """BASELINE config 4 at the named pedigree size: 15 generations x 1 000 animals, 2 % sires / 30 % dams, related matings,
+    10 % of the non-founders with both parents unknown, 5 % missing calls; a 64-SNP chunk against the oracle port."""
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    rows = synth.make_pedigree(15000, 15, sire_frac=0.02, dam_frac=0.3, seed=1234, related_mating_p=0.25, unknown_parents_frac=0.10)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 64, seed=1234), 0.01, seed=1234), 0.05, seed=1235)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    assert eng.schedule.info["n_loopy"] > 500
+    out = eng.correct(obs, 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    o = go.correct_matrix_parallel(rows, rows[:, 0], obs, 0.5, 0.64, back=2, init_filter_p=0.95, tiethreshold=0.4)
+    assert _same_f16(eng.raw_host(), o["raw"])
+    assert eng.stats["test_p"] == o["test_p"] or (np.isnan(eng.stats["test_p"]) and np.isnan(o["test_p"]))
+    assert np.array_equal(out, o["corrected"]), int((out != o["corrected"]).sum())
+    assert np.array_equal(eng.stats["corrected_per_animal"], o["corrected_per_animal"])
+    assert np.array_equal(eng.stats["excluded_per_animal"], o["excluded_per_animal"])
+
+
+@pytest.mark.timeout(1500)
+def test_config5_trio_scan_one_million_animals():
+    """BASELINE config 5 pedigree (1M animals, 10 generations) x 1 024 SNPs, 2 % missing: k_trio_scan against the oracle's
+    scan on 12 000 sampled trios, tested counts included; founders against the oracle's founder list."""
+    import torch
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    n, s = 1000000, 1024
+    rows = synth.make_pedigree(n, 10, seed=1234)
+    rs = np.random.default_rng(9)
+    # the scan does not care whether the data are Mendelian: random calls exercise every (kid, sire, dam) combination
+    obs = rs.integers(0, 3, size=(n, s), dtype=np.uint8)
+    obs[rs.random((n, s)) < 0.02] = 9
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    inc, tested = eng.trio_scan(obs)
+    has = np.nonzero((rows[:, 1] > 0) & (rows[:, 2] > 0))[0]
+    sel = has[rs.choice(len(has), 12000, replace=False)]
+    sub_ids = np.unique(np.concatenate([rows[sel, 0], rows[sel, 1], rows[sel, 2]]))
+    sub_rows = sub_ids - 1                                   # ids are 1 .. n in row order
+    ri, rt = go.trio_scan(go.OraclePedigree(rows[np.isin(rows[:, 0], rows[sel, 0])]), [int(x) for x in sub_ids], obs[sub_rows])
+    pos = {int(k): i for i, k in enumerate(sub_ids)}
+    idx = np.array([pos[int(k)] for k in rows[sel, 0]])
+    assert np.array_equal(inc[sel], ri[idx]) and np.array_equal(tested[sel], rt[idx])
+    assert inc[sel].sum() > 0 and (tested[sel] < s).any()
+    nopar = np.nonzero((rows[:, 1] == 0) | (rows[:, 2] == 0))[0]
+    assert (inc[nopar] == 0).all() and (tested[nopar] == 0).all()
+    f = eng.schedule.founders()
+    assert np.array_equal(np.sort(f), np.sort(rows[nopar, 0]))
+    del eng
+    torch.cuda.empty_cache()

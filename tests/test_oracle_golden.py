@@ -141,3 +141,19 @@ def test_oracle_preindex_matches_reference(name):
                     assert len(f) == (3 ** w if w else 0)
                     assert np.array_equal(f, g["freq_" + c][i][:len(f)])
     assert k == len(g["quantQ"])
+
+
+def test_parallel_oracle_driver_equals_the_single_process_oracle():
+    """correct_matrix_parallel (columns dealt to processes, the matrix-wide maximum / quantile taken once in between) is
+    the checker of the BASELINE-size GPU tests: it must return exactly what Oracle.correct_matrix returns."""
+    from genofix_b200 import synth
+    from oracle import genofix_oracle as go
+    rows = synth.make_pedigree(160, 6, sire_frac=0.2, dam_frac=0.5, seed=3, related_mating_p=0.3, unknown_parents_frac=0.05)
+    obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 30, seed=3), 0.03, seed=3), 0.02, seed=4)
+    a = go.Oracle(rows, rows[:, 0]).correct_matrix(obs, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4)
+    b = go.correct_matrix_parallel(rows, rows[:, 0], obs, 0.5, 0.64, back=2, init_filter_p=0.9, tiethreshold=0.4, procs=3)
+    assert np.array_equal(a["corrected"], b["corrected"]) and (a["corrected"] != obs).any()
+    assert a["test_p"] == b["test_p"]
+    assert np.array_equal(a["raw"].view(np.uint16), b["raw"].view(np.uint16))
+    assert np.array_equal(a["corrected_per_animal"], b["corrected_per_animal"])
+    assert np.array_equal(a["excluded_per_animal"], b["excluded_per_animal"])

@@ -238,6 +238,23 @@ def run_trio_scan(args, torch, dist, world, rank, local):
             dist.all_reduce(inc)
             dist.all_reduce(tst)
 
+    # the same matrix as column chunks of 2048 SNPs (one 512-byte tile per row and chunk), the layout SURVEY 8(d)'s tile rule
+    # describes: consecutive rows of a chunk are adjacent in HBM, so a litter is one contiguous read
+    CW = 2048
+    chunks = [(packed[:, a // 16:min(wpr, (a + CW) // 16)].contiguous(), min(CW, s_rank - a)) for a in range(0, s_rank, CW)]
+    inc_c = torch.empty(n, dtype=torch.int64, device=dev)
+    tst_c = torch.empty(n, dtype=torch.int64, device=dev)
+
+    def step_chunked():
+        inc_c.zero_()
+        tst_c.zero_()
+        for p_c, s_c in chunks:
+            _lib.check(L.gfx_trio_scan_add(sched.handle, p_c.data_ptr(), s_c, p_c.shape[1], inc_c.data_ptr(), tst_c.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+        if world > 1:
+            dist.all_reduce(inc_c)
+            dist.all_reduce(tst_c)
+
     def step_e2e():
         staged.copy_(pin_in, non_blocking=True)
         _lib.check(L.gfx_trio_scan(sched.handle, staged.data_ptr(), s_rank, wpr, inc.data_ptr(), tst.data_ptr(),
@@ -271,6 +288,18 @@ def run_trio_scan(args, torch, dist, world, rank, local):
     ms = t0.elapsed_time(t1)
     stop.set()
     th.join(timeout=2)
+    for _ in range(3):
+        step_chunked()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        step_chunked()
+    c1.record()
+    barrier()
+    ms_chunked = c0.elapsed_time(c1)
+    if not (torch.equal(inc_c, inc) and torch.equal(tst_c, tst)):
+        raise SystemExit("bench.py: the chunked scan disagrees with the scan of the row-major matrix")
     step_e2e()
     barrier()
     w0 = time.perf_counter()
@@ -278,10 +307,10 @@ def run_trio_scan(args, torch, dist, world, rank, local):
         step_e2e()
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3
-    tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms, e2e_ms, ms_chunked], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(tm[0]), float(tm[1])
+    ms, e2e_ms, ms_chunked = float(tm[0]), float(tm[1]), float(tm[2])
     # the same scan against a torch restatement on a sample of trios (torch is the checker here, not the product)
     k = sched._keep
     has = np.nonzero((k["sire"] >= 0) & (k["dam"] >= 0))[0]
@@ -321,7 +350,12 @@ def run_trio_scan(args, torch, dist, world, rank, local):
                     roofline=dict(bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
                                   kernel="k_trio_scan (one warp per family)", algorithmic_bytes_per_cell=SCAN_BYTES_PER_CELL,
                                   peak_source="MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                                  timed="inside the step: the scan is the step"),
+                                  timed="inside the step: the scan is the step",
+                                  chunked=dict(layout="%d column chunks of %d SNPs, each [n, %d words] contiguous" % (len(chunks), CW, CW // 16),
+                                               ms_per_step=ms_chunked / args.steps,
+                                               achieved=n * s_rank * SCAN_BYTES_PER_CELL / (ms_chunked / args.steps / 1e3) / 1e9,
+                                               frac=n * s_rank * SCAN_BYTES_PER_CELL / (ms_chunked / args.steps / 1e3) / 1e9 / peak,
+                                               launches_per_step=len(chunks))),
                     clocks=clocks_summary(samples), verified="64 sampled trios equal a torch restatement" if world == 1 else None)
         print(json.dumps(line))
 

@@ -1622,7 +1622,9 @@ struct FocalArgs {
   uint2* wl;              // per deferred cell: (focal, snp)
   uint2* st;              // per deferred cell: x = live state | first unresolved job << 8, y = applied | excluded << 16
   int4* skc;              // per deferred cell: class counts of the children term (K0, K1, K2, usable children)
-  uint8_t* sbits;         // per deferred cell: decision bits of every job (0xFF = to be computed), row stride maxj
+  uint8_t* sbits;         // per deferred cell: decision bits of every job (0xFF = to be computed), at sboff[cell]
+  uint32_t* sboff;        // per deferred cell: first byte of its run in sbits (one byte per job of its animal)
+  unsigned long long sb_cap;
   uint2* items;           // deferred jobs: (cell slot, job index within the animal)
   unsigned long long wl_cap, item_cap;
   uint2* items_sorted;    // the same items grouped by job entry (same blanket, same side): convergent warps
@@ -2002,7 +2004,7 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
   const ParentCache none{-9, -9, 3u, 3u, 0u, 0u};
   ApplyState S{obs0, 0, 0, false, false};
   bool parked = false;
-  unsigned long long slot = 0;
+  unsigned long long slot = 0, sb = 0;
   int first = 0;
   for (int e = e0; e < e1; ++e) {
     const int ent = a.entry[e];
@@ -2062,14 +2064,17 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
     }
     if (ok && !parked) { apply_bits(a, row, j, rxf, bits, S); continue; }
     if (!parked) {
-      if (e1 - e0 > a.maxj) return false;
-      slot = atomicAdd(a.wl_count, 1ull);
-      if (slot >= a.wl_cap) return false;
+      // one byte of decision bits per job of this animal (a many-mate sire has dozens, a dam one), then the cell's slot
+      // (one atomic for both: slot number in the low word of the counter, bytes handed out in the high word)
+      const unsigned long long got = atomicAdd(a.wl_count, ((unsigned long long)(e1 - e0) << 32) | 1ull);
+      slot = got & 0xFFFFFFFFull;
+      sb = got >> 32;
+      if (slot >= a.wl_cap || sb + (unsigned long long)(e1 - e0) > a.sb_cap) return false;
       parked = true;
       first = e - e0;
     }
-    if (ok) { a.sbits[slot * a.maxj + (e - e0)] = (uint8_t)bits; continue; }
-    a.sbits[slot * a.maxj + (e - e0)] = 0xFF;
+    if (ok) { a.sbits[sb + (e - e0)] = (uint8_t)bits; continue; }
+    a.sbits[sb + (e - e0)] = 0xFF;
     const unsigned long long it = atomicAdd(a.item_count, 1ull);
     if (it < a.item_cap) {
       a.items[it] = make_uint2((uint32_t)slot, (uint32_t)(e - e0) | flag);
@@ -2083,6 +2088,7 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
                               (S.gate_done ? 0x40000000u : 0u) | (S.gate ? 0x20000000u : 0u),
                           (uint32_t)S.applied | ((uint32_t)S.excluded << 16));
   a.skc[slot] = make_int4(K.k0, K.k1, K.k2, K.ninc);
+  a.sboff[slot] = (uint32_t)sb;
   return (first & 0x8000) == 0;
 }
 
@@ -2305,7 +2311,7 @@ __global__ void __launch_bounds__(1024) k_jobs_scan(FocalArgs a) {
 __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
   unsigned long long n = *a.item_count;
   if (n > a.item_cap) n = a.item_cap;
-  unsigned long long ncell = *a.wl_count;
+  unsigned long long ncell = *a.wl_count & 0xFFFFFFFFull;
   if (ncell > a.wl_cap) ncell = a.wl_cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -2323,7 +2329,7 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
 // Warps draw 32 items at a time from a global counter (the general eliminations have a long tail).
 template <int MODE, int PER>
 __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list, unsigned long long n, unsigned long long* ticket) {
-  unsigned long long ncell = *a.wl_count;
+  unsigned long long ncell = *a.wl_count & 0xFFFFFFFFull;
   if (ncell > a.wl_cap) ncell = a.wl_cap;
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -2348,7 +2354,7 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
         const int ji = (int)(it.y & ~GFX_ITEM_LITERAL);
         uint32_t bits;
         if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, (it.y & GFX_ITEM_LITERAL) != 0u, &bits))
-          a.sbits[(unsigned long long)it.x * a.maxj + ji] = (uint8_t)bits;
+          a.sbits[(unsigned long long)a.sboff[it.x] + ji] = (uint8_t)bits;
         else
           again = true;
       }
@@ -2394,7 +2400,7 @@ __global__ void __launch_bounds__(KJ_THREADS, KG_BLOCKS * 128 / KJ_THREADS) k_co
 
 // Finishes the serial walk of every parked cell once all its jobs have bits.
 __global__ void __launch_bounds__(128) k_correct_apply(FocalArgs a) {
-  unsigned long long n = *a.wl_count;
+  unsigned long long n = *a.wl_count & 0xFFFFFFFFull;
   if (n > a.wl_cap) n = a.wl_cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -2410,7 +2416,8 @@ __global__ void __launch_bounds__(128) k_correct_apply(FocalArgs a) {
     ApplyState S{(int)(st.x & 0xFFu), (int)(st.y & 0xFFFFu), (int)(st.y >> 16), (st.x & 0x40000000u) != 0,
                  (st.x & 0x20000000u) != 0};
     const int first = (int)((st.x >> 8) & 0x7FFFu);
-    for (int e = e0 + first; e < e1; ++e) apply_bits(a, row, j, rxf, a.sbits[i * a.maxj + (e - e0)], S);
+    const unsigned long long sb = a.sboff[i];
+    for (int e = e0 + first; e < e1; ++e) apply_bits(a, row, j, rxf, a.sbits[sb + (e - e0)], S);
     write_cell(a, row, j, obs0, S);
   }
 }
@@ -2483,7 +2490,7 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   tail += (4 - (((uintptr_t)tail / 4) & 3)) & 3;   // 16-byte alignment
   a.wl_count = (unsigned long long*)tail;
   a.item_count = a.wl_count + 2;
-  const int maxj_p = ((maxj + 7) / 8) * 8;
+  (void)maxj;
   a.n_keys = n_keys; a.e_base = e_base;
   const int64_t nk4 = ((int64_t)n_keys + 3) / 4 * 4;
   a.key_count = tail + 16;            // zeroed with the 8 counters
@@ -2491,7 +2498,7 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.key_cur = a.key_off + nk4;
   char* base = (char*)(a.key_cur + nk4);
   const int64_t avail = (char*)(snapshot + scratch_words) - base;
-  const int64_t per_slot = 16 + 8 + 8 + 16 + 16 + maxj_p;
+  const int64_t per_slot = 16 + 8 + 8 + 4 + 16 + 16 + 12;   // class counts, cell, state, sbits offset, items x 2, 12 decision bytes
   const int64_t scap = avail > 0 ? avail / per_slot : 0;
   if (scap < 1024) return fail(GFX_E_INVALID, "scratch too small for the deferred-cell lists");
   a.skc = (int4*)base;                           base += scap * 16;
@@ -2499,10 +2506,13 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.st = (uint2*)base;                           base += scap * 8;
   a.items = (uint2*)base;                        base += scap * 16;
   a.items_sorted = (uint2*)base;                 base += scap * 16;
+  a.sboff = (uint32_t*)base;                     base += scap * 4;
   a.sbits = (uint8_t*)base;
+  a.sb_cap = (unsigned long long)scap * 12ull < 0x7FFFFFF0ull ? (unsigned long long)scap * 12ull : 0x7FFFFFF0ull;   // 31 bits: the
+  // high word of the slot counter keeps counting after the lists are full
   a.wl_cap = (unsigned long long)scap;
   a.item_cap = (unsigned long long)scap * 2;
-  a.maxj = maxj_p;
+  a.maxj = 0;
   GFX_CUDA(cudaMemsetAsync(a.deferred, 0, ((char*)(a.key_count + nk4)) - (char*)a.deferred, stream));  // bitmap + counters + key counts
   a.task_count = a.wl_count + 1;
   a.focal_order = focal_order;
@@ -2569,6 +2579,10 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
 // live in registers, so the parents cross the L2 -> SM link once per family instead of once per kid (the per-trio
 // form moved 3 rows per kid and was bound by that link: 7 TB/s of L2 reads for 2.6 TB/s of algorithmic bytes).
 // Families are walked in groups of 4 kids (more per group costs occupancy).  No atomics: a kid belongs to one family.
+// Round 2 tried a TILE-MAJOR task order (all families of a 2048-SNP column tile, then the next tile) so that a dam's
+// second read -- as a parent, about one generation of rows after her read as a kid -- would hit L2: DRAM read stayed at
+// 1.29x the algorithmic bytes (4.82 GB vs 4.85 GB for 3.75 GB at 300k animals) while the per-task index chain and the
+// per-(tile, kid) reductions doubled the instructions: 0.58 -> 0.35 of the roofline; not kept (profiles/r2_summary.md).
 #ifndef GFX_FAM_BLOCKS
 #define GFX_FAM_BLOCKS 4
 #endif
@@ -2619,7 +2633,7 @@ __device__ __forceinline__ void trio_family_group(const uint32_t* __restrict__ p
       a += __shfl_xor_sync(0xffffffffu, a, o);
       b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) { inc[rows[k]] = a; tested[rows[k]] = b; }
+    if (lane == 0) { inc[rows[k]] += a; tested[rows[k]] += b; }   // a kid belongs to one family: no other writer in this launch
   }
 }
 
@@ -2647,19 +2661,34 @@ __global__ void __launch_bounds__(256, GFX_FAM_BLOCKS) k_trio_scan(const uint32_
   }
 }
 
-extern "C" int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
-                             int64_t* tested, void* stream) {
+static int launch_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
+                            int64_t* tested, bool zero, cudaStream_t stream) {
   if (!s || !packed || !inc || !tested || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_trio_scan: bad argument");
   if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
-  GFX_CUDA(cudaMemsetAsync(inc, 0, sizeof(int64_t) * s->h.n_rows, (cudaStream_t)stream));
-  GFX_CUDA(cudaMemsetAsync(tested, 0, sizeof(int64_t) * s->h.n_rows, (cudaStream_t)stream));
+  if (wpr % 4 || (((uintptr_t)packed) % 16)) return fail(GFX_E_INVALID, "gfx_trio_scan: rows must be 16-byte aligned (wpr % 4 == 0)");
+  if (zero) {
+    GFX_CUDA(cudaMemsetAsync(inc, 0, sizeof(int64_t) * s->h.n_rows, stream));
+    GFX_CUDA(cudaMemsetAsync(tested, 0, sizeof(int64_t) * s->h.n_rows, stream));
+  }
   const int nt = (int)s->h.trio_row.size();
   if (nt == 0) return GFX_OK;
   const int nfam = (int)s->h.fam_off.size() - 1;
-  k_trio_scan<<<grid_for((int64_t)nfam * 32, 256, s->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+  k_trio_scan<<<grid_for((int64_t)nfam * 32, 256, s->num_sms, 8), 256, 0, stream>>>(
       packed, wpr, (n_snps + 15) / 16, n_snps, s->trio_row, s->fam_off, nfam, s->prow, (long long*)inc, (long long*)tested);
   GFX_LAUNCHED();
   return GFX_OK;
+}
+
+extern "C" int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
+                             int64_t* tested, void* stream) {
+  return launch_trio_scan(s, packed, n_snps, wpr, inc, tested, true, (cudaStream_t)stream);
+}
+
+// The same scan ADDED to the counters: for a matrix held as column chunks (the pipeline's own resident layout), one
+// call per chunk.
+extern "C" int gfx_trio_scan_add(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
+                                 int64_t* tested, void* stream) {
+  return launch_trio_scan(s, packed, n_snps, wpr, inc, tested, false, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -278,7 +278,9 @@ class Engine(object):
         self.hist = t.empty(65537, dtype=t.int64, device=dev)
         self.elut = t.empty(65536, dtype=t.float64, device=dev)
         # snapshot + fallback bitmap + lists of parked cells / deferred jobs (~76 bytes per parked cell)
-        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 64 + 4 * n + max(1 << 18, n * self.s // 4),
+        # (>= 64 MB of lists: with many-mate sires a small matrix parks most of its suspect cells, and a cell that finds no
+        # slot is redone by the slow whole-cell kernel -- 90 % of the step on the reference's example pedigree before)
+        self.snapshot = t.empty(n * (self.wpr + 32 * ((self.s + 1023) // 1024)) + 64 + 4 * n + max(1 << 24, n * self.s // 4),
                                 dtype=t.int32, device=dev)
         self.tallies = t.zeros(2 * n, dtype=t.int32, device=dev)
         self.host_in = t.empty((n, self.ldc), dtype=t.uint8, pin_memory=True)
@@ -607,6 +609,20 @@ class Engine(object):
                                         inc.data_ptr(), tst.data_ptr(), self._stream()))
         return inc.cpu().numpy(), tst.cpu().numpy()
 
+
+    def trio_scan_chunks(self, chunks):
+        """The scan of a matrix held as column chunks (the pipeline's resident layout): `chunks` = iterable of
+        (packed int32 cuda tensor [n, wpr_i], n_snps_i).  Returns device int64 tensors (inconsistent, tested)."""
+        t = self.torch
+        dev = t.device("cuda", t.cuda.current_device())
+        inc = t.zeros(self.n, dtype=t.int64, device=dev)
+        tst = t.zeros(self.n, dtype=t.int64, device=dev)
+        for p, s_i in chunks:
+            if p.shape[0] != self.n or p.dtype != t.int32 or not p.is_contiguous():
+                raise ValueError("chunk must be a contiguous int32 tensor [%d, wpr]" % self.n)
+            _lib.check(self.L.gfx_trio_scan_add(self.schedule.handle, p.data_ptr(), int(s_i), p.shape[1], inc.data_ptr(),
+                                                tst.data_ptr(), self._stream()))
+        return inc, tst
 
     def load_host(self, G):
         """Upload a uint8 [n, s] host matrix (0,1,2,9) and pack it (the first lines of `correct()`)."""

@@ -205,8 +205,12 @@ int gfx_check_device_status(const gfx_schedule* s, void* stream);
  * pedigree/error_checker.py:138-153): for every genotyped animal with both parents genotyped,
  * the number of SNPs where all three calls are present (tested) and the number where
  * P(kid | sire, dam) = 0 under bayesnet/model.py:28-30 (inconsistent).  int64 [n_rows] each.
+ * Rows must be 16-byte aligned (wpr % 4 == 0).  gfx_trio_scan zeroes the counters first; gfx_trio_scan_add
+ * adds to them (a matrix held as column chunks: one call per chunk, SURVEY 8(d) tile rule).
  * ------------------------------------------------------------------------------------------- */
 int gfx_trio_scan(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
+                  int64_t* inconsistent_dev, int64_t* tested_dev, void* stream);
+int gfx_trio_scan_add(const gfx_schedule* s, const uint32_t* packed_dev, int64_t n_snps, int64_t wpr,
                   int64_t* inconsistent_dev, int64_t* tested_dev, void* stream);
 
 /* Founders (gfutils/extract_founders.py:106-110): HOST call.  restrict_host is NULL or n_ped flags;

@@ -79,6 +79,9 @@ GFX_HD int gfx_highbit(uint64_t m) {
 //     (sum_p prior(p) T(x | p, .)) instead of opening a digit for it.
 // Returns 0, or 1 if more than `wmax` variables would be open at once (out = NaN).
 // tab[3] receives the unnormalised total P(evidence in the component).
+// TS = distance between consecutive table entries in doubles: 1 for a private table, the number of threads that
+// interleave their tables in one shared-memory array otherwise (entry i of a thread at tab[i * TS]: bank = thread).
+template <int TS = 1>
 __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const uint8_t* code, uint64_t obs,
                                              uint64_t comp, uint64_t cand, double* tab, double out[3], int wmax) {
   // needed factors: connected to q and not barren (reverse topological sweep)
@@ -171,11 +174,11 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
         for (int a = 0; a < na; ++a)
           for (int c = 0; c < nb; ++c)
             f9[a * 3 + c] = x == 0 ? sa[a] * da[c] : (x == 2 ? sb[a] * db[c] : sa[a] * db[c] + sb[a] * da[c]);
-      double* dst = v_obs ? tab : tab + x * size;
+      double* dst = v_obs ? tab : tab + (size_t)x * size * TS;
       int ia = 0, ca = 0, ib = 0, cb = 0;
       for (int base = 0; base < size; base += run) {
         const double f = f9[(na == 3 ? ia : 0) * 3 + (nb == 3 ? ib : 0)];
-        for (int i = base; i < base + run; ++i) dst[i] = tab[i] * f;
+        for (int i = base; i < base + run; ++i) dst[i * TS] = tab[i * TS] * f;
         if (na == 3) { ca += run; if (ca == s_str) { ca = 0; ia = ia == 2 ? 0 : ia + 1; } }
         if (nb == 3) { cb += run; if (cb == d_str) { cb = 0; ib = ib == 2 ? 0 : ib + 1; } }
       }
@@ -188,17 +191,18 @@ __host__ __device__ inline int gfx_eliminate(const GfxBlanket& b, int q, const u
       const int str = gfx_pow3(k);
       const int nsize = size / 3;
       for (int i = 0, src = 0; i < nsize; src += 2 * str)
-        for (int lo = 0; lo < str; ++lo, ++i, ++src) tab[i] = (tab[src] + tab[src + str]) + tab[src + 2 * str];
+        for (int lo = 0; lo < str; ++lo, ++i, ++src)
+          tab[i * TS] = (tab[src * TS] + tab[(src + str) * TS]) + tab[(src + 2 * str) * TS];
       for (int mm = k; mm + 1 < w; ++mm) open[mm] = open[mm + 1];
       --w;
       size = nsize;
     }
   }
-  const double s = (tab[0] + tab[1]) + tab[2];
+  const double s = (tab[0] + tab[1 * TS]) + tab[2 * TS];
   out[0] = tab[0] / s;
-  out[1] = tab[1] / s;
-  out[2] = tab[2] / s;
-  tab[3] = s;
+  out[1] = tab[1 * TS] / s;
+  out[2] = tab[2 * TS] / s;
+  tab[3 * TS] = s;
   return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1167,17 +1168,23 @@ __device__ __forceinline__ bool peel_query(const LazyBlanket& L, int q, int qoth
 
 // Marginal of q (qother: the second focal animal of a pair, forced unobserved, or -1).
 // *total = unnormalised P(evidence in the component).
+// First tier of the general elimination: tables of up to 3^GFX_WMAX_S entries in SHARED memory, one per job of the
+// block, interleaved (entry i of slot t at stab[i * GFX_STAB_SLOTS + t]: conflict free).  The 729-entry private tables
+// live in local memory, 93 KB per warp of 16 jobs, and missed L1 four times out of five (profiles/r2_summary.md).
+#define GFX_WMAX_S 4
+#define GFX_TAB_S 81
+#define GFX_STAB_SLOTS 64     // 4 warps x KG_ITEMS jobs per block of k_correct_jobs_general
 __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, uint8_t* code,
-                                       double* tab, double out[3], double* total);
+                                       double* tab, double out[3], double* total, double* stab);
 // general query with its own scratch (kept out of line so the common path stays small)
 __device__ __noinline__ int query_general(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, double out[3],
-                                          double* total) {
+                                          double* total, double* stab) {
   double tab[GFX_TAB];
   uint8_t code[GFX_MAXN];
-  return query_lazy(L, bl, q, qother, code, tab, out, total);
+  return query_lazy(L, bl, q, qother, code, tab, out, total, stab);
 }
 __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& bl, int q, int qother, uint8_t* code,
-                                       double* tab, double out[3], double* total) {
+                                       double* tab, double out[3], double* total, double* stab) {
   uint64_t known = 1ull << q, obs = 0, comp = 1ull << q, queue = 1ull << q, cand = 0;
   if (qother >= 0) known |= 1ull << qother;
   while (queue) {
@@ -1215,6 +1222,13 @@ __device__ __noinline__ int query_lazy(const LazyBlanket& L, const BlanketDev& b
     return 0;
   }
   GfxBlanket b{L.n, L.p1, L.p2, nullptr};
+  if (stab) {
+    if (!gfx_eliminate<GFX_STAB_SLOTS>(b, q, code, obs, comp, cand, stab, out, GFX_WMAX_S)) {
+      GFX_COUNT(bl, 2, 1);
+      *total = stab[3 * GFX_STAB_SLOTS];
+      return 0;
+    }
+  }
   int bad = gfx_eliminate(b, q, code, obs, comp, cand, tab, out, GFX_WMAX);
   GFX_COUNT(bl, 2, 1);
   if (bad) {
@@ -1308,7 +1322,7 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
           CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
           LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
           double anc[3], tot;
-          if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot)) atomicExch(a.status, 1);
+          if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot, nullptr)) atomicExch(a.status, 1);
           const uint16_t sc = gfx_anc_score(anc, obs);
           uint32_t m = 0;
           bool kids = false;
@@ -1806,7 +1820,7 @@ __device__ __forceinline__ bool kids_literal_known(int nk, const KidCounts& K, b
 // when a test falls inside the guard band, when the fast kernel already found that (`literal`), or for posteriors.
 template <int MODE>
 __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, int64_t j, int obs0, uint32_t rxf,
-                                         const KidCounts& K, bool literal, uint32_t* bits_out) {
+                                         const KidCounts& K, bool literal, uint32_t* bits_out, double* stab) {
   const uint32_t tp = a.c.tp_raw;
   const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
   const int job = a.nf == 2 ? (ent >> 1) : ent;
@@ -1843,7 +1857,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
       if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
       else if constexpr (MODE == 1) return false;
-      else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
+      else if (query_general(LB, a.bl, qme, qot, anc, &tot_me, stab)) atomicExch(a.status, 1);
     } else {
       GFX_COUNT(a.bl, 1, 1);
     }
@@ -1854,7 +1868,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
       if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
         if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (MODE == 1) return false;
-          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
+          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot, stab)) atomicExch(a.status, 1);
         }
       }
     }
@@ -2095,6 +2109,8 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
 template <bool GENERAL>
 __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s_kv, uint32_t* s_cls, int row, int e0, int e1,
                                              int64_t j) {
+  double* const stab = nullptr;   // the whole-cell fallback keeps its tables private
+
   const uint32_t tp = a.c.tp_raw;
   const int obs0 = cell_code(a.c.live, a.c.wpr, row, j);   // snapshot state of the focal animal
   int cur = obs0;                                          // live state, updated job after job
@@ -2151,7 +2167,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
       if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
         if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
         else if constexpr (!GENERAL) return false;
-        else if (query_general(LB, a.bl, qme, qot, anc, &tot_me)) atomicExch(a.status, 1);
+        else if (query_general(LB, a.bl, qme, qot, anc, &tot_me, stab)) atomicExch(a.status, 1);
       } else {
         GFX_COUNT(a.bl, 1, 1);
       }
@@ -2162,7 +2178,7 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
         if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp) &&
             !xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (!GENERAL) return false;
-          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot)) atomicExch(a.status, 1);
+          else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot, stab)) atomicExch(a.status, 1);
         }
       }
       if (tot_me == 0.0 || tot_ot == 0.0) anc[0] = anc[1] = anc[2] = nan("");
@@ -2328,7 +2344,8 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
 // round A = tree message passing; what it cannot answer is handed to round B = general elimination.
 // Warps draw 32 items at a time from a global counter (the general eliminations have a long tail).
 template <int MODE, int PER>
-__device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list, unsigned long long n, unsigned long long* ticket) {
+__device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list, unsigned long long n, unsigned long long* ticket,
+                                           double* stab = nullptr) {
   unsigned long long ncell = *a.wl_count & 0xFFFFFFFFull;
   if (ncell > a.wl_cap) ncell = a.wl_cap;
   const int lane = threadIdx.x & 31;
@@ -2353,7 +2370,7 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
         const KidCounts K{kc.x, kc.y, kc.z, kc.w};
         const int ji = (int)(it.y & ~GFX_ITEM_LITERAL);
         uint32_t bits;
-        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, (it.y & GFX_ITEM_LITERAL) != 0u, &bits))
+        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, (it.y & GFX_ITEM_LITERAL) != 0u, &bits, stab))
           a.sbits[(unsigned long long)a.sboff[it.x] + ji] = (uint8_t)bits;
         else
           again = true;
@@ -2395,7 +2412,11 @@ __global__ void __launch_bounds__(KJ_THREADS, KJ_BLOCKS * 128 / KJ_THREADS) k_co
 #define KG_ITEMS 16   // jobs per ticket of the general round (measured: 16 beats 32 and 8)
 #endif
 __global__ void __launch_bounds__(KJ_THREADS, KG_BLOCKS * 128 / KJ_THREADS) k_correct_jobs_general(FocalArgs a) {
-  jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6);
+  // one shared-memory table slot per job in flight: warp w, lane l < KG_ITEMS -> slot w * KG_ITEMS + l
+  __shared__ double s_tab[GFX_TAB_S * GFX_STAB_SLOTS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* stab = (lane < KG_ITEMS && wib * KG_ITEMS + lane < GFX_STAB_SLOTS) ? s_tab + wib * KG_ITEMS + lane : nullptr;
+  jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6, stab);
 }
 
 // Finishes the serial walk of every parked cell once all its jobs have bits.
@@ -2661,6 +2682,146 @@ __global__ void __launch_bounds__(256, GFX_FAM_BLOCKS) k_trio_scan(const uint32_
   }
 }
 
+// ---- TMA-staged variant of the scan ----------------------------------------------------------------------------------
+// The same family walk, but the row segments come through shared memory: lane 0 of every warp issues 1-D bulk copies
+// (cp.async.bulk global -> shared, SASS UBLKCP, completion counted in bytes on an mbarrier) of the next 512-byte segment
+// of the sire's, the dam's and the kids' rows into a warp-private ring of GFX_TMA_STAGES stages while the warp scans the
+// current segment from shared memory.  No per-lane address arithmetic, no registers held by loads in flight, and
+// GFX_TMA_STAGES - 1 segments of every row in flight per warp.
+#ifndef GFX_TMA_STAGES
+#define GFX_TMA_STAGES 3
+#endif
+#ifndef GFX_TRIO_TMA_DEFAULT
+#define GFX_TRIO_TMA_DEFAULT 0
+#endif
+#define GFX_TMA_ROWS 6        // sire, dam, up to 4 kids
+#define GFX_TMA_WARPS 8
+#define GFX_TMA_SMEM (GFX_TMA_WARPS * GFX_TMA_STAGES * GFX_TMA_ROWS * 512 + GFX_TMA_WARPS * GFX_TMA_STAGES * 8)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+template <int NK>
+__device__ __forceinline__ void trio_family_group_tma(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nquads, int64_t n_snps,
+                                                      int row_s, int row_d, const int32_t* __restrict__ rows, int lane, uint4* buf,
+                                                      uint64_t* bars, uint32_t& parity, long long* __restrict__ inc,
+                                                      long long* __restrict__ tested) {
+  const char* rp[2 + NK];
+  rp[0] = reinterpret_cast<const char*>(packed + (int64_t)row_s * wpr);
+  rp[1] = reinterpret_cast<const char*>(packed + (int64_t)row_d * wpr);
+  int n_inc[NK], n_tst[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    rp[2 + k] = reinterpret_cast<const char*>(packed + (int64_t)rows[k] * wpr);
+    n_inc[k] = 0; n_tst[k] = 0;
+  }
+  const int64_t row_bytes = nquads * 16;
+  const int64_t nsteps = (nquads + 31) >> 5;
+  auto issue = [&](int64_t step) {
+    if (lane == 0) {
+      const int st = (int)(step % GFX_TMA_STAGES);
+      const int64_t off = step * 512;
+      const uint32_t bytes = (uint32_t)(row_bytes - off < 512 ? row_bytes - off : 512);
+      mbar_expect_tx(bars + st, bytes * (2 + NK));
+#pragma unroll
+      for (int r = 0; r < 2 + NK; ++r) tma_load_1d(buf + (st * GFX_TMA_ROWS + r) * 32, rp[r] + off, bytes, bars + st);
+    }
+  };
+  for (int64_t p = 0; p < GFX_TMA_STAGES - 1 && p < nsteps; ++p) issue(p);
+  for (int64_t step = 0; step < nsteps; ++step) {
+    const int st = (int)(step % GFX_TMA_STAGES);
+    // the stage refilled here was read in the previous iteration; the __syncwarp below closed those reads
+    if (step + GFX_TMA_STAGES - 1 < nsteps) issue(step + GFX_TMA_STAGES - 1);
+    mbar_wait(bars + st, (parity >> st) & 1u);
+    parity ^= 1u << st;
+    const int64_t q = step * 32 + lane;
+    if (q < nquads) {
+      const uint4 sq = buf[(st * GFX_TMA_ROWS + 0) * 32 + lane], dq = buf[(st * GFX_TMA_ROWS + 1) * 32 + lane];
+      uint4 kq[NK];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) kq[k] = buf[(st * GFX_TMA_ROWS + 2 + k) * 32 + lane];
+      const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t s = sw[i], d = dw[i];
+        uint32_t valid = 0x55555555u;
+        const int64_t rem = n_snps - (q * 4 + i) * 16;
+        if (rem < 16) valid = rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & 0x55555555u);
+        const uint32_t s0 = ~(s | (s >> 1)), s2 = (s >> 1) & ~s;
+        const uint32_t d0 = ~(d | (d >> 1)), d2 = (d >> 1) & ~d;
+        const uint32_t par_ok = ~(s & (s >> 1)) & ~(d & (d >> 1)) & valid;
+        const uint32_t no0 = s2 | d2, no2 = s0 | d0, no1 = (s0 & d0) | (s2 & d2);   // kid states the parents exclude
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+          const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
+          const uint32_t k0 = ~(kk | (kk >> 1)), k1 = kk & ~(kk >> 1), k2 = (kk >> 1) & ~kk;
+          const uint32_t present = ~(kk & (kk >> 1)) & par_ok;
+          const uint32_t bad = (k0 & no0) | (k2 & no2) | (k1 & no1);      // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
+          n_tst[k] += __popc(present);
+          n_inc[k] += __popc(bad & present);
+        }
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    int a = n_inc[k], b = n_tst[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { inc[rows[k]] += a; tested[rows[k]] += b; }
+  }
+}
+
+__global__ void __launch_bounds__(GFX_TMA_WARPS * 32) k_trio_scan_tma(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nwords,
+                                                                      int64_t n_snps, const int32_t* __restrict__ trio_row,
+                                                                      const int32_t* __restrict__ fam_off, int n_fam,
+                                                                      const int32_t* __restrict__ prow, long long* __restrict__ inc,
+                                                                      long long* __restrict__ tested) {
+  extern __shared__ __align__(128) unsigned char s_tma[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint4* buf = reinterpret_cast<uint4*>(s_tma) + (size_t)wib * GFX_TMA_STAGES * GFX_TMA_ROWS * 32;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tma + GFX_TMA_WARPS * GFX_TMA_STAGES * GFX_TMA_ROWS * 512) + wib * GFX_TMA_STAGES;
+  if (lane == 0) {
+    for (int i = 0; i < GFX_TMA_STAGES; ++i) mbar_init(bars + i, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t parity = 0;   // bit s: phase the next wait on stage s looks for
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int64_t nquads = (nwords + 3) >> 2;
+  for (int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n_fam; f += warps) {
+    const int t0 = fam_off[f], t1 = fam_off[f + 1];
+    const int r0 = trio_row[t0];
+    const int rs = prow[2 * r0], rd = prow[2 * r0 + 1];
+    for (int g0 = t0; g0 < t1; g0 += 4) {
+      const int nk = min(4, t1 - g0);
+      const int32_t* rows = trio_row + g0;
+      if (nk == 4) trio_family_group_tma<4>(packed, wpr, nquads, n_snps, rs, rd, rows, lane, buf, bars, parity, inc, tested);
+      else if (nk == 3) trio_family_group_tma<3>(packed, wpr, nquads, n_snps, rs, rd, rows, lane, buf, bars, parity, inc, tested);
+      else if (nk == 2) trio_family_group_tma<2>(packed, wpr, nquads, n_snps, rs, rd, rows, lane, buf, bars, parity, inc, tested);
+      else trio_family_group_tma<1>(packed, wpr, nquads, n_snps, rs, rd, rows, lane, buf, bars, parity, inc, tested);
+    }
+  }
+}
+
 static int launch_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, int64_t* inc,
                             int64_t* tested, bool zero, cudaStream_t stream) {
   if (!s || !packed || !inc || !tested || n_snps <= 0) return fail(GFX_E_INVALID, "gfx_trio_scan: bad argument");
@@ -2673,8 +2834,21 @@ static int launch_trio_scan(const gfx_schedule* s, const uint32_t* packed, int64
   const int nt = (int)s->h.trio_row.size();
   if (nt == 0) return GFX_OK;
   const int nfam = (int)s->h.fam_off.size() - 1;
-  k_trio_scan<<<grid_for((int64_t)nfam * 32, 256, s->num_sms, 8), 256, 0, stream>>>(
-      packed, wpr, (n_snps + 15) / 16, n_snps, s->trio_row, s->fam_off, nfam, s->prow, (long long*)inc, (long long*)tested);
+  static const int use_tma = []() { const char* e = getenv("GFX_TRIO_TMA"); return e ? atoi(e) : GFX_TRIO_TMA_DEFAULT; }();
+  if (use_tma) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, []() {
+      attr_err = cudaFuncSetAttribute(k_trio_scan_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GFX_TMA_SMEM);
+    });
+    GFX_CUDA(attr_err);
+    const int per_sm = (int)(220 * 1024 / GFX_TMA_SMEM) < 1 ? 1 : (int)(220 * 1024 / GFX_TMA_SMEM);
+    k_trio_scan_tma<<<grid_for((int64_t)nfam * 32, GFX_TMA_WARPS * 32, s->num_sms, per_sm), GFX_TMA_WARPS * 32, GFX_TMA_SMEM, stream>>>(
+        packed, wpr, (n_snps + 15) / 16, n_snps, s->trio_row, s->fam_off, nfam, s->prow, (long long*)inc, (long long*)tested);
+  } else {
+    k_trio_scan<<<grid_for((int64_t)nfam * 32, 256, s->num_sms, 8), 256, 0, stream>>>(
+        packed, wpr, (n_snps + 15) / 16, n_snps, s->trio_row, s->fam_off, nfam, s->prow, (long long*)inc, (long long*)tested);
+  }
   GFX_LAUNCHED();
   return GFX_OK;
 }

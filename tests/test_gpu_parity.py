@@ -1141,3 +1141,44 @@ def test_config5_trio_scan_one_million_animals():
     assert np.array_equal(np.sort(f), np.sort(rows[nopar, 0]))
     del eng
     torch.cuda.empty_cache()
+
+
+_TMA_WORKER = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from genofix_b200.engine import Engine
+from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+z = np.load(sys.argv[2])
+eng = Engine(PedigreeDAG.from_table(z["rows"]), z["ids"], 2)
+inc, tested = eng.trio_scan(z["obs"])
+np.savez(sys.argv[3], inc=inc, tested=tested)
+"""
+
+
+@pytest.mark.timeout(600)
+def test_tma_staged_trio_scan_variant_matches_the_default_kernel(tmp_path):
+    """GFX_TRIO_TMA=1 selects k_trio_scan_tma (row segments staged by cp.async.bulk + mbarrier, SASS UBLKCP): same tallies as
+    the default kernel and as the oracle, on ragged widths (last segment shorter than 512 bytes, last word partial)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    for s in (1003, 2048, 5000):
+        rows, ids, obs = _random_case(31 + s, n=500, gens=6, s=s, miss=0.03, drop=0.1)
+        inp, out = os.path.join(str(tmp_path), "in%d.npz" % s), os.path.join(str(tmp_path), "out%d.npz" % s)
+        np.savez(inp, rows=rows, ids=ids, obs=obs)
+        script = os.path.join(str(tmp_path), "w.py")
+        with open(script, "w") as f:
+            f.write(_TMA_WORKER)
+        env = dict(os.environ, GFX_TRIO_TMA="1")
+        r = subprocess.run([sys.executable, script, ROOT, inp, out], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        z = np.load(out)
+        inc, tested = Engine(PedigreeDAG.from_table(rows), ids, 2).trio_scan(obs)
+        assert np.array_equal(z["inc"], inc) and np.array_equal(z["tested"], tested)
+        ri, rt = go.trio_scan(go.OraclePedigree(rows), [int(x) for x in ids], obs)
+        assert np.array_equal(z["inc"], ri) and np.array_equal(z["tested"], rt)

@@ -271,13 +271,20 @@ def test_packed_container_roundtrip(tmp_path):
     for a, b in [(0, 1003), (16, 516), (992, 1003), (160, 176)]:
         blk = g.packed_columns(a, b)
         assert np.array_equal(blk, pack_codes(G[:, a:b])), (a, b)
+    for a, b in [(5, 100), (33, 1003), (1, 2), (15, 17), (999, 1003)]:      # starts inside a word: shifted across word boundaries
+        blk = g.packed_columns(a, b)
+        assert np.array_equal(blk, pack_codes(G[:, a:b])), (a, b)
     with pytest.raises(ValueError):
-        g.packed_columns(5, 100)
+        g.packed_columns(5, 2000)
     g2 = PackedGens(path, mode="r+")
     g2.store_columns(16, 516, pack_codes((G[:, 16:516] + 1) % 3))
     g2.packed.flush()
     M = PackedGens(path).getMatrix(range(100, 137))
     assert np.array_equal(M[:, 16:516], (G[:, 16:516] + 1) % 3) and np.array_equal(M[:, :16], G[:, :16]) and np.array_equal(M[:, 516:], G[:, 516:])
+    g2.store_columns(603, 777, pack_codes((G[:, 603:777] + 2) % 3))             # unaligned write-back
+    g2.packed.flush()
+    M2 = PackedGens(path).getMatrix(range(100, 137))
+    assert np.array_equal(M2[:, 603:777], (G[:, 603:777] + 2) % 3) and np.array_equal(M2[:, 516:603], G[:, 516:603]) and np.array_equal(M2[:, 777:], G[:, 777:])
     # text -> container
     txt = tmp_path / "g.ssv"
     with open(txt, "w") as f:

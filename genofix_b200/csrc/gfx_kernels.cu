@@ -881,13 +881,37 @@ struct LazyBlanket {
 #ifdef GFX_DEBUG_COUNTERS
   uint32_t* xflags = nullptr;   // events of one xpeel query: 1 observed extra child, 2 its other parent unobserved, 4 DOWN frame, 8 depth > 3
 #endif
+  // statuses of all nodes fetched up front (prefetch()): 2 bits per node.  The walks below are chains of dependent
+  // steps; with the lazy form every step waited for its own two loads (the deferred-job kernels ran at 20 % issue
+  // utilisation on long-scoreboard stalls), with the prefetch all loads of a job are in flight at once.
+  uint64_t pre_lo = 0, pre_hi = 0;
+  bool pre = false;
   __device__ __forceinline__ int status(int t) const {
+    if (pre) return (int)(((t < 32 ? pre_lo >> (2 * t) : pre_hi >> (2 * (t - 32)))) & 3ull);
     const int r = __ldg(rows + t);
     if (r < 0) return 3;
     const int cd = cell_code(c.live, c.wpr, r, j);
     if (cd == 3) return 3;
     if (filter && cell_rx(c, r, j) >= cut) return 3;   // suspect node: not evidence (:230-238)
     return cd;
+  }
+  __device__ __forceinline__ void prefetch() {
+    uint64_t lo = 0, hi = 0;
+    const int64_t wo = j >> 4;
+    const int sh = 2 * (int)(j & 15);
+#pragma unroll 4
+    for (int t = 0; t < n; ++t) {
+      const int r = __ldg(rows + t);
+      uint32_t st = 3u;
+      if (r >= 0) {
+        const uint32_t cd = (__ldg(c.live + (int64_t)r * c.wpr + wo) >> sh) & 3u;
+        const uint32_t rx = filter ? (uint32_t)__ldg(c.raw + (int64_t)r * c.ld_raw + j) : 0u;
+        st = (cd == 3u || (filter && rx >= cut)) ? 3u : cd;
+      }
+      if (t < 32) lo |= (uint64_t)st << (2 * t);
+      else hi |= (uint64_t)st << (2 * (t - 32));
+    }
+    pre_lo = lo; pre_hi = hi; pre = true;
   }
 };
 
@@ -1168,9 +1192,11 @@ __device__ __forceinline__ bool peel_query(const LazyBlanket& L, int q, int qoth
 
 // Marginal of q (qother: the second focal animal of a pair, forced unobserved, or -1).
 // *total = unnormalised P(evidence in the component).
-// First tier of the general elimination: tables of up to 3^GFX_WMAX_S entries in SHARED memory, one per job of the
-// block, interleaved (entry i of slot t at stab[i * GFX_STAB_SLOTS + t]: conflict free).  The 729-entry private tables
-// live in local memory, 93 KB per warp of 16 jobs, and missed L1 four times out of five (profiles/r2_summary.md).
+// Optional first tier of the general elimination (-DGFX_GENERAL_SMEM_TIER): tables of up to 3^GFX_WMAX_S entries in
+// SHARED memory, one per job of the block, interleaved (entry i of slot t at stab[i * GFX_STAB_SLOTS + t]: conflict
+// free) -- the 729-entry private tables live in local memory, 93 KB per warp of 16 jobs, and miss L1 four times out of
+// five.  MEASURED AND NOT ENABLED: the kernel's duration is set by its widest jobs, which fail the first tier and run
+// twice; k_correct_jobs_general 2.66 -> 5.30 ms per 4096-SNP chunk, exact either way (profiles/r2_summary.md).
 #define GFX_WMAX_S 4
 #define GFX_TAB_S 81
 #define GFX_STAB_SLOTS 64     // 4 warps x KG_ITEMS jobs per block of k_correct_jobs_general
@@ -1855,6 +1881,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     double tot_me = 1.0, tot_ot = 1.0;
     const int sme = a.nf == 2 ? side : 0;
     if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
+      LB.prefetch();
       if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
       else if constexpr (MODE == 1) return false;
       else if (query_general(LB, a.bl, qme, qot, anc, &tot_me, stab)) atomicExch(a.status, 1);
@@ -1866,6 +1893,7 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
       // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
       double tmp[3];
       if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
+        if (!LB.pre) LB.prefetch();
         if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
           if constexpr (MODE == 1) return false;
           else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot, stab)) atomicExch(a.status, 1);
@@ -2412,11 +2440,15 @@ __global__ void __launch_bounds__(KJ_THREADS, KJ_BLOCKS * 128 / KJ_THREADS) k_co
 #define KG_ITEMS 16   // jobs per ticket of the general round (measured: 16 beats 32 and 8)
 #endif
 __global__ void __launch_bounds__(KJ_THREADS, KG_BLOCKS * 128 / KJ_THREADS) k_correct_jobs_general(FocalArgs a) {
+#ifdef GFX_GENERAL_SMEM_TIER
   // one shared-memory table slot per job in flight: warp w, lane l < KG_ITEMS -> slot w * KG_ITEMS + l
   __shared__ double s_tab[GFX_TAB_S * GFX_STAB_SLOTS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* stab = (lane < KG_ITEMS && wib * KG_ITEMS + lane < GFX_STAB_SLOTS) ? s_tab + wib * KG_ITEMS + lane : nullptr;
   jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6, stab);
+#else
+  jobs_round<2, KG_ITEMS>(a, a.items, a.wl_count[5], a.wl_count + 6, nullptr);
+#endif
 }
 
 // Finishes the serial walk of every parked cell once all its jobs have bits.

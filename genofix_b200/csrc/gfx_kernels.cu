@@ -65,6 +65,7 @@ struct gfx_schedule {
   int32_t *anc6 = nullptr, *rank_blanket = nullptr, *prow = nullptr;
   uint8_t* rank_flags = nullptr;
   int32_t *child_off = nullptr, *child_row = nullptr, *child_other = nullptr;
+  int32_t* rank_kids = nullptr;      // children rows per rank row, every list starting at a multiple of 4 entries (16-byte bulk copies)
   int32_t *bl_off = nullptr, *bl_row = nullptr;
   int8_t *bl_p1 = nullptr, *bl_p2 = nullptr, *bl_last = nullptr, *bl_q0 = nullptr, *bl_q1 = nullptr;
   uint64_t* bl_kid = nullptr;
@@ -81,8 +82,10 @@ struct gfx_schedule {
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
   uint32_t* rank_lut6 = nullptr;     // 64 entries (obs | sire << 2 | dam << 4): score | class << 16
   uint16_t* rank_class_sc = nullptr; // score of each of the <= 8 classes
+  bool rank_form3 = false;           // the score table is the one k_mendel_rank3's boolean network computes
+  int rank_ncls = 0;
   std::vector<RankRow> rank_rows_h;     // per-row records of the rank kernel, heaviest first
-  struct RankTasks { int64_t nwords; RankRow* dev; uint32_t n; };
+  struct RankTasks { int64_t nwords; int form; RankRow* dev; uint32_t n; };
   std::vector<RankTasks> rank_tasks;    // task tables, one per matrix width seen so far
   std::mutex rank_mutex;
   double* kv = nullptr;        // 108 doubles, children-heuristic element table
@@ -131,7 +134,7 @@ static void build_rank_lut(std::vector<uint2>& lut) {
 // CHECKED here against all 256 grand-parent variants of the full table.  Distinct scores get a class id
 // (class 0 = score 0) for the (class, m) histogram; obs = 3 maps to the marker 0xFFFF.
 static bool build_rank_fast(const std::vector<uint2>& lut, std::vector<uint32_t>& lut6, std::vector<uint16_t>& class_sc,
-                            std::string& err) {
+                            int& ncls_out, std::string& err) {
   lut6.assign(64, 0);
   class_sc.assign(8, 0);
   int ncls = 1;
@@ -161,6 +164,27 @@ static bool build_rank_fast(const std::vector<uint2>& lut, std::vector<uint32_t>
     }
     lut6[idx] = (uint32_t)sc | ((uint32_t)c << 16);
   }
+  ncls_out = ncls;
+  return true;
+}
+
+// k_mendel_rank3 computes the score class of a cell with both parents observed from a fixed boolean network over the
+// six code bits (classes 0, 0.5, 1, 2 -- the values 2 * (max - own) takes on Mendel's table, bayesnet/model.py:27-38).
+// This is the same network on the host; the schedule checks it against the table built by inference and only then
+// lets the kernel use it.
+static int rank3_class(int o, int sv, int dv) {
+  const int o0 = o & 1, o1 = o >> 1, s0 = sv & 1, s1 = sv >> 1, d0 = dv & 1, d1 = dv >> 1;
+  const int u = o0 ^ s1 ^ d1, v = o1 ^ (s1 & d1), t3 = (u | v) & (s0 ^ 1), aa = s1 | d1;
+  const int q = (aa & ((o0 | o1) ^ 1)) | ((aa ^ 1) & o1);
+  const int c2 = q & (s0 ^ d0), c1 = s0 & d0 & (o0 ^ 1);
+  return ((t3 & (d0 ^ 1)) | c1) | (((t3 & (d0 ^ 1)) | c2) << 1);
+}
+static bool rank3_network_matches(const std::vector<uint32_t>& lut6) {
+  static const uint16_t sc[4] = {0x0000u, 0x3800u, 0x3C00u, 0x4000u};
+  for (int o = 0; o < 3; ++o)
+    for (int sv = 0; sv < 3; ++sv)
+      for (int dv = 0; dv < 3; ++dv)
+        if ((lut6[o | (sv << 2) | (dv << 4)] & 0xFFFFu) != sc[rank3_class(o, sv, dv)]) return false;
   return true;
 }
 
@@ -170,7 +194,7 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->huge_pool, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc};
+                  s->big_pool, s->big_flags, s->huge_pool, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc, s->rank_kids};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : s->rank_tasks)
@@ -206,9 +230,11 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   build_rank_lut(lut);
   std::vector<uint32_t> lut6;
   std::vector<uint16_t> class_sc;
-  if (!build_rank_fast(lut, lut6, class_sc, err)) { delete s; return fail(GFX_E_INVALID, err); }
+  if (!build_rank_fast(lut, lut6, class_sc, s->rank_ncls, err)) { delete s; return fail(GFX_E_INVALID, err); }
+  s->rank_form3 = rank3_network_matches(lut6);
   std::vector<RankRow>& rank_rows = s->rank_rows_h;
   rank_rows.resize(h.n_rows);
+  std::vector<int32_t> rank_kids;
   {
     std::vector<int32_t> order(h.n_rows);
     for (int r = 0; r < h.n_rows; ++r) order[r] = r;
@@ -217,9 +243,13 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
     });
     for (int i = 0; i < h.n_rows; ++i) {
       const int r = order[i];
-      rank_rows[i] = RankRow{r, h.child_off[r], h.child_off[r + 1] - h.child_off[r], h.rank_flags[r],
+      const int nk = h.child_off[r + 1] - h.child_off[r];
+      rank_rows[i] = RankRow{r, (int32_t)rank_kids.size(), nk, h.rank_flags[r],
                              h.anc6[(size_t)r * 6], h.anc6[(size_t)r * 6 + 1], 0, 0};
+      for (int c = 0; c < nk; ++c) rank_kids.push_back(h.child_row[h.child_off[r] + c]);
+      while (rank_kids.size() % 4) rank_kids.push_back(-1);
     }
+    for (int c = 0; c < 32; ++c) rank_kids.push_back(-1);
   }
   std::vector<double> kv(108);
   gfx_fill_kv(kv.data());
@@ -235,6 +265,7 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   UP(single_entry, single_entry);
   UP(app_order, h.app_order); UP(single_order, h.single_order);
   UP(loopy_rows, loopy); UP(trio_row, h.trio_row); UP(fam_off, h.fam_off); UP(rank_lut, lut); UP(rank_lut6, lut6); UP(rank_class_sc, class_sc); UP(kv, kv); UP(status, status);
+  UP(rank_kids, rank_kids);
 #undef UP
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_pool, sizeof(double) * (size_t)GFX_TAB_BIG * GFX_BIG_SLOTS);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * (GFX_BIG_SLOTS + GFX_HUGE_SLOTS));
@@ -561,7 +592,7 @@ __device__ __noinline__ void r2_hist_patterns(unsigned long long* hist, uint32_t
 
 // Per-cell path with the full table; handles every case (and is the definition the fast path is tested against).
 template <bool HIST>
-__device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t row, int64_t w, uint32_t w0, bool has_anc,
+__device__ __noinline__ void r2_slow_word(const RankArgs& a, uint32_t* s_bins, int64_t row, int64_t w, uint32_t w0, bool has_anc,
                                           int c0, int c1) {
   uint32_t wa[6];
   if (has_anc) {
@@ -605,7 +636,7 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
     outw[k] = pair;
   }
   if (HIST)
-    r2_hist_patterns(a.hist, reinterpret_cast<uint32_t*>(smem + R2_BINS_OFF), outw, w0 & (w0 >> 1) & 0x55555555u, lim);
+    r2_hist_patterns(a.hist, s_bins, outw, w0 & (w0 >> 1) & 0x55555555u, lim);
   r2_store(a.raw + row * a.ld_raw + w * 16, outw);
 }
 
@@ -616,6 +647,7 @@ __device__ __noinline__ void r2_slow_word(const RankArgs& a, char* smem, int64_t
 template <bool HIST>
 __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a) {
   extern __shared__ __align__(16) char smem[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   {
     uint32_t* s_fast = reinterpret_cast<uint32_t*>(smem + R2_FAST_OFF);
     for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
@@ -695,7 +727,7 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
           // neither ancestors nor children: every score is 1.0 (:102)
           // (words with a missing cell take the per-cell path: patching the marker in here costs 32 predicated
           // instructions on every word, missing or not)
-          if (tail || (HIST && miss)) { r2_slow_word<HIST>(a, smem, row, w, w0, false, c0, c1); continue; }
+          if (tail || (HIST && miss)) { r2_slow_word<HIST>(a, s_bins, row, w, w0, false, c0, c1); continue; }
 #pragma unroll
           for (int k = 0; k < 8; ++k) outw[k] = 0x3C003C00u;
           if (HIST) {
@@ -725,7 +757,7 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
           if (any & 0xFC00FC00u) slow = true;                                               // packed-half path: m < 1024
           if (!has_anc && (miss || anyv != 0x55555555u)) slow = true;                        // 1.0 cells among child scores
         }
-        if (slow) { r2_slow_word<HIST>(a, smem, row, w, w0, has_anc, c0, c1); continue; }
+        if (slow) { r2_slow_word<HIST>(a, s_bins, row, w, w0, has_anc, c0, c1); continue; }
         if (has_anc) {
           // 4-row transposition of 2-bit fields: one byte obs | sire << 2 | dam << 4 per cell
           const uint32_t M2 = 0x33333333u, M4 = 0x0F0F0F0Fu;
@@ -814,6 +846,491 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
       // the marker class only ever has m = 0 (an unobserved cell receives no children units)
       const uint32_t pat = sc == 0xFFFFu ? 65536u : (uint32_t)gfx_half_add(gfx_child_score((uint32_t)m), sc);
       if (sum) atomicAdd(&a.hist[pat], sum);
+    }
+    for (int i = t; i < (int)R2_BIN_N; i += blockDim.x) {
+      const uint32_t v = s_bins[i];
+      if (!v) continue;
+      const uint32_t bin = i == (int)R2_SLOT_ZERO ? 0u : (i == (int)R2_SLOT_MISS ? 65536u : R2_BIN_LO + i);
+      atomicAdd(&a.hist[bin], (unsigned long long)v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mendel rank kernel, third form: score classes from a boolean network, scores from PRMT byte tables, TMA-staged inputs
+// ------------------------------------------------------------------------------------------------
+// Same results as k_mendel_rank (bit for bit, scores and histogram; scripts/bench_rank_forms.py compares the two on a
+// dozen data sets).  What changes is where the time goes (profiles/r2_ncu_lines_rank.txt: 349 warp instructions per
+// 32-word step in the form above, 25 % task / loop overhead, 25 % the children loop, 13 % the one-cell table lookups and
+// 8 % shared-memory atomics; 32 shared-memory operations per step):
+//  * with both parents observed the ancestor score of a cell is 2 * (max - own) of one row of Mendel's table: four values
+//    (0, 0.5, 1, 2).  Its 2-bit class is computed for the 16 cells of a word at once by a network of nine LOP3 over the six
+//    code bit planes (rank3_class is the same network on the host; the schedule checks it against the table built by
+//    inference).  PRMT then serves as the table: the class nibbles of four cells select the high bytes of their float16
+//    scores from a 4-byte constant, a second PRMT interleaves them with zero low bytes -- an output word (two scores) per
+//    PRMT, no shared memory.  [Two earlier versions of this kernel looked the scores up two cells at a time in a 4096-entry
+//    shared-memory table: 6.6-8.7 wavefronts per LDS.64 (bank conflicts on an index that is mostly the own genotype), the
+//    LSU pipe 46 % busy, 2.3 short-scoreboard stalls per issue -- profiles/r2_ncu_rank3_table.txt.]
+//  * childless rows (2/3 of the cells of config 2) tally their histogram as three popcounts of class masks per word, kept
+//    in registers and added to the lane-private (class, m = 0) counters once per TASK;
+//  * one specialised loop per kind of row (the dispatch tests of the form above ran on every step);
+//  * TMA-staged inputs, pipelined two tasks deep (below): nothing of the prefetch pipeline lives in registers;
+//  * a child word address is one IMAD.WIDE (row * bytes-per-row + the lane's column pointer), child rows are broadcast
+//    by shuffles from one register per lane.
+#ifndef R3_THREADS
+#define R3_THREADS 640   // 96 registers: no spills (a spilled pipeline variable costs a memory latency per task)
+#endif
+// words per task by number of children of the row (at most R3_CHUNK = 128: one staging stage)
+#ifndef R3_WORDS_LIGHT
+#define R3_WORDS_LIGHT 128   // childless
+#endif
+#ifndef R3_WORDS_MID
+#define R3_WORDS_MID 128     // 1..7 children
+#endif
+#ifndef R3_WORDS_HEAVY
+#define R3_WORDS_HEAVY 32    // 8..63 children
+#endif
+#ifndef R3_WORDS_HUGE
+#define R3_WORDS_HUGE 32     // >= 64 children
+#endif
+#define R3_CM_OFF 0u          // u32 [4 classes][32 m][32 lanes]
+#define R3_BINS_OFF 16384u    // u32 [8192] patterns 0x3000..0x4FFF
+#define R3_SMEM 49152u
+
+// prmt.b32 with the full selector: bit 3 of a selector nibble replicates the sign of the chosen byte
+__device__ __forceinline__ uint32_t r3_prmt(uint32_t x, uint32_t y, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(sel));
+  return r;
+}
+
+struct R3Kids {
+  uint32_t o0, o1, o2;             // parent's cell is 0 / 1 / 2 (bit 2i)
+  uint32_t bl0, bl1, bh0, bh1;     // byte t: cells 4t, 4t + 2, 4t + 1, 4t + 3
+  uint32_t allmiss;
+};
+// four child words: units of float16(1/3) per cell (bayesnet/model.py:93-116, other parent unknown, D7)
+__device__ __forceinline__ void r3_round(R3Kids& K, const uint32_t wc[4]) {
+  uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1 (4 children * 2 units = 8 < 16)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint32_t cl = wc[u], ch = wc[u] >> 1;
+    K.allmiss &= cl & ch;
+    const uint32_t one = ~cl & K.o1;                            // child 0 or 2 under a heterozygous parent: 1 unit
+    const uint32_t two = ~cl & ((ch & K.o0) | (~ch & K.o2));    // child 2 under parent 0, child 0 under parent 2: 2 units
+    const uint32_t contrib = one | (two << 1);
+    acc_lo += contrib & 0x33333333u;
+    acc_hi += (contrib >> 2) & 0x33333333u;
+  }
+  K.bl0 += acc_lo & 0x0F0F0F0Fu; K.bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
+  K.bh0 += acc_hi & 0x0F0F0F0Fu; K.bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+}
+__device__ __forceinline__ void r3_flush(R3Kids& K, uint32_t m16[8]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    m16[2 * t] += __byte_perm(K.bl0, K.bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+    m16[2 * t + 1] += __byte_perm(K.bl1, K.bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+  }
+  K.bl0 = K.bl1 = K.bh0 = K.bh1 = 0;
+}
+#define R3_LOAD_FULL(c)                                                                     \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                           \
+    const int r = __shfl_sync(0xffffffffu, kid, (c) + u);                                   \
+    nx[u] = __ldg(reinterpret_cast<const uint32_t*>(pw + (int64_t)r * wprb));               \
+  }
+#define R3_LOAD_TAIL(c)                                                                     \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                           \
+    const int r = __shfl_sync(0xffffffffu, kid, ((c) + u) & 31);                            \
+    nx[u] = 0xFFFFFFFFu;                                                                    \
+    if (u < 3 && r >= 0) nx[u] = __ldg(reinterpret_cast<const uint32_t*>(pw + (int64_t)r * wprb)); \
+  }
+// the first round (children 0..3) of the word column pw points to: requested one step ahead of its use
+__device__ __forceinline__ void r3_children_first(const char* pw, int wprb, int nk, int kid, uint32_t nx[4]) {
+  if (nk >= 4) { R3_LOAD_FULL(0) } else { R3_LOAD_TAIL(0) }
+}
+// m16[k] = m(cell 2k) | m(cell 2k + 1) << 16 over the nk genotyped children of the row, at the word column pw points
+// to; allmiss bit 2i: every child is missing at cell i.  kid: lane i holds the row of child i (i < 32, -1 beyond nk);
+// nx: the words of children 0..3 (r3_children_first).  All 32 lanes must call this (shuffles).
+// over: bit 0 some m >= 32 (beyond the (class, m) counters), bit 1 some m >= 1024 (beyond the packed-half path).
+__device__ __forceinline__ void r3_children(const char* pw, int wprb, const int32_t* __restrict__ child_row, int c0, int nk,
+                                            int kid, int lane, uint32_t w0, uint32_t nx[4], uint32_t m16[8], uint32_t& allmiss,
+                                            uint32_t& over) {
+  const uint32_t M = 0x55555555u;
+  R3Kids K;
+  K.o0 = ~(w0 | (w0 >> 1)) & M;
+  K.o1 = (w0 & ~(w0 >> 1)) & M;
+  K.o2 = ((w0 >> 1) & ~w0) & M;
+  K.bl0 = K.bl1 = K.bh0 = K.bh1 = 0;
+  K.allmiss = 0xFFFFFFFFu;
+  uint32_t wc[4];
+  if (nk <= 32) {
+    // one batch (every row of a livestock dam, most sires): no outer loop, the byte counters (at most 64) are the result
+    const int full = nk >> 2, rem = nk & 3;
+    for (int i = 1; i < full; ++i) {        // a full round followed by a full round
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wc[u] = nx[u];
+      R3_LOAD_FULL(4 * i)
+      r3_round(K, wc);
+    }
+    if (full > 0) {                           // the last full round
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wc[u] = nx[u];
+      if (rem) { R3_LOAD_TAIL(4 * full) }
+      r3_round(K, wc);
+    }
+    if (rem) r3_round(K, nx);                 // 1..3 children (the others read as missing)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      m16[2 * t] = __byte_perm(K.bl0, K.bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+      m16[2 * t + 1] = __byte_perm(K.bl1, K.bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
+    }
+    over = ((K.bl0 | K.bl1 | K.bh0 | K.bh1) & 0xE0E0E0E0u) ? 1u : 0u;
+    allmiss = K.allmiss & M;
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m16[k] = 0;
+  for (int base = 0; base < nk; base += 32) {
+    const int cnt = min(32, nk - base);
+    int kidn = -1;
+    if (base + 32 < nk && lane < nk - base - 32) kidn = __ldg(child_row + c0 + base + 32 + lane);   // next batch of 32
+    const int full = cnt >> 2, rem = cnt & 3;
+    if (base > 0) {
+      if (full > 0) { R3_LOAD_FULL(0) } else { R3_LOAD_TAIL(0) }
+    }
+    for (int i = 1; i < full; ++i) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wc[u] = nx[u];
+      R3_LOAD_FULL(4 * i)
+      r3_round(K, wc);
+    }
+    if (full > 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wc[u] = nx[u];
+      if (rem) { R3_LOAD_TAIL(4 * full) }
+      r3_round(K, wc);
+    }
+    if (rem) r3_round(K, nx);
+    r3_flush(K, m16);                         // 8 rounds * 8 units = 64 per byte
+    kid = kidn;
+  }
+  uint32_t any = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) any |= m16[k];
+  over = ((any & 0xFFE0FFE0u) ? 1u : 0u) | ((any & 0xFC00FC00u) ? 2u : 0u);
+  allmiss = K.allmiss & M;
+}
+
+// Score classes of the 16 cells of a word whose own, sire and dam cells are all observed: bit 2i of b0 / b1 = low / high
+// bit of the class of cell i (0 -> 0, 1 -> 0.5, 2 -> 1, 3 -> 2); the odd bits are garbage.
+__device__ __forceinline__ void r3_classes(uint32_t w0, uint32_t wS, uint32_t wD, uint32_t& b0, uint32_t& b1) {
+  const uint32_t o0 = w0, o1 = w0 >> 1, s0 = wS, s1 = wS >> 1, d0 = wD, d1 = wD >> 1;
+  const uint32_t u = o0 ^ s1 ^ d1;                  // both parents homozygous: own low bit differs from the expected child's
+  const uint32_t v = o1 ^ (s1 & d1);                //                          own high bit differs
+  const uint32_t t3 = (u | v) & ~s0;
+  const uint32_t aa = s1 | d1;
+  const uint32_t q = (aa & ~(o0 | o1)) | (~aa & o1);   // one heterozygous parent: own is the homozygote the other parent excludes
+  const uint32_t c2 = q & (s0 ^ d0);
+  const uint32_t c1 = s0 & d0 & ~o0;                // both heterozygous, own homozygous: 0.5
+  b1 = (t3 & ~d0) | c2;
+  b0 = (t3 & ~d0) | c1;
+}
+// class nibbles: V nibble n = class of cell 2n, W nibble n = class of cell 2n + 1
+#define R3_NIBBLES(b0, b1)                                                              \
+  const uint32_t C_ = ((b0) & 0x55555555u) | (((b1) << 1) & 0xAAAAAAAAu);               \
+  const uint32_t V = C_ & 0x33333333u, W = (C_ >> 2) & 0x33333333u
+// four bytes TAB[class] for the cells 0, 2, 4, 6 (V) or 1, 3, 5, 7 (W) of the low / high half of the nibble word
+#define R3_BYTES(TAB, X, hi) r3_prmt(TAB, 0u, (hi) ? ((X) >> 16) : (X))
+// word k (cells 2k, 2k + 1) = [0, byte k of E, 0, byte k of O]; every table byte has a clear sign bit, so its sign is the zero
+#define R3_WORD(E, O, k) r3_prmt(E, O, 0x4C08u + 0x1111u * (uint32_t)(k))
+#define R3_SCORE_TAB 0x403C3800u    // high bytes of float16 0, 0.5, 1, 2
+#define R3_CLASS_TAB 0x30201000u    // class << 4: as byte 1 / 3 of a word it is the offset class * 4096 of the (class, m) counters
+
+struct R3Task {
+  int row, c0, nk, fl, rS, rD, wbeg, wend;
+};
+__device__ __forceinline__ R3Task r3_decode(const int4& q0, const int4& q1) {
+  return R3Task{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+}
+
+// ---- TMA staging (cp.async.bulk + mbarrier), one private area per warp -------------------------------------
+// A task covers at most R3_CHUNK words of a row.  Its inputs -- the own, sire and dam row segments (<= 512 bytes each)
+// and the rows of its first 32 children (128 bytes) -- are fetched by four bulk copies that one lane issues while the
+// PREVIOUS task runs; the 32-byte task records travel the same way one task further ahead.  Nothing of this pipeline
+// lives in registers: the first version kept the records and first words in flight in registers, ptxas spilled them
+// and every spill store waited for its load (profiles/r2_ncu_rank3_regpipe.txt: 42 % of the stall samples).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+#ifndef R3_CHUNK
+#define R3_CHUNK 128   // words per task at most
+#endif
+#define R3_STAGE_BYTES (3u * R3_CHUNK * 4u + 128u)     // own, sire, dam segments, child rows
+#define R3_REC_OFF (2u * R3_STAGE_BYTES)               // two 32-byte record slots
+#define R3_BAR_OFF (R3_REC_OFF + 64u)                  // mbarriers: data[2], record[2]
+#define R3_WARP_BYTES ((R3_BAR_OFF + 32u + 127u) / 128u * 128u)
+#define R3_WARP_OFF (R3_SMEM + 128u)
+#define R3_DYN_SMEM (R3_WARP_OFF + (R3_THREADS / 32) * R3_WARP_BYTES)
+
+__device__ __forceinline__ void r3_issue_record(const RankArgs& a, char* wsm, uint32_t task, int slot) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + R3_BAR_OFF) + 2 + slot;
+  mbar_expect_tx(bar, 32u);
+  tma_load_1d(wsm + R3_REC_OFF + 32u * slot, a.tasks + task, 32u, bar);
+}
+__device__ __forceinline__ void r3_issue_data(const RankArgs& a, char* wsm, const R3Task& T, int stage) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + R3_BAR_OFF) + stage;
+  char* st = wsm + (uint32_t)stage * R3_STAGE_BYTES;
+  const uint32_t bytes = (uint32_t)((T.wend - T.wbeg + 3) & ~3) * 4u;
+  const bool pk = (T.fl & 1) && T.rS >= 0 && T.rD >= 0;
+  const uint32_t kb = T.nk > 0 ? (uint32_t)((min(T.nk, 32) + 3) & ~3) * 4u : 0u;
+  mbar_expect_tx(bar, bytes * (pk ? 3u : 1u) + kb);
+  tma_load_1d(st, a.packed + (int64_t)T.row * a.wpr + T.wbeg, bytes, bar);
+  if (pk) {
+    tma_load_1d(st + R3_CHUNK * 4u, a.packed + (int64_t)T.rS * a.wpr + T.wbeg, bytes, bar);
+    tma_load_1d(st + 2u * R3_CHUNK * 4u, a.packed + (int64_t)T.rD * a.wpr + T.wbeg, bytes, bar);
+  }
+  if (kb) tma_load_1d(st + 3u * R3_CHUNK * 4u, a.child_row + T.c0, kb, bar);
+}
+
+template <bool HIST>
+__global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  // k_mendel_rank_generic (loopy rows, disjoint cells) may start as soon as SMs free up: it waits for this grid at its end
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+  char* const wsm = smem + R3_WARP_OFF + (threadIdx.x >> 5) * R3_WARP_BYTES;
+  {
+    if (HIST) {
+      uint4* z = reinterpret_cast<uint4*>(smem + R3_CM_OFF);
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+      z = reinterpret_cast<uint4*>(smem + R3_BINS_OFF);
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<uint32_t*>(smem + R3_SMEM) = 0u;   // block-local ticket counter
+    if (lane == 0) {
+      uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + R3_BAR_OFF);
+      for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const uint32_t lane4 = (uint32_t)lane * 4u;
+  const uint32_t lane44 = lane4 * 0x00010001u;
+  const uint32_t M = 0x55555555u;
+  const __half2 C3 = r2_h2(0x35553555u);    // float16(1/3) = 1365 / 4096
+  const __half2 K3 = r2_h2(0xDD55DD55u);    // -1024 * float16(1/3) = -341.25
+  uint32_t* s_bins = reinterpret_cast<uint32_t*>(smem + R3_BINS_OFF);
+  uint32_t utailw = (HIST && (a.n_snps & 15)) ? (uint32_t)(a.nwords - 1) : 0xFFFFFFFFu;   // ragged last word: per-cell path
+  asm volatile("" : "+r"(utailw));
+  const int wprb = (int)(a.wpr * 4);
+  // Tasks: records dealt round-robin to the blocks (static, balanced because the table is ordered by cost), tickets from a
+  // shared-memory counter inside the block (as in k_mendel_rank).  [One global counter instead: same-address atomics
+  // retire at ~2 ns each, 54 000 draws took longer than the kernel; draws of 4 or 8 consecutive tasks left a tail of one
+  // draw, 25-50 % of a warp's life -- 112 / 144 / 215 us per chunk against 87, profiles/r2_rank3_variants.md.]
+  // Task number i of a warp uses data stage i & 1 and record slot i & 1; the phase parity of both is (i >> 1) & 1.
+  uint32_t* s_ticket = reinterpret_cast<uint32_t*>(smem + R3_SMEM);
+  const uint32_t tasks = a.n_tasks;
+  uint32_t tk = 0;
+  if (lane == 0) tk = atomicAdd(s_ticket, 3u);
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  uint32_t t0 = R2_TASK_OF(tk), t1 = R2_TASK_OF(tk + 1u), t2 = R2_TASK_OF(tk + 2u);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(wsm + R3_BAR_OFF);
+  R3Task T = R3Task{0, 0, 0, 0, 0, 0, 0, 0};
+  if (t0 < tasks) {
+    if (lane == 0) {
+      r3_issue_record(a, wsm, t0, 0);
+      if (t1 < tasks) r3_issue_record(a, wsm, t1, 1);
+    }
+    mbar_wait(bars + 2, 0u);
+    T = r3_decode(*reinterpret_cast<const int4*>(wsm + R3_REC_OFF), *reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 16u));
+    __syncwarp();
+    if (lane == 0) r3_issue_data(a, wsm, T, 0);
+  }
+  for (uint32_t it = 0; t0 < tasks; ++it) {
+    // ---- pipeline: the next task's inputs, the record of the one after, the next ticket -------------------
+    if (t1 < tasks) {
+      const uint32_t sl = (it + 1u) & 1u;
+      mbar_wait(bars + 2 + sl, ((it + 1u) >> 1) & 1u);
+      if (lane == 0) {
+        // the record stays in its slot until this task is over (it is read again when it becomes the current one)
+        const R3Task T1 = r3_decode(*reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl), *reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl + 16u));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        r3_issue_data(a, wsm, T1, (int)sl);
+      }
+    }
+    uint32_t next = 0;
+    if (lane == 0) {
+      if (t2 < tasks) r3_issue_record(a, wsm, t2, (int)(it & 1u));
+      next = atomicAdd(s_ticket, 1u);
+    }
+    // ---- the task ---------------------------------------------------------------------------------------
+    const int wbeg = T.wbeg, row = T.row, c0 = T.c0, nk = T.nk;
+    const uint32_t uwend = (uint32_t)T.wend;
+    const bool has_anc = T.fl & 1, loopy = T.fl & 2;
+    const bool parents_ok = has_anc && T.rS >= 0 && T.rD >= 0;
+    uint16_t* rawrow = a.raw + (int64_t)row * a.ld_raw;
+    asm volatile("" : "+l"(rawrow));   // pinned: ptxas otherwise re-derives the 64-bit product on every step
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(wsm + (it & 1u) * R3_STAGE_BYTES) + lane;   // own; + R3_CHUNK sire; + 2 R3_CHUNK dam
+    mbar_wait(bars + (it & 1u), (it >> 1) & 1u);
+    uint32_t w = (uint32_t)(wbeg + lane);
+    if (loopy && !parents_ok) {
+      // every word of this row belongs to k_mendel_rank_generic
+    } else if (!has_anc && nk == 0) {
+      // ---- neither ancestors nor children: every score is 1.0 (:102) ---------------------------------
+      uint32_t ones = 0;
+      for (; w < uwend; w += 32u, sw += 32) {
+        if (HIST) {
+          const uint32_t w0 = sw[0];
+          if (w == utailw || (w0 & (w0 >> 1) & M)) { r2_slow_word<HIST>(a, s_bins, row, w, w0, false, c0, c0); continue; }
+          ones += 16u;
+        }
+        const uint4 v = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+        __stcs(reinterpret_cast<uint4*>(rawrow + (uint64_t)w * 16u), v);
+        __stcs(reinterpret_cast<uint4*>(rawrow + (uint64_t)w * 16u) + 1, v);
+      }
+      if (HIST) {
+        ones = __reduce_add_sync(0xffffffffu, ones);
+        if (lane == 0 && ones) atomicAdd(&s_bins[0x3C00u - R2_BIN_LO], ones);
+      }
+    } else if (has_anc && !parents_ok) {
+      // ---- a parent without a genotype: the grand-parents matter, per-cell path with the full table --
+      for (; w < uwend; w += 32u, sw += 32) r2_slow_word<HIST>(a, s_bins, row, w, sw[0], true, c0, c0 + nk);
+    } else if (has_anc && nk == 0) {
+      // ---- childless, both parents genotyped ----------------------------------------------------------
+      uint32_t n1 = 0, n2 = 0, n3 = 0, nw = 0;   // cells of class 1, 2, 3; words
+      for (; w < uwend; w += 32u, sw += 32) {
+        const uint32_t w0 = sw[0], wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
+        const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
+        if (pm != 0u || w == utailw || (w0 & (w0 >> 1) & M)) {   // a missing own cell: marker (or 1.0) on the per-cell path
+          if (!(pm != 0u && loopy)) r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0);
+          continue;
+        }
+        uint32_t b0, b1;
+        r3_classes(w0, wS, wD, b0, b1);
+        R3_NIBBLES(b0, b1);
+        const uint32_t e0 = R3_BYTES(R3_SCORE_TAB, V, 0), e1 = R3_BYTES(R3_SCORE_TAB, V, 1);
+        const uint32_t o0 = R3_BYTES(R3_SCORE_TAB, W, 0), o1 = R3_BYTES(R3_SCORE_TAB, W, 1);
+        uint32_t outw[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { outw[k] = R3_WORD(e0, o0, k); outw[4 + k] = R3_WORD(e1, o1, k); }
+        r2_store(rawrow + (uint64_t)w * 16u, outw);
+        if (HIST) {
+          n1 += __popc(b0 & ~b1 & M);
+          n2 += __popc(~b0 & b1 & M);
+          n3 += __popc(b0 & b1 & M);
+          nw += 16u;
+        }
+      }
+      if (HIST) {
+        const uint32_t n0 = nw - n1 - n2 - n3;
+        if (n0) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + lane4), n0);
+        if (n1) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 4096u + lane4), n1);
+        if (n2) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 8192u + lane4), n2);
+        if (n3) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 12288u + lane4), n3);
+      }
+    } else {
+      // ---- rows with children: both parents genotyped, or a founder (score = the children term alone, class 0) ----
+      const int kid = lane < nk ? (int)sw[3 * R3_CHUNK] : -1;
+      uint32_t nx[4];
+      r3_children_first(reinterpret_cast<const char*>(a.packed + min(w, uwend - 1u)), wprb, nk, kid, nx);
+      for (uint32_t wb = (uint32_t)wbeg; wb < uwend; wb += 32u, w += 32u, sw += 32) {
+        const uint32_t w0 = sw[0];
+        uint32_t m16[8], allmiss, over;
+        r3_children(reinterpret_cast<const char*>(a.packed + min(w, uwend - 1u)), wprb, a.child_row, c0, nk, kid, lane, w0, nx, m16, allmiss, over);
+        // the next step's first child words travel while this step is scored
+        if (wb + 32u < uwend) r3_children_first(reinterpret_cast<const char*>(a.packed + min(w + 32u, uwend - 1u)), wprb, nk, kid, nx);
+        if (w >= uwend) continue;
+        const bool big = over & 1u;                            // (class, m) counters hold m < 32
+        const uint32_t miss = w0 & (w0 >> 1) & M;
+        uint32_t outw[8];
+        if (has_anc) {
+          const uint32_t wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
+          const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
+          if (pm != 0u || w == utailw || miss || (over & 2u)) {   // packed-half path: m < 1024; own observed
+            if (!(pm != 0u && loopy)) r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0 + nk);
+            continue;
+          }
+          uint32_t b0, b1;
+          r3_classes(w0, wS, wD, b0, b1);
+          R3_NIBBLES(b0, b1);
+          const uint32_t e0 = R3_BYTES(R3_SCORE_TAB, V, 0), e1 = R3_BYTES(R3_SCORE_TAB, V, 1);
+          const uint32_t o0 = R3_BYTES(R3_SCORE_TAB, W, 0), o1 = R3_BYTES(R3_SCORE_TAB, W, 1);
+          const uint32_t ce0 = R3_BYTES(R3_CLASS_TAB, V, 0), ce1 = R3_BYTES(R3_CLASS_TAB, V, 1);
+          const uint32_t co0 = R3_BYTES(R3_CLASS_TAB, W, 0), co1 = R3_BYTES(R3_CLASS_TAB, W, 1);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t anc = (k < 4) ? R3_WORD(e0, o0, k & 3) : R3_WORD(e1, o1, k & 3);
+            if (HIST && !big) {
+              const uint32_t cw = (k < 4) ? R3_WORD(ce0, co0, k & 3) : R3_WORD(ce1, co1, k & 3);
+              const uint32_t t = cw + (m16[k] << 7) + lane44;
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + (t & 0xFFFFu)), 1u);
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + (t >> 16)), 1u);
+            }
+            const __half2 cs = __hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3);
+            outw[k] = r2_u(__hadd2(cs, r2_h2(anc)));
+          }
+        } else {
+          // a cell that is missing or has no genotyped child scores 1.0, not the children term: per-cell path
+          if (w == utailw || miss || allmiss != 0u || (over & 2u)) {
+            r2_slow_word<HIST>(a, s_bins, row, w, w0, false, c0, c0 + nk);
+            continue;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (HIST && !big) {
+              const uint32_t t = (m16[k] << 7) + lane44;
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + (t & 0xFFFFu)), 1u);
+              atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + (t >> 16)), 1u);
+            }
+            outw[k] = r2_u(__hfma2(r2_h2(m16[k] + 0x64006400u), C3, K3));
+          }
+        }
+        if (HIST && big) {
+          uint32_t tmp[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) tmp[k] = outw[k];
+          r2_hist_patterns(a.hist, s_bins, tmp, 0u, 16);
+        }
+        r2_store(rawrow + (uint64_t)w * 16u, outw);
+      }
+    }
+    // ---- rotate the pipeline ------------------------------------------------------------------------------
+    {
+      const uint32_t sl = (it + 1u) & 1u;
+      T = r3_decode(*reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl), *reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl + 16u));
+    }
+    t0 = t1; t1 = t2;
+    next = __shfl_sync(0xffffffffu, next, 0);
+    t2 = R2_TASK_OF(next);
+  }
+  if (!HIST) return;
+  // ---- retire: counters -> float16 patterns -> global histogram ------------------------------------
+  __syncthreads();
+  {
+    const uint32_t* s_cm = reinterpret_cast<const uint32_t*>(smem + R3_CM_OFF);
+    const int t = threadIdx.x;
+    if (t < 128) {
+      const int cls = t >> 5, m = t & 31;
+      unsigned long long sum = 0;
+      for (int l = 0; l < 32; ++l) sum += s_cm[t * 32 + ((l + t) & 31)];
+      const uint16_t sc = (uint16_t)((R3_SCORE_TAB >> (8 * cls)) & 0xFFu) << 8;
+      if (sum) atomicAdd(&a.hist[gfx_half_add(gfx_child_score((uint32_t)m), sc)], sum);
     }
     for (int i = t; i < (int)R2_BIN_N; i += blockDim.x) {
       const uint32_t v = s_bins[i];
@@ -1375,6 +1892,9 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
       }
     }
   }
+  // launched with programmatic stream serialisation behind k_mendel_rank / k_mendel_rank3: the two grids write disjoint
+  // cells, so this one runs in the shadow of the other's tail and only has to outlive it (stream order for what follows)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, uint16_t* raw,
@@ -1384,6 +1904,11 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   const int64_t nwords = (n_snps + 15) / 16;
   if (n_snps <= 0 || wpr < nwords || ld_raw < nwords * 16 || (ld_raw % 8) != 0 || (((uintptr_t)raw) % 16) != 0)
     return fail(GFX_E_INVALID, "gfx_mendel_rank: need wpr >= ceil(s/16), ld_raw >= 16*ceil(s/16), ld_raw % 8 == 0, raw 16-byte aligned");
+  // k_mendel_rank3 needs Mendel's table (rank3_network_matches); GFX_RANK_FORM=2 selects the previous form (A/B runs)
+  const char* form_env = getenv("GFX_RANK_FORM");
+  // ... and rows that bulk copies can address: 16-byte aligned segments, at most 2^31 bytes per row
+  const bool form3 = s->rank_form3 && !(form_env && form_env[0] == '2') && (wpr % 4) == 0 && (((uintptr_t)packed) % 16) == 0 &&
+                     wpr <= 0x1FFFFFFFll;
   // task table for this matrix width (built once, cached in the schedule)
   const RankRow* tasks_dev = nullptr;
   uint32_t n_tasks = 0;
@@ -1391,12 +1916,21 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     std::lock_guard<std::mutex> lock(const_cast<gfx_schedule*>(s)->rank_mutex);
     gfx_schedule* ms = const_cast<gfx_schedule*>(s);
     for (auto& t : ms->rank_tasks)
-      if (t.nwords == nwords) { tasks_dev = t.dev; n_tasks = t.n; }
+      if (t.nwords == nwords && t.form == (form3 ? 3 : 2)) { tasks_dev = t.dev; n_tasks = t.n; }
     if (!tasks_dev) {
       std::vector<RankRow> tasks;
       tasks.reserve((size_t)s->h.n_rows * ((nwords + 127) / 128 + 1));
       for (const RankRow& r : s->rank_rows_h) {
-        const int64_t cw = r.nk >= 8 ? R2_WORDS_HEAVY : (r.nk >= 1 ? R2_WORDS_MID : R2_WORDS_LIGHT);
+        int64_t cw;
+        if (form3) {
+          // rows are cut into equal parts of at most R3_WORDS_* words (multiples of 32): long tasks for cheap rows (per-task
+          // set-up), short ones for rows with many children (the heaviest tasks start first, but a 1 000-kid sire must not be one)
+          const int64_t maxw = r.nk == 0 ? R3_WORDS_LIGHT : (r.nk < 8 ? R3_WORDS_MID : (r.nk < 64 ? R3_WORDS_HEAVY : R3_WORDS_HUGE));
+          const int64_t parts = (nwords + maxw - 1) / maxw;
+          cw = ((nwords + parts - 1) / parts + 31) / 32 * 32;
+        } else {
+          cw = r.nk >= 8 ? R2_WORDS_HEAVY : (r.nk >= 1 ? R2_WORDS_MID : R2_WORDS_LIGHT);
+        }
         for (int64_t w = 0; w < nwords; w += cw) {
           RankRow t = r;
           t.pad0 = (int32_t)w;
@@ -1412,12 +1946,12 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
       if (e != cudaSuccess) { cudaFree(dev); return fail(GFX_E_CUDA, std::string("task table upload: ") + cudaGetErrorString(e)); }
       // tables are never evicted: another lane (host thread on the same schedule) may be about to launch on one, and a
       // table is 32 bytes per task -- a few MB per distinct matrix width
-      ms->rank_tasks.push_back({nwords, dev, (uint32_t)tasks.size()});
+      ms->rank_tasks.push_back({nwords, form3 ? 3 : 2, dev, (uint32_t)tasks.size()});
       tasks_dev = dev;
       n_tasks = (uint32_t)tasks.size();
     }
   }
-  RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, tasks_dev, n_tasks, s->child_row,
+  RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, tasks_dev, n_tasks, s->rank_kids,
              s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist};
   {
     // once per process (one process per GPU); guarded: several lanes call this concurrently
@@ -1427,14 +1961,25 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
       attr_err = cudaFuncSetAttribute(k_mendel_rank<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM);
       if (attr_err == cudaSuccess)
         attr_err = cudaFuncSetAttribute(k_mendel_rank<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_DYN_SMEM);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(k_mendel_rank3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R3_DYN_SMEM);
+      if (attr_err == cudaSuccess)
+        attr_err = cudaFuncSetAttribute(k_mendel_rank3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R3_DYN_SMEM);
     });
     GFX_CUDA(attr_err);
   }
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
-  int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
-  if (blocks < 1) blocks = 1;
-  if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
-  else k_mendel_rank<false><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
+  if (form3) {
+    int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R3_THREADS / 32) - 1) / (R3_THREADS / 32), s->num_sms);
+    if (blocks < 1) blocks = 1;
+    if (hist) k_mendel_rank3<true><<<blocks, R3_THREADS, R3_DYN_SMEM, stream>>>(a);
+    else k_mendel_rank3<false><<<blocks, R3_THREADS, R3_DYN_SMEM, stream>>>(a);
+  } else {
+    int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
+    if (blocks < 1) blocks = 1;
+    if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
+    else k_mendel_rank<false><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
+  }
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
     GenericRankArgs g{packed, wpr, n_snps, raw, ld_raw, s->loopy_rows, s->n_loopy_rows, s->rank_blanket, s->child_off, s->child_row,
@@ -1442,7 +1987,17 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
                       BlanketDev{s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->big_pool, s->big_flags, s->huge_pool, s->debug ? s->counters : nullptr},
                       s->bl_kid, s->status, (unsigned long long*)hist};
     const int64_t total = (int64_t)s->n_loopy_rows * ((nwords + 31) / 32) * 32;   // one warp per 32 words
-    k_mendel_rank_generic<<<grid_for(total, 128, s->num_sms, 8), 128, 0, stream>>>(g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid_for(total, 128, s->num_sms, 8));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GFX_CUDA(cudaLaunchKernelEx(&cfg, k_mendel_rank_generic, g));
     GFX_LAUNCHED();
   }
   return GFX_OK;
@@ -2729,25 +3284,6 @@ __global__ void __launch_bounds__(256, GFX_FAM_BLOCKS) k_trio_scan(const uint32_
 #define GFX_TMA_ROWS 6        // sire, dam, up to 4 kids
 #define GFX_TMA_WARPS 8
 #define GFX_TMA_SMEM (GFX_TMA_WARPS * GFX_TMA_STAGES * GFX_TMA_ROWS * 512 + GFX_TMA_WARPS * GFX_TMA_STAGES * 8)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-
 template <int NK>
 __device__ __forceinline__ void trio_family_group_tma(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nquads, int64_t n_snps,
                                                       int row_s, int row_d, const int32_t* __restrict__ rows, int lane, uint4* buf,

@@ -82,6 +82,14 @@ struct gfx_schedule {
   uint2* rank_lut = nullptr;   // 4096 entries: f16 scores for obs = 0,1,2 (+ pad)
   uint32_t* rank_lut6 = nullptr;     // 64 entries (obs | sire << 2 | dam << 4): score | class << 16
   uint16_t* rank_class_sc = nullptr; // score of each of the <= 8 classes
+  // work lists of k_mendel_rank3 / k_mendel_rank_generic_wl: a ring of 8 (lanes share the schedule, a few launches are in
+  // flight at a time); a slot is handed out again only behind the event of its last consumer.  Headers are all zero at rest.
+  struct WlSlot { uint2* buf = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; };
+  WlSlot rank_wl[8];
+  uint32_t* rank_wl_hdr = nullptr;
+  uint32_t rank_wl_next = 0;
+  cudaEvent_t rank_ev0 = nullptr, rank_ev1 = nullptr;   // gfx_rank_timing: recorded around the dominant rank kernel
+  bool rank_timing = false;
   bool rank_form3 = false;           // the score table is the one k_mendel_rank3's boolean network computes
   int rank_ncls = 0;
   std::vector<RankRow> rank_rows_h;     // per-row records of the rank kernel, heaviest first
@@ -194,11 +202,17 @@ extern "C" void gfx_schedule_destroy(gfx_schedule* s) {
                   s->bl_off, s->bl_row, s->bl_p1, s->bl_p2, s->bl_last, s->bl_q0, s->bl_q1, s->job_row0, s->job_row1,
                   s->job_bl, s->app_focal_row, s->app_focal_off, s->app_entry, s->single_row, s->single_bl,
                   s->single_off, s->single_entry, s->loopy_rows, s->trio_row, s->rank_lut, s->kv, s->status,
-                  s->big_pool, s->big_flags, s->huge_pool, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc, s->rank_kids};
+                  s->big_pool, s->big_flags, s->huge_pool, s->bl_kid, s->counters, s->bl_tree, s->app_order, s->single_order, s->bl_slotrow, s->bl_slotbad, s->fam_off, s->rank_lut6, s->rank_class_sc, s->rank_kids, s->rank_wl_hdr};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& t : s->rank_tasks)
     if (t.dev) cudaFree(t.dev);
+  for (auto& w : s->rank_wl) {
+    if (w.buf) cudaFree(w.buf);
+    if (w.done) cudaEventDestroy(w.done);
+  }
+  if (s->rank_ev0) cudaEventDestroy(s->rank_ev0);
+  if (s->rank_ev1) cudaEventDestroy(s->rank_ev1);
   delete s;
 }
 
@@ -271,6 +285,8 @@ extern "C" int gfx_schedule_create(const gfx_pedigree_desc* ped, gfx_schedule** 
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->big_flags, sizeof(int) * (GFX_BIG_SLOTS + GFX_HUGE_SLOTS));
   if (e == cudaSuccess) e = cudaMemset(s->big_flags, 0, sizeof(int) * (GFX_BIG_SLOTS + GFX_HUGE_SLOTS));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->huge_pool, sizeof(double) * (size_t)GFX_TAB_HUGE * GFX_HUGE_SLOTS);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->rank_wl_hdr, sizeof(uint32_t) * 64 * 32);
+  if (e == cudaSuccess) e = cudaMemset(s->rank_wl_hdr, 0, sizeof(uint32_t) * 64 * 32);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->counters, sizeof(unsigned long long) * 16);
   if (e == cudaSuccess) e = cudaMemset(s->counters, 0, sizeof(unsigned long long) * 16);
   if (e != cudaSuccess) {
@@ -468,6 +484,9 @@ struct RankArgs {
   const uint32_t* lut6;
   const uint16_t* class_sc;
   unsigned long long* hist;   // 65537 bins or nullptr (HIST = false)
+  uint32_t* wl_hdr;           // k_mendel_rank3: work list of k_mendel_rank_generic_wl: [0] number of entries (zero at launch), or nullptr
+  uint2* wl;                  //                 its (row, word) entries
+  uint32_t wl_cap;
 };
 
 // 896 threads per SM: ptxas gets 72 registers instead of 64, which ends the spilling of the prefetched words and the
@@ -893,9 +912,9 @@ __global__ void __launch_bounds__(R2_THREADS, R2_CTAS) k_mendel_rank(RankArgs a)
 #ifndef R3_WORDS_HUGE
 #define R3_WORDS_HUGE 32     // >= 64 children
 #endif
-#define R3_CM_OFF 0u          // u32 [4 classes][32 m][32 lanes]
-#define R3_BINS_OFF 16384u    // u32 [8192] patterns 0x3000..0x4FFF
-#define R3_SMEM 49152u
+#define R3_CM_OFF 0u          // u32 [4 classes][64 m][32 lanes]
+#define R3_BINS_OFF 32768u    // u32 [8192] patterns 0x3000..0x4FFF
+#define R3_SMEM 65536u
 
 // prmt.b32 with the full selector: bit 3 of a selector nibble replicates the sign of the chosen byte
 __device__ __forceinline__ uint32_t r3_prmt(uint32_t x, uint32_t y, uint32_t sel) {
@@ -904,6 +923,18 @@ __device__ __forceinline__ uint32_t r3_prmt(uint32_t x, uint32_t y, uint32_t sel
   return r;
 }
 
+// x >> k on the FMA pipe (IMAD.HI): the kernel is bound by the ALU pipe (LOP3 / SHF / PRMT: one warp instruction per two
+// cycles per scheduler, profiles/r2_ncu_rank3.txt: 59 % busy against 17 % for the FMA pipe)
+#ifndef R3_FMA_SHIFTS
+#define R3_FMA_SHIFTS 0   // measured: 80.3 us with, 78.2 us without (IMAD.HI is no cheaper than SHF here)
+#endif
+__device__ __forceinline__ uint32_t r3_shr(uint32_t x, int k) {
+#if R3_FMA_SHIFTS
+  return __umulhi(x, 1u << (32 - k));
+#else
+  return x >> k;
+#endif
+}
 struct R3Kids {
   uint32_t o0, o1, o2;             // parent's cell is 0 / 1 / 2 (bit 2i)
   uint32_t bl0, bl1, bh0, bh1;     // byte t: cells 4t, 4t + 2, 4t + 1, 4t + 3
@@ -914,16 +945,16 @@ __device__ __forceinline__ void r3_round(R3Kids& K, const uint32_t wc[4]) {
   uint32_t acc_lo = 0, acc_hi = 0;          // nibble n: cell 2n / cell 2n + 1 (4 children * 2 units = 8 < 16)
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const uint32_t cl = wc[u], ch = wc[u] >> 1;
+    const uint32_t cl = wc[u], ch = r3_shr(wc[u], 1);
     K.allmiss &= cl & ch;
     const uint32_t one = ~cl & K.o1;                            // child 0 or 2 under a heterozygous parent: 1 unit
     const uint32_t two = ~cl & ((ch & K.o0) | (~ch & K.o2));    // child 2 under parent 0, child 0 under parent 2: 2 units
-    const uint32_t contrib = one | (two << 1);
+    const uint32_t contrib = two * 2u + one;                    // disjoint bits: the sum is the union (one IMAD)
     acc_lo += contrib & 0x33333333u;
-    acc_hi += (contrib >> 2) & 0x33333333u;
+    acc_hi += r3_shr(contrib, 2) & 0x33333333u;
   }
-  K.bl0 += acc_lo & 0x0F0F0F0Fu; K.bl1 += (acc_lo >> 4) & 0x0F0F0F0Fu;
-  K.bh0 += acc_hi & 0x0F0F0F0Fu; K.bh1 += (acc_hi >> 4) & 0x0F0F0F0Fu;
+  K.bl0 += acc_lo & 0x0F0F0F0Fu; K.bl1 += r3_shr(acc_lo, 4) & 0x0F0F0F0Fu;
+  K.bh0 += acc_hi & 0x0F0F0F0Fu; K.bh1 += r3_shr(acc_hi, 4) & 0x0F0F0F0Fu;
 }
 __device__ __forceinline__ void r3_flush(R3Kids& K, uint32_t m16[8]) {
 #pragma unroll
@@ -951,7 +982,7 @@ __device__ __forceinline__ void r3_children_first(const char* pw, int wprb, int 
 // m16[k] = m(cell 2k) | m(cell 2k + 1) << 16 over the nk genotyped children of the row, at the word column pw points
 // to; allmiss bit 2i: every child is missing at cell i.  kid: lane i holds the row of child i (i < 32, -1 beyond nk);
 // nx: the words of children 0..3 (r3_children_first).  All 32 lanes must call this (shuffles).
-// over: bit 0 some m >= 32 (beyond the (class, m) counters), bit 1 some m >= 1024 (beyond the packed-half path).
+// over: bit 0 some m >= 64 (beyond the (class, m) counters), bit 1 some m >= 1024 (beyond the packed-half path).
 __device__ __forceinline__ void r3_children(const char* pw, int wprb, const int32_t* __restrict__ child_row, int c0, int nk,
                                             int kid, int lane, uint32_t w0, uint32_t nx[4], uint32_t m16[8], uint32_t& allmiss,
                                             uint32_t& over) {
@@ -984,7 +1015,7 @@ __device__ __forceinline__ void r3_children(const char* pw, int wprb, const int3
       m16[2 * t] = __byte_perm(K.bl0, K.bh0, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
       m16[2 * t + 1] = __byte_perm(K.bl1, K.bh1, 0x0400u + 0x0101u * t) & 0x00FF00FFu;
     }
-    over = ((K.bl0 | K.bl1 | K.bh0 | K.bh1) & 0xE0E0E0E0u) ? 1u : 0u;
+    over = ((K.bl0 | K.bl1 | K.bh0 | K.bh1) & 0xC0C0C0C0u) ? 1u : 0u;
     allmiss = K.allmiss & M;
     return;
   }
@@ -1017,14 +1048,14 @@ __device__ __forceinline__ void r3_children(const char* pw, int wprb, const int3
   uint32_t any = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) any |= m16[k];
-  over = ((any & 0xFFE0FFE0u) ? 1u : 0u) | ((any & 0xFC00FC00u) ? 2u : 0u);
+  over = ((any & 0xFFC0FFC0u) ? 1u : 0u) | ((any & 0xFC00FC00u) ? 2u : 0u);
   allmiss = K.allmiss & M;
 }
 
 // Score classes of the 16 cells of a word whose own, sire and dam cells are all observed: bit 2i of b0 / b1 = low / high
 // bit of the class of cell i (0 -> 0, 1 -> 0.5, 2 -> 1, 3 -> 2); the odd bits are garbage.
 __device__ __forceinline__ void r3_classes(uint32_t w0, uint32_t wS, uint32_t wD, uint32_t& b0, uint32_t& b1) {
-  const uint32_t o0 = w0, o1 = w0 >> 1, s0 = wS, s1 = wS >> 1, d0 = wD, d1 = wD >> 1;
+  const uint32_t o0 = w0, o1 = r3_shr(w0, 1), s0 = wS, s1 = r3_shr(wS, 1), d0 = wD, d1 = r3_shr(wD, 1);
   const uint32_t u = o0 ^ s1 ^ d1;                  // both parents homozygous: own low bit differs from the expected child's
   const uint32_t v = o1 ^ (s1 & d1);                //                          own high bit differs
   const uint32_t t3 = (u | v) & ~s0;
@@ -1037,14 +1068,14 @@ __device__ __forceinline__ void r3_classes(uint32_t w0, uint32_t wS, uint32_t wD
 }
 // class nibbles: V nibble n = class of cell 2n, W nibble n = class of cell 2n + 1
 #define R3_NIBBLES(b0, b1)                                                              \
-  const uint32_t C_ = ((b0) & 0x55555555u) | (((b1) << 1) & 0xAAAAAAAAu);               \
-  const uint32_t V = C_ & 0x33333333u, W = (C_ >> 2) & 0x33333333u
+  const uint32_t C_ = ((b0) & 0x55555555u) | (((b1) * 2u) & 0xAAAAAAAAu);               \
+  const uint32_t V = C_ & 0x33333333u, W = r3_shr(C_, 2) & 0x33333333u
 // four bytes TAB[class] for the cells 0, 2, 4, 6 (V) or 1, 3, 5, 7 (W) of the low / high half of the nibble word
-#define R3_BYTES(TAB, X, hi) r3_prmt(TAB, 0u, (hi) ? ((X) >> 16) : (X))
+#define R3_BYTES(TAB, X, hi) r3_prmt(TAB, 0u, (hi) ? r3_shr(X, 16) : (X))
 // word k (cells 2k, 2k + 1) = [0, byte k of E, 0, byte k of O]; every table byte has a clear sign bit, so its sign is the zero
 #define R3_WORD(E, O, k) r3_prmt(E, O, 0x4C08u + 0x1111u * (uint32_t)(k))
 #define R3_SCORE_TAB 0x403C3800u    // high bytes of float16 0, 0.5, 1, 2
-#define R3_CLASS_TAB 0x30201000u    // class << 4: as byte 1 / 3 of a word it is the offset class * 4096 of the (class, m) counters
+#define R3_CLASS_TAB 0x60402000u    // class << 5: as byte 1 / 3 of a word it is the offset class * 8192 of the (class, m) counters
 
 struct R3Task {
   int row, c0, nk, fl, rS, rD, wbeg, wend;
@@ -1078,6 +1109,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+#ifndef R3_XSTEP
+#define R3_XSTEP 1       // the first child words of the next step are requested before the current step is scored
+#endif
 #ifndef R3_CHUNK
 #define R3_CHUNK 128   // words per task at most
 #endif
@@ -1108,6 +1142,20 @@ __device__ __forceinline__ void r3_issue_data(const RankArgs& a, char* wsm, cons
   if (kb) tma_load_1d(st + 3u * R3_CHUNK * 4u, a.child_row + T.c0, kb, bar);
 }
 
+// a word of a loopy row in which a parent cell is missing belongs to the general inference: the active lanes of the warp
+// append theirs to the work list with one atomic
+__device__ __forceinline__ void r3_push(const RankArgs& a, int row, uint32_t w) {
+  if (!a.wl_hdr) return;   // scanning form of the consumer
+  const uint32_t act = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(act) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(a.wl_hdr, (uint32_t)__popc(act));
+  base = __shfl_sync(act, base, leader);
+  const uint32_t at = base + (uint32_t)__popc(act & ((1u << lane) - 1u));
+  if (at < a.wl_cap) a.wl[at] = make_uint2((uint32_t)row, w);
+}
+
 template <bool HIST>
 __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
   extern __shared__ __align__(128) char smem[];
@@ -1118,7 +1166,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
   {
     if (HIST) {
       uint4* z = reinterpret_cast<uint4*>(smem + R3_CM_OFF);
-      for (int i = threadIdx.x; i < 1024; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < 2048; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
       z = reinterpret_cast<uint4*>(smem + R3_BINS_OFF);
       for (int i = threadIdx.x; i < 2048; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     }
@@ -1191,6 +1239,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
     uint32_t w = (uint32_t)(wbeg + lane);
     if (loopy && !parents_ok) {
       // every word of this row belongs to k_mendel_rank_generic
+      for (; w < uwend; w += 32u) r3_push(a, row, w);
     } else if (!has_anc && nk == 0) {
       // ---- neither ancestors nor children: every score is 1.0 (:102) ---------------------------------
       uint32_t ones = 0;
@@ -1218,7 +1267,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
         const uint32_t w0 = sw[0], wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
         const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
         if (pm != 0u || w == utailw || (w0 & (w0 >> 1) & M)) {   // a missing own cell: marker (or 1.0) on the per-cell path
-          if (!(pm != 0u && loopy)) r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0);
+          if (pm != 0u && loopy) r3_push(a, row, w);
+          else r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0);
           continue;
         }
         uint32_t b0, b1;
@@ -1240,30 +1290,38 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
       if (HIST) {
         const uint32_t n0 = nw - n1 - n2 - n3;
         if (n0) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + lane4), n0);
-        if (n1) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 4096u + lane4), n1);
-        if (n2) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 8192u + lane4), n2);
-        if (n3) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 12288u + lane4), n3);
+        if (n1) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 8192u + lane4), n1);
+        if (n2) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 16384u + lane4), n2);
+        if (n3) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + 24576u + lane4), n3);
       }
     } else {
       // ---- rows with children: both parents genotyped, or a founder (score = the children term alone, class 0) ----
       const int kid = lane < nk ? (int)sw[3 * R3_CHUNK] : -1;
       uint32_t nx[4];
+#if R3_XSTEP
       r3_children_first(reinterpret_cast<const char*>(a.packed + min(w, uwend - 1u)), wprb, nk, kid, nx);
+#endif
       for (uint32_t wb = (uint32_t)wbeg; wb < uwend; wb += 32u, w += 32u, sw += 32) {
         const uint32_t w0 = sw[0];
         uint32_t m16[8], allmiss, over;
+#if !R3_XSTEP
+        r3_children_first(reinterpret_cast<const char*>(a.packed + min(w, uwend - 1u)), wprb, nk, kid, nx);
+#endif
         r3_children(reinterpret_cast<const char*>(a.packed + min(w, uwend - 1u)), wprb, a.child_row, c0, nk, kid, lane, w0, nx, m16, allmiss, over);
         // the next step's first child words travel while this step is scored
+#if R3_XSTEP
         if (wb + 32u < uwend) r3_children_first(reinterpret_cast<const char*>(a.packed + min(w + 32u, uwend - 1u)), wprb, nk, kid, nx);
+#endif
         if (w >= uwend) continue;
-        const bool big = over & 1u;                            // (class, m) counters hold m < 32
+        const bool big = over & 1u;                            // (class, m) counters hold m < 64
         const uint32_t miss = w0 & (w0 >> 1) & M;
         uint32_t outw[8];
         if (has_anc) {
           const uint32_t wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
           const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
           if (pm != 0u || w == utailw || miss || (over & 2u)) {   // packed-half path: m < 1024; own observed
-            if (!(pm != 0u && loopy)) r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0 + nk);
+            if (pm != 0u && loopy) r3_push(a, row, w);
+            else r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0 + nk);
             continue;
           }
           uint32_t b0, b1;
@@ -1325,8 +1383,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
   {
     const uint32_t* s_cm = reinterpret_cast<const uint32_t*>(smem + R3_CM_OFF);
     const int t = threadIdx.x;
-    if (t < 128) {
-      const int cls = t >> 5, m = t & 31;
+    if (t < 256) {
+      const int cls = t >> 6, m = t & 63;
       unsigned long long sum = 0;
       for (int l = 0; l < 32; ++l) sum += s_cm[t * 32 + ((l + t) & 31)];
       const uint16_t sc = (uint16_t)((R3_SCORE_TAB >> (8 * cls)) & 0xFFu) << 8;
@@ -1827,6 +1885,47 @@ struct GenericRankArgs {
 // Rows whose blanket is not the plain tree.  A warp scans 32 words of such a row: words in which both parents
 // are observed in all 16 cells are d-separated from the loop and belong to k_mendel_rank (same test there);
 // the others are processed two at a time, one cell per lane, with the full inference.
+// one cell per lane (two words of 16 cells per warp step): full inference on the row's blanket
+__device__ __forceinline__ void generic_rank_cell(const GenericRankArgs& a, int row, int64_t j, bool mine, int lane, double* tab,
+                                                  uint8_t* code) {
+  uint32_t r = 0x3C00u;
+  if (mine) {
+    const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
+    if (obs != 3) {
+      const int bid = a.rank_blanket[row];
+      const int off = a.bl.off[bid];
+      CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
+      LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
+      double anc[3], tot;
+      if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot, nullptr)) atomicExch(a.status, 1);
+      const uint16_t sc = gfx_anc_score(anc, obs);
+      uint32_t m = 0;
+      bool kids = false;
+      for (int c = a.child_off[row]; c < a.child_off[row + 1]; ++c) {
+        const int k = cell_code(a.packed, a.wpr, a.child_row[c], j);
+        if (k != 3) kids = true;
+        if (k == 0) m += obs;            // [0,1,2][obs]
+        else if (k == 2) m += 2 - obs;   // [2,1,0][obs]
+      }
+      r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
+    } else if (a.hist) {
+      r = 0xFFFFu;
+    }
+    a.raw[(int64_t)row * a.ld_raw + j] = (uint16_t)r;
+  }
+  if (a.hist) {
+    // one atomic per distinct pattern of the warp
+    const bool count = mine && j < a.n_snps;
+    const uint32_t act = __ballot_sync(0xffffffffu, count);
+    if (count) {
+      const uint32_t peers = __match_any_sync(act, r);
+      if (lane == __ffs(peers) - 1) atomicAdd(&a.hist[r == 0xFFFFu ? 65536u : r], (unsigned long long)__popc(peers));
+    }
+  }
+}
+
+// Scanning form (behind k_mendel_rank, and behind k_mendel_rank3 when the work list would be too large): a warp scans 32
+// words of a loopy row and processes the flagged ones two at a time.
 __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) {
   const int nwords = (int)((a.n_snps + 15) / 16);
   const int chunks = (nwords + 31) / 32;
@@ -1856,45 +1955,44 @@ __global__ void __launch_bounds__(128) k_mendel_rank_generic(GenericRankArgs a) 
       const int wsel = lane < 16 ? wa : wb;
       const bool mine = wsel >= 0;
       const int64_t j = (int64_t)(wbase + (mine ? wsel : 0)) * 16 + (lane & 15);
-      uint32_t r = 0x3C00u;
-      if (mine) {
-        const int obs = j < a.n_snps ? cell_code(a.packed, a.wpr, row, j) : 3;
-        if (obs != 3) {
-          const int bid = a.rank_blanket[row];
-          const int off = a.bl.off[bid];
-          CellCtx cc{a.packed, a.wpr, nullptr, 0, nullptr, nullptr, 0};
-          LazyBlanket LB{cc, a.bl.row + off, a.bl.p1 + off, a.bl.p2 + off, a.bl_kid + off, a.bl.off[bid + 1] - off, j, 0u, false};
-          double anc[3], tot;
-          if (query_lazy(LB, a.bl, a.bl.q0[bid], -1, code, tab, anc, &tot, nullptr)) atomicExch(a.status, 1);
-          const uint16_t sc = gfx_anc_score(anc, obs);
-          uint32_t m = 0;
-          bool kids = false;
-          for (int c = a.child_off[row]; c < a.child_off[row + 1]; ++c) {
-            const int k = cell_code(a.packed, a.wpr, a.child_row[c], j);
-            if (k != 3) kids = true;
-            if (k == 0) m += obs;            // [0,1,2][obs]
-            else if (k == 2) m += 2 - obs;   // [2,1,0][obs]
-          }
-          r = kids ? gfx_half_add(gfx_child_score(m), sc) : sc;
-        } else if (a.hist) {
-          r = 0xFFFFu;
-        }
-        a.raw[(int64_t)row * a.ld_raw + j] = (uint16_t)r;
-      }
-      if (a.hist) {
-        // one atomic per distinct pattern of the warp
-        const bool count = mine && j < a.n_snps;
-        const uint32_t act = __ballot_sync(0xffffffffu, count);
-        if (count) {
-          const uint32_t peers = __match_any_sync(act, r);
-          if (lane == __ffs(peers) - 1) atomicAdd(&a.hist[r == 0xFFFFu ? 65536u : r], (unsigned long long)__popc(peers));
-        }
-      }
+      generic_rank_cell(a, row, j, mine, lane, tab, code);
     }
   }
   // launched with programmatic stream serialisation behind k_mendel_rank / k_mendel_rank3: the two grids write disjoint
   // cells, so this one runs in the shadow of the other's tail and only has to outlive it (stream order for what follows)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Work-list form (behind k_mendel_rank3, which meets every flagged word of a loopy row anyway and records it): hdr[0] is the
+// number of entries (row, word).  With nothing on the list -- genotypes without missing calls -- the grid ends as soon as it
+// has seen the count; its launch is hidden behind the producer (programmatic dependent launch).  The last block to leave
+// puts the header back to zero: headers live in a ring owned by the schedule and are not cleared by the host.
+__global__ void __launch_bounds__(128) k_mendel_rank_generic_wl(GenericRankArgs a, uint32_t* hdr, const uint2* __restrict__ wl) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the list is complete when the producer grid has finished
+  __shared__ uint32_t s_n;
+  if (threadIdx.x == 0) s_n = *reinterpret_cast<volatile uint32_t*>(hdr);
+  __syncthreads();
+  const uint32_t n = s_n;
+  if (n != 0u) {
+    double tab[GFX_TAB];
+    uint8_t code[GFX_MAXN];
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = 2u * ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); e < n; e += 2u * nwarps) {
+      const uint32_t mye = e + (lane >> 4);
+      const bool mine = mye < n;
+      int row = 0;
+      int64_t j = 0;
+      if (mine) {
+        const uint2 ent = wl[mye];
+        row = (int)ent.x;
+        j = (int64_t)ent.y * 16 + (lane & 15);
+      }
+      generic_rank_cell(a, row, j, mine, lane, tab, code);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(hdr + 1, 1u) == gridDim.x - 1u) { hdr[1] = 0u; hdr[0] = 0u; }
 }
 
 static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int64_t n_snps, int64_t wpr, uint16_t* raw,
@@ -1952,7 +2050,7 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     }
   }
   RankArgs a{packed, wpr, (int)nwords, n_snps, raw, ld_raw, s->h.n_rows, s->anc6, tasks_dev, n_tasks, s->rank_kids,
-             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist};
+             s->rank_lut, s->rank_lut6, s->rank_class_sc, (unsigned long long*)hist, nullptr, nullptr, 0u};
   {
     // once per process (one process per GPU); guarded: several lanes call this concurrently
     static std::once_flag attr_once;
@@ -1969,16 +2067,43 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     GFX_CUDA(attr_err);
   }
   if (hist) GFX_CUDA(cudaMemsetAsync(hist, 0, 65537 * sizeof(uint64_t), stream));
+  uint2* wl = nullptr;
+  uint32_t* wl_hdr = nullptr;
+  int wl_slot = -1;
   if (form3) {
     int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R3_THREADS / 32) - 1) / (R3_THREADS / 32), s->num_sms);
     if (blocks < 1) blocks = 1;
+    // work list of the loopy rows: worst case every word of every loopy row; beyond 256 MB the consumer scans instead
+    const int64_t wl_cap = (int64_t)s->n_loopy_rows * nwords;
+    if (s->n_loopy_rows > 0 && wl_cap <= (32ll << 20)) {
+      gfx_schedule* ms = const_cast<gfx_schedule*>(s);
+      std::lock_guard<std::mutex> lock(ms->rank_mutex);
+      wl_slot = (int)(ms->rank_wl_next++ % 8u);
+      gfx_schedule::WlSlot& W = ms->rank_wl[wl_slot];
+      if (!W.done) GFX_CUDA(cudaEventCreateWithFlags(&W.done, cudaEventDisableTiming));
+      if (W.cap < (size_t)wl_cap) {
+        if (W.used) GFX_CUDA(cudaEventSynchronize(W.done));
+        if (W.buf) cudaFree(W.buf);
+        W.buf = nullptr; W.cap = 0; W.used = false;
+        GFX_CUDA(cudaMalloc((void**)&W.buf, sizeof(uint2) * (size_t)wl_cap));
+        W.cap = (size_t)wl_cap;
+      }
+      if (W.used) GFX_CUDA(cudaStreamWaitEvent(stream, W.done, 0));
+      wl = W.buf;
+      wl_hdr = s->rank_wl_hdr + 32 * wl_slot;
+      a.wl_hdr = wl_hdr; a.wl = wl; a.wl_cap = (uint32_t)wl_cap;
+    }
+    if (s->rank_timing) GFX_CUDA(cudaEventRecord(s->rank_ev0, stream));
     if (hist) k_mendel_rank3<true><<<blocks, R3_THREADS, R3_DYN_SMEM, stream>>>(a);
     else k_mendel_rank3<false><<<blocks, R3_THREADS, R3_DYN_SMEM, stream>>>(a);
+    if (s->rank_timing) GFX_CUDA(cudaEventRecord(s->rank_ev1, stream));
   } else {
     int blocks = (int)std::min<int64_t>(((int64_t)n_tasks + (R2_THREADS / 32) - 1) / (R2_THREADS / 32), s->num_sms * R2_CTAS);
     if (blocks < 1) blocks = 1;
+    if (s->rank_timing) GFX_CUDA(cudaEventRecord(s->rank_ev0, stream));
     if (hist) k_mendel_rank<true><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
     else k_mendel_rank<false><<<blocks, R2_THREADS, R2_DYN_SMEM, stream>>>(a);
+    if (s->rank_timing) GFX_CUDA(cudaEventRecord(s->rank_ev1, stream));
   }
   GFX_LAUNCHED();
   if (s->n_loopy_rows > 0) {
@@ -1988,7 +2113,7 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
                       s->bl_kid, s->status, (unsigned long long*)hist};
     const int64_t total = (int64_t)s->n_loopy_rows * ((nwords + 31) / 32) * 32;   // one warp per 32 words
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid_for(total, 128, s->num_sms, 8));
+    cfg.gridDim = dim3((unsigned)(wl ? s->num_sms * 4 : grid_for(total, 128, s->num_sms, 8)));
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
@@ -1997,9 +2122,34 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GFX_CUDA(cudaLaunchKernelEx(&cfg, k_mendel_rank_generic, g));
+    if (wl) {
+      GFX_CUDA(cudaLaunchKernelEx(&cfg, k_mendel_rank_generic_wl, g, wl_hdr, (const uint2*)wl));
+      gfx_schedule* ms = const_cast<gfx_schedule*>(s);
+      std::lock_guard<std::mutex> lock(ms->rank_mutex);
+      GFX_CUDA(cudaEventRecord(ms->rank_wl[wl_slot].done, stream));
+      ms->rank_wl[wl_slot].used = true;
+    } else {
+      GFX_CUDA(cudaLaunchKernelEx(&cfg, k_mendel_rank_generic, g));
+    }
     GFX_LAUNCHED();
   }
+  return GFX_OK;
+}
+
+extern "C" int gfx_rank_timing(gfx_schedule* s, int enable) {
+  if (!s || s->device < 0) return fail(GFX_E_INVALID, "bad schedule");
+  if (enable && !s->rank_ev0) {
+    GFX_CUDA(cudaEventCreate(&s->rank_ev0));
+    GFX_CUDA(cudaEventCreate(&s->rank_ev1));
+  }
+  s->rank_timing = enable != 0;
+  return GFX_OK;
+}
+
+extern "C" int gfx_rank_last_kernel_ms(gfx_schedule* s, float* ms) {
+  if (!s || !ms || !s->rank_ev0) return fail(GFX_E_INVALID, "gfx_rank_last_kernel_ms: timing was never switched on");
+  GFX_CUDA(cudaEventSynchronize(s->rank_ev1));
+  GFX_CUDA(cudaEventElapsedTime(ms, s->rank_ev0, s->rank_ev1));
   return GFX_OK;
 }
 

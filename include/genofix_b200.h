@@ -196,6 +196,13 @@ int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
  * on (enable = 1) or off.  Counting is off by default; it serialises on atomics. */
 int gfx_debug_counters(gfx_schedule* s, int enable, uint64_t* out16_host);
 
+/* Diagnostics: times the dominant kernel of gfx_mendel_rank / gfx_mendel_rank_hist (k_mendel_rank3, or k_mendel_rank) by
+ * itself -- two CUDA events recorded on the launching stream right around that launch, not around the histogram memset and
+ * the loopy-row consumer of the same call.  gfx_rank_timing(s, 1) switches the recording on (one caller at a time),
+ * gfx_rank_last_kernel_ms waits for the last recorded launch and returns its duration in milliseconds. */
+int gfx_rank_timing(gfx_schedule* s, int enable);
+int gfx_rank_last_kernel_ms(gfx_schedule* s, float* ms);
+
 /* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); returns and clears it.
  * Synchronises the stream. */
 int gfx_check_device_status(const gfx_schedule* s, void* stream);

@@ -513,11 +513,21 @@ class Oracle(object):
 
     # ---- decision rule :741-744, :809-824 (pairs), :932-938 (singles) ------------------------
     @staticmethod
-    def _decide(G, E, focal_row, j, p, obsprob, parent_rows, tie, threshold, err_thresh):
-        """Returns (new_code or None, counted_error, counted_excluded)."""
+    def _decide(G, E, focal_row, j, p, obsprob, parent_rows, tie, threshold, err_thresh, emp=None, single=False):
+        """Returns (new_code or None, counted_error, counted_excluded).  emp: the LD index (emp_index) -- the posterior is then
+        replaced by its mean with the weighted window frequencies of the focal animal's LIVE row (:746-779 pairs: only the
+        best states and their probability change; :883-908 singles: the observed state's probability too)."""
         obs = G[focal_row, j]  # LIVE matrix
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
+            if emp is not None:
+                norm = emp_state_probs(G[focal_row], j, emp)
+                comb = np.nanmean([np.asarray(p, dtype=float), norm * emp["weight"]], 0, dtype=float)
+                if single or np.nansum(comb) > 0:
+                    comb = np.divide(comb, np.sum(comb))
+                p = comb
+                if single:
+                    obsprob = 0. if obs == 9 else comb[obs]
             mx = np.nanmax(p)
         with np.errstate(invalid="ignore"):
             states = np.where(np.array(p >= (mx - tie), dtype=bool))[0]
@@ -539,7 +549,7 @@ class Oracle(object):
 
     # ---- correct_genotypes3.py:531-950 -------------------------------------------------------
     def correct_matrix(self, G, threshold_pair, threshold_single, back=2, init_filter_p=0.9,
-                       tiethreshold=0.05, err_thresh=1, raw=None, keep_posteriors=False, transformed=None):
+                       tiethreshold=0.05, err_thresh=1, raw=None, keep_posteriors=False, transformed=None, emp=None):
         """transformed = (E, test_p): ranks already transformed and the threshold already taken over the WHOLE matrix
         of which G is a block of columns (correct_matrix_parallel); the correction of a column needs nothing else."""
         ped = self.ped
@@ -551,6 +561,8 @@ class Oracle(object):
             if raw is None:
                 raw = self.mendel_rank(G0, back)
             E, test_p = self.transform(raw, G0, init_filter_p)
+            if emp is not None:
+                E, test_p = emp_blend_ranks(E, G0, emp, init_filter_p)     # :619-667
         corrected_n = np.zeros(len(self.ids), dtype=np.int32)
         excluded_n = np.zeros(len(self.ids), dtype=np.int32)
         pairs = set()
@@ -578,7 +590,7 @@ class Oracle(object):
                     for focal, p, op in ((s, ps, ops), (d, pd_, opd)):
                         fr = self.row[focal]
                         new, ne, nx = self._decide(G, E, fr, j, p, op, prow[focal], tiethreshold,
-                                                   threshold_pair, err_thresh)
+                                                   threshold_pair, err_thresh, emp=emp)
                         corrected_n[fr] += ne
                         excluded_n[fr] += nx
                         if new is not None:
@@ -597,7 +609,7 @@ class Oracle(object):
             for j in sorted(res.keys()):
                 p, op = res[j]
                 new, ne, nx = self._decide(G, E, fr, j, p, op if G[fr, j] != 9 else 0., prow[kid],
-                                           tiethreshold, threshold_single, err_thresh)
+                                           tiethreshold, threshold_single, err_thresh, emp=emp, single=True)
                 corrected_n[fr] += ne
                 if new is not None:
                     G[fr, j] = new
@@ -679,6 +691,82 @@ def count_joint_frq(table, mask, w, pseudocount, sum_inner_count=True):
                 val = (obs / (i + 1)) + val
         out[values] = val
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# the empirical (LD-window) blend: jalleledist3.py:101-117 (getCountTable), correct_genotypes3.py:69-82 (getEmpProbs),
+# :619-667 (ranks), :746-779 / :883-908 (decisions)
+# --------------------------------------------------------------------------------------------
+def emp_index(G, surround, pseudocount=1e-4, weight=3, mask=None):
+    """The index JointAllellicDistribution(...).countJointFrqAll(table) holds, as arrays: per SNP of the matrix its window
+    [wstart, wstart + wlen) in column order (D11 at the chromosome end) and the 3^wlen stored frequencies in
+    itertools.product order (first window SNP = most significant digit)."""
+    G = np.asarray(G)
+    S = G.shape[1]
+    mask = np.ones(G.shape, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+    wstart, wlen, freq = np.zeros(S, dtype=np.int64), np.zeros(S, dtype=np.int64), []
+    for i in range(S):
+        a, b = ld_window(S, i, surround)
+        w = max(b - a, 0)
+        wstart[i], wlen[i] = a, w
+        if w == 0:
+            freq.append(np.zeros(0))
+            continue
+        res = count_joint_frq(G[:, a:b], mask[:, a:b], w, pseudocount)
+        freq.append(np.array([res[v] for v in itertools.product([0, 1, 2], repeat=w)]))
+    return dict(wstart=wstart, wlen=wlen, freq=freq, weight=weight)
+
+
+def emp_count_table(row, j, emp):
+    """getCountTable: stored frequency of each state of SNP j given the animal's calls in j's window.  A missing call (9) in
+    the window is summed over its completions: what jalleledist3.py:84-96 sets out to do before it raises, so
+    this case has no reference behaviour; without missing calls it is the reference's lookup.  When the window does not
+    hold SNP j itself (D11: the last SNP of the chromosome) the three keys are the same one."""
+    a, w = int(emp["wstart"][j]), int(emp["wlen"][j])
+    tab = emp["freq"][j].reshape((3,) * w) if w > 0 else emp["freq"][j]
+    out = []
+    for state in (0, 1, 2):
+        idx = []
+        for c in range(a, a + w):
+            if c == j:
+                idx.append(state)
+            else:
+                v = int(row[c])
+                idx.append(v if v in (0, 1, 2) else slice(None))
+        out.append(np.sum(tab[tuple(idx)]))
+    return out
+
+
+def emp_state_probs(row, j, emp):
+    """:752-755 / :888-889: the count table normalised to sum 1 (the pseudocount keeps the sum positive)."""
+    c = emp_count_table(row, j, emp)
+    return np.divide(c, np.nansum(c))
+
+
+def emp_blend_ranks(E, G, emp, init_filter_p):
+    """correct_genotypes3.py:619-667: every observed cell's rank becomes the mean of itself and weight * (max - own) of its
+    normalised window frequencies; then the matrix is divided by its maximum, missing cells are set to 1 and the threshold is
+    the init_filter_p quantile (linear interpolation this time, :667)."""
+    E = np.array(E, dtype=np.float64)
+    G = np.asarray(G)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for j in range(G.shape[1]):
+            a, w = int(emp["wstart"][j]), int(emp["wlen"][j])
+            if not (a <= j < a + w):
+                continue      # :629-631 "missing SNP_id": a window that does not hold its own SNP (D11) is skipped here
+            for r in range(G.shape[0]):
+                obs = G[r, j]
+                if obs in (0, 1, 2):
+                    c = emp_count_table(G[r], j, emp)
+                    if np.nansum(c) > 0:
+                        norm = np.divide(c, np.nansum(c))
+                        empdiff = np.nanmax(norm) - norm[obs]
+                        E[r, j] = np.mean([E[r, j], empdiff * emp["weight"]])
+        E = np.divide(E, np.nanmax(E))
+        E[G == 9] = 1
+        q = np.quantile(E.flatten(), [0.95, 0.99, init_filter_p])
+    return E, q[2]
 
 
 # --------------------------------------------------------------------------------------------

@@ -176,14 +176,51 @@ def make_preidx(name):
                         reference_seconds=dt, **arrays)
     print("%s: %d animals x %d SNPs, cut %s, kept %s, reference %.1f s" % (name, len(ids), obs.shape[1], cut, kept, dt))
 
+# correctMatrix WITH the empirical (LD-window) blend of the ranks (:619-656): the reference builds the index itself
+EMP_CASES = {
+    "emp_a": dict(ped=dict(n_animals=90, n_generations=5, sire_frac=0.3, dam_frac=0.6, seed=7),
+                  n_snps=40, err=0.07, miss=0.0, drop=0.0, params=dict(GENOFIX_DEFAULTS, init_filter_p=0.8, tiethreshold=0.0),
+                  emp=dict(surround=1, pseudocount=0.0001, weight_empirical=3)),
+    "emp_b": dict(ped=dict(n_animals=96, n_generations=6, sire_frac=0.25, dam_frac=0.5, seed=11,
+                           related_mating_p=0.6, unknown_parents_frac=0.1),
+                  n_snps=26, err=0.04, miss=0.0, drop=0.12,
+                  # no tie band: a tie writes a 9 and the next window lookup over that cell raises in the reference (D4)
+                  params=dict(SIMULATE_DEFAULTS, tiethreshold=0.0, threshold_pair=0.3, threshold_single=0.4, init_filter_p=0.7),
+                  emp=dict(surround=2, pseudocount=0.0001, weight_empirical=2)),
+}
+
+
 def make_case(name):
-    case = CASES[name]
+    case = CASES[name] if name in CASES else EMP_CASES[name]
     ped_rows, ids, truth, obs = build_inputs(case)
     cols = ["SNP%d" % i for i in range(case["n_snps"])]
     df = pd.DataFrame(obs, index=[int(x) for x in ids], columns=cols)
     t0 = time.time()
-    r = rh.run_correct_matrix(df, ped_rows, **case["params"])
+    r = rh.run_correct_matrix(df, ped_rows, emp=case.get("emp"),
+                              truth_df=pd.DataFrame(truth, index=df.index, columns=cols), **case["params"])
     dt = time.time() - t0
+    extra = {}
+    if case.get("emp"):
+        import itertools
+        emp = case["emp"]
+        idx = r["emp_index"]
+        wmax = 2 * emp["surround"] + 1
+        freq = np.full((len(cols), 3 ** wmax), np.nan)
+        wstart = np.zeros(len(cols), dtype=np.int64)
+        wlen = np.zeros(len(cols), dtype=np.int64)
+        for i, c in enumerate(cols):
+            win = idx.getWindow(c)
+            wlen[i] = len(win)
+            wstart[i] = cols.index(win[0]) if win else 0
+            for k, v in enumerate(itertools.product([0, 1, 2], repeat=len(win))):
+                freq[i, k] = idx.snp2frequency[c][tuple(zip(win, v))]
+        rowi = {int(k): i for i, k in enumerate(ids)}
+        rec = []
+        for snp, res in r["emp_results"]:
+            for (kid, o), v in res.items():
+                rec.append([rowi[int(kid)], cols.index(snp), int(o)] + [float(x) for x in v])
+        extra = dict(emp_surround=emp["surround"], emp_pseudocount=emp["pseudocount"], emp_weight=emp["weight_empirical"],
+                     emp_freq=freq, emp_wstart=wstart, emp_wlen=wlen, emp_probs=np.array(rec, dtype=np.float64).reshape(-1, 6))
     m = re.search(r"setting initial filter to (\S+) quantile threshold", r["stdout"])
     test_p = float(m.group(1))
     m = re.search(r"n errors pairs\+single: not rank1 excluded (\d+) passed (\d+)", r["stdout"])
@@ -214,7 +251,7 @@ def make_case(name):
         pair_post=np.array(prec, dtype=np.float64).reshape(-1, 10),
         single_post=np.array(srec, dtype=np.float64).reshape(-1, 5),
         params=np.array([case["params"][k] for k in ("threshold_pair", "threshold_single", "back",
-                                                     "init_filter_p", "tiethreshold", "err_thresh")], dtype=np.float64))
+                                                     "init_filter_p", "tiethreshold", "err_thresh")], dtype=np.float64), **extra)
     print("%s: %d x %d, reference correctMatrix %.1fs, %d cells changed, errors_all=%d, test_p=%r, raw NaN=%d" % (
         name, obs.shape[0], obs.shape[1], dt, int((r["corrected"] != obs).sum()), errors_all, test_p,
         int(np.isnan(r["raw"].astype(float)).sum())))

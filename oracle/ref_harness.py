@@ -146,32 +146,50 @@ def pedigree_from_rows(rows):
 
 def run_correct_matrix(genotypes_df, ped_rows, threshold_pair, threshold_single, back=2,
                        init_filter_p=0.9, filter_e=0.7, tiethreshold=0.05, err_thresh=1,
-                       quiet=True):
-    """Run reference CorrectGenotypes.correctMatrix(empC=None) deterministically.
+                       quiet=True, emp=None, truth_df=None):
+    """Run reference CorrectGenotypes.correctMatrix deterministically.
+
+    emp=None: correctMatrix(empC=None), the configuration that completes at HEAD.
+    emp=dict(surround=, pseudocount=, weight_empirical=): the reference builds its own LD index on the same matrix
+    (JointAllellicDistribution + countJointFrqAll, unmodified) and blends it into the ranks (:619-656).  The index
+    OBJECT gets a `frequency` attribute first: initializerEmp (:34-40) copies `empC.frequency`, which jalleledist3
+    objects do not have; no reference source is touched.  The matrix must not hold missing calls
+    (getCountTable raises on any 9 in a window).  With an index the reference's debug statistics read the true
+    genotypes (`debugreal`, :781-782) whenever DEBUGDIR is set, which Stats() needs: pass truth_df.
 
     Returns dict(corrected=ndarray uint8, raw=ndarray f16 [N,S], pair_results=list, single_results=list,
-    stdout=str)."""
+    stdout=str[, emp_results=list of (SNP_id, {(kid, observed): 3 floats}), emp_index=the reference's index])."""
     ref = load()
     cg3 = ref["cg3"]
     ped = pedigree_from_rows(ped_rows)
     log = []
     buf = io.StringIO()
+    empC = None
+    kw = {}
     with tempfile.TemporaryDirectory() as dbg, deterministic_pools(log):
         ctx = contextlib.redirect_stdout(buf) if quiet else contextlib.nullcontext()
         with ctx, np.errstate(all="ignore"):
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
+                if emp is not None:
+                    jad3 = ref["jad3"]
+                    empC = jad3.JointAllellicDistribution("1", list(genotypes_df.columns), surround_size=emp["surround"],
+                                                          pseudocount=emp.get("pseudocount", 0.0001))
+                    empC.countJointFrqAll(genotypes_df, mask=None, threads=1)
+                    empC.frequency = {}
+                    kw["weight_empirical"] = emp.get("weight_empirical", 3)
                 c = cg3.CorrectGenotypes(elimination_order="MinNeighbors")
-                out = c.correctMatrix(genotypes_df, ped, None, threshold_pair, threshold_single,
+                out = c.correctMatrix(genotypes_df, ped, empC, threshold_pair, threshold_single,
                                       back=back, init_filter_p=init_filter_p, filter_e=filter_e,
                                       tiethreshold=tiethreshold, threads=1, err_thresh=err_thresh,
-                                      DEBUGDIR=dbg, debugreal=None)
+                                      DEBUGDIR=dbg, debugreal=truth_df if emp is not None else None, **kw)
     ids = list(genotypes_df.index)
     row = {k: i for i, k in enumerate(ids)}
     raw = np.ones(genotypes_df.shape, dtype=np.float16)
     pair_results = []
     single_results = []
+    emp_results = []
     for name, args, kwargs, res in log:
         if name == "mendelProbsSingle":
             raw[row[args[0]], :] = np.squeeze(res[1])
@@ -179,8 +197,13 @@ def run_correct_matrix(genotypes_df, ped_rows, threshold_pair, threshold_single,
             pair_results.append((int(args[0]), int(args[1]), res))
         elif name == "correctSingle":
             single_results.append((int(args[0]), res))
-    return dict(corrected=out.to_numpy().astype(np.uint8), raw=raw, pair_results=pair_results,
-                single_results=single_results, stdout=buf.getvalue())
+        elif name == "getEmpProbs":
+            emp_results.append((args[1], res))
+    r = dict(corrected=out.to_numpy().astype(np.uint8), raw=raw, pair_results=pair_results,
+             single_results=single_results, stdout=buf.getvalue())
+    if emp is not None:
+        r.update(emp_results=emp_results, emp_index=empC)
+    return r
 
 
 def run_mendel_probs(genotypes_df, ped_rows, back=2):

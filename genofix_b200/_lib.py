@@ -20,7 +20,7 @@ EXPORTS = [
     "gfx_schedule_destroy", "gfx_schedule_info", "gfx_schedule_copy", "gfx_pack2", "gfx_unpack2",
     "gfx_mendel_rank", "gfx_mendel_rank_hist", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_rank_rowsum_f16", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
     "gfx_check_device_status", "gfx_debug_counters", "gfx_rank_timing", "gfx_rank_last_kernel_ms", "gfx_trio_scan", "gfx_trio_scan_add", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
-    "gfx_kids_term_host", "gfx_gene_drop", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
+    "gfx_kids_term_host", "gfx_emp_rank_blend", "gfx_emp_apply", "gfx_gene_drop", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
 ]
 
 
@@ -40,6 +40,11 @@ class CorrectParams(C.Structure):
     _fields_ = [("test_p", C.c_double), ("suspect_t", C.c_double), ("tiethreshold", C.c_double),
                 ("threshold", C.c_double), ("err_thresh", C.c_double), ("cutraw_dev", C.c_void_p),
                 ("tp_raw", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class EmpIndex(C.Structure):
+    _fields_ = [("wstart_dev", C.c_void_p), ("wlen_dev", C.c_void_p), ("foff_dev", C.c_void_p), ("freq_dev", C.c_void_p),
+                ("weight", C.c_double), ("max_window", C.c_int32), ("reserved", C.c_int32)]
 
 
 class GfxError(RuntimeError):
@@ -86,6 +91,8 @@ def lib():
     L.gfx_build_cut_table.argtypes = [vp, C.c_double, C.c_double, vp, C.POINTER(C.c_uint32)]
     L.gfx_check_device_status.argtypes = [vp, vp]
     L.gfx_debug_counters.argtypes = [vp, C.c_int, vp]
+    L.gfx_emp_rank_blend.argtypes = [vp, i64, i64, i64, vp, i64, vp, C.POINTER(EmpIndex), vp, i64, vp]
+    L.gfx_emp_apply.argtypes = [vp, i32, vp, vp, i64, i64, vp, i64, vp, C.POINTER(EmpIndex), C.POINTER(CorrectParams), vp, C.c_double, vp, vp]
     L.gfx_rank_timing.argtypes = [vp, C.c_int]
     L.gfx_rank_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.gfx_trio_scan.argtypes = [vp, vp, i64, i64, vp, vp, vp]

@@ -3662,6 +3662,225 @@ extern "C" int gfx_window_counts(const uint32_t* packed, const uint32_t* mask, i
 // ------------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------------
+// the empirical (LD-window) blend of correctMatrix(empC != None): correct_genotypes3.py:619-667 (ranks), :746-779 and
+// :883-908 (decisions); jalleledist3.py:101-117 (getCountTable)
+// ------------------------------------------------------------------------------------------------
+#define GFX_EMP_WMAX 9
+struct EmpDev {
+  const int32_t* wstart;
+  const int32_t* wlen;
+  const int64_t* foff;
+  const double* freq;
+  double weight;
+};
+// getCountTable: stored frequency of each state of SNP j given the calls of one animal (row pointer rp, 2-bit codes) in
+// j's window; a missing call in the window is summed over its completions, first window SNP = slowest digit, plain
+// left-to-right additions (the reference raises there, SURVEY D4: the oracle defines this case).  When the window does
+// not hold SNP j itself (the last SNP of a chromosome, D11) the three values are the same entry.
+__device__ __forceinline__ void emp_count_table(const uint32_t* __restrict__ rp, int64_t j, const EmpDev& X, double c[3]) {
+  const int a = X.wstart[j], w = X.wlen[j];
+  const double* __restrict__ f = X.freq + X.foff[j];
+  int base = 0, tstride = 0, nmiss = 0, mstride[GFX_EMP_WMAX];
+  int stride = 1;
+  for (int k = w - 1; k >= 0; --k) {      // last window SNP = fastest digit
+    const int64_t col = a + k;
+    if (col == j) tstride = stride;
+    else {
+      const int v = (int)((rp[col >> 4] >> (2 * (col & 15))) & 3u);
+      if (v == 3) mstride[nmiss++] = stride;   // collected fastest digit first
+      else base += v * stride;
+    }
+    stride *= 3;
+  }
+  if (nmiss == 0) {
+    c[0] = f[base]; c[1] = f[base + tstride]; c[2] = f[base + 2 * tstride];
+    return;
+  }
+  int total = 1;
+  for (int k = 0; k < nmiss; ++k) total *= 3;
+  for (int s = 0; s < 3; ++s) {
+    double acc = 0.0;
+    for (int m = 0; m < total; ++m) {       // m counts in C order: the slowest missing digit is the most significant
+      int off = base + s * tstride, r = m;
+      for (int k = 0; k < nmiss; ++k) { off += (r % 3) * mstride[k]; r /= 3; }
+      acc = m == 0 ? f[off] : acc + f[off];
+    }
+    c[s] = acc;
+  }
+}
+// :752-755 / :888-889: the table normalised to sum 1; false when the sum is not positive (:754 keeps the previous value
+// then; with a positive pseudocount it cannot happen)
+__device__ __forceinline__ bool emp_state_probs(const uint32_t* rp, int64_t j, const EmpDev& X, double nrm[3]) {
+  double c[3];
+  emp_count_table(rp, j, X, c);
+  const double tot = (c[0] + c[1]) + c[2];
+  if (!(tot > 0.0)) return false;
+  nrm[0] = c[0] / tot; nrm[1] = c[1] / tot; nrm[2] = c[2] / tot;
+  return true;
+}
+
+// ranks (:619-656): E(cell) = mean(E, weight * (max - own) of the normalised window frequencies) for every observed cell of a
+// SNP whose window holds it; the division by the new maximum, the missing cells and the quantile follow on the tensors.
+__global__ void __launch_bounds__(256) k_emp_rank_blend(const uint32_t* __restrict__ packed, int64_t n, int64_t n_snps, int64_t wpr,
+                                                        const uint16_t* __restrict__ raw, int64_t ld_raw,
+                                                        const double* __restrict__ elut, EmpDev X, double* __restrict__ e_out,
+                                                        int64_t ld_e) {
+  const int64_t total = n * n_snps;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / n_snps, j = t - r * n_snps;
+    const uint32_t* rp = packed + r * wpr;
+    const int obs = (int)((rp[j >> 4] >> (2 * (j & 15))) & 3u);
+    const uint32_t rx = raw[r * ld_raw + j];
+    double E = (obs == 3 || rx == 0xFFFFu) ? 1.0 : elut[rx];
+    const int a = X.wstart[j], w = X.wlen[j];
+    if (obs != 3 && j >= a && j < a + w) {
+      double nrm[3];
+      if (emp_state_probs(rp, j, X, nrm)) {
+        double mx = nrm[0];
+        if (nrm[1] > mx) mx = nrm[1];
+        if (nrm[2] > mx) mx = nrm[2];
+        const double empdiff = mx - nrm[obs];
+        E = (E + empdiff * X.weight) / 2.0;      // np.mean of the two
+      }
+    }
+    e_out[r * ld_e + j] = E;
+  }
+}
+
+// decisions (:714-845 pairs, :866-944 singles) with an index: one thread per focal animal walks its jobs in canonical order
+// and, inside a job, the SNPs in column order -- the window evidence is the animal's LIVE row, so its cells are no longer
+// independent of each other (a correction at SNP j changes the evidence of j + 1 and of the next job).  The posteriors of
+// the jobs come from the inference kernels (post, computed on the generation-start snapshot, sentinel = no result).
+struct EmpApplyArgs {
+  int nf, n_focal;
+  const int32_t* focal_row;
+  const int32_t* focal_off;
+  const int32_t* entry;
+  uint32_t* live;
+  const uint32_t* snapshot;
+  int64_t n_snps, wpr;
+  const uint16_t* raw;
+  int64_t ld_raw;
+  const double* elut;
+  const int32_t* prow;
+  EmpDev X;
+  double tie, threshold, err_thresh, sentinel;
+  const double* post;
+  int32_t* tallies;
+  int n_rows;
+};
+__global__ void __launch_bounds__(64) k_emp_apply(EmpApplyArgs a) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= a.n_focal) return;
+  const int row = a.focal_row[f];
+  uint32_t* rp = a.live + (int64_t)row * a.wpr;
+  const uint32_t* sp = a.snapshot + (int64_t)row * a.wpr;
+  int applied = 0, excluded = 0;
+  for (int e = a.focal_off[f]; e < a.focal_off[f + 1]; ++e) {
+    const int ent = a.entry[e];
+    const double* P = a.post + (int64_t)ent * a.n_snps * 3;
+    for (int64_t j = 0; j < a.n_snps; ++j) {
+      const double p0 = P[3 * j];
+      if (p0 == a.sentinel) continue;
+      const double p[3] = {p0, P[3 * j + 1], P[3 * j + 2]};
+      const int cur = (int)((rp[j >> 4] >> (2 * (j & 15))) & 3u);
+      const int obs0 = (int)((sp[j >> 4] >> (2 * (j & 15))) & 3u);
+      double nrm[3];
+      if (!emp_state_probs(rp, j, a.X, nrm)) continue;
+      double comb[3];
+      for (int i = 0; i < 3; ++i) {
+        const double nw = nrm[i] * a.X.weight;
+        comb[i] = p[i] == p[i] ? (p[i] + nw) / 2.0 : nw;       // np.nanmean over the two rows
+      }
+      double nsum = 0.0;
+      for (int i = 0; i < 3; ++i) if (comb[i] == comb[i]) nsum += comb[i];
+      if (a.nf == 1 || nsum > 0.0) {
+        const double tot = (comb[0] + comb[1]) + comb[2];
+        comb[0] /= tot; comb[1] /= tot; comb[2] /= tot;
+      }
+      double mx = nan("");
+      for (int i = 0; i < 3; ++i) if (comb[i] == comb[i] && !(mx >= comb[i])) mx = comb[i];
+      uint32_t states = 0;
+      const double cut = mx - a.tie;
+      for (int i = 0; i < 3; ++i) if (comb[i] >= cut) states |= 1u << i;
+      double op;
+      if (a.nf == 2) op = obs0 <= 2 ? p[obs0] : nan("");      // pairs keep the Mendelian probability of the snapshot state (:811)
+      else op = cur == 3 ? 0.0 : comb[cur];                   // singles: the blended one (:904)
+      const bool cond = cur == 3 || (!((states >> cur) & 1u) && (mx - op) >= a.threshold);
+      if (!cond) continue;
+      double mr = 0.0;
+      for (int q = 0; q < 2; ++q) {
+        const int pr = a.prow[2 * row + q];
+        if (pr >= 0) {
+          const uint32_t rx = a.raw[(int64_t)pr * a.ld_raw + j];
+          const double ev = rx == 0xFFFFu ? 1.0 : a.elut[rx];
+          if (ev > mr) mr = ev;
+        }
+      }
+      const uint32_t rxf = a.raw[(int64_t)row * a.ld_raw + j];
+      const double ef = rxf == 0xFFFFu ? 1.0 : a.elut[rxf];
+      if (ef * a.err_thresh >= mr) {
+        const int nw = __popc(states) == 1 ? (__ffs(states) - 1) : 3;
+        const int sh = 2 * (int)(j & 15);
+        rp[j >> 4] = (rp[j >> 4] & ~(3u << sh)) | ((uint32_t)nw << sh);   // the row belongs to this thread
+        ++applied;
+      } else {
+        ++excluded;
+      }
+    }
+  }
+  if (applied) atomicAdd(a.tallies + row, applied);
+  if (excluded && a.nf == 2) atomicAdd(a.tallies + a.n_rows + row, excluded);
+}
+
+static int emp_index_check(const gfx_emp_index* idx) {
+  if (!idx || !idx->wstart_dev || !idx->wlen_dev || !idx->foff_dev || !idx->freq_dev) return fail(GFX_E_INVALID, "null LD index");
+  if (idx->max_window > GFX_EMP_WMAX) return fail(GFX_E_INVALID, "LD windows of more than 9 SNPs are not supported");
+  return GFX_OK;
+}
+
+extern "C" int gfx_emp_rank_blend(const uint32_t* packed, int64_t n, int64_t n_snps, int64_t wpr, const uint16_t* raw,
+                                  int64_t ld_raw, const double* elut, const gfx_emp_index* idx, double* e_out, int64_t ld_e,
+                                  void* stream) {
+  if (!packed || !raw || !elut || !e_out || n <= 0 || n_snps <= 0) return fail(GFX_E_INVALID, "null argument");
+  int rc = emp_index_check(idx);
+  if (rc != GFX_OK) return rc;
+  EmpDev X{idx->wstart_dev, idx->wlen_dev, idx->foff_dev, idx->freq_dev, idx->weight};
+  k_emp_rank_blend<<<grid_for(n * n_snps, 256, device_sms(), 8), 256, 0, (cudaStream_t)stream>>>(packed, n, n_snps, wpr, raw, ld_raw,
+                                                                                                 elut, X, e_out, ld_e);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+extern "C" int gfx_emp_apply(const gfx_schedule* s, int32_t generation, uint32_t* live, const uint32_t* snapshot, int64_t n_snps,
+                             int64_t wpr, const uint16_t* raw, int64_t ld_raw, const double* elut, const gfx_emp_index* idx,
+                             const gfx_correct_params* p, const double* post, double post_sentinel, int32_t* tallies, void* stream) {
+  if (!s || !live || !snapshot || !raw || !elut || !p || !post || !tallies) return fail(GFX_E_INVALID, "null argument");
+  if (s->device < 0) return fail(GFX_E_INVALID, "host-only schedule passed to a kernel entry point");
+  int rc = emp_index_check(idx);
+  if (rc != GFX_OK) return rc;
+  EmpApplyArgs a;
+  if (generation >= 0) {
+    if (generation >= s->h.info.n_generations) return fail(GFX_E_INVALID, "generation out of range");
+    const int f0 = s->h.app_gen_off[generation];
+    a.nf = 2; a.n_focal = s->h.app_gen_off[generation + 1] - f0;
+    a.focal_row = s->app_focal_row + f0; a.focal_off = s->app_focal_off + f0; a.entry = s->app_entry;
+  } else {
+    a.nf = 1; a.n_focal = (int)s->h.single_row.size();
+    a.focal_row = s->single_row; a.focal_off = s->single_off; a.entry = s->single_entry;
+  }
+  if (a.n_focal <= 0) return GFX_OK;
+  a.live = live; a.snapshot = snapshot; a.n_snps = n_snps; a.wpr = wpr; a.raw = raw; a.ld_raw = ld_raw; a.elut = elut;
+  a.prow = s->prow;
+  a.X = EmpDev{idx->wstart_dev, idx->wlen_dev, idx->foff_dev, idx->freq_dev, idx->weight};
+  a.tie = p->tiethreshold; a.threshold = p->threshold; a.err_thresh = p->err_thresh; a.sentinel = post_sentinel;
+  a.post = post; a.tallies = tallies; a.n_rows = s->h.n_rows;
+  k_emp_apply<<<(a.n_focal + 63) / 64, 64, 0, (cudaStream_t)stream>>>(a);
+  GFX_LAUNCHED();
+  return GFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 extern "C" int gfx_build_cut_table(const double* elut, double test_p, double suspect_t, uint16_t* cutraw, uint32_t* tp_raw) {
   if (!elut || !cutraw || !tp_raw) return fail(GFX_E_INVALID, "null argument");
   // finite non-negative half patterns 0 .. 0x7C00 order like their values and E is monotone in the score

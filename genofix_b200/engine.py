@@ -407,6 +407,126 @@ class Engine(object):
         E[codes == 3] = 1.0
         return E
 
+    # ---- correctMatrix with an LD index (correct_genotypes3.py:619-667, :746-779, :883-908) ---------------------
+    def emp_index_device(self, wstart, wlen, freq, weight):
+        """Device copy of an LD index for the s columns of the loaded chunk: per column its window [wstart, wstart + wlen) and
+        its 3^wlen stored frequencies (float64, itertools.product order)."""
+        t = self.torch
+        dev = self.codes.device
+        wstart = np.ascontiguousarray(wstart, dtype=np.int32)
+        wlen = np.ascontiguousarray(wlen, dtype=np.int32)
+        if len(wstart) != self.s or len(wlen) != self.s:
+            raise ValueError("the LD index must cover every column of the matrix")
+        if wlen.max(initial=0) > 9:
+            raise ValueError("LD windows of more than 9 SNPs are not supported")
+        sizes = np.array([3 ** int(w) if w > 0 else 0 for w in wlen], dtype=np.int64)
+        foff = np.zeros(self.s, dtype=np.int64)
+        foff[1:] = np.cumsum(sizes)[:-1]
+        flat = np.zeros(max(int(sizes.sum()), 1), dtype=np.float64)
+        for j in range(self.s):
+            if sizes[j]:
+                f = np.asarray(freq[j], dtype=np.float64).reshape(-1)
+                flat[foff[j]:foff[j] + sizes[j]] = f[:sizes[j]]
+        keep = dict(wstart=t.from_numpy(wstart).to(dev), wlen=t.from_numpy(wlen).to(dev), foff=t.from_numpy(foff).to(dev),
+                    freq=t.from_numpy(flat).to(dev))
+        idx = _lib.EmpIndex(keep["wstart"].data_ptr(), keep["wlen"].data_ptr(), keep["foff"].data_ptr(), keep["freq"].data_ptr(),
+                            float(weight), int(wlen.max(initial=0)), 0)
+        return idx, keep
+
+    def correct_emp(self, G, index, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1):
+        """correctMatrix with an LD index.  index = (wstart, wlen, freq, weight) over the columns of G.  The ranks are blended
+        with the window frequencies on the device (gfx_emp_rank_blend), re-normalised and re-coded as dense ranks of their
+        distinct values (the correction kernels compare 16-bit codes), the posteriors of every generation come from the
+        inference kernels run on a scratch copy, and gfx_emp_apply walks each focal animal's jobs and SNPs in order."""
+        t = self.torch
+        G = np.asarray(G)
+        if G.ndim != 2 or G.shape[0] != self.n:
+            raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+        self._alloc(G.shape[1])
+        hin = self.host_in.numpy()
+        _parallel_copy(hin[:, :self.s], G)
+        if self.ldc > self.s:
+            hin[:, self.s:] = 9
+        self.codes.copy_(self.host_in, non_blocking=True)
+        self.load_codes_device(self.codes)
+        self.mendel_rank_device()
+        self.thresholds_device(init_filter_p)                      # elut of the Mendelian ranks (:593-603)
+        idx, keep = self.emp_index_device(*index)
+        dev = self.codes.device
+        E = t.empty((self.n, self.s), dtype=t.float64, device=dev)
+        _lib.check(self.L.gfx_emp_rank_blend(self.packed_orig.data_ptr(), self.n, self.s, self.wpr, self.raw.data_ptr(), self.ld_raw,
+                                             self.elut.data_ptr(), C.byref(idx), E.data_ptr(), self.s, self._stream()))
+        missing = self.codes[:, :self.s] > 2
+        nan = t.isnan(E)
+        mx = t.where(nan, t.full_like(E, -np.inf), E).max()         # np.nanmax (:658)
+        E = E / mx
+        E[missing] = 1.0                                             # :660
+        flat = E.flatten()
+        self.packed_live.copy_(self.packed_orig)
+        self.tallies.zero_()
+        if bool(t.isnan(flat).any()):
+            self.test_p = float("nan")                               # D16: a NaN rank poisons the quantile, nothing is suspect
+        else:
+            srt = t.sort(flat).values
+            pos = init_filter_p * (flat.numel() - 1)                 # np.quantile, method 'linear' (:667)
+            lo = int(np.floor(pos))
+            hi = min(lo + 1, flat.numel() - 1)
+            ab = srt[[lo, hi]].cpu().numpy()
+            self.test_p = float(_lerp(ab[0], ab[1], pos - lo))
+            vals, inv = t.unique(flat, sorted=True, return_inverse=True)
+            if vals.numel() > 0x7C01:
+                raise ValueError("more than 31745 distinct blended rank values in one matrix: correct it in narrower column chunks")
+            elut = np.full(65536, np.nan)
+            elut[:vals.numel()] = vals.cpu().numpy()
+            self.host_elut.numpy()[:] = elut
+            self.elut.copy_(self.host_elut)
+            self.raw[:, :self.s] = inv.reshape(self.n, self.s).to(t.int16)
+            tp_raw = C.c_uint32(0)
+            _lib.check(self.L.gfx_build_cut_table(self.host_elut.data_ptr(), self.test_p, SUSPECT_T, self.host_cutraw.data_ptr(),
+                                                  C.byref(tp_raw)))
+            self.cutraw.copy_(self.host_cutraw)
+            self.tp_raw = int(tp_raw.value)
+            self.elut_host = elut
+            info = self.schedule.info
+            gen_off = self.schedule.array(1)
+            scratch_live = t.empty_like(self.packed_live)
+            scratch_tallies = t.zeros_like(self.tallies)
+            for g in range(info["n_generations"] + 1):
+                pairs = g < info["n_generations"]
+                rows = int(gen_off[g + 1] - gen_off[g]) * 2 if pairs else info["n_singles"]
+                if rows <= 0:
+                    continue
+                pp = _lib.CorrectParams(self.test_p, SUSPECT_T, float(tiethreshold), float(threshold_pair if pairs else threshold_single),
+                                        float(err_thresh), self.cutraw.data_ptr(), self.tp_raw, 0)
+                post = t.full((rows, self.s, 3), POST_SENTINEL, dtype=t.float64, device=dev)
+                scratch_live.copy_(self.packed_live)
+                if pairs:
+                    _lib.check(self.L.gfx_correct_pairs(
+                        self.schedule.handle, g, scratch_live.data_ptr(), self.s, self.wpr, self.raw.data_ptr(), self.ld_raw,
+                        self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(), self.snapshot.numel(), post.data_ptr(),
+                        scratch_tallies.data_ptr(), self._stream()))
+                else:
+                    _lib.check(self.L.gfx_correct_singles(
+                        self.schedule.handle, scratch_live.data_ptr(), self.s, self.wpr, self.raw.data_ptr(), self.ld_raw,
+                        self.elut.data_ptr(), C.byref(pp), self.snapshot.data_ptr(), self.snapshot.numel(), post.data_ptr(),
+                        scratch_tallies.data_ptr(), self._stream()))
+                # the snapshot region of the scratch buffer holds the matrix at the start of the generation
+                _lib.check(self.L.gfx_emp_apply(self.schedule.handle, g if pairs else -1, self.packed_live.data_ptr(),
+                                                self.snapshot.data_ptr(), self.s, self.wpr, self.raw.data_ptr(), self.ld_raw,
+                                                self.elut.data_ptr(), C.byref(idx), C.byref(pp), post.data_ptr(), POST_SENTINEL,
+                                                self.tallies.data_ptr(), self._stream()))
+        self.unpack_device(self.codes)
+        self.host_out.copy_(self.codes, non_blocking=True)
+        self.check_status()
+        tall = self.tallies.cpu().numpy()
+        self.n_nan = int(nan.sum())
+        self.stats = dict(test_p=self.test_p, n_nan=self.n_nan, corrected_per_animal=tall[:self.n].copy(),
+                          excluded_per_animal=tall[self.n:].copy(), posteriors=None)
+        out = np.empty((self.n, self.s), dtype=np.uint8)
+        _parallel_copy(out, self.host_out.numpy()[:, :self.s])
+        del keep
+        return out
+
     # ---- end-to-end on host buffers ----------------------------------------------------------------
     def correct(self, G, threshold_pair, threshold_single, init_filter_p=0.9, tiethreshold=0.05, err_thresh=1,
                 keep_posteriors=False):

@@ -191,6 +191,42 @@ int gfx_correct_singles(const gfx_schedule* s, uint32_t* packed_live_dev,
                         const gfx_correct_params* params, uint32_t* scratch_dev, int64_t scratch_words,
                         double* post_dev, int32_t* tallies_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The empirical (LD-window) blend of correctMatrix(empC != None).
+ *
+ * gfx_emp_index: the index of empirical/jalleledist3.py as device arrays -- per SNP column its window [wstart, wstart + wlen)
+ * (jalleledist3.py:62-75, D11 at the chromosome end), the offset of its 3^wlen stored frequencies in freq_dev (state tuples in
+ * itertools.product order, :31) and weight_empirical.  Windows of at most 9 SNPs.
+ *
+ * gfx_emp_rank_blend: correct_genotypes3.py:619-656 for every cell -- e_out[r, j] = mean(E[r, j], weight * (max - own) of the
+ * normalised window frequencies of the animal's calls, getEmpProbs :69-82 / getCountTable jalleledist3.py:101-117) for observed
+ * cells of SNPs whose window holds them, E[r, j] (1 for missing cells) otherwise; E = elut[raw].  A missing call inside the
+ * window is summed over its completions (the reference raises there).
+ *
+ * gfx_emp_apply: the serial apply step of one generation of pairs (generation >= 0, :714-845) or of the singles (-1, :866-944)
+ * with the blended decision (:746-779 / :883-908): post_dev holds the posteriors of the jobs (gfx_correct_pairs / _singles on a
+ * scratch copy of the matrix, cells without a result = post_sentinel), snapshot_dev the matrix at the start of the generation,
+ * live_dev the matrix being corrected (its window cells are the evidence).  One thread per focal animal, jobs in canonical
+ * order, SNPs in column order.  tallies_dev as in gfx_correct_pairs.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* wstart_dev;
+  const int32_t* wlen_dev;
+  const int64_t* foff_dev;
+  const double* freq_dev;
+  double weight;
+  int32_t max_window;
+  int32_t reserved;
+} gfx_emp_index;
+
+int gfx_emp_rank_blend(const uint32_t* packed_dev, int64_t n, int64_t n_snps, int64_t wpr, const uint16_t* raw_dev,
+                       int64_t ld_raw, const double* elut_dev, const gfx_emp_index* index, double* e_out_dev, int64_t ld_e,
+                       void* stream);
+int gfx_emp_apply(const gfx_schedule* s, int32_t generation, uint32_t* live_dev, const uint32_t* snapshot_dev, int64_t n_snps,
+                  int64_t wpr, const uint16_t* raw_dev, int64_t ld_raw, const double* elut_dev, const gfx_emp_index* index,
+                  const gfx_correct_params* params, const double* post_dev, double post_sentinel, int32_t* tallies_dev,
+                  void* stream);
+
 /* Diagnostics: reads and clears 16 device counters (queries, parent-only answers, eliminations, big-table
  * reruns, nodes touched, suspect cells, job evaluations, children visited, ...) and switches counting
  * on (enable = 1) or off.  Counting is off by default; it serialises on atomics. */

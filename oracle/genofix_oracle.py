@@ -733,7 +733,14 @@ def emp_count_table(row, j, emp):
             else:
                 v = int(row[c])
                 idx.append(v if v in (0, 1, 2) else slice(None))
-        out.append(np.sum(tab[tuple(idx)]))
+        sub = tab[tuple(idx)]
+        if np.ndim(sub) == 0:
+            out.append(sub)                      # the reference's single key (np.sum of one value)
+        else:
+            acc = None                           # completions in C order (first window SNP slowest), left to right
+            for v in np.asarray(sub).reshape(-1):
+                acc = v if acc is None else acc + v
+            out.append(acc)
     return out
 
 

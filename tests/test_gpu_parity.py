@@ -895,6 +895,76 @@ def test_count_joint_frq_all_matches_reference_index(sur):
             assert np.array_equal(np.asarray(emp.getCountTable(ev, snp), dtype=float), ct[a, j])
 
 
+# ---- the empirical (LD-window) blend: correctMatrix WITH an index ----------------
+def _ld_index(obs, names, surround, pseudocount):
+    import pandas as pd
+    from genofix_b200.empirical.jalleledist3 import JointAllellicDistribution
+    emp = JointAllellicDistribution("1", names, surround_size=surround, pseudocount=pseudocount)
+    emp.countJointFrqAll(pd.DataFrame(obs, index=np.arange(1, obs.shape[0] + 1), columns=names))
+    return emp
+
+
+@pytest.mark.parametrize("name", ["emp_a", "emp_b"])
+def test_empirical_blend_matches_reference_golden(name):
+    """The reference's own correctMatrix run with an LD index it built itself (oracle/ref_harness.run_correct_matrix(emp=...)):
+    index, threshold, corrected calls and error count, through the reference-facing class."""
+    import pandas as pd
+    from genofix_b200.correct_genotypes3 import CorrectGenotypes
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    g = load_golden(name)
+    obs = g["obs"]
+    names = ["SNP%d" % i for i in range(obs.shape[1])]
+    emp = _ld_index(obs, names, int(g["emp_surround"]), float(g["emp_pseudocount"]))
+    for j, snp in enumerate(names):
+        w = int(g["emp_wlen"][j])
+        if w:
+            assert np.array_equal(emp._freq[snp][:3 ** w], g["emp_freq"][j, :3 ** w]), snp
+    tp, ts, back, q, tie, et = g["params"]
+    cg = CorrectGenotypes()
+    df = pd.DataFrame(obs, index=[int(x) for x in g["ids"]], columns=names)
+    out = cg.correctMatrix(df, PedigreeDAG.from_table(g["ped_rows"]), emp, tp, ts, back=int(back), init_filter_p=q,
+                           tiethreshold=tie, err_thresh=et, weight_empirical=float(g["emp_weight"]))
+    assert cg.last_stats["test_p"] == float(g["test_p"])
+    got = out.to_numpy()
+    assert np.array_equal(got, g["corrected"]), "%d corrected calls differ" % int((got != g["corrected"]).sum())
+    assert int(cg.last_stats["corrected_per_animal"].sum()) == int(g["errors_all"])
+    # and the run without an index gives something else: the blend is really in the decision
+    plain = cg.correctMatrix(df, PedigreeDAG.from_table(g["ped_rows"]), None, tp, ts, back=int(back), init_filter_p=q,
+                             tiethreshold=tie, err_thresh=et).to_numpy()
+    assert not np.array_equal(plain, got)
+
+
+@pytest.mark.parametrize("seed,surround,miss", [(5, 1, 0.0), (6, 2, 0.03), (7, 3, 0.02)])
+def test_empirical_blend_matches_oracle_on_seeded_inputs(seed, surround, miss):
+    """Seeded matrices, also with missing calls inside the windows (summed over their completions: the oracle defines that
+    case, the reference raises) and with a tie band, which writes 9s that later windows then see."""
+    from genofix_b200 import synth
+    from genofix_b200.correct_genotypes3 import ld_index_arrays
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    from oracle import genofix_oracle as go
+    rows = synth.make_pedigree(150, 6, sire_frac=0.25, dam_frac=0.5, seed=seed, related_mating_p=0.3)
+    s = 48
+    obs = synth.inject_errors(synth.gene_drop(rows, s, seed=seed), 0.05, seed=seed)
+    if miss:
+        obs = synth.inject_missing(obs, miss, seed=seed)
+    names = ["SNP%d" % i for i in range(s)]
+    emp = _ld_index(obs, names, surround, 1e-4)
+    oemp = go.emp_index(obs, surround, 1e-4, weight=3)
+    for j, snp in enumerate(names):
+        w = int(oemp["wlen"][j])
+        if w:
+            assert np.array_equal(emp._freq[snp][:3 ** w], oemp["freq"][j]), snp
+    params = dict(back=2, init_filter_p=0.8, tiethreshold=0.1, err_thresh=1)
+    want = go.Oracle(rows, rows[:, 0]).correct_matrix(obs, 0.4, 0.5, emp=oemp, **params)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    got = eng.correct_emp(obs, ld_index_arrays(emp, names, 3), 0.4, 0.5, init_filter_p=0.8, tiethreshold=0.1, err_thresh=1)
+    assert eng.stats["test_p"] == want["test_p"]
+    assert np.array_equal(got, want["corrected"]), "%d corrected calls differ" % int((got != want["corrected"]).sum())
+    assert np.array_equal(eng.stats["corrected_per_animal"], want["corrected_per_animal"])
+    assert int((got != obs).sum()) > 10
+
+
 # ---- entry points end to end (VERDICT r1 item 8) and the multi-GPU product path (item 1d / 5) -----------------------
 def _write_case(tmp, n=600, gens=6, s=1300, seed=3):
     import os

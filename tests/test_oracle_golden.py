@@ -6,6 +6,7 @@ import pytest
 
 from conftest import load_golden
 from oracle.genofix_oracle import Oracle
+from oracle import genofix_oracle as go
 
 CASES = ["toy_a", "toy_b", "deep", "nan_loop", "example_fam"]
 
@@ -157,3 +158,24 @@ def test_parallel_oracle_driver_equals_the_single_process_oracle():
     assert np.array_equal(a["raw"].view(np.uint16), b["raw"].view(np.uint16))
     assert np.array_equal(a["corrected_per_animal"], b["corrected_per_animal"])
     assert np.array_equal(a["excluded_per_animal"], b["excluded_per_animal"])
+
+
+@pytest.mark.parametrize("name", ["emp_a", "emp_b"])
+def test_oracle_empirical_blend_equals_reference(name):
+    """correctMatrix WITH an LD index (correct_genotypes3.py:619-667 ranks, :746-779 / :883-908 decisions): the oracle's index,
+    every getEmpProbs result, the threshold the reference printed, the corrected calls and the error count."""
+    g = load_golden(name)
+    obs = g["obs"]
+    emp = go.emp_index(obs, int(g["emp_surround"]), float(g["emp_pseudocount"]), float(g["emp_weight"]))
+    assert np.array_equal(emp["wstart"], g["emp_wstart"]) and np.array_equal(emp["wlen"], g["emp_wlen"])
+    for j in range(obs.shape[1]):
+        assert np.array_equal(emp["freq"][j], g["emp_freq"][j, :3 ** int(emp["wlen"][j])])
+    for r, j, o, a, b, c in g["emp_probs"]:
+        assert np.array_equal(go.emp_state_probs(obs[int(r)], int(j), emp), [a, b, c])
+    P = g["params"]
+    res = go.Oracle(g["ped_rows"], g["ids"]).correct_matrix(obs, P[0], P[1], back=int(P[2]), init_filter_p=P[3], tiethreshold=P[4],
+                                                            err_thresh=P[5], emp=emp)
+    assert res["test_p"] == float(g["test_p"])
+    assert np.array_equal(res["corrected"], g["corrected"])
+    assert int(res["corrected_per_animal"].sum()) == int(g["errors_all"])
+    assert int((res["corrected"] != obs).sum()) > 0

@@ -3,8 +3,11 @@
 
 Same command line as the reference entry point (src/genofix.py:94-112).  Differences, all forced by the
 state of the reference at HEAD:
-  * -P/--empC is optional and ignored with a warning: the empirical (LD) blend cannot run in the reference
-    (D3/D4), so correction uses the Mendelian model only (the reference's `empC=None` path);
+  * -P/--empC is optional.  Without it correction uses the Mendelian model only (the reference's `empC=None` path, the
+    one that completes at HEAD).  With it, <folder>/<chromosome>/empiricalIndex.idx.gz (written by empirical/preindex.py) is
+    loaded per chromosome (:209) and blended into ranks and decisions (correct_genotypes3.py:619-667, :746-779, :883-908; the
+    reference dies in its pool initializer there, D3).  A chromosome is then ONE matrix: the LD windows must not be cut, so
+    -C/--chunksize does not apply (the reference passes the whole chromosome to every chunk call as well, D5);
   * every chunk is corrected from its own columns and written back by column (the reference passes the whole
     chromosome and slices rows, D5);
   * chunks are dealt round-robin to the GPUs of the box when launched under torchrun: every rank reads only the
@@ -48,7 +51,7 @@ def build_parser():
                    choices=["weightedminfill", "minneighbors", "minweight", "minfill"])
     p.add_argument("-T", "--threads", dest="threads", type=int, default=multiprocessing.cpu_count())
     p.add_argument("-P", "--empC", dest="empC", required=False, default=None,
-                   help="prior empirical distribution folder (ignored: see module docstring)")
+                   help="folder with prior empirical distribution for ld snps /chr/empiricalIndex.idx.gz (optional)")
     p.add_argument("-C", "--chunksize", dest="chunksize", type=int, default=10000)
     return p
 
@@ -60,8 +63,6 @@ def main(argv=None):
     rank, world = parallel.init_from_env()
     pedigree = PedigreeDAG.from_file(args.pedigree)
     genomein = pd.read_csv(args.snps, sep=" ", names=["chrom", "snpid", "cm", "pos"], engine="c")
-    if args.empC is not None and rank == 0:
-        print("WARNING: -P/--empC is ignored; the empirical blend is not executable in the reference at HEAD")
     print("building cache index from %s" % args.genotypes_input_file)
     packed_input = args.genotypes_input_file.endswith(".g2b")
     if packed_input:
@@ -88,6 +89,9 @@ def main(argv=None):
             print("chromosome skipped %s" % chromosome)
             continue
         found = [x for x in chromosome2snp[chromosome] if x in pos]
+        if args.empC is not None:
+            jobs.append((chromosome, found, np.array([pos[x] for x in found], dtype=np.int64)))   # windows must not be cut
+            continue
         for cols in chunk(found, args.chunksize):
             jobs.append((chromosome, cols, np.array([pos[x] for x in cols], dtype=np.int64)))
     mine = chunks_for_rank(len(jobs), rank, world)
@@ -97,7 +101,7 @@ def main(argv=None):
     def contiguous(idx):
         return len(idx) > 0 and int(idx[-1]) - int(idx[0]) + 1 == len(idx) and bool(np.all(np.diff(idx) == 1))
     # 2-bit blocks straight from the container when every chunk of this rank is a run of consecutive file columns
-    use_packed = packed_input and all(contiguous(jobs[ji][2]) for ji in mine)
+    use_packed = packed_input and all(contiguous(jobs[ji][2]) for ji in mine) and args.empC is None
     from genofix_b200.engine import engine_for
     eng = engine_for(pedigree, np.asarray(ids, dtype=np.int64), args.lookback)
 
@@ -117,11 +121,24 @@ def main(argv=None):
         for f in shard_dir.glob("chunk_%06d_*.npy" % ji):
             f.unlink()
     tall = np.zeros(len(ids), dtype=np.int64)
-    for k, (out, stats) in enumerate(eng.correct_chunks(inputs(), args.threshold_pairs, args.threshold_singles,
-                                                        init_filter_p=args.initquantilefilter, tiethreshold=args.tiethreshold,
-                                                        packed_io=use_packed)):
-        np.save(shard_dir / ("chunk_%06d_%s.npy" % (mine[k], "p" if use_packed else "u")), out)
-        tall += stats["corrected_per_animal"]
+    if args.empC is not None:
+        import gzip
+        import pickle
+        from genofix_b200.correct_genotypes3 import ld_index_arrays
+        for k, G in enumerate(inputs()):
+            chromosome, cols, _ = jobs[mine[k]]
+            empC = pickle.load(gzip.open("%s/%s/empiricalIndex.idx.gz" % (args.empC, chromosome)))       # :209
+            print("surround size is %s " % empC.surround_size)
+            out = eng.correct_emp(G, ld_index_arrays(empC, cols, args.weight_empirical), args.threshold_pairs,
+                                  args.threshold_singles, init_filter_p=args.initquantilefilter, tiethreshold=args.tiethreshold)
+            np.save(shard_dir / ("chunk_%06d_u.npy" % mine[k]), out)
+            tall += eng.stats["corrected_per_animal"]
+    else:
+        for k, (out, stats) in enumerate(eng.correct_chunks(inputs(), args.threshold_pairs, args.threshold_singles,
+                                                            init_filter_p=args.initquantilefilter, tiethreshold=args.tiethreshold,
+                                                            packed_io=use_packed)):
+            np.save(shard_dir / ("chunk_%06d_%s.npy" % (mine[k], "p" if use_packed else "u")), out)
+            tall += stats["corrected_per_animal"]
     if world > 1:
         import torch
         dev = "cuda" if torch.cuda.is_available() else "cpu"

@@ -1035,6 +1035,43 @@ def test_genofix_entry_point_text_and_container_inputs(tmp_path):
 
 
 @pytest.mark.timeout(900)
+def test_genofix_entry_point_with_an_ld_index(tmp_path):
+    """src/genofix.py -P <index folder>: indexes pickled per chromosome (the layout empirical/preindex.py writes), every
+    chromosome corrected as one matrix with the LD blend; equal to Engine.correct_emp per chromosome."""
+    import gzip
+    import os
+    import pickle
+    import sys
+    import pandas as pd
+    from conftest import ROOT
+    from genofix_b200.correct_genotypes3 import ld_index_arrays
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    tmp = str(tmp_path)
+    rows, obs, names = _write_case(tmp, n=300, gens=5, s=90, seed=9)          # chromosome 2 would start at column 700: one chromosome
+    sys.path.insert(0, os.path.join(ROOT, "src"))
+    try:
+        from empirical.jalleledist3 import JointAllellicDistribution
+    finally:
+        sys.path.pop(0)
+    emp = JointAllellicDistribution(1, names, surround_size=2)
+    emp.countJointFrqAll(pd.DataFrame(obs, index=[int(x) for x in rows[:, 0]], columns=names))
+    os.makedirs(tmp + "/idx/1")
+    with gzip.open(tmp + "/idx/1/empiricalIndex.idx.gz", "wb") as f:
+        pickle.dump(emp, f)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    want = eng.correct_emp(obs, ld_index_arrays(emp, names, 1.9), 0.5, 0.64, init_filter_p=0.95, tiethreshold=0.4)
+    tall = eng.stats["corrected_per_animal"].copy()
+    assert (want != obs).any()
+    _run(["src/genofix.py", "-p", tmp + "/ped.fam", "-s", tmp + "/snps.map", "-o", tmp + "/out", "-i", tmp + "/geno.ssv",
+          "-P", tmp + "/idx"])
+    got = pd.read_csv(tmp + "/out/simulatedgenome_corrected_errors_threshold.ssv", sep=" ", index_col=0)
+    assert np.array_equal(got.to_numpy(dtype=np.uint8), want)
+    t = pd.read_csv(tmp + "/out/corrections_per_animal.tsv", sep="\t", header=None, index_col=0)
+    assert np.array_equal(t.iloc[:, 0].to_numpy(), tall)
+
+
+@pytest.mark.timeout(900)
 def test_simulate_and_founder_entry_points(tmp_path):
     """src/simulate/simulate.py (host and --device_sim) and src/gfutils/extract_founders.py run end to end."""
     import os

@@ -3344,6 +3344,45 @@ extern "C" int gfx_correct_singles(const gfx_schedule* s, uint32_t* live, int64_
 #ifndef GFX_FAM_BLOCKS
 #define GFX_FAM_BLOCKS 4
 #endif
+// One 16-byte quad (64 SNPs) of a family: the parents' four words against the four words of each of NK kids.  Both scan
+// kernels are bound by the ALU pipe (LOP3 / SHF issue every second cycle per scheduler), not by memory, so the quad is
+// written for few logic operations: the masks of the kid states the parents exclude (no0 / no1 / no2) are pre-masked with
+// "both parents observed and the SNP exists", which makes a kid's inconsistency bit three LOP3 (a missing kid matches no
+// state) and lets `bad & present` go; the bits of two words are merged (even | odd << 1, an IMAD) before each POPC; the
+// ragged tail of a row is a separate instantiation, the full quads carry no validity arithmetic.
+template <int NK, bool RAGGED>
+__device__ __forceinline__ void trio_quad(const uint4& sq, const uint4& dq, const uint4 (&kq)[NK], int64_t first_snp, int64_t n_snps,
+                                          int (&n_inc)[NK], int (&n_tst)[NK]) {
+  const uint32_t M = 0x55555555u;
+  const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
+  uint32_t b_even[NK], p_even[NK];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t s = sw[i], d = dw[i], s1 = s >> 1, d1 = d >> 1;
+    uint32_t valid = M;
+    if (RAGGED) {
+      const int64_t rem = n_snps - (first_snp + 16 * i);
+      valid = rem >= 16 ? M : (rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & M));
+    }
+    const uint32_t par_ok = ~((s & s1) | (d & d1)) & valid;
+    const uint32_t s0 = ~(s | s1), s2 = s1 & ~s, d0 = ~(d | d1), d2 = d1 & ~d;
+    const uint32_t no0 = (s2 | d2) & par_ok, no2 = (s0 | d0) & par_ok, no1 = ((s0 & d0) | (s2 & d2)) & par_ok;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
+      const uint32_t kh = kk >> 1;
+      const uint32_t lo = (kk & no1) | (~kk & no0);               // kid 1 -> no1, kid 0 -> no0 (low bit of the code selects)
+      const uint32_t bad = (kh & ~kk & no2) | (~kh & lo);         // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
+      const uint32_t present = ~(kk & kh) & par_ok;
+      if ((i & 1) == 0) { b_even[k] = bad; p_even[k] = present; }
+      else {
+        n_inc[k] += __popc(bad * 2u + b_even[k]);                 // disjoint bit positions: one popcount for two words
+        n_tst[k] += __popc(present * 2u + p_even[k]);
+      }
+    }
+  }
+}
+
 // NK kids of one family (compile-time count: no predicated work for absent kids)
 template <int NK>
 __device__ __forceinline__ void trio_family_group(const uint32_t* __restrict__ packed, int64_t wpr, int64_t nquads, int64_t n_snps,
@@ -3361,28 +3400,8 @@ __device__ __forceinline__ void trio_family_group(const uint32_t* __restrict__ p
     uint4 kq[NK];
 #pragma unroll
     for (int k = 0; k < NK; ++k) kq[k] = __ldg(pk[k] + q);
-    const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t s = sw[i], d = dw[i];
-      uint32_t valid = 0x55555555u;
-      const int64_t rem = n_snps - (q * 4 + i) * 16;
-      if (rem < 16) valid = rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & 0x55555555u);
-      const uint32_t s0 = ~(s | (s >> 1)), s2 = (s >> 1) & ~s;
-      const uint32_t d0 = ~(d | (d >> 1)), d2 = (d >> 1) & ~d;
-      const uint32_t par_ok = ~(s & (s >> 1)) & ~(d & (d >> 1)) & valid;
-      const uint32_t no0 = s2 | d2, no2 = s0 | d0, no1 = (s0 & d0) | (s2 & d2);   // kid states the parents exclude
-#pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
-        const uint32_t k0 = ~(kk | (kk >> 1)), k1 = kk & ~(kk >> 1), k2 = (kk >> 1) & ~kk;
-        const uint32_t present = ~(kk & (kk >> 1)) & par_ok;
-        // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
-        const uint32_t bad = (k0 & no0) | (k2 & no2) | (k1 & no1);
-        n_tst[k] += __popc(present);
-        n_inc[k] += __popc(bad & present);
-      }
-    }
+    if ((q + 1) * 64 <= n_snps) trio_quad<NK, false>(sq, dq, kq, q * 64, n_snps, n_inc, n_tst);
+    else trio_quad<NK, true>(sq, dq, kq, q * 64, n_snps, n_inc, n_tst);
   }
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
@@ -3473,27 +3492,8 @@ __device__ __forceinline__ void trio_family_group_tma(const uint32_t* __restrict
       uint4 kq[NK];
 #pragma unroll
       for (int k = 0; k < NK; ++k) kq[k] = buf[(st * GFX_TMA_ROWS + 2 + k) * 32 + lane];
-      const uint32_t sw[4] = {sq.x, sq.y, sq.z, sq.w}, dw[4] = {dq.x, dq.y, dq.z, dq.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t s = sw[i], d = dw[i];
-        uint32_t valid = 0x55555555u;
-        const int64_t rem = n_snps - (q * 4 + i) * 16;
-        if (rem < 16) valid = rem <= 0 ? 0u : (((1u << (2 * rem)) - 1u) & 0x55555555u);
-        const uint32_t s0 = ~(s | (s >> 1)), s2 = (s >> 1) & ~s;
-        const uint32_t d0 = ~(d | (d >> 1)), d2 = (d >> 1) & ~d;
-        const uint32_t par_ok = ~(s & (s >> 1)) & ~(d & (d >> 1)) & valid;
-        const uint32_t no0 = s2 | d2, no2 = s0 | d0, no1 = (s0 & d0) | (s2 & d2);   // kid states the parents exclude
-#pragma unroll
-        for (int k = 0; k < NK; ++k) {
-          const uint32_t kk = i == 0 ? kq[k].x : (i == 1 ? kq[k].y : (i == 2 ? kq[k].z : kq[k].w));
-          const uint32_t k0 = ~(kk | (kk >> 1)), k1 = kk & ~(kk >> 1), k2 = (kk >> 1) & ~kk;
-          const uint32_t present = ~(kk & (kk >> 1)) & par_ok;
-          const uint32_t bad = (k0 & no0) | (k2 & no2) | (k1 & no1);      // P(kid | sire, dam) = 0  (bayesnet/model.py:28-30)
-          n_tst[k] += __popc(present);
-          n_inc[k] += __popc(bad & present);
-        }
-      }
+      if ((q + 1) * 64 <= n_snps) trio_quad<NK, false>(sq, dq, kq, q * 64, n_snps, n_inc, n_tst);
+      else trio_quad<NK, true>(sq, dq, kq, q * 64, n_snps, n_inc, n_tst);
     }
     __syncwarp();
   }

@@ -635,12 +635,14 @@ def run_cuda(args):
     phases["mendel_rank"] = sum(rk_ms)
     phase_share = {k: v / ms / lanes for k, v in phases.items()}   # lanes run concurrently: share of lane time
     kernel_block = dict(bound="hbm", achieved=iso_ach, peak=peak, unit="GB/s", frac=iso_ach / peak, traffic=traffic,
-                        name="k_mendel_rank3<HIST> (Mendel rank fused with the score histogram): the HBM-bound peeling kernel "
-                             "BASELINE.json's north_star names",
+                        name=("k_mendel_rank<HIST> (second form: the engine picks it for matrices with more than 0.5 % missing calls)"
+                              if getattr(eng.schedule, "_rank_form", 0) == 2 else "k_mendel_rank3<HIST>") +
+                             " (Mendel rank fused with the score histogram): the HBM-bound peeling kernel BASELINE.json's "
+                             "north_star names",
                         timed="alone: 10 launches on the bench inputs right after the timed region, L2 flushed (256 MB written) "
                               "before each (burst peak applies); CUDA events recorded by the library on the launching stream "
                               "right around this kernel (gfx_rank_timing); us_per_call is the whole gfx_mendel_rank_hist call "
-                              "(histogram memset + this kernel + k_mendel_rank_generic_wl for loopy rows)",
+                              "(histogram memset + this kernel + the loopy-row consumer k_mendel_rank_generic[_wl])",
                         us_per_launch=iso_ms * 1e3, us_per_call=call_ms * 1e3, achieved_per_call=n * widths[0] * RANK_BYTES_PER_CELL /
                         (call_ms / 1e3) / 1e9, algorithmic_bytes_per_cell=RANK_BYTES_PER_CELL,
                         cells_per_launch=n * widths[0], achieved_in_step=ach, frac_in_step=ach / peak,

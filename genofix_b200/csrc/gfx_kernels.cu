@@ -90,6 +90,7 @@ struct gfx_schedule {
   uint32_t rank_wl_next = 0;
   cudaEvent_t rank_ev0 = nullptr, rank_ev1 = nullptr;   // gfx_rank_timing: recorded around the dominant rank kernel
   bool rank_timing = false;
+  std::atomic<int> rank_form_pref{0};   // gfx_rank_form: 0 = third form when possible, 2 = second form
   bool rank_form3 = false;           // the score table is the one k_mendel_rank3's boolean network computes
   int rank_ncls = 0;
   std::vector<RankRow> rank_rows_h;     // per-row records of the rank kernel, heaviest first
@@ -2005,7 +2006,7 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
   // k_mendel_rank3 needs Mendel's table (rank3_network_matches); GFX_RANK_FORM=2 selects the previous form (A/B runs)
   const char* form_env = getenv("GFX_RANK_FORM");
   // ... and rows that bulk copies can address: 16-byte aligned segments, at most 2^31 bytes per row
-  const bool form3 = s->rank_form3 && !(form_env && form_env[0] == '2') && (wpr % 4) == 0 && (((uintptr_t)packed) % 16) == 0 &&
+  const bool form3 = s->rank_form3 && !(form_env ? form_env[0] == '2' : s->rank_form_pref.load() == 2) && (wpr % 4) == 0 && (((uintptr_t)packed) % 16) == 0 &&
                      wpr <= 0x1FFFFFFFll;
   // task table for this matrix width (built once, cached in the schedule)
   const RankRow* tasks_dev = nullptr;
@@ -2121,7 +2122,8 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool pdl = []() { const char* e = getenv("GFX_RANK_PDL"); return !(e && e[0] == '0'); }();
+    cfg.numAttrs = pdl ? 1 : 0;
     if (wl) {
       GFX_CUDA(cudaLaunchKernelEx(&cfg, k_mendel_rank_generic_wl, g, wl_hdr, (const uint2*)wl));
       gfx_schedule* ms = const_cast<gfx_schedule*>(s);
@@ -2133,6 +2135,17 @@ static int launch_mendel_rank(const gfx_schedule* s, const uint32_t* packed, int
     }
     GFX_LAUNCHED();
   }
+  return GFX_OK;
+}
+
+// k_mendel_rank3 is the kernel for matrices whose words are mostly complete (its fast paths need own, sire and dam cells
+// observed); on matrices full of missing calls nearly every word takes the per-cell path, for which the second form is the
+// leaner host (no staging, 80 KB instead of 134 KB of shared memory: config 4 runs 15.4 ms per step with it, 20.5 ms with the
+// third form).  The caller knows the missing fraction from the previous chunk's histogram (bin 65536) and says which to use.
+extern "C" int gfx_rank_form(gfx_schedule* s, int form) {
+  if (!s) return fail(GFX_E_INVALID, "null argument");
+  if (form != 0 && form != 2 && form != 3) return fail(GFX_E_INVALID, "gfx_rank_form: 0 (automatic), 2 or 3");
+  s->rank_form_pref.store(form == 3 ? 0 : form);
   return GFX_OK;
 }
 

@@ -333,7 +333,14 @@ class Engine(object):
         self._hist_ready = False
         self.host_hist.copy_(self.hist, non_blocking=True)
         self.torch.cuda.current_stream().synchronize()
-        elut, test_p, n_nan = rank_transform_table(self.host_hist.numpy().view(np.uint64), init_filter_p)
+        hist = self.host_hist.numpy().view(np.uint64)
+        # the next chunks of this matrix: k_mendel_rank3 needs words without missing calls for its fast paths; with more than
+        # 0.5 % missing cells (8 % of the words) the second form is the leaner kernel (gfx_rank_form)
+        form = 2 if int(hist[65536]) * 200 > self.n * self.s else 0
+        if form != getattr(self.schedule, "_rank_form", 0):
+            _lib.check(self.L.gfx_rank_form(self.schedule.handle, form))
+            self.schedule._rank_form = form
+        elut, test_p, n_nan = rank_transform_table(hist, init_filter_p)
         self.host_elut.numpy()[:] = elut
         self.elut.copy_(self.host_elut, non_blocking=True)
         tp_raw = C.c_uint32(0)

@@ -232,6 +232,12 @@ int gfx_emp_apply(const gfx_schedule* s, int32_t generation, uint32_t* live_dev,
  * on (enable = 1) or off.  Counting is off by default; it serialises on atomics. */
 int gfx_debug_counters(gfx_schedule* s, int enable, uint64_t* out16_host);
 
+/* Which rank kernel the next gfx_mendel_rank / gfx_mendel_rank_hist calls on this schedule use: 0 = k_mendel_rank3 whenever the
+ * score table is Mendel's and the rows are 16-byte aligned (default), 2 = k_mendel_rank, the leaner kernel when nearly every word
+ * holds a missing call (the caller knows the missing fraction of the previous chunk from bin 65536 of its histogram).  Both
+ * give the same scores and histogram bit for bit (correct_genotypes3.py:85-166). */
+int gfx_rank_form(gfx_schedule* s, int form);
+
 /* Diagnostics: times the dominant kernel of gfx_mendel_rank / gfx_mendel_rank_hist (k_mendel_rank3, or k_mendel_rank) by
  * itself -- two CUDA events recorded on the launching stream right around that launch, not around the histogram memset and
  * the loopy-row consumer of the same call.  gfx_rank_timing(s, 1) switches the recording on (one caller at a time),

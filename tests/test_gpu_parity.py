@@ -385,6 +385,70 @@ def test_fused_rank_histogram_equals_two_passes(case):
     assert np.array_equal(np.where(raw1 == 0xFFFF, 0x3C00, raw1), plain)
 
 
+@pytest.mark.parametrize("case", ["clean_wide", "missing", "ragged", "deep_loopy_missing", "deep_loopy_clean", "huge_litters"])
+def test_rank_kernel_third_form_equals_second_form(case):
+    """k_mendel_rank3 (boolean-network classes, PRMT tables, TMA-staged tasks, work list for loopy rows) against
+    k_mendel_rank (GFX_RANK_FORM=2): every score pattern and every one of the 65 537 histogram bins, fused and plain."""
+    import os
+    import torch
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    if case == "clean_wide":
+        rows = synth.make_pedigree(2000, 6, seed=4)
+        obs = synth.inject_errors(synth.gene_drop(rows, 4096, seed=4), 0.01, seed=4)
+    elif case == "missing":
+        rows = synth.make_pedigree(1200, 6, seed=3)
+        obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 517, seed=3), 0.01, seed=3), 0.02, seed=3)
+    elif case == "ragged":
+        rows = synth.make_pedigree(500, 3, seed=7)
+        obs = synth.inject_missing(synth.inject_errors(synth.gene_drop(rows, 17, seed=7), 0.01, seed=7), 0.3, seed=7)
+    elif case.startswith("deep_loopy"):
+        rows = synth.make_pedigree(1500, 15, sire_frac=0.02, dam_frac=0.3, seed=11, related_mating_p=0.25, unknown_parents_frac=0.1)
+        obs = synth.inject_errors(synth.gene_drop(rows, 640, seed=11), 0.01, seed=11)
+        if case.endswith("missing"):
+            obs = synth.inject_missing(obs, 0.05, seed=11)
+    else:
+        n = 3000    # two sires with 1 498 children each: m >= 64 and m >= 1024 paths
+        rows = np.zeros((n, 4), dtype=np.int64)
+        rows[:, 0] = np.arange(1, n + 1)
+        rows[:, 3] = 1 + (np.arange(n) % 2)
+        rows[0, 3] = rows[1, 3] = 1
+        rows[2, 3] = rows[3, 3] = 2
+        rows[4:, 1] = 1 + (np.arange(n - 4) % 2)
+        rows[4:, 2] = 3 + (np.arange(n - 4) % 2)
+        obs = synth.inject_errors(synth.gene_drop(rows, 333, seed=5), 0.02, seed=5)
+    eng = Engine(PedigreeDAG.from_table(rows), rows[:, 0], 2)
+    eng._alloc(obs.shape[1])
+    hin = eng.host_in.numpy()
+    hin[:, :eng.s] = obs
+    hin[:, eng.s:] = 9
+    eng.codes.copy_(eng.host_in)
+    eng.load_codes_device(eng.codes)
+    old = os.environ.get("GFX_RANK_FORM")
+    try:
+        res = {}
+        for form in ("2", "3"):
+            os.environ["GFX_RANK_FORM"] = form
+            for fused in (True, False):
+                eng.raw.fill_(-21846)
+                eng.mendel_rank_device(fused=fused)
+                torch.cuda.synchronize()
+                res[(form, fused)] = (eng.raw[:, :eng.s].cpu().numpy().view(np.uint16).copy(),
+                                      eng.hist.cpu().numpy().copy() if fused else None)
+    finally:
+        if old is None:
+            os.environ.pop("GFX_RANK_FORM", None)
+        else:
+            os.environ["GFX_RANK_FORM"] = old
+    for fused in (True, False):
+        a, b = res[("2", fused)], res[("3", fused)]
+        assert np.array_equal(a[0], b[0]), "%d scores differ" % int((a[0] != b[0]).sum())
+        if fused:
+            assert np.array_equal(a[1], b[1])
+            assert int(a[1].sum()) == obs.size
+
+
 def test_pipelined_chunks_equal_chunk_by_chunk_calls():
     """Engine.correct_chunks (three streams, two buffer sets) against Engine.correct on every chunk, including a
     ragged last chunk that forces a re-allocation in the middle of the pipeline."""

@@ -1078,6 +1078,27 @@ __device__ __forceinline__ void r3_classes(uint32_t w0, uint32_t wS, uint32_t wD
 #define R3_SCORE_TAB 0x403C3800u    // high bytes of float16 0, 0.5, 1, 2
 #define R3_CLASS_TAB 0x60402000u    // class << 5: as byte 1 / 3 of a word it is the offset class * 8192 of the (class, m) counters
 
+// One childless word with own, sire and dam cells observed: 16 scores out, class counts up.
+template <bool HIST>
+__device__ __forceinline__ void r3_leaf_word(uint32_t w0, uint32_t wS, uint32_t wD, uint16_t* dst, uint32_t& n1, uint32_t& n2,
+                                             uint32_t& n3) {
+  const uint32_t M = 0x55555555u;
+  uint32_t b0, b1;
+  r3_classes(w0, wS, wD, b0, b1);
+  R3_NIBBLES(b0, b1);
+  const uint32_t e0 = R3_BYTES(R3_SCORE_TAB, V, 0), e1 = R3_BYTES(R3_SCORE_TAB, V, 1);
+  const uint32_t o0 = R3_BYTES(R3_SCORE_TAB, W, 0), o1 = R3_BYTES(R3_SCORE_TAB, W, 1);
+  uint32_t outw[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { outw[k] = R3_WORD(e0, o0, k); outw[4 + k] = R3_WORD(e1, o1, k); }
+  r2_store(dst, outw);
+  if (HIST) {
+    n1 += __popc(b0 & ~b1 & M);
+    n2 += __popc(~b0 & b1 & M);
+    n3 += __popc(b0 & b1 & M);
+  }
+}
+
 struct R3Task {
   int row, c0, nk, fl, rS, rD, wbeg, wend;
 };
@@ -1110,6 +1131,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+#ifndef R3_LEAF2
+#define R3_LEAF2 0       // childless rows: two words per lane and iteration -- measured: 84.9 us against 78.0 us with one
+#endif
 #ifndef R3_XSTEP
 #define R3_XSTEP 1       // the first child words of the next step are requested before the current step is scored
 #endif
@@ -1264,6 +1288,30 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
     } else if (has_anc && nk == 0) {
       // ---- childless, both parents genotyped ----------------------------------------------------------
       uint32_t n1 = 0, n2 = 0, n3 = 0, nw = 0;   // cells of class 1, 2, 3; words
+      // R3_LEAF2: two words per lane and iteration (w and w + 32) so that two dependent chains interleave; slower (kept for the record)
+#if R3_LEAF2
+      for (; w < uwend; w += 64u, sw += 64) {
+        const bool hasB = w + 32u < uwend;
+        const uint32_t a0 = sw[0], aS = sw[R3_CHUNK], aD = sw[2 * R3_CHUNK];
+        const uint32_t c0w = sw[32], cS = sw[R3_CHUNK + 32], cD = sw[2 * R3_CHUNK + 32];      // inside the stage even without a word B
+        const uint32_t pmA = ((aS & (aS >> 1)) | (aD & (aD >> 1))) & M, pmB = ((cS & (cS >> 1)) | (cD & (cD >> 1))) & M;
+        const bool okA = pmA == 0u && w != utailw && (a0 & (a0 >> 1) & M) == 0u;
+        const bool okB = hasB && pmB == 0u && w + 32u != utailw && (c0w & (c0w >> 1) & M) == 0u;
+        if (okA && okB) {
+          r3_leaf_word<HIST>(a0, aS, aD, rawrow + (uint64_t)w * 16u, n1, n2, n3);
+          r3_leaf_word<HIST>(c0w, cS, cD, rawrow + (uint64_t)(w + 32u) * 16u, n1, n2, n3);
+          nw += 32u;
+          continue;
+        }
+        if (okA) { r3_leaf_word<HIST>(a0, aS, aD, rawrow + (uint64_t)w * 16u, n1, n2, n3); nw += 16u; }
+        else if (pmA != 0u && loopy) r3_push(a, row, w);
+        else r2_slow_word<HIST>(a, s_bins, row, w, a0, true, c0, c0);
+        if (!hasB) continue;
+        if (okB) { r3_leaf_word<HIST>(c0w, cS, cD, rawrow + (uint64_t)(w + 32u) * 16u, n1, n2, n3); nw += 16u; }
+        else if (pmB != 0u && loopy) r3_push(a, row, w + 32u);
+        else r2_slow_word<HIST>(a, s_bins, row, w + 32u, c0w, true, c0, c0);
+      }
+#else
       for (; w < uwend; w += 32u, sw += 32) {
         const uint32_t w0 = sw[0], wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
         const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
@@ -1272,22 +1320,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
           else r2_slow_word<HIST>(a, s_bins, row, w, w0, true, c0, c0);
           continue;
         }
-        uint32_t b0, b1;
-        r3_classes(w0, wS, wD, b0, b1);
-        R3_NIBBLES(b0, b1);
-        const uint32_t e0 = R3_BYTES(R3_SCORE_TAB, V, 0), e1 = R3_BYTES(R3_SCORE_TAB, V, 1);
-        const uint32_t o0 = R3_BYTES(R3_SCORE_TAB, W, 0), o1 = R3_BYTES(R3_SCORE_TAB, W, 1);
-        uint32_t outw[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { outw[k] = R3_WORD(e0, o0, k); outw[4 + k] = R3_WORD(e1, o1, k); }
-        r2_store(rawrow + (uint64_t)w * 16u, outw);
-        if (HIST) {
-          n1 += __popc(b0 & ~b1 & M);
-          n2 += __popc(~b0 & b1 & M);
-          n3 += __popc(b0 & b1 & M);
-          nw += 16u;
-        }
+        r3_leaf_word<HIST>(w0, wS, wD, rawrow + (uint64_t)w * 16u, n1, n2, n3);
+        nw += 16u;
       }
+#endif
       if (HIST) {
         const uint32_t n0 = nw - n1 - n2 - n3;
         if (n0) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + lane4), n0);

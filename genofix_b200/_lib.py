@@ -19,7 +19,7 @@ EXPORTS = [
     "gfx_last_error", "gfx_version", "gfx_launch_count", "gfx_schedule_create", "gfx_schedule_create_host",
     "gfx_schedule_destroy", "gfx_schedule_info", "gfx_schedule_copy", "gfx_pack2", "gfx_unpack2",
     "gfx_mendel_rank", "gfx_mendel_rank_hist", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_rank_rowsum_f16", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
-    "gfx_check_device_status", "gfx_debug_counters", "gfx_rank_form", "gfx_rank_timing", "gfx_rank_last_kernel_ms", "gfx_trio_scan", "gfx_trio_scan_add", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
+    "gfx_check_device_status", "gfx_reset_device_status", "gfx_debug_counters", "gfx_rank_form", "gfx_rank_timing", "gfx_rank_last_kernel_ms", "gfx_trio_scan", "gfx_trio_scan_add", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
     "gfx_kids_term_host", "gfx_emp_rank_blend", "gfx_emp_apply", "gfx_gene_drop", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
 ]
 
@@ -90,6 +90,7 @@ def lib():
     L.gfx_confusion.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp]
     L.gfx_build_cut_table.argtypes = [vp, C.c_double, C.c_double, vp, C.POINTER(C.c_uint32)]
     L.gfx_check_device_status.argtypes = [vp, vp]
+    L.gfx_reset_device_status.argtypes = [vp]
     L.gfx_debug_counters.argtypes = [vp, C.c_int, vp]
     L.gfx_emp_rank_blend.argtypes = [vp, i64, i64, i64, vp, i64, vp, C.POINTER(EmpIndex), vp, i64, vp]
     L.gfx_emp_apply.argtypes = [vp, i32, vp, vp, i64, i64, vp, i64, vp, C.POINTER(EmpIndex), C.POINTER(CorrectParams), vp, C.c_double, vp, vp]

@@ -90,6 +90,7 @@ struct gfx_schedule {
   uint32_t rank_wl_next = 0;
   cudaEvent_t rank_ev0 = nullptr, rank_ev1 = nullptr;   // gfx_rank_timing: recorded around the dominant rank kernel
   bool rank_timing = false;
+  std::atomic<int> too_wide{0};         // sticky: a GFX_E_TOO_WIDE seen by any lane of this schedule fails every later check
   std::atomic<int> rank_form_pref{0};   // gfx_rank_form: 0 = third form when possible, 2 = second form
   bool rank_form3 = false;           // the score table is the one k_mendel_rank3's boolean network computes
   int rank_ncls = 0;
@@ -352,11 +353,24 @@ extern "C" int gfx_check_device_status(const gfx_schedule* s, void* stream) {
   int st = 0;
   GFX_CUDA(cudaMemcpyAsync(&st, s->status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   GFX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  gfx_schedule* ms = const_cast<gfx_schedule*>(s);
   if (st != 0) {
     int zero = 0;
     GFX_CUDA(cudaMemcpy(s->status, &zero, sizeof(int), cudaMemcpyHostToDevice));
-    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX_HUGE (13) simultaneously unobserved variables");
+    ms->too_wide.store(1);
   }
+  // lanes share the schedule and its one status word: the lane that reads the word first clears it, so the flag stays up on
+  // the host side and every lane's check fails from then on (no chunk with unevaluated cells is handed out as valid)
+  if (ms->too_wide.load())
+    return fail(GFX_E_TOO_WIDE, "a blanket needed more than GFX_WMAX_HUGE (13) simultaneously unobserved variables");
+  return GFX_OK;
+}
+
+extern "C" int gfx_reset_device_status(gfx_schedule* s) {
+  if (!s || s->device < 0) return fail(GFX_E_INVALID, "bad schedule");
+  int zero = 0;
+  GFX_CUDA(cudaMemcpy(s->status, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  s->too_wide.store(0);
   return GFX_OK;
 }
 

@@ -449,6 +449,7 @@ class Engine(object):
         G = np.asarray(G)
         if G.ndim != 2 or G.shape[0] != self.n:
             raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+        _lib.check(self.L.gfx_reset_device_status(self.schedule.handle))
         self._alloc(G.shape[1])
         hin = self.host_in.numpy()
         _parallel_copy(hin[:, :self.s], G)
@@ -541,6 +542,7 @@ class Engine(object):
         G = np.asarray(G)
         if G.ndim != 2 or G.shape[0] != self.n:
             raise ValueError("genotype matrix must be [%d, n_snps]" % self.n)
+        _lib.check(self.L.gfx_reset_device_status(self.schedule.handle))
         self._alloc(G.shape[1])
         hin = self.host_in.numpy()
         _parallel_copy(hin[:, :self.s], G)
@@ -595,6 +597,8 @@ class Engine(object):
         own layout (gfutils.packedgens.PackedGens.packed_columns / pack_codes) and the results are packed blocks of
         the same shape: a quarter of the bytes cross PCIe and the pack / unpack kernels are skipped."""
         t = self.torch
+        if not getattr(self, "_lane", False):       # a lane of MultiLane: the owner has reset the shared status word
+            _lib.check(self.L.gfx_reset_device_status(self.schedule.handle))
         it = iter(chunks)
         dt_io = np.uint32 if packed_io else np.uint8
 
@@ -900,6 +904,9 @@ class MultiLane(object):
         results = [None] * len(chunks)
         done = [threading.Event() for _ in chunks]
         errs = []
+        _lib.check(self.engines[0].L.gfx_reset_device_status(self.schedule.handle))
+        for eng in self.engines:
+            eng._lane = True
 
         def lane(l, eng):
             mine = list(range(l, len(chunks), L))

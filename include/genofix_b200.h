@@ -245,9 +245,11 @@ int gfx_rank_form(gfx_schedule* s, int form);
 int gfx_rank_timing(gfx_schedule* s, int enable);
 int gfx_rank_last_kernel_ms(gfx_schedule* s, float* ms);
 
-/* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); returns and clears it.
- * Synchronises the stream. */
+/* Device-side error flag raised by the inference kernels (e.g. GFX_E_TOO_WIDE); synchronises the stream.  The flag is sticky
+ * per schedule: engines that share a schedule (lanes) share its one status word, so once any of them has seen the error every
+ * later check fails as well, until gfx_reset_device_status (called at the start of a top-level correction call). */
 int gfx_check_device_status(const gfx_schedule* s, void* stream);
+int gfx_reset_device_status(gfx_schedule* s);
 
 /* ---------------------------------------------------------------------------------------------
  * Empirical Mendelian-consistency scan (BASELINE config 5; trio selection of

@@ -108,3 +108,73 @@ def test_preindex_host_logic_reproduces_reference_indexes(name, monkeypatch):
                     if w:
                         assert np.array_equal(empC._freq[s_], g["freq_" + c][i][:3 ** w])
     assert k == len(g["quantQ"])
+
+
+# ---- the LD index handed to the blend kernels (correct_genotypes3.ld_index_arrays) and the lookup surface -----------------
+@pytest.mark.parametrize("name", ["emp_a", "emp_b"])
+def test_ld_index_arrays_and_lookups_match_the_reference(name, monkeypatch):
+    """countJointFrqAll with the oracle-backed stand-in for k_window_counts fills the product's index; its stored frequencies,
+    the arrays gfx_emp_rank_blend / gfx_emp_apply receive, getCountTable and getEmpProbs are then the reference's
+    (tests/golden/emp_*.npz: the frequencies of the index the reference built and every getEmpProbs result it returned)."""
+    import multiprocessing
+    from genofix_b200 import correct_genotypes3 as cg3
+    from genofix_b200.empirical import jalleledist3 as jad
+    g = load_golden(name)
+    obs = g["obs"]
+    S = obs.shape[1]
+    names = ["SNP%d" % i for i in range(S)]
+    monkeypatch.setattr(jad, "window_counts_device", _stand_in_window_counts)
+    emp = jad.JointAllellicDistribution("1", names, surround_size=int(g["emp_surround"]), pseudocount=float(g["emp_pseudocount"]))
+    df = pd.DataFrame(obs, index=[int(x) for x in g["ids"]], columns=names)
+    emp.countJointFrqAll(df)
+    wstart, wlen, freq, weight = cg3.ld_index_arrays(emp, names, float(g["emp_weight"]))
+    assert np.array_equal(wstart, g["emp_wstart"]) and np.array_equal(wlen, g["emp_wlen"]) and weight == float(g["emp_weight"])
+    for j in range(S):
+        assert np.array_equal(freq[j], g["emp_freq"][j, :3 ** int(wlen[j])]), j
+    # getEmpProbs on the window chunk of a SNP, like correctMatrix calls it (:624-633)
+    cg3.initializerEmp(emp)
+    want = {}
+    for r, j, o, a, b, c in g["emp_probs"]:
+        want.setdefault(int(j), {})[(int(g["ids"][int(r)]), int(o))] = np.array([a, b, c])
+    for j in sorted(want)[::3]:
+        win = emp.getWindow(names[j])
+        got = cg3.CorrectGenotypes.getEmpProbs(df.loc[:, win].copy(), names[j])
+        assert set(got) == set(want[j])
+        for k, v in got.items():
+            assert np.array_equal(np.asarray(v, dtype=float), want[j][k]), (j, k)
+    # a window that reaches outside the columns is refused (the reference would treat the SNP as unobserved and raise, D4)
+    with pytest.raises(ValueError):
+        cg3.ld_index_arrays(emp, names[1:], 3.0)
+    with pytest.raises(KeyError):
+        cg3.ld_index_arrays(emp, names + ["nope"], 3.0)
+
+
+def test_oracle_blend_with_missing_calls_sums_over_completions():
+    """The case the reference cannot run (a 9 inside a window raises): the oracle's count table is the sum of the
+    stored frequencies over every completion of the missing calls, and without missing calls it is the single stored entry."""
+    import itertools
+    rs = np.random.default_rng(3)
+    G = rs.integers(0, 3, size=(200, 9)).astype(np.uint8)
+    emp = go.emp_index(G, 2, 1e-4, weight=3)
+    row = G[5].copy()
+    j = 4
+    a, w = int(emp["wstart"][j]), int(emp["wlen"][j])
+    tab = emp["freq"][j].reshape((3,) * w)
+    full = go.emp_count_table(row, j, emp)
+    for s in range(3):
+        idx = [int(row[c]) if c != j else s for c in range(a, a + w)]
+        assert full[s] == tab[tuple(idx)]
+    row[3] = 9
+    row[6] = 9
+    part = go.emp_count_table(row, j, emp)
+    for s in range(3):
+        tot = 0.0
+        first = True
+        for x3, x6 in itertools.product(range(3), repeat=2):          # column 3 slower than column 6: C order
+            idx = [int(row[c]) for c in range(a, a + w)]
+            idx[3 - a], idx[6 - a], idx[j - a] = x3, x6, s
+            tot = tab[tuple(idx)] if first else tot + tab[tuple(idx)]
+            first = False
+        assert part[s] == tot
+    p = go.emp_state_probs(row, j, emp)
+    assert abs(float(np.sum(p)) - 1.0) < 1e-12

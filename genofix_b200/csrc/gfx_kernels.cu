@@ -1145,8 +1145,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-#ifndef R3_LEAF2
-#define R3_LEAF2 0       // childless rows: two words per lane and iteration -- measured: 84.9 us against 78.0 us with one
+#ifndef R3_PROXY_FENCE
+#define R3_PROXY_FENCE 1   // measured: 77.4 us per call with and without
 #endif
 #ifndef R3_XSTEP
 #define R3_XSTEP 1       // the first child words of the next step are requested before the current step is scored
@@ -1257,7 +1257,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
       if (lane == 0) {
         // the record stays in its slot until this task is over (it is read again when it becomes the current one)
         const R3Task T1 = r3_decode(*reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl), *reinterpret_cast<const int4*>(wsm + R3_REC_OFF + 32u * sl + 16u));
+        // the stage refilled here was read two iterations ago and the shuffle that closes every iteration has all lanes past
+        // those reads; the proxy fence (generic reads before async writes of the same shared memory) costs nothing measurable
+#if R3_PROXY_FENCE
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         r3_issue_data(a, wsm, T1, (int)sl);
       }
     }
@@ -1302,30 +1306,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
     } else if (has_anc && nk == 0) {
       // ---- childless, both parents genotyped ----------------------------------------------------------
       uint32_t n1 = 0, n2 = 0, n3 = 0, nw = 0;   // cells of class 1, 2, 3; words
-      // R3_LEAF2: two words per lane and iteration (w and w + 32) so that two dependent chains interleave; slower (kept for the record)
-#if R3_LEAF2
-      for (; w < uwend; w += 64u, sw += 64) {
-        const bool hasB = w + 32u < uwend;
-        const uint32_t a0 = sw[0], aS = sw[R3_CHUNK], aD = sw[2 * R3_CHUNK];
-        const uint32_t c0w = sw[32], cS = sw[R3_CHUNK + 32], cD = sw[2 * R3_CHUNK + 32];      // inside the stage even without a word B
-        const uint32_t pmA = ((aS & (aS >> 1)) | (aD & (aD >> 1))) & M, pmB = ((cS & (cS >> 1)) | (cD & (cD >> 1))) & M;
-        const bool okA = pmA == 0u && w != utailw && (a0 & (a0 >> 1) & M) == 0u;
-        const bool okB = hasB && pmB == 0u && w + 32u != utailw && (c0w & (c0w >> 1) & M) == 0u;
-        if (okA && okB) {
-          r3_leaf_word<HIST>(a0, aS, aD, rawrow + (uint64_t)w * 16u, n1, n2, n3);
-          r3_leaf_word<HIST>(c0w, cS, cD, rawrow + (uint64_t)(w + 32u) * 16u, n1, n2, n3);
-          nw += 32u;
-          continue;
-        }
-        if (okA) { r3_leaf_word<HIST>(a0, aS, aD, rawrow + (uint64_t)w * 16u, n1, n2, n3); nw += 16u; }
-        else if (pmA != 0u && loopy) r3_push(a, row, w);
-        else r2_slow_word<HIST>(a, s_bins, row, w, a0, true, c0, c0);
-        if (!hasB) continue;
-        if (okB) { r3_leaf_word<HIST>(c0w, cS, cD, rawrow + (uint64_t)(w + 32u) * 16u, n1, n2, n3); nw += 16u; }
-        else if (pmB != 0u && loopy) r3_push(a, row, w + 32u);
-        else r2_slow_word<HIST>(a, s_bins, row, w + 32u, c0w, true, c0, c0);
-      }
-#else
       for (; w < uwend; w += 32u, sw += 32) {
         const uint32_t w0 = sw[0], wS = sw[R3_CHUNK], wD = sw[2 * R3_CHUNK];
         const uint32_t pm = ((wS & (wS >> 1)) | (wD & (wD >> 1))) & M;
@@ -1337,7 +1317,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_mendel_rank3(RankArgs a) {
         r3_leaf_word<HIST>(w0, wS, wD, rawrow + (uint64_t)w * 16u, n1, n2, n3);
         nw += 16u;
       }
-#endif
       if (HIST) {
         const uint32_t n0 = nw - n1 - n2 - n3;
         if (n0) atomicAdd(reinterpret_cast<uint32_t*>(smem + R3_CM_OFF + lane4), n0);

@@ -20,7 +20,7 @@ EXPORTS = [
     "gfx_schedule_destroy", "gfx_schedule_info", "gfx_schedule_copy", "gfx_pack2", "gfx_unpack2",
     "gfx_mendel_rank", "gfx_mendel_rank_hist", "gfx_rank_hist", "gfx_rank_rowsum", "gfx_rank_rowsum_f16", "gfx_correct_pairs", "gfx_correct_singles", "gfx_build_cut_table",
     "gfx_check_device_status", "gfx_reset_device_status", "gfx_debug_counters", "gfx_rank_form", "gfx_rank_timing", "gfx_rank_last_kernel_ms", "gfx_trio_scan", "gfx_trio_scan_add", "gfx_founders", "gfx_window_counts", "gfx_infer_host", "gfx_infer_pair_host",
-    "gfx_kids_term_host", "gfx_emp_rank_blend", "gfx_emp_apply", "gfx_gene_drop", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
+    "gfx_kids_term_host", "gfx_emp_rank_blend", "gfx_emp_apply", "gfx_gene_drop", "gfx_gene_drop_linked", "gfx_haps_to_codes", "gfx_inject_errors", "gfx_confusion",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
     L.gfx_correct_pairs.argtypes = [vp, i32, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
     L.gfx_correct_singles.argtypes = [vp, vp, i64, i64, vp, i64, vp, C.POINTER(CorrectParams), vp, i64, vp, vp, vp]
     L.gfx_gene_drop.argtypes = [i32, vp, vp, vp, vp, i32, i64, i64, C.c_uint64, vp, vp]
+    L.gfx_gene_drop_linked.argtypes = [i32, vp, vp, vp, vp, i32, i64, i64, C.c_uint64, i32, vp, vp, vp, vp, vp]
     L.gfx_haps_to_codes.argtypes = [vp, i64, i64, i64, vp, vp]
     L.gfx_inject_errors.argtypes = [vp, i64, i64, i64, C.c_double, C.c_uint64, vp]
     L.gfx_confusion.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp]

@@ -4004,6 +4004,121 @@ extern "C" int gfx_gene_drop(int32_t n, const int32_t* sire_row_dev, const int32
   return GFX_OK;
 }
 
+// ---- gene drop with linkage: quickgsim's meiosis (quickgsim/genome.py:74-115) ------------------------------------------
+// Per gamete and chromosome: n = max(1, Poisson(morgans)) crossovers (one obligatory, :75-79), placed on distinct interior
+// markers 1 .. n_markers - 2 with probability proportional to the genetic distance to the previous marker (:81-86, Chrom.cm_to_p
+// :35-41), sorted; the gamete starts on a random strand and switches at every crossover marker (:98-113).  Everything a
+// gamete needs is a function of (seed, animal, side, chromosome) through the counter-based generator, so every thread
+// (animal, word) recomputes the few crossovers of the chromosomes its word touches: no shared state, no ordering between
+// threads, results independent of the launch geometry.  Successive weighted draws with rejection of repeats are the same
+// distribution as numpy's choice(p, replace=False).
+#define GFX_MAX_XOVER 12
+struct LinkMap {
+  int n_chrom;
+  const int32_t* chrom_start;   // [n_chrom + 1] first SNP of every chromosome (SNPs in map order)
+  const float* morgans;         // [n_chrom]
+  const float* cum_p;           // [n_snps] per chromosome: cumulative crossover probability up to and including the marker
+};                              //          (0 at the first marker, 1 at the last but one and the last)
+__device__ __forceinline__ int gfx_poisson(float lambda, uint64_t& st) {
+  // inversion by sequential search (lambda is a chromosome length in Morgans: ~1)
+  const float u = (float)((gfx_mix64(st += 0x9E3779B97F4A7C15ull) >> 40) + 0.5f) * (1.0f / 16777216.0f);
+  float p = __expf(-lambda), c = p;
+  int k = 0;
+  while (u > c && k < 64) { ++k; p *= lambda / (float)k; c += p; }
+  return k;
+}
+// crossover markers (local indices, ascending) and the start strand of one gamete on one chromosome
+__device__ __forceinline__ int gfx_gamete_plan(const LinkMap& L, int c, uint64_t seed, uint64_t animal, int side, int* brk, int* start) {
+  const int s0 = L.chrom_start[c], nm = L.chrom_start[c + 1] - s0;
+  uint64_t st = gfx_rand(seed ^ 0xC2B2AE3D27D4EB4Full, animal * 2ull + (uint64_t)side, (uint64_t)c);
+  *start = (int)(gfx_mix64(st += 0x9E3779B97F4A7C15ull) >> 63);
+  if (nm < 3) return 0;                                   // no interior marker: the whole chromosome is one segment (:83-86)
+  int n = gfx_poisson(L.morgans[c], st);
+  if (n < 1) n = 1;                                        // obligatory crossover
+  if (n > nm - 2) n = nm - 2;
+  if (n > GFX_MAX_XOVER) n = GFX_MAX_XOVER;
+  const float* cp = L.cum_p + s0;
+  int got = 0;
+  for (int tries = 0; got < n && tries < 8 * GFX_MAX_XOVER; ++tries) {
+    const float u = (float)((gfx_mix64(st += 0x9E3779B97F4A7C15ull) >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    int lo = 1, hi = nm - 2;                               // first marker whose cumulative probability reaches u
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cp[mid] >= u) hi = mid; else lo = mid + 1; }
+    bool dup = false;
+    for (int k = 0; k < got; ++k) dup |= brk[k] == lo;
+    if (!dup) brk[got++] = lo;
+  }
+  for (int i = 1; i < got; ++i) {                          // insertion sort
+    const int v = brk[i];
+    int k = i - 1;
+    while (k >= 0 && brk[k] > v) { brk[k + 1] = brk[k]; --k; }
+    brk[k + 1] = v;
+  }
+  return got;
+}
+__global__ void __launch_bounds__(128) k_gene_drop_linked(const int32_t* __restrict__ order, int n_level, const int32_t* __restrict__ sire_row,
+                                                          const int32_t* __restrict__ dam_row, int64_t nwords, int64_t wpr, int64_t n_snps,
+                                                          uint64_t seed, LinkMap L, uint32_t* __restrict__ hap) {
+  const int64_t total = (int64_t)n_level * nwords;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / nwords, w = i - k * nwords;
+    const int r = order[k];
+    const int prow[2] = {sire_row[r], dam_row[r]};
+    const uint64_t rnd = gfx_rand(seed, (uint64_t)r, (uint64_t)w);
+    uint32_t out = 0;
+    // chromosome of the word's first SNP
+    const int64_t j0 = w * 16;
+    int c = 0;
+    {
+      int lo = 0, hi = L.n_chrom - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (L.chrom_start[mid] <= j0) lo = mid; else hi = mid - 1; }
+      c = lo;
+    }
+    for (int side = 0; side < 2; ++side) {
+      uint32_t alle;   // transmitted allele of every SNP of the word at the even bit positions
+      if (prow[side] < 0) {
+        alle = (uint32_t)((side == 0 ? gfx_mix64(rnd) : (gfx_mix64(rnd) >> 32)) & 0x55555555u);     // founder: frequency 1/2
+      } else {
+        const uint32_t h = hap[(int64_t)prow[side] * wpr + w];
+        uint32_t pick = 0;                                  // bit 2i set: SNP i comes from the parent's maternal strand
+        int cc = c, brk[GFX_MAX_XOVER], start = 0, nb = -1;
+        for (int b = 0; b < 16; ++b) {
+          const int64_t j = j0 + b;
+          if (j >= n_snps) break;
+          while (cc + 1 < L.n_chrom && j >= L.chrom_start[cc + 1]) { ++cc; nb = -1; }
+          if (nb < 0) nb = gfx_gamete_plan(L, cc, seed, (uint64_t)r, side, brk, &start);
+          const int local = (int)(j - L.chrom_start[cc]);
+          int strand = start;
+          for (int q = 0; q < nb; ++q) strand ^= (int)(brk[q] <= local);
+          pick |= (uint32_t)strand << (2 * b);
+        }
+        alle = ((h & ~pick) | ((h >> 1) & pick)) & 0x55555555u;
+      }
+      out |= alle << side;
+    }
+    hap[(int64_t)r * wpr + w] = out;
+  }
+}
+
+extern "C" int gfx_gene_drop_linked(int32_t n, const int32_t* sire_row_dev, const int32_t* dam_row_dev, const int32_t* order_dev,
+                                    const int32_t* level_off_host, int32_t n_levels, int64_t n_snps, int64_t wpr, uint64_t seed,
+                                    int32_t n_chrom, const int32_t* chrom_start_dev, const float* morgans_dev, const float* cum_p_dev,
+                                    uint32_t* hap_dev, void* stream) {
+  if (n <= 0 || !sire_row_dev || !dam_row_dev || !order_dev || !level_off_host || n_levels <= 0 || !hap_dev || n_snps <= 0 ||
+      n_chrom <= 0 || !chrom_start_dev || !morgans_dev || !cum_p_dev)
+    return fail(GFX_E_INVALID, "gfx_gene_drop_linked: bad argument");
+  const int64_t nwords = (n_snps + 15) / 16;
+  if (wpr < nwords) return fail(GFX_E_INVALID, "gfx_gene_drop_linked: wpr too small");
+  LinkMap L{n_chrom, chrom_start_dev, morgans_dev, cum_p_dev};
+  for (int l = 0; l < n_levels; ++l) {
+    const int cnt = level_off_host[l + 1] - level_off_host[l];
+    if (cnt <= 0) continue;
+    k_gene_drop_linked<<<grid_for((int64_t)cnt * nwords, 128, device_sms(), 16), 128, 0, (cudaStream_t)stream>>>(
+        order_dev + level_off_host[l], cnt, sire_row_dev, dam_row_dev, nwords, wpr, n_snps, seed, L, hap_dev);
+    GFX_LAUNCHED();
+  }
+  return GFX_OK;
+}
+
 // genotype code = number of 1-alleles; cells beyond n_snps (and the padding words) become 3 = missing
 __global__ void __launch_bounds__(256) k_haps_to_codes(const uint32_t* __restrict__ hap, int64_t n, int64_t n_snps, int64_t wpr,
                                                        uint32_t* __restrict__ packed) {

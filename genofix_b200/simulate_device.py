@@ -1,8 +1,10 @@
 """Gene drop, error injection and evaluation on the device.
 
-The reference simulates with quickgsim (simulate.py:187-340) and scores with pandas (simulate.py:426-515); with the
-empirical LD model off only the marginal Mendelian structure of the data matters, so SNPs are dropped independently
-(free recombination).  The generators are counter based (splitmix64 of seed, row, word): results depend on the seed
+The reference simulates with quickgsim (simulate.py:187-340) and scores with pandas (simulate.py:426-515).  Without a genetic
+map SNPs are dropped independently (free recombination: all the Mendelian path sees); with one (`linkage_map`) the drop follows
+quickgsim's meiosis (quickgsim/genome.py:74-115): per gamete and chromosome max(1, Poisson(length in Morgans)) crossovers on
+interior markers, placed with probability proportional to the genetic distance to the previous marker, random start strand.
+The generators are counter based (splitmix64 of seed, row, word): results depend on the seed
 only, not on the launch geometry.  They are NOT the numpy generators of genofix_b200.synth (different streams)."""
 import ctypes as C
 
@@ -29,6 +31,37 @@ def levels_from_parents(sire_row, dam_row):
     order = np.argsort(depth, kind="stable").astype(np.int32)
     level_off = np.concatenate([[0], np.cumsum(np.bincount(depth))]).astype(np.int32)
     return order, level_off
+
+
+def linkage_arrays(chrom, cm):
+    """(chrom_start int32 [C + 1], morgans float32 [C], cum_p float32 [S]) of a genetic map given per SNP in map order:
+    quickgsim.genome.Chrom.finalise_chrom_configuration / cm_to_p (:21-41): a chromosome is max(cM) / 100 Morgans long; the
+    crossover probability of an interior marker is its genetic distance to the previous marker over the sum of those of the
+    interior markers (first and last marker excluded); cum_p is the running sum per chromosome."""
+    chrom = np.asarray(chrom)
+    cm = np.asarray(cm, dtype=np.float64)
+    if len(chrom) != len(cm):
+        raise ValueError("one chromosome and one cM position per SNP")
+    cuts = [0] + [i for i in range(1, len(chrom)) if chrom[i] != chrom[i - 1]] + [len(chrom)]
+    if len(set(chrom[a] for a in cuts[:-1])) != len(cuts) - 1:
+        raise ValueError("SNPs must be grouped by chromosome (map order)")
+    start = np.array(cuts, dtype=np.int32)
+    morgans = np.zeros(len(cuts) - 1, dtype=np.float32)
+    cum_p = np.zeros(len(chrom), dtype=np.float32)
+    for c in range(len(cuts) - 1):
+        a, b = cuts[c], cuts[c + 1]
+        pos = cm[a:b]
+        m = float(pos.max()) / 100.0
+        morgans[c] = m
+        if b - a >= 3:
+            d = np.diff(pos, prepend=0.0)[1:-1]                  # interior markers
+            tot = d.sum()
+            p = d / tot if tot > 0 else np.full(len(d), 1.0 / len(d))
+            cp = np.cumsum(p)
+            cp[-1] = 1.0
+            cum_p[a + 1:b - 1] = cp
+            cum_p[b - 1] = 1.0
+    return start, morgans, cum_p
 
 
 class DeviceSimulator(object):
@@ -58,12 +91,27 @@ class DeviceSimulator(object):
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
 
-    def gene_drop(self):
-        """packed truth genotypes, int32 cuda tensor [n, wpr] (the kernels' 2-bit layout)"""
+    def gene_drop(self, linkage_map=None, first_level=0):
+        """packed truth genotypes, int32 cuda tensor [n, wpr] (the kernels' 2-bit layout).  linkage_map = (chromosome of every
+        SNP, cM position of every SNP), SNPs in map order: quickgsim's meiosis instead of free recombination.
+        first_level > 0 keeps the haplotypes of the shallower levels as they are in self.hap (tests set founders by hand)."""
         t = self.torch
-        _lib.check(self.L.gfx_gene_drop(self.n, self.sire.data_ptr(), self.dam.data_ptr(), self.order.data_ptr(),
-                                        self.level_off.ctypes.data_as(C.c_void_p), len(self.level_off) - 1, self.s, self.wpr,
-                                        C.c_uint64(self.seed), self.hap.data_ptr(), self._stream()))
+        lo = self.level_off[first_level:]
+        if linkage_map is None:
+            _lib.check(self.L.gfx_gene_drop(self.n, self.sire.data_ptr(), self.dam.data_ptr(), self.order.data_ptr(),
+                                            lo.ctypes.data_as(C.c_void_p), len(lo) - 1, self.s, self.wpr,
+                                            C.c_uint64(self.seed), self.hap.data_ptr(), self._stream()))
+        else:
+            start, morgans, cum_p = linkage_arrays(*linkage_map)
+            if int(start[-1]) != self.s:
+                raise ValueError("the genetic map must cover every SNP")
+            dev = self.hap.device
+            keep = [t.from_numpy(start).to(dev), t.from_numpy(morgans).to(dev), t.from_numpy(cum_p).to(dev)]
+            _lib.check(self.L.gfx_gene_drop_linked(self.n, self.sire.data_ptr(), self.dam.data_ptr(), self.order.data_ptr(),
+                                                   lo.ctypes.data_as(C.c_void_p), len(lo) - 1, self.s, self.wpr,
+                                                   C.c_uint64(self.seed), len(morgans), keep[0].data_ptr(), keep[1].data_ptr(),
+                                                   keep[2].data_ptr(), self.hap.data_ptr(), self._stream()))
+            t.cuda.current_stream().synchronize()
         truth = t.empty((self.n, self.wpr), dtype=t.int32, device=self.hap.device)
         _lib.check(self.L.gfx_haps_to_codes(self.hap.data_ptr(), self.n, self.s, self.wpr, truth.data_ptr(), self._stream()))
         return truth

@@ -299,7 +299,8 @@ int gfx_kids_term_host(int32_t n, const uint8_t* kid, const uint8_t* par, double
 
 /* ---------------------------------------------------------------------------------------------
  * Simulator pieces on the device (simulate.py:187-340 gene drop + error injection, :426-515 evaluation;
- * quickgsim/genome.py:86-115 meiosis reduced to independent loci, i.e. free recombination).
+ * quickgsim/genome.py:86-115 meiosis: gfx_gene_drop reduces it to independent loci, i.e. free recombination, gfx_gene_drop_linked
+ * follows it crossover by crossover).
  *   gfx_gene_drop      hap_dev uint32 [n, wpr]: bit 2i = paternal, bit 2i+1 = maternal allele of SNP i.  Rows are processed
  *                      level by level: order_dev lists the rows, level_off_host[l..l+1] delimits level l, the parents of a
  *                      level are in earlier levels; sire_row / dam_row = -1 for founders (alleles with frequency 1/2).
@@ -310,6 +311,15 @@ int gfx_kids_term_host(int32_t n, const uint8_t* kid, const uint8_t* par, double
 int gfx_gene_drop(int32_t n, const int32_t* sire_row_dev, const int32_t* dam_row_dev, const int32_t* order_dev,
                   const int32_t* level_off_host, int32_t n_levels, int64_t n_snps, int64_t wpr, uint64_t seed,
                   uint32_t* hap_dev, void* stream);
+/* The same drop with linkage: quickgsim's meiosis (quickgsim/genome.py:74-115).  SNPs are in map order, chromosome c holds the
+ * SNPs chrom_start[c] .. chrom_start[c + 1] - 1; per gamete and chromosome max(1, Poisson(morgans[c])) crossovers on distinct
+ * interior markers drawn with the probabilities whose running sum per chromosome is cum_p (Chrom.cm_to_p, :35-41: proportional
+ * to the genetic distance to the previous marker; 0 at the first marker, 1 from the last but one on), random start strand,
+ * strands alternate at the crossover markers.  All map arrays on the device. */
+int gfx_gene_drop_linked(int32_t n, const int32_t* sire_row_dev, const int32_t* dam_row_dev, const int32_t* order_dev,
+                         const int32_t* level_off_host, int32_t n_levels, int64_t n_snps, int64_t wpr, uint64_t seed,
+                         int32_t n_chrom, const int32_t* chrom_start_dev, const float* morgans_dev, const float* cum_p_dev,
+                         uint32_t* hap_dev, void* stream);
 int gfx_haps_to_codes(const uint32_t* hap_dev, int64_t n, int64_t n_snps, int64_t wpr, uint32_t* packed_dev, void* stream);
 int gfx_inject_errors(uint32_t* packed_dev, int64_t n, int64_t n_snps, int64_t wpr, double rate, uint64_t seed, void* stream);
 int gfx_confusion(const uint32_t* truth_dev, const uint32_t* obs_dev, const uint32_t* fixed_dev, int64_t n, int64_t n_snps,

@@ -87,15 +87,24 @@ def drop_rows(pedigree):
     return rows
 
 
-def run_on_device(args, pedigree, snps, out_dir):
-    """The whole loop on the device: simulate.py:187-340 (drop + errors), the correction, :426-515 (scoring)."""
+def run_on_device(args, pedigree, snps, out_dir, genomein=None):
+    """The whole loop on the device: simulate.py:187-340 (drop + errors), the correction, :426-515 (scoring).  With the map's
+    chromosome and cM columns the drop follows quickgsim's meiosis (crossovers per chromosome), else free recombination."""
     import torch
     from genofix_b200.engine import Engine
     from genofix_b200.simulate_device import DeviceSimulator
     rows = drop_rows(pedigree)
     n, s = len(rows), len(snps)
     sim = DeviceSimulator(rows, s, seed=1234)
-    truth = sim.gene_drop()
+    linkage = None
+    if genomein is not None:
+        chrom, cm = np.asarray(genomein["chrom"])[:s], np.asarray(genomein["cm"], dtype=float)[:s]
+        grouped = len(set(chrom[[0] + [i for i in range(1, s) if chrom[i] != chrom[i - 1]]])) == 1 + int(np.count_nonzero(chrom[1:] != chrom[:-1]))
+        if grouped and np.all(np.isfinite(cm)) and cm.max() > 0:
+            linkage = (chrom, cm)
+        else:
+            print("genetic map not usable (SNPs not grouped by chromosome or no cM positions): free recombination")
+    truth = sim.gene_drop(linkage_map=linkage)
     obs = sim.inject_errors(truth, args.error_rate / 100)
     fixed = obs.clone()
     eng = Engine(pedigree, rows[:, 0], args.lookback)
@@ -131,7 +140,7 @@ def main(argv=None):
     if args.first_n_snps is not None:
         snps = snps[:args.first_n_snps]
     if args.device_sim:
-        return run_on_device(args, pedigree, snps, out_dir)
+        return run_on_device(args, pedigree, snps, out_dir, genomein)
     if args.founders_haplo_file or args.founders_geno_file:
         raise NotImplementedError("founder genotype import is part of the simulator, outside this path")
     if args.prior_pop_genome is None:

@@ -959,6 +959,79 @@ def test_count_joint_frq_all_matches_reference_index(sur):
             assert np.array_equal(np.asarray(emp.getCountTable(ev, snp), dtype=float), ct[a, j])
 
 
+def test_linked_gene_drop_follows_quickgsim_meiosis():
+    """gfx_gene_drop_linked (quickgsim/genome.py:74-115; the reference's generator is unseeded, so properties): with parents
+    whose two strands are all-0 / all-1 the transmitted alleles ARE the strand sequence: per gamete and chromosome at least one
+    switch, never at the first or the last marker, their number distributed like max(1, Poisson(Morgans)), their positions
+    like the genetic distances; Mendelian consistency; determinism in the seed."""
+    import torch
+    from genofix_b200.simulate_device import DeviceSimulator, linkage_arrays
+    n_kids, s = 4000, 1000
+    rows = np.zeros((2 + n_kids, 4), dtype=np.int64)
+    rows[:, 0] = np.arange(1, 3 + n_kids)
+    rows[0, 3], rows[1, 3] = 1, 2
+    rows[2:, 1], rows[2:, 2], rows[2:, 3] = 1, 2, 1
+    # three chromosomes: 400 markers / 1.5 M evenly spaced, 350 markers / 0.6 M with a hot interval, 250 markers / 2.5 M
+    chrom = np.array([1] * 400 + [2] * 350 + [3] * 250)
+    cm2 = np.concatenate([np.linspace(0.1, 10, 175), np.linspace(50, 60, 175)])       # 40 cM between markers 174 and 175
+    cm = np.concatenate([np.linspace(0.375, 150, 400), cm2, np.linspace(1, 250, 250)])
+    start, morgans, cum_p = linkage_arrays(chrom, cm)
+    assert list(start) == [0, 400, 750, 1000] and np.allclose(morgans, [1.5, 0.6, 2.5])
+    sim = DeviceSimulator(rows, s, seed=77)
+    het = torch.full((sim.wpr,), 0xAAAAAAAA - (1 << 32), dtype=torch.int32, device=sim.hap.device)   # strand 0 all 0, strand 1 all 1
+    sim.hap[0] = het
+    sim.hap[1] = het
+    truth = sim.gene_drop(linkage_map=(chrom, cm), first_level=1)
+    hap = sim.hap[2:].cpu().numpy().view(np.uint32)
+    j = np.arange(s)
+    bits = (hap[:, j // 16] >> (2 * (j % 16)).astype(np.uint32)) & 3
+    for side in (0, 1):
+        strand = (bits >> side) & 1                                  # [kids, s]: which strand of the parent
+        for c, (a, b) in enumerate(zip(start[:-1], start[1:])):
+            seg = strand[:, a:b]
+            sw = seg[:, 1:] != seg[:, :-1]                           # sw[:, i]: switch AT marker i + 1
+            nsw = sw.sum(axis=1)
+            assert nsw.min() >= 1                                    # obligatory crossover
+            assert not sw[:, -1].any()                               # never at the last marker; the first cannot show by construction
+            lam = float(morgans[c])
+            k = np.arange(60)
+            from math import exp, factorial
+            pk = np.array([exp(-lam) * lam ** i / factorial(i) for i in k])
+            expect = (np.maximum(k, 1) * pk).sum()
+            assert abs(nsw.mean() - expect) < 5 * np.sqrt(max(lam, 0.3) / n_kids) + 0.02, (side, c, nsw.mean(), expect)
+            assert 0.45 < seg[:, 0].mean() < 0.55                    # random start strand
+        # the hot interval of chromosome 2 (40 of the 59.8 cM between its interior markers): a gamete with n crossovers on
+        # distinct markers holds it with probability ~ 1 - (1 - p)^n, so its share of all crossovers is E[that] / E[n]
+        seg = strand[:, start[1]:start[2]]
+        sw = seg[:, 1:] != seg[:, :-1]
+        p_hot = 40.0 / (cm2[-2] - cm2[0])
+        lam = float(morgans[1])
+        pn = {n: exp(-lam) * lam ** n / factorial(n) for n in range(2, 40)}
+        pn[1] = exp(-lam) * (1 + lam)
+        share = sum(q * (1 - (1 - p_hot) ** n) for n, q in pn.items()) / sum(q * n for n, q in pn.items())
+        assert abs(sw[:, 174].sum() / sw.sum() - share) < 0.03
+    codes = truth[2:].cpu().numpy().view(np.uint32)
+    g = (codes[:, j // 16] >> (2 * (j % 16)).astype(np.uint32)) & 3
+    assert g.max() <= 2                                              # het x het parents: every genotype possible, none missing
+    sim2 = DeviceSimulator(rows, s, seed=77)
+    sim2.hap[0] = het
+    sim2.hap[1] = het
+    sim2.gene_drop(linkage_map=(chrom, cm), first_level=1)
+    assert torch.equal(sim.hap, sim2.hap)
+    # a multi-generation drop with random founders is Mendelian-consistent
+    from genofix_b200 import synth
+    from genofix_b200.engine import Engine
+    from genofix_b200.pedigree.pedigree_dag import PedigreeDAG
+    prow = synth.make_pedigree(600, 5, seed=3)
+    sim3 = DeviceSimulator(prow, s, seed=5)
+    t3 = sim3.gene_drop(linkage_map=(chrom, cm))
+    eng = Engine(PedigreeDAG.from_table(prow), prow[:, 0], 2)
+    eng._alloc(s)
+    eng.use_packed(t3[:, :eng.wpr].contiguous(), s)
+    inc, tested = eng.trio_scan()
+    assert int(inc.sum()) == 0 and int(tested.sum()) > 0
+
+
 # ---- the empirical (LD-window) blend: correctMatrix WITH an index (VERDICT r1 item 7, SURVEY 8(f) rank 2) ----------------
 def _ld_index(obs, names, surround, pseudocount):
     import pandas as pd

@@ -607,7 +607,7 @@ class Engine(object):
 
         def io_shape(s_):
             return (self.n, ((((s_ + 15) // 16) + 3) // 4) * 4) if packed_io else (self.n, s_)
-        state = {"ev_comp": [None, None], "ev_out": [None, None], "hold": [None, None]}
+        state = {"ev_comp": [None, None], "ev_out": [None, None], "hold": [None, None], "staged": 0}
 
         def pinned_view(arr, s):
             """torch view of a caller array the copy engines can reach directly, else None (staged copy)"""
@@ -637,7 +637,13 @@ class Engine(object):
                 else:
                     _parallel_copy(self.p_in[slot].numpy()[:, :self.s], G)
             state["hold"][slot] = (G, src)    # keep the caller's memory alive until the copy has run
+            order = getattr(self, "_copy_order", None)   # a lane of MultiLane: (CopyOrder, global chunk numbers of this lane)
+            kglob = order[1][state["staged"]] if order is not None else -1
+            state["staged"] += 1
+            before = order[0].wait_for(kglob - 1) if order is not None else None
             with t.cuda.stream(self.s_in):
+                if before is not None:
+                    self.s_in.wait_event(before)                     # uploads in chunk order (CopyOrder)
                 if state["ev_comp"][slot] is not None:
                     self.s_in.wait_event(state["ev_comp"][slot])     # the kernels that read p_packed[slot] are done
                 if packed_io:
@@ -648,6 +654,8 @@ class Engine(object):
                                                 self.p_packed[slot].data_ptr(), self.wpr, self._stream()))
                 ev = t.cuda.Event()
                 ev.record(self.s_in)
+            if order is not None:
+                order[0].publish(kglob, ev)
             return ev
 
         def finish(slot, s, test_p, n_nan, k, out, direct):
@@ -863,6 +871,41 @@ def pinned_array(shape, dtype=np.uint8):
     return t.empty(tuple(shape), dtype=getattr(t, dtype.name), pin_memory=True).numpy()
 
 
+class CopyOrder(object):
+    """Host-to-device copies of MultiLane's chunks in chunk order.  Every lane stages its chunks on its own stream; without
+    an order the first L uploads share the link and ALL arrive after L transfer times, with the GPU idle until then.  With
+    it chunk k's upload waits (on the device) for chunk k - 1's, so chunk 0 is complete after one transfer time and its
+    kernels run under the uploads of chunks 1 .. L - 1.  publish() / wait_for() are host-side; the ordering itself is a
+    stream-wait on the previous upload's event."""
+
+    def __init__(self, n_chunks):
+        import threading
+        self._cv = threading.Condition()
+        self._events = [None] * n_chunks
+        self._published = [False] * n_chunks
+        self._failed = False
+
+    def wait_for(self, k):
+        """Event of chunk k's upload once its lane has enqueued it (None: no such chunk, or a lane failed)."""
+        if k < 0 or k >= len(self._events):
+            return None
+        with self._cv:
+            while not self._published[k] and not self._failed:
+                self._cv.wait(timeout=0.05)
+            return self._events[k]
+
+    def publish(self, k, event):
+        with self._cv:
+            self._events[k] = event
+            self._published[k] = True
+            self._cv.notify_all()
+
+    def fail(self):
+        with self._cv:
+            self._failed = True
+            self._cv.notify_all()
+
+
 class MultiLane(object):
     """L engines on one schedule, one host thread and one set of streams each: independent chunks are corrected
     concurrently, so that the latency-bound correction kernels of one chunk share the GPU with those of another and
@@ -905,11 +948,13 @@ class MultiLane(object):
         done = [threading.Event() for _ in chunks]
         errs = []
         _lib.check(self.engines[0].L.gfx_reset_device_status(self.schedule.handle))
+        order = CopyOrder(len(chunks))
         for eng in self.engines:
             eng._lane = True
 
         def lane(l, eng):
             mine = list(range(l, len(chunks), L))
+            eng._copy_order = (order, mine)
             try:
                 gen = eng.correct_chunks((chunks[k] for k in mine), threshold_pair, threshold_single, init_filter_p=init_filter_p,
                                          tiethreshold=tiethreshold, err_thresh=err_thresh,
@@ -919,8 +964,11 @@ class MultiLane(object):
                     done[k].set()
             except BaseException as e:  # noqa: B902
                 errs.append(e)
+                order.fail()
                 for k in mine:
                     done[k].set()
+            finally:
+                eng._copy_order = None
         th = [threading.Thread(target=lambda l=l: (self.engines[0].torch.cuda.set_device(self.device), lane(l, self.engines[l])))
               for l in range(L)]
         for x in th:

@@ -458,3 +458,37 @@ def test_count_table_and_emp_probs_match_reference(sur):
             assert obs == G[kid - 1, j]
             got[kid - 1] = v
         assert np.array_equal(got, ep[j], equal_nan=True), snp
+
+
+def test_copy_order_hands_out_upload_events_in_chunk_order():
+    """MultiLane's upload order (engine.CopyOrder): chunk k's lane blocks until chunk k - 1's upload has been enqueued and
+    receives its event; out-of-range chunks and a failed lane release every waiter with None."""
+    import threading
+    import time
+    from genofix_b200.engine import CopyOrder
+    order = CopyOrder(5)
+    assert order.wait_for(-1) is None and order.wait_for(5) is None
+    got = {}
+
+    def lane(l):
+        for k in range(l, 5, 3):
+            got[k] = order.wait_for(k - 1)
+            time.sleep(0.01 * ((k * 7) % 3))
+            order.publish(k, "upload-%d" % k)
+    th = [threading.Thread(target=lane, args=(l,)) for l in (2, 1, 0)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(timeout=10)
+        assert not x.is_alive()
+    assert got == {0: None, 1: "upload-0", 2: "upload-1", 3: "upload-2", 4: "upload-3"}
+    # a lane that dies before publishing must not leave the others waiting
+    order = CopyOrder(3)
+    res = []
+    w = threading.Thread(target=lambda: res.append(order.wait_for(0)))
+    w.start()
+    time.sleep(0.05)
+    assert w.is_alive()
+    order.fail()
+    w.join(timeout=10)
+    assert not w.is_alive() and res == [None]

@@ -2546,7 +2546,7 @@ __device__ __forceinline__ KidCounts kids_counts(const CellCtx& c, const int32_t
                                                  const int32_t* __restrict__ child_other, int nk, int64_t wo, int sh,
                                                  const uint2* s_ku) {
   uint32_t a01 = 0, a2n = 0;
-  for (int i = 0; i < nk; ++i) {
+  for (int i = 0; i < nk; ++i) {   // (#pragma unroll 4 measured: no change)
     const int r = __ldg(child_row + i), o = __ldg(child_other + i);
     const uint32_t k = (__ldg(c.live + (int64_t)r * c.wpr + wo) >> sh) & 3u;
     const uint32_t pp = o >= 0 ? ((__ldg(c.live + (int64_t)o * c.wpr + wo) >> sh) & 3u) : 3u;
@@ -2855,9 +2855,17 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
     if (!parked) {
       // one byte of decision bits per job of this animal (a many-mate sire has dozens, a dam one), then the cell's slot
       // (one atomic for both: slot number in the low word of the counter, bytes handed out in the high word)
-      const unsigned long long got = atomicAdd(a.wl_count, ((unsigned long long)(e1 - e0) << 32) | 1ull);
-      slot = got & 0xFFFFFFFFull;
-      sb = got >> 32;
+      // The lanes of the warp that park at this job draw together (same animal, so the same e1 - e0): one same-address
+      // atomic with a returned value per lane was 8 % of the kernel's stall samples (profiles/r2_stalls_k_correct_gen0.txt).
+      const uint32_t act = __activemask();
+      const int ln = threadIdx.x & 31, leader = __ffs(act) - 1, nact = __popc(act);
+      unsigned long long got = 0;
+      if (ln == leader)
+        got = atomicAdd(a.wl_count, ((unsigned long long)(e1 - e0) * (unsigned long long)nact << 32) | (unsigned long long)nact);
+      got = __shfl_sync(act, got, leader);
+      const unsigned long long rk = (unsigned long long)__popc(act & ((1u << ln) - 1u));
+      slot = (got & 0xFFFFFFFFull) + rk;
+      sb = (got >> 32) + rk * (unsigned long long)(e1 - e0);
       if (slot >= a.wl_cap || sb + (unsigned long long)(e1 - e0) > a.sb_cap) return false;
       parked = true;
       first = e - e0;
@@ -3026,6 +3034,8 @@ __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
   const int64_t tasks = (int64_t)a.n_focal * chunks;
   const uint32_t tp = a.c.tp_raw;
   for (;;) {
+    // one (animal, SNP range) task per draw, drawn when needed.  [Measured and rejected: requesting the next ticket before
+    // the current task is worked on (10.43 vs 10.45 ms per chunk), draws of 2 / 4 consecutive tasks (+0.1 / +0.3 ms).]
     unsigned long long task = 0;
     if (lane == 0) task = atomicAdd(a.task_count, 1ull);
     task = __shfl_sync(0xffffffffu, task, 0);
@@ -3046,6 +3056,8 @@ __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
       if (j < a.n_snps) {
         sus = cell_rx(a.c, row, j) >= tp;
         if (a.nf == 2)
+          // [measured and rejected: the mates' rows kept in shared memory per task and four mates' scores requested
+          //  together: 10.60 vs 10.45 ms per chunk]
           for (int e = e0; e < e1 && !sus; ++e) {
             const int ent = a.entry[e];
             const int mrow = (ent & 1) == 0 ? a.job_row1[ent >> 1] : a.job_row0[ent >> 1];
@@ -3125,6 +3137,8 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
   if (ncell > a.wl_cap) ncell = a.wl_cap;
   const int lane = threadIdx.x & 31;
   for (;;) {
+    // [measured and rejected: the next ticket requested before these items are worked on -- a busy warp then sits on a
+    //  batch that an idle one would have taken: 11.12 vs 10.45 ms per chunk]
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(ticket, 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
@@ -3184,7 +3198,7 @@ __global__ void __launch_bounds__(KJ_THREADS, KJ_BLOCKS * 128 / KJ_THREADS) k_co
 #define KG_BLOCKS 4
 #endif
 #ifndef KG_ITEMS
-#define KG_ITEMS 16   // jobs per ticket of the general round (measured: 16 beats 32 and 8)
+#define KG_ITEMS 32   // jobs per ticket of the general round (with the one-pass table products: 32 -> 9.03 ms per chunk, 16 -> 9.2, 8 -> 9.75)
 #endif
 __global__ void __launch_bounds__(KJ_THREADS, KG_BLOCKS * 128 / KJ_THREADS) k_correct_jobs_general(FocalArgs a) {
 #ifdef GFX_GENERAL_SMEM_TIER

@@ -2722,6 +2722,9 @@ __device__ __forceinline__ void write_cell(const FocalArgs& a, int row, int64_t 
 // its parents' otherwise; anc64 = 64 * P(q) = [al_S al_D, al_S be_D + be_S al_D, be_S be_D].  The statuses of the
 // focal animal's own parents (slots 0 / 1 of every blanket of this animal) come from the per-cell cache (rows pS / pD,
 // codes, raw patterns): they differ between the jobs of a cell only through `cut`.
+#ifndef GFX_FAST_ANC_EAGER
+#define GFX_FAST_ANC_EAGER 0
+#endif
 struct ParentCache { int rS, rD; uint32_t cS, cD, xS, xD; };
 __device__ __forceinline__ int slot_status_cached(const CellCtx& c, int r, const ParentCache& P, int64_t wo, int sh, int64_t j,
                                                   uint32_t cut) {
@@ -2735,6 +2738,13 @@ __device__ __forceinline__ bool fast_anc(const CellCtx& c, const int32_t* __rest
   int st[2];
   st[0] = slot_status_cached(c, __ldg(srow + 0), P, wo, sh, j, cut);
   st[1] = slot_status_cached(c, __ldg(srow + 1), P, wo, sh, j, cut);
+#if GFX_FAST_ANC_EAGER
+  // the grand-parents' statuses are requested together with the parents' (one memory latency instead of two when a
+  // parent is unobserved or suspect; wasted loads when both parents count)
+  int st2[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) st2[g] = slot_status(c, __ldg(srow + 2 + g), wo, sh, j, cut);
+#endif
   int al[2];
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
@@ -2744,7 +2754,11 @@ __device__ __forceinline__ bool fast_anc(const CellCtx& c, const int32_t* __rest
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int s2 = 2 * f + 2 + g;
+#if GFX_FAST_ANC_EAGER
+      const int t2 = st2[2 * f + g];
+#else
       const int t2 = slot_status(c, __ldg(srow + s2), wo, sh, j, cut);
+#endif
       if (t2 <= 2) { a2[g] = 8 - 4 * t2; continue; }
       if (t2 == 4) { a2[g] = -1; continue; }            // no parents: f is a founder of the blanket
       if ((bad >> s2) & 1u) return false;
@@ -3021,8 +3035,9 @@ __device__ __forceinline__ bool correct_cell(const FocalArgs& a, const double* s
 #define GFX_LEAN_CHUNK_SINGLES 1024
 #endif
 #ifndef KC_BLOCKS
-#define KC_BLOCKS 6
-#endif
+#define KC_BLOCKS 8   // 64 registers (44 bytes of spills) and 32 warps per SM: 8.49 ms per chunk alone against 8.81 with 6 blocks
+#endif                // (78 registers), 39.2 against 40.1 ms per 3-lane bench step; 7 blocks: 8.61 / 38.8 ms
+
 template <int GFX_LEAN_CHUNK_T>
 __global__ void __launch_bounds__(128, KC_BLOCKS) k_correct(FocalArgs a) {
   __shared__ uint16_t s_list[4][GFX_LEAN_CHUNK_T];
@@ -3331,8 +3346,10 @@ static int run_correct(const gfx_schedule* s, int nf, int n_jobs, const int32_t*
   a.task_count = a.wl_count + 1;
   a.focal_order = focal_order;
   const int64_t tasks = (int64_t)n_focal * ((n_snps + GFX_CORRECT_CHUNK - 1) / GFX_CORRECT_CHUNK);
+  // the fallback kernel returns at once unless a cell was sent to it (lists full, posteriors requested): a small grid,
+  // its blocks stride over the tasks [24 blocks per SM cost 34 us per generation for nothing]
   int64_t blocks = tasks;
-  const int64_t cap = (int64_t)s->num_sms * 24;
+  const int64_t cap = (int64_t)s->num_sms * 8;
   if (blocks > cap) blocks = cap;
   const int lean_chunk = nf == 2 ? GFX_LEAN_CHUNK : GFX_LEAN_CHUNK_SINGLES;
   const int64_t wtasks = (int64_t)n_focal * ((n_snps + lean_chunk - 1) / lean_chunk);

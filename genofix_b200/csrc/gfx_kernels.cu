@@ -2526,6 +2526,15 @@ __device__ __noinline__ bool kids_term_dev(const CellCtx& c, const int32_t* chil
 // GFX_GUARD_EPS; inside that band (exact ties like 0.75 - 0.25 vs 0.5 are common) the job is replayed literally,
 // in numpy's summation order, by the deferred-job kernels.  Calls stay bit-exact, the fast path needs no float64
 // children sum at all.
+// Flags of a deferred job item (high bits of its job number): what the kernels before have already found out about it,
+// so that no walk that is known to fail is repeated (the deferred kernels re-ran the plain peeling of every item and the
+// general round re-ran the message passing that had just failed).
+#define GFX_ITEM_LITERAL 0x80000000u      // plain peeling answered the job, only the literal children sum is missing
+#define GFX_ITEM_OWN_NOPEEL 0x40000000u   // plain peeling fails on the focal animal's side
+#define GFX_ITEM_MATE_NOPEEL 0x20000000u  // ... succeeds there and fails on the mate's side
+#define GFX_ITEM_OWN_NOX 0x10000000u      // message passing fails on the focal animal's side
+#define GFX_ITEM_MATE_NOX 0x08000000u     // ... succeeds there and fails on the mate's side
+#define GFX_ITEM_FLAGS 0xF8000000u
 #define GFX_GUARD_EPS 1e-9
 #define GFX_BITS_GUARD 0xFFFFFFFFu
 struct KidCounts { int k0, k1, k2, ninc; };   // ninc: usable (genotyped, non-missing) children
@@ -2593,7 +2602,9 @@ __device__ __forceinline__ bool kids_literal_known(int nk, const KidCounts& K, b
 // when a test falls inside the guard band, when the fast kernel already found that (`literal`), or for posteriors.
 template <int MODE>
 __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, int64_t j, int obs0, uint32_t rxf,
-                                         const KidCounts& K, bool literal, uint32_t* bits_out, double* stab) {
+                                         const KidCounts& K, uint32_t flags, uint32_t* bits_out, double* stab,
+                                         uint32_t* fail_flag = nullptr) {
+  const bool literal = (flags & GFX_ITEM_LITERAL) != 0u;
   const uint32_t tp = a.c.tp_raw;
   const uint32_t idxf = rxf == 0xFFFFu ? 65536u : rxf;
   const int job = a.nf == 2 ? (ent >> 1) : ent;
@@ -2627,10 +2638,11 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
     const uint32_t tree = a.bl_tree[bid];                   // bit s: ancestry of focal s is a plain tree
     double tot_me = 1.0, tot_ot = 1.0;
     const int sme = a.nf == 2 ? side : 0;
-    if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
+    if ((flags & GFX_ITEM_OWN_NOPEEL) ||
+        !slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], j, LB.cut, anc)) {
       LB.prefetch();
-      if (xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
-      else if constexpr (MODE == 1) return false;
+      if (!(flags & GFX_ITEM_OWN_NOX) && xpeel_query(LB, qme, qot, anc, &tot_me)) { GFX_COUNT(a.bl, 8, 1); }
+      else if constexpr (MODE == 1) { if (fail_flag) *fail_flag = GFX_ITEM_OWN_NOX; return false; }
       else if (query_general(LB, a.bl, qme, qot, anc, &tot_me, stab)) atomicExch(a.status, 1);
     } else {
       GFX_COUNT(a.bl, 1, 1);
@@ -2639,10 +2651,11 @@ __device__ __forceinline__ bool job_bits(const FocalArgs& a, int row, int ent, i
       // the joint of correctPair is 0/0 when EITHER animal's component has P(evidence) = 0; a
       // tree-shaped ancestry has no evidence below unobserved nodes, so its total is exactly 1
       double tmp[3];
-      if (!slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
+      if ((flags & GFX_ITEM_MATE_NOPEEL) ||
+          !slot_peel(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], j, LB.cut, tmp)) {
         if (!LB.pre) LB.prefetch();
-        if (!xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
-          if constexpr (MODE == 1) return false;
+        if ((flags & GFX_ITEM_MATE_NOX) || !xpeel_query(LB, qot, qme, tmp, &tot_ot)) {
+          if constexpr (MODE == 1) { if (fail_flag) *fail_flag = GFX_ITEM_MATE_NOX; return false; }
           else if (query_general(LB, a.bl, qot, qme, tmp, &tot_ot, stab)) atomicExch(a.status, 1);
         }
       }
@@ -2783,7 +2796,6 @@ __device__ __forceinline__ bool fast_anc(const CellCtx& c, const int32_t* __rest
 // gets a slot in the deferred list: its state is parked, the remaining easy jobs still deposit their bits there, the
 // hard jobs become items for k_correct_jobs, and k_correct_apply finishes the walk.  Returns false if the whole cell
 // must go to the fallback kernel (no slot left, posteriors requested), in which case nothing has been written.
-#define GFX_ITEM_LITERAL 0x80000000u   // item flag: plain peeling answered the job, only the literal children sum is missing
 __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku, int f, int row, int e0, int e1, int64_t j) {
   const int64_t wo = j >> 4;
   const int sh = 2 * (int)(j & 15);
@@ -2837,11 +2849,13 @@ __device__ __forceinline__ bool lean_cell(const FocalArgs& a, const uint2* s_ku,
         const uint32_t cut = __ldg(a.c.cutraw + pidx);
         const int sme = a.nf == 2 ? side : 0;
         ok = fast_anc(a.c, a.bl_slotrow + ((int64_t)bid * 2 + sme) * 14, a.bl_slotbad[bid * 2 + sme], P, wo, sh, j, cut, anc64);
+        if (!ok) flag = GFX_ITEM_OWN_NOPEEL;
         if (ok && a.nf == 2 && !((a.bl_tree[bid] >> (side ^ 1)) & 1u)) {
           // the mate's component must have P(evidence) > 0 (:242-245 joint = False): certain when it peels plainly
           int tmp[3];
           ok = fast_anc(a.c, a.bl_slotrow + ((int64_t)bid * 2 + (side ^ 1)) * 14, a.bl_slotbad[bid * 2 + (side ^ 1)], none, wo, sh, j,
                         cut, tmp);
+          if (!ok) flag = GFX_ITEM_MATE_NOPEEL;
         }
       }
       if (!ok) GFX_COUNT(a.bl, 8, 1);
@@ -3136,7 +3150,7 @@ __global__ void __launch_bounds__(256) k_jobs_scatter(FocalArgs a) {
     const uint2 it = a.items[i];
     // items of cells that found no slot were never counted; they keep their cell on the fallback path
     if (it.x >= ncell) continue;
-    const int key = a.focal_off[a.wl[it.x].x] + (int)(it.y & ~GFX_ITEM_LITERAL) - a.e_base;
+    const int key = a.focal_off[a.wl[it.x].x] + (int)(it.y & ~GFX_ITEM_FLAGS) - a.e_base;
     const uint32_t pos = a.key_off[key] + atomicAdd(a.key_cur + key, 1u);
     a.items_sorted[pos] = it;
   }
@@ -3172,12 +3186,16 @@ __device__ __forceinline__ void jobs_round(const FocalArgs& a, const uint2* list
         const uint32_t rxf = cell_rx(a.c, row, j);
         const int4 kc = a.skc[it.x];
         const KidCounts K{kc.x, kc.y, kc.z, kc.w};
-        const int ji = (int)(it.y & ~GFX_ITEM_LITERAL);
-        uint32_t bits;
-        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, (it.y & GFX_ITEM_LITERAL) != 0u, &bits, stab))
+        const int ji = (int)(it.y & ~GFX_ITEM_FLAGS);
+        uint32_t bits, why = 0u;
+        if (job_bits<MODE>(a, row, a.entry[a.focal_off[f] + ji], j, obs0, rxf, K, it.y & GFX_ITEM_FLAGS, &bits, stab, &why)) {
           a.sbits[(unsigned long long)a.sboff[it.x] + ji] = (uint8_t)bits;
-        else
+        } else {
           again = true;
+          // what the general round need not try again; when the focal side was answered by message passing here, its
+          // plain peeling is known to fail as well
+          it.y |= why | (why == GFX_ITEM_MATE_NOX ? GFX_ITEM_MATE_NOPEEL : GFX_ITEM_OWN_NOPEEL);
+        }
       }
     }
     if (MODE == 1) {
